@@ -1,0 +1,134 @@
+/* ssb.h — C-ABI of the B200-native ssa_sdpd engine (libssb_core.so + one model unit per model).
+ *
+ * The reference engine has NO foreign-function interface: its ABI is a process contract
+ * (`ssa_sdpd.exe -s SEED -t THREADS`, cwd = result directory, exit code; E/propensity_file_template.cpp:101-142,
+ * spatialpy/solvers/solver.py:553-597, E = spatialpy/solvers/c_base/ssa_sdpd-c-simulation-engine) with every
+ * model input baked in as C++ literals (solver.py:100-158).  This header is the in-process replacement of
+ * that contract: plain pointers and sizes, no C++ or torch types, all functions return 0 on success and a
+ * non-zero code on failure (the Python side raises SimulationError("Solver execution failed, return code = N"),
+ * matching solver.py:595-597).  No function calls exit() or throws across the boundary.
+ *
+ * Ownership: every pointer inside `ssb_model` is BORROWED for the duration of ssb_create() only (the engine
+ * copies to device memory); the library never frees caller memory.  One handle is single-threaded; distinct
+ * handles may run concurrently on distinct GPUs.
+ */
+#ifndef SSB_H
+#define SSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_ABI_VERSION 1
+
+/* error codes */
+#define SSB_OK 0
+#define SSB_ERR_NAN 1          /* NaN/Inf in x, v or rho — reference: check_particle_nan() exit(1), E/src/particle.cpp:88-126 */
+#define SSB_ERR_RDME 2         /* negative population / propensity overflow — reference exit(1) sites, E/src/simulate_rdme.cpp:279,293,345,388,399,467 */
+#define SSB_ERR_CUDA 3
+#define SSB_ERR_ARG 4
+#define SSB_ERR_IO 5
+#define SSB_ERR_CANCELLED 6    /* ssb_cancel() — reference: SIGINT to the process group on timeout, solver.py:579-586 */
+#define SSB_ERR_MODEL_UNIT 7   /* model unit missing / compiled for different sizes */
+
+/* flags (ssb_model.flags) */
+#define SSB_FLAG_CORRECTED_NSM_SELECT 1u   /* draw the reaction/diffusion channel with the textbook NSM rule instead of the reference's
+                                              rand1*srrate rule (simulate_rdme.cpp:253-261,317-321) */
+#define SSB_FLAG_CORRECTED_STOICH 2u       /* index the dense stoichiometry as N[s][rxn] instead of the reference's transposed/out-of-bounds
+                                              read (E/src/model.cpp:186-187) */
+#define SSB_FLAG_NO_VTK 4u                 /* stage outputs (ssb_get_output) but do not write outputN.vtk files */
+#define SSB_FLAG_SKIP_STATIC_FORCES 8u     /* static domains: skip F/Fbp/Frho (never consumed when static, simulate.cpp:68,137); default on via Python */
+
+/* Flat model description.  Replaces the generated-literal inputs of solver.py:100-419. */
+typedef struct ssb_model {
+    int32_t abi_version;            /* SSB_ABI_VERSION */
+    uint32_t flags;
+    int64_t n_particles;            /* __NUMBER_OF_VOXELS__ (solver.py:138) */
+    int32_t dimension;              /* system->dimension (solver.py:407-413) */
+    int32_t static_domain;          /* system->static_domain (solver.py:381) */
+    int32_t num_types;              /* ParticleSystem::num_types = len(listOfTypeIDs)-1 (solver.py:379) */
+    int32_t num_chem_species;       /* S_c (solver.py:106-111) */
+    int32_t num_chem_rxns;
+    int32_t num_stoch_species;      /* S_d (solver.py:112-117) */
+    int32_t num_stoch_rxns;
+    int32_t num_data_fn;
+    double dt;                      /* system->dt (solver.py:389) */
+    uint32_t nt;                    /* system->nt (solver.py:390) */
+    uint32_t n_output_steps;
+    const uint32_t *output_steps;   /* get_next_output() table (solver.py:290-299) */
+    double h, rho0, c0, P0;         /* solver.py:391-398 */
+    double xlo, xhi, ylo, yhi, zlo, zhi;   /* solver.py:400-405 */
+    double gravity[3];              /* solver.py:415-417 */
+    /* particles, index = id (init_create_particle, solver.py:312-331) */
+    const double *x;                /* [N*3] xyz interleaved */
+    const int32_t *type;            /* [N], 1-based */
+    const double *nu, *mass, *c, *rho;   /* [N] each */
+    const int32_t *solid;           /* [N] solidTag = domain.fixed */
+    const uint32_t *u0;             /* [N*S] voxel-major input_u0 (solver.py:211-220); also seeds C[] (template:77-81) */
+    const double *data_fn;          /* [ndf*N] input_data_fn (solver.py:239-249) */
+    const int32_t *N_dense;         /* [S*R] input_N_dense row-major species x rxn (solver.py:223-233) */
+    const int64_t *irN, *jcN;       /* CSC of N (solver.py:235-236) */
+    const int32_t *prN;             /* (solver.py:237) */
+    const int64_t *irG, *jcG;       /* dependency graph CSC, columns [species..., reactions...] (solver.py:256-257) */
+    const double *diffusion_matrix; /* [S*num_types] input_subdomain_diffusion_matrix (solver.py:269-286) */
+    const char *const *species_names; /* [S] input_species_names (solver.py:259-263) */
+    /* sSSA window controller: tau = rdme_epsilon / max_i max_s Ddiag_i[s]  (<=0 selects the default 0.05) */
+    double rdme_epsilon;
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t reserved;
+} ssb_model;
+
+typedef struct ssb_handle ssb_handle;
+
+/* progress callback: called from the stepping thread after each engine step; return non-zero to cancel */
+typedef int (*ssb_progress_cb)(void *user, uint32_t step, uint32_t nt);
+
+/* Library / device */
+int ssb_abi_version(void);
+int ssb_device_count(int *count);
+
+/* Lifecycle.  ssb_create copies the model to the device (replaces init_all_particles + initialize_rdme,
+ * template:134-138).  ssb_load_kernels dlopen()s the per-model unit compiled by codegen (replaces linking
+ * the generated model.cpp, E/build/SConstruct). */
+int ssb_create(const ssb_model *model, ssb_handle **out);
+int ssb_load_kernels(ssb_handle *h, const char *model_unit_path);
+int ssb_destroy(ssb_handle *h);
+
+/* Run trajectories first_traj .. first_traj+ntraj-1; trajectory k uses seed+k (solver.py:558-559) and writes
+ * output%u.vtk + output0_boundingBox.vtk into out_dirs[k-first_traj] (E/src/output.cpp:104-229).
+ * Replaces `exe -s seed -t T` (solver.py:553-569) and run_simulation() (E/src/simulate_threads.cpp:171-312). */
+int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t first_traj,
+            const char *const *out_dirs, ssb_progress_cb cb, void *cb_user);
+
+/* Step-wise control (parity taps and benchmarking): reset state to the model's initial condition for one
+ * trajectory, then advance n engine steps (each = 3 SDPD substeps + RDME, simulate_threads.cpp:232-281).
+ * No files are written by ssb_step. */
+int ssb_reset(ssb_handle *h, uint64_t seed);
+int ssb_step(ssb_handle *h, uint32_t nsteps);
+
+/* Counters: ParticleSystem::total_reactions / total_diffusion (E/include/particle_system.hpp:79-80) of the most
+ * recent trajectory, the wall seconds of its stepping loop, and the number of sSSA windows launched. */
+int ssb_counters(ssb_handle *h, int64_t *reactions, int64_t *diffusions, double *seconds, int64_t *windows);
+
+/* Parity taps: copy a named per-particle field, in particle-id order, to caller memory.
+ * Names: x v vt F Fbp (f64, N*3) | rho old_rho Frho bvf_phi mass nu srrate sdrate (f64, N) | type solid (i32, N)
+ *        C Q (f64, N*S_c, voxel-major) | xx (u32, N*S_d) | Ddiag (f64, N*S_d) | rrate (f64, N*R)
+ *        nbr_count (i32, N).  `bytes` is the capacity of `dst`; returns SSB_ERR_ARG on mismatch. */
+int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t bytes);
+/* Neighbour lists in id space (CSR): ptr[N+1] int64, idx[nnz] int32 (neighbour ids), dist/dWdr/Dij[nnz] f64.
+ * Call with idx == NULL to obtain nnz in *nnz_out. */
+int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, double *dist, double *dWdr, double *Dij,
+                      int64_t *nnz_out);
+
+int ssb_cancel(ssb_handle *h);                 /* async-signal-safe flag; the running ssb_run returns SSB_ERR_CANCELLED */
+const char *ssb_last_error(ssb_handle *h);     /* message for the last non-zero return (valid until next call) */
+
+/* Kernel accounting for bench.py: number of engine kernels launched since the last ssb_reset/ssb_run start. */
+int ssb_launch_count(ssb_handle *h, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB_H */

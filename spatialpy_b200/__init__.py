@@ -1,0 +1,4 @@
+"""B200-native ssa_sdpd engine for SpatialPy (drop-in `Solver`; CUDA sm_100a, fp64, no CPU fallback)."""
+from .flatmodel import FlatModel, ReactionSource  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,1215 @@
+// ssb_core.cu — libssb_core.so: the model-independent half of the B200-native ssa_sdpd engine.
+//
+//   * K1  cell-list neighbour search: cell keys -> counting sort (one radix digit = the cell key, ties broken by
+//         previous storage index so the order is deterministic) -> SoA permutation -> index-only ELL neighbour lists.
+//         Replaces buildKDTree (E/src/simulate_threads.cpp:80-108) + Particle::find_neighbors (E/src/particle.cpp:240-294)
+//         with ANN's inclusion rule 0 < sum_d (q_d-p_d)^2 <= h*h (E/external/ANN/src/kd_fix_rad_search.cpp:160-178).
+//   * step scheduler: run_simulation (E/src/simulate_threads.cpp:171-312) as a single CUDA stream of kernels; the
+//         model-specialised kernels come from the per-model unit (ssb_model_unit.cuh) through SsbModelUnit.
+//   * K8  output staging: gather to particle-id order on the device, one D2H into pinned memory, and a host writer
+//         thread producing the reference's ASCII VTK byte format (E/src/output.cpp:104-229) while the GPU steps on
+//         (mirrors output_system_thread, simulate_threads.cpp:60-73).
+//   * the C-ABI of include/ssb.h.
+// E = /root/reference/spatialpy/solvers/c_base/ssa_sdpd-c-simulation-engine.  No CPU fallback exists: every entry point
+// fails with SSB_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/ssb.h"
+#include "ssb_device.cuh"
+#include "ssb_unit_abi.h"
+
+#define CORE_BLOCK 256
+
+// =====================================================================================================
+// device kernels
+// =====================================================================================================
+struct CellGrid {
+    double lo[3];
+    double inv_cell[3];
+    int n[3];
+    int ncells;
+    int dim;
+};
+
+__device__ __forceinline__ int cell_coord(double x, double lo, double inv, int n) {
+    int c = (int) floor((x - lo) * inv);
+    return min(max(c, 0), n - 1);
+}
+
+__device__ __forceinline__ int cell_key(const CellGrid &g, double x, double y, double z, int &cx, int &cy, int &cz) {
+    cx = cell_coord(x, g.lo[0], g.inv_cell[0], g.n[0]);
+    cy = cell_coord(y, g.lo[1], g.inv_cell[1], g.n[1]);
+    cz = cell_coord(z, g.lo[2], g.inv_cell[2], g.n[2]);
+    return (cz * g.n[1] + cy) * g.n[0] + cx;
+}
+
+__global__ void k_cell_keys(int N, CellGrid g, const double *x, const double *y, const double *z, int *key, int *cell_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int cx, cy, cz;
+    int k = cell_key(g, x[i], y[i], z[i], cx, cy, cz);
+    key[i] = k;
+    atomicAdd(&cell_count[k], 1);
+}
+
+// exclusive scan, three phases (tile = 1024 elements per block)
+#define SCAN_TILE 1024
+__global__ void k_scan_tiles(int n, const int *in, int *out, int *tile_sums) {
+    __shared__ int sh[SCAN_TILE];
+    int base = blockIdx.x * SCAN_TILE;
+    for (int t = threadIdx.x; t < SCAN_TILE; t += blockDim.x) sh[t] = (base + t < n) ? in[base + t] : 0;
+    __syncthreads();
+    // each thread scans 4 consecutive items serially, then a block scan of the per-thread sums
+    int t4 = threadIdx.x * 4;
+    int a0 = sh[t4], a1 = sh[t4 + 1], a2 = sh[t4 + 2], a3 = sh[t4 + 3];
+    int sum = a0 + a1 + a2 + a3;
+    __shared__ int warp_sums[8];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < 8) ? warp_sums[lane] : 0;
+        for (int o = 1; o < 8; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        if (lane < 8) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    int excl = incl - sum + (wid > 0 ? warp_sums[wid - 1] : 0);
+    if (base + t4 < n) out[base + t4] = excl;
+    if (base + t4 + 1 < n) out[base + t4 + 1] = excl + a0;
+    if (base + t4 + 2 < n) out[base + t4 + 2] = excl + a0 + a1;
+    if (base + t4 + 3 < n) out[base + t4 + 3] = excl + a0 + a1 + a2;
+    if (threadIdx.x == blockDim.x - 1) tile_sums[blockIdx.x] = excl + sum;
+}
+__global__ void k_scan_sums(int ntiles, int *tile_sums, int *total_out) {
+    // single block: serial-in-chunks exclusive scan of the tile sums
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        int idx = base + threadIdx.x;
+        int v = (idx < ntiles) ? tile_sums[idx] : 0;
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        __shared__ int ws[32];
+        if (lane == 31) ws[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int w = (lane < (blockDim.x >> 5)) ? ws[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            ws[lane] = w;
+        }
+        __syncthreads();
+        int excl = incl - v + (wid > 0 ? ws[wid - 1] : 0) + carry;
+        if (idx < ntiles) tile_sums[idx] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void k_scan_add(int n, int *out, const int *tile_sums) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += tile_sums[i / SCAN_TILE];
+}
+
+__global__ void k_scatter(int N, const int *key, const int *cell_start, int *cursor, int *perm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int k = key[i];
+    int slot = atomicAdd(&cursor[k], 1);
+    perm[cell_start[k] + slot] = i;
+}
+
+// one thread per cell: order the cell's members by previous storage index (deterministic result whatever the
+// atomic arrival order was), and flag a non-identity permutation.
+__global__ void k_sort_cells(int ncells, const int *cell_start, int N, int *perm, int *nonidentity) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    int b = cell_start[c], e = (c + 1 < ncells) ? cell_start[c + 1] : N;
+    int n = e - b;
+    int *a = perm + b;
+    if (n > 1) {
+        if (n <= 48) {
+            for (int i = 1; i < n; i++) { int v = a[i]; int j = i - 1; while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; } a[j + 1] = v; }
+        } else {  // heap sort for crowded (clamped boundary) cells
+            for (int start = n / 2 - 1; start >= 0; start--) {
+                int root = start;
+                while (2 * root + 1 < n) { int ch = 2 * root + 1; if (ch + 1 < n && a[ch] < a[ch + 1]) ch++; if (a[root] < a[ch]) { int t = a[root]; a[root] = a[ch]; a[ch] = t; root = ch; } else break; }
+            }
+            for (int end = n - 1; end > 0; end--) {
+                int t = a[0]; a[0] = a[end]; a[end] = t;
+                int root = 0;
+                while (2 * root + 1 < end) { int ch = 2 * root + 1; if (ch + 1 < end && a[ch] < a[ch + 1]) ch++; if (a[root] < a[ch]) { int t2 = a[root]; a[root] = a[ch]; a[ch] = t2; root = ch; } else break; }
+            }
+        }
+    }
+    bool moved = false;
+    for (int i = 0; i < n; i++) moved |= (a[i] != b + i);
+    if (moved) *nonidentity = 1;
+}
+
+#define PERM_MAX64 96
+#define PERM_MAX32 40
+struct PermTable {
+    int n64, n32;
+    const double *src64[PERM_MAX64];
+    double *dst64[PERM_MAX64];
+    const int *src32[PERM_MAX32];
+    int *dst32[PERM_MAX32];
+};
+__global__ void k_permute(int N, const int *perm, const PermTable *T) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    int src = perm[p];
+    for (int f = 0; f < T->n64; f++) T->dst64[f][p] = T->src64[f][src];
+    for (int f = 0; f < T->n32; f++) T->dst32[f][p] = T->src32[f][src];
+}
+
+// neighbour search: query = live x_i, data = snapshot x0 (cell-sorted).  One thread per particle; the three
+// x-adjacent cells of a (cy,cz) row form one contiguous particle range.
+__global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (i < V.N) {
+        const int N = V.N, dim = V.dim, cap = V.nbr_cap;
+        const double h = V.h;
+        const double h2 = __dmul_rn(h, h);             // ANNdist dist = system->h * system->h (particle.cpp:253)
+        const double qx = V.x[0][i], qy = V.x[1][i], qz = V.x[2][i];
+        int cx, cy, cz;
+        cell_key(g, qx, qy, qz, cx, cy, cz);
+        const int x_lo = max(cx - 1, 0), x_hi = min(cx + 1, g.n[0] - 1);
+        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.n[2] - 1); zz++) {
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.n[1] - 1); yy++) {
+                const int row = (zz * g.n[1] + yy) * g.n[0];
+                const int b = cell_start[row + x_lo];
+                const int e = (row + x_hi + 1 < g.ncells) ? cell_start[row + x_hi + 1] : N;
+                for (int j = b; j < e; j++) {
+                    const double d2 = ssb_dist2(dim, qx, qy, qz, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+                    if (d2 <= h2 && d2 != 0.0) {        // kd_fix_rad_search.cpp:168-176 (ANN_ALLOW_SELF_MATCH = false)
+                        const double r = sqrt(d2);
+                        if (r > h) continue;            // particle.cpp:160-162
+                        if (cnt < cap) V.nbr[(size_t) cnt * N + i] = j;
+                        cnt++;
+                    }
+                }
+            }
+        }
+        V.nbr_count[i] = min(cnt, cap);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
+    if ((threadIdx.x & 31) == 0 && cnt > 0) atomicMax(max_count, cnt);
+}
+
+__global__ void k_iota(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
+__global__ void k_copy64(int n, const double *src, double *dst) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] = src[i]; }
+
+// gather storage order -> id order (output staging and parity taps)
+__global__ void k_unperm64(int N, const int *id, const double *src, double *dst, int stride, int offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[(size_t) id[i] * stride + offset] = src[i];
+}
+__global__ void k_unperm32(int N, const int *id, const int *src, int *dst, int stride, int offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[(size_t) id[i] * stride + offset] = src[i];
+}
+// neighbour list taps in id space
+__global__ void k_nbr_count_by_id(int N, const int *id, const int *cnt, long long *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[id[i]] = cnt[i];
+}
+__global__ void k_nbr_export(SsbView V, const long long *ptr, int *idx, double *dist, double *dWdr, double *Dij) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N;
+    const double alpha = ssb_alpha(V.dim, V.h);
+    long long base = ptr[V.id[i]];
+    const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+    for (int k = 0; k < V.nbr_count[i]; k++) {
+        int j = V.nbr[(size_t) k * N + i];
+        double d2 = ssb_dist2(V.dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+        double r = sqrt(d2);
+        idx[base + k] = V.id[j];
+        dist[base + k] = r;
+        dWdr[base + k] = ssb_dWdr(alpha, r, V.h);
+        Dij[base + k] = V.Dij ? V.Dij[(size_t) k * N + i]
+                              : ssb_Dij(d2, r, V.h, V.mass[i], V.mass[j], V.rho_search[i], V.rho_search[j]);
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct OutputJob {
+    int valid = 0;
+    unsigned step = 0;
+    unsigned file_index = 0;
+    int rdme_initialized = 0;
+    std::string dir;
+    cudaEvent_t ready = nullptr;
+    // pinned staging (id order)
+    double *x = nullptr;     // N*3
+    double *v = nullptr;     // N*3
+    double *scal = nullptr;  // 4*N: rho, mass, bvf, nu
+    int *type = nullptr;     // N
+    double *C = nullptr;     // Sc*N (species-major)
+    unsigned *xx = nullptr;  // Sd*N (species-major)
+};
+
+struct ssb_handle {
+    ssb_model m;       // scalars (pointers inside are NOT retained)
+    int N = 0, S = 0, R = 0;
+    // host copies of the initial condition
+    std::vector<double> hx, hnu, hmass, hrho, hdata_fn, hdmat;
+    std::vector<int> htype, hsolid;
+    std::vector<unsigned> hu0, hout_steps;
+    std::vector<std::string> species_names;
+    // device
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::vector<void *> allocs;
+    SsbView V;
+    // permuted field tables (current / alternate buffers)
+    std::vector<double **> f64_slots;  // addresses of the view pointers
+    std::vector<double *> f64_alt;
+    std::vector<int **> i32_slots;
+    std::vector<int *> i32_alt;
+    PermTable *d_permtable = nullptr;
+    // cell list
+    CellGrid grid;
+    int *d_key = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr, *d_perm = nullptr;
+    int *d_tile_sums = nullptr, *d_flags = nullptr;  // d_flags[0]=nonidentity [1]=max nbr count
+    unsigned long long *d_maxbits = nullptr;
+    double *d_stage = nullptr;   // device staging for output/taps (id order)
+    size_t stage_bytes = 0;
+    double *d_dmat = nullptr;
+    double *rho_buf[2] = {nullptr, nullptr};
+    // model unit
+    void *unit_dl = nullptr;
+    const SsbModelUnit *unit = nullptr;
+    // run state
+    unsigned current_step = 0;
+    int rdme_initialized = 0;
+    uint64_t seed = 0, epoch = 0;
+    int inbox_buf = 0;
+    double tau = 0.0;
+    int nbr_valid = 0;
+    int64_t launches = 0, windows = 0;
+    int64_t total_reactions = 0, total_diffusion = 0;
+    double step_seconds = 0.0;
+    std::atomic<int> cancel{0};
+    std::string err;
+    // output
+    OutputJob jobs[2];
+    int job_cursor = 0;
+    std::thread writer;
+    std::mutex mu;
+    std::condition_variable cv;
+    int writer_pending[2] = {0, 0};
+    int writer_quit = 0;
+    int writer_error = 0;
+};
+
+static int fail(ssb_handle *h, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(h, SSB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dalloc(ssb_handle *h, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count > 0 ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) { h->allocs.push_back(q); *p = (T *) q; }
+    return e;
+}
+
+static inline unsigned gridN(int n) { return (unsigned) ((n + CORE_BLOCK - 1) / CORE_BLOCK); }
+
+// ----------------------------------------------------------------------------------------------------
+// VTK writer (host thread) — byte format of E/src/output.cpp:104-229
+// ----------------------------------------------------------------------------------------------------
+struct Buf {
+    std::vector<char> d;
+    size_t n = 0;
+    void reserve(size_t extra) { if (n + extra > d.size()) d.resize((n + extra) * 2 + 4096); }
+    void putf(const char *fmt, ...) {
+        reserve(512);
+        va_list ap;
+        va_start(ap, fmt);
+        n += (size_t) vsnprintf(d.data() + n, 512, fmt, ap);
+        va_end(ap);
+    }
+};
+
+// "%lf " with exactly printf's rounding: fast path through integer arithmetic when the scaled value is far from a
+// rounding tie, otherwise snprintf.
+static inline void put_lf(Buf &b, double v) {
+    b.reserve(400);
+    char *p = b.d.data() + b.n;
+    double a = fabs(v);
+    if (a < 1e9 && a == a) {
+        double scaled = a * 1e6;
+        double fl = floor(scaled);
+        double frac = scaled - fl;
+        // a*1e6 carries at most ~1 ulp of error (~1.2e-7 at 1e9*1e6 scale is too coarse, so restrict the band)
+        double tol = scaled * 4.5e-16 + 1e-300;
+        if (fabs(frac - 0.5) > tol * 4 + 1e-9) {   // only a near-tie can round differently from printf
+            unsigned long long q = (unsigned long long) fl + (frac > 0.5 ? 1ull : 0ull);
+            unsigned long long ip = q / 1000000ull, fp = q % 1000000ull;
+            char tmp[32];
+            int len = 0;
+            if (signbit(v)) *p++ = '-';
+            if (ip == 0) tmp[len++] = '0';
+            while (ip) { tmp[len++] = (char) ('0' + ip % 10); ip /= 10; }
+            while (len) *p++ = tmp[--len];
+            *p++ = '.';
+            for (int k = 5; k >= 0; k--) { p[k] = (char) ('0' + fp % 10); fp /= 10; }
+            p += 6;
+            *p++ = ' ';
+            b.n = (size_t) (p - b.d.data());
+            return;
+        }
+    }
+    b.n += (size_t) snprintf(p, 400, "%lf ", v);
+}
+
+static inline void put_u(Buf &b, unsigned v) {
+    b.reserve(16);
+    char *p = b.d.data() + b.n;
+    char tmp[12];
+    int len = 0;
+    if (v == 0) tmp[len++] = '0';
+    while (v) { tmp[len++] = (char) ('0' + v % 10); v /= 10; }
+    while (len) *p++ = tmp[--len];
+    *p++ = ' ';
+    b.n = (size_t) (p - b.d.data());
+}
+
+static int write_vtk(ssb_handle *h, const OutputJob &J) {
+    const int np = h->N;
+    const int Sc = h->V.Sc, Sd = h->V.Sd;
+    char filename[4096];
+    if (J.step == 0 && J.file_index == 0) {
+        snprintf(filename, sizeof(filename), "%s/output0_boundingBox.vtk", J.dir.c_str());
+        FILE *fp = fopen(filename, "w+");
+        if (!fp) return SSB_ERR_IO;
+        fprintf(fp, "# vtk DataFile Version 4.1\n");
+        fprintf(fp, "Generated by ssa_sdpd\n");
+        fprintf(fp, "ASCII\n");
+        fprintf(fp, "DATASET RECTILINEAR_GRID\n");
+        fprintf(fp, "DIMENSIONS 2 2 2\n");
+        fprintf(fp, "X_COORDINATES 2 double\n");
+        fprintf(fp, "%lf %lf\n", h->m.xlo, h->m.xhi);
+        fprintf(fp, "Y_COORDINATES 2 double\n");
+        fprintf(fp, "%lf %lf\n", h->m.ylo, h->m.yhi);
+        fprintf(fp, "Z_COORDINATES 2 double\n");
+        fprintf(fp, "%lf %lf\n", h->m.zlo, h->m.zhi);
+        fclose(fp);
+    }
+    snprintf(filename, sizeof(filename), "%s/output%u.vtk", J.dir.c_str(), J.file_index);
+    FILE *fp = fopen(filename, "w+");
+    if (!fp) return SSB_ERR_IO;
+    Buf b;
+    b.d.resize((size_t) np * 64 + 65536);
+    auto flush = [&]() { if (b.n) fwrite(b.d.data(), 1, b.n, fp); b.n = 0; };
+    b.putf("# vtk DataFile Version 4.1\n");
+    b.putf("Generated by SpatialPy\n");
+    b.putf("ASCII\n");
+    b.putf("DATASET POLYDATA\n");
+    b.putf("POINTS %i float\n", np);
+    for (int i = 0; i < np; i++) {
+        b.reserve(128);
+        b.n += (size_t) snprintf(b.d.data() + b.n, 128, "%.10e %.10e %.10e ", J.x[i * 3], J.x[i * 3 + 1], J.x[i * 3 + 2]);
+        if ((i + 1) % 3 == 0) b.d[b.n++] = '\n';
+        if (b.n > (1u << 22)) flush();
+    }
+    b.putf("\n");
+    b.putf("VERTICES %i %i\n", np, 2 * np);
+    for (int i = 0; i < np; i++) {
+        b.reserve(32);
+        b.d[b.n++] = '1'; b.d[b.n++] = ' ';
+        put_u(b, (unsigned) i);
+        b.d[b.n - 1] = '\n';
+        if (b.n > (1u << 22)) flush();
+    }
+    b.putf("\n");
+    b.putf("POINT_DATA %i\n", np);
+    int num_fields = 7;
+    if (J.rdme_initialized) num_fields += Sd;      // output.cpp:151-154: undercounts in output0
+    if (Sc > 0) num_fields += Sc;
+    b.putf("FIELD FieldData %i\n", num_fields);
+    b.putf("id 1 %i int\n", np);
+    for (int i = 0; i < np; i++) { put_u(b, (unsigned) i); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+    b.putf("\n");
+    b.putf("type 1 %i int\n", np);
+    for (int i = 0; i < np; i++) { put_u(b, (unsigned) J.type[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+    b.putf("\n");
+    b.putf("v 3 %i double\n", np);
+    for (int i = 0; i < np; i++) {
+        put_lf(b, J.v[i * 3]); put_lf(b, J.v[i * 3 + 1]); put_lf(b, J.v[i * 3 + 2]);
+        if ((i + 1) % 3 == 0) { b.reserve(2); b.d[b.n++] = '\n'; }
+        if (b.n > (1u << 22)) flush();
+    }
+    b.putf("\n");
+    const char *scal_names[4] = {"rho", "mass", "bvf_phi", "nu"};
+    for (int f = 0; f < 4; f++) {
+        b.putf("%s 1 %i double\n", scal_names[f], np);
+        const double *a = J.scal + (size_t) f * np;
+        for (int i = 0; i < np; i++) { put_lf(b, a[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+        b.putf("\n");
+    }
+    for (int s = 0; s < Sc; s++) {
+        b.putf("C[%s] 1 %i double\n", h->species_names[s].c_str(), np);
+        const double *a = J.C + (size_t) s * np;
+        for (int i = 0; i < np; i++) { put_lf(b, a[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+        b.putf("\n");
+    }
+    for (int s = 0; s < Sd; s++) {
+        b.putf("D[%s] 1 %i int\n", h->species_names[s].c_str(), np);
+        const unsigned *a = J.xx + (size_t) s * np;
+        for (int i = 0; i < np; i++) { put_u(b, a[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+        b.putf("\n");
+    }
+    flush();
+    fclose(fp);
+    return 0;
+}
+
+static void writer_main(ssb_handle *h) {
+    cudaSetDevice(h->device);
+    int next = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(h->mu);
+            h->cv.wait(lk, [&] { return h->writer_pending[next] || h->writer_quit; });
+            if (!h->writer_pending[next] && h->writer_quit) return;
+        }
+        OutputJob &J = h->jobs[next];
+        cudaEventSynchronize(J.ready);
+        int rc = write_vtk(h, J);
+        {
+            std::lock_guard<std::mutex> lk(h->mu);
+            if (rc) h->writer_error = rc;
+            h->writer_pending[next] = 0;
+        }
+        h->cv.notify_all();
+        next ^= 1;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// cell grid
+// ----------------------------------------------------------------------------------------------------
+static void setup_grid(ssb_handle *h) {
+    const int N = h->N;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < N; i++)
+        for (int d = 0; d < 3; d++) { double v = h->hx[(size_t) i * 3 + d]; if (v < lo[d]) lo[d] = v; if (v > hi[d]) hi[d] = v; }
+    CellGrid &g = h->grid;
+    g.dim = h->m.dimension;
+    long long total = 1;
+    const double hh = h->m.h;
+    for (int d = 0; d < 3; d++) {
+        double L = hi[d] - lo[d];
+        int n = 1;
+        if (d < g.dim && L > 0 && hh > 0) {
+            double q = floor(L / hh);
+            n = (q < 1) ? 1 : (q > 4096 ? 4096 : (int) q);
+        }
+        g.n[d] = n;
+        total *= n;
+    }
+    // keep the cell table proportionate to the particle count (sparse / elongated domains)
+    long long cap = (long long) 4 * N + 1024;
+    while (total > cap) {
+        int big = 0;
+        for (int d = 1; d < 3; d++) if (g.n[d] > g.n[big]) big = d;
+        total /= g.n[big];
+        g.n[big] = (g.n[big] + 1) / 2;
+        total *= g.n[big];
+    }
+    for (int d = 0; d < 3; d++) {
+        double L = hi[d] - lo[d];
+        g.lo[d] = lo[d];
+        // cell edge L/n >= h by construction; the last cell is closed by clamping
+        g.inv_cell[d] = (g.n[d] > 1 && L > 0) ? (double) g.n[d] / L : 0.0;
+    }
+    g.ncells = (int) total;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// C-ABI
+// ----------------------------------------------------------------------------------------------------
+extern "C" int ssb_abi_version(void) { return SSB_ABI_VERSION; }
+
+extern "C" int ssb_device_count(int *count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (count) *count = (e == cudaSuccess) ? c : 0;
+    return e == cudaSuccess ? SSB_OK : SSB_ERR_CUDA;
+}
+
+extern "C" const char *ssb_last_error(ssb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+static void register_f64(ssb_handle *h, double **slot) { h->f64_slots.push_back(slot); }
+static void register_i32(ssb_handle *h, int **slot) { h->i32_slots.push_back(slot); }
+
+extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
+    if (!m || !out) return SSB_ERR_ARG;
+    *out = nullptr;
+    if (m->abi_version != SSB_ABI_VERSION) return SSB_ERR_ARG;
+    if (m->n_particles <= 0 || m->n_particles > 2000000000LL) return SSB_ERR_ARG;
+    if (m->dimension < 1 || m->dimension > 3) return SSB_ERR_ARG;
+    ssb_handle *h = new ssb_handle();
+    *out = h;  // returned even on failure so the caller can read ssb_last_error, then ssb_destroy
+    h->m = *m;
+    const int N = h->N = (int) m->n_particles;
+    const int S = h->S = (m->num_stoch_species > m->num_chem_species) ? m->num_stoch_species : m->num_chem_species;
+    const int Sc = m->num_chem_species, Sd = m->num_stoch_species;
+    const int Rd = m->num_stoch_rxns, ndf = m->num_data_fn;
+    if (!(m->h > 0.0)) return fail(h, SSB_ERR_ARG, "h (basis function width) can not be zero.");
+    // host copies (the caller's buffers are only borrowed for this call)
+    h->hx.assign(m->x, m->x + (size_t) N * 3);
+    h->htype.assign(m->type, m->type + N);
+    h->hnu.assign(m->nu, m->nu + N);
+    h->hmass.assign(m->mass, m->mass + N);
+    h->hrho.assign(m->rho, m->rho + N);
+    h->hsolid.assign(m->solid, m->solid + N);
+    if (S > 0) h->hu0.assign(m->u0, m->u0 + (size_t) N * S);
+    if (ndf > 0) h->hdata_fn.assign(m->data_fn, m->data_fn + (size_t) N * ndf);
+    if (S > 0) h->hdmat.assign(m->diffusion_matrix, m->diffusion_matrix + (size_t) S * m->num_types);
+    h->hout_steps.assign(m->output_steps, m->output_steps + m->n_output_steps);
+    for (int s = 0; s < S; s++) h->species_names.push_back(m->species_names ? m->species_names[s] : "S");
+    for (int i = 0; i < N; i++)
+        if (h->htype[i] < 1 || h->htype[i] > m->num_types) return fail(h, SSB_ERR_ARG, "particle %d has type %d outside 1..%d", i, h->htype[i], m->num_types);
+    h->m.x = nullptr; h->m.type = nullptr; h->m.nu = h->m.mass = h->m.c = h->m.rho = nullptr; h->m.solid = nullptr;
+    h->m.u0 = nullptr; h->m.data_fn = nullptr; h->m.N_dense = nullptr; h->m.irN = h->m.jcN = nullptr; h->m.prN = nullptr;
+    h->m.irG = h->m.jcG = nullptr; h->m.diffusion_matrix = nullptr; h->m.species_names = nullptr; h->m.output_steps = nullptr;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(h, SSB_ERR_CUDA, "no CUDA device available: the ssa_sdpd B200 engine has no CPU fallback");
+    h->device = m->device;
+    if (h->device < 0 || h->device >= ndev) return fail(h, SSB_ERR_ARG, "device %d out of range (%d devices)", h->device, ndev);
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+
+    SsbView &V = h->V;
+    memset(&V, 0, sizeof(V));
+    V.N = N; V.dim = m->dimension; V.static_domain = m->static_domain; V.num_types = m->num_types;
+    V.Sc = Sc; V.Rc = m->num_chem_rxns; V.Sd = Sd; V.Rd = Rd; V.ndf = ndf;
+    V.flags = m->flags;
+    V.dt = m->dt; V.h = m->h; V.rho0 = m->rho0; V.c0 = m->c0; V.P0 = m->P0;
+    for (int d = 0; d < 3; d++) V.gravity[d] = m->gravity[d];
+
+    // permuted per-particle fields (each gets a current and an alternate buffer)
+    for (int d = 0; d < 3; d++) { register_f64(h, &V.x[d]); register_f64(h, &V.v[d]); register_f64(h, &V.vt[d]); register_f64(h, &V.F[d]); register_f64(h, &V.Fbp[d]); }
+    register_f64(h, &V.rho); register_f64(h, &V.old_rho); register_f64(h, &V.Frho); register_f64(h, &V.bvf);
+    register_f64(h, &V.mass); register_f64(h, &V.nu);
+    if (h->f64_slots.size() + 2 > PERM_MAX64) return fail(h, SSB_ERR_ARG, "too many fields");
+    for (auto slot : h->f64_slots) { CK(dalloc(h, slot, (size_t) N)); double *alt; CK(dalloc(h, &alt, (size_t) N)); h->f64_alt.push_back(alt); }
+    // species-major blocks are permuted row by row; allocate as blocks and register rows through shadow pointers
+    CK(dalloc(h, &V.C, (size_t) Sc * N)); CK(dalloc(h, &V.Q, (size_t) Sc * N));
+    CK(dalloc(h, &V.xx, (size_t) Sd * N)); CK(dalloc(h, &V.data_fn, (size_t) ndf * N));
+    register_i32(h, &V.type); register_i32(h, &V.solid); register_i32(h, &V.id);
+    for (auto slot : h->i32_slots) { CK(dalloc(h, slot, (size_t) N)); int *alt; CK(dalloc(h, &alt, (size_t) N)); h->i32_alt.push_back(alt); }
+    if ((size_t) (2 * Sc + ndf) + h->f64_slots.size() > PERM_MAX64 || (size_t) Sd + h->i32_slots.size() > PERM_MAX32)
+        return fail(h, SSB_ERR_ARG, "too many species for the permutation table");
+    // non-permuted scratch
+    if (V.static_domain) { for (int d = 0; d < 3; d++) V.x0[d] = nullptr; }   // aliased to x after allocation (below)
+    else { for (int d = 0; d < 3; d++) CK(dalloc(h, &V.x0[d], (size_t) N)); }
+    CK(dalloc(h, &V.rho_new, (size_t) N));
+    CK(dalloc(h, &V.nbr_count, (size_t) N));
+    CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, h->stream));
+    CK(dalloc(h, &V.rrate, (size_t) Rd * N)); CK(dalloc(h, &V.srrate, (size_t) N)); CK(dalloc(h, &V.sdrate, (size_t) N));
+    CK(dalloc(h, &V.tnext, (size_t) N)); CK(dalloc(h, &V.Ddiag, (size_t) Sd * N));
+    CK(dalloc(h, &V.inbox[0], (size_t) Sd * N)); CK(dalloc(h, &V.inbox[1], (size_t) Sd * N));
+    CK(dalloc(h, &V.inbox_src[0], (size_t) N)); CK(dalloc(h, &V.inbox_src[1], (size_t) N));
+    CK(dalloc(h, &V.err_flag, 4)); CK(dalloc(h, &V.counters, 4));
+    CK(dalloc(h, &h->d_dmat, (size_t) S * m->num_types));
+    if (S > 0) CK(cudaMemcpyAsync(h->d_dmat, h->hdmat.data(), sizeof(double) * S * m->num_types, cudaMemcpyHostToDevice, h->stream));
+    V.dmat = h->d_dmat;
+    // alternates for the species blocks
+    {
+        double *alt;
+        CK(dalloc(h, &alt, (size_t) (2 * Sc + ndf) * N)); h->f64_alt.push_back(alt);   // one block: [C | Q | data_fn]
+        int *ialt;
+        CK(dalloc(h, &ialt, (size_t) Sd * N)); h->i32_alt.push_back(ialt);
+    }
+    CK(dalloc(h, &h->d_permtable, 1));
+    // cell list
+    setup_grid(h);
+    CK(dalloc(h, &h->d_key, (size_t) N)); CK(dalloc(h, &h->d_perm, (size_t) N));
+    CK(dalloc(h, &h->d_cell_count, (size_t) h->grid.ncells + 1)); CK(dalloc(h, &h->d_cell_start, (size_t) h->grid.ncells + 1));
+    CK(dalloc(h, &h->d_cursor, (size_t) h->grid.ncells + 1));
+    CK(dalloc(h, &h->d_tile_sums, (size_t) (h->grid.ncells / SCAN_TILE + 2)));
+    CK(dalloc(h, &h->d_flags, 8));
+    CK(dalloc(h, &h->d_maxbits, 2));
+    // staging: the largest of an output snapshot and any single tap
+    size_t per = (size_t) 3 * 8 * 2 + 4 * 8 + 8 + (size_t) Sc * 8 + (size_t) Sd * 8 + (size_t) Rd * 8 + 64;
+    h->stage_bytes = per * N + 4096;
+    CK(cudaMalloc((void **) &h->d_stage, h->stage_bytes));
+    h->allocs.push_back(h->d_stage);
+    for (int b = 0; b < 2; b++) {
+        OutputJob &J = h->jobs[b];
+        CK(cudaEventCreateWithFlags(&J.ready, cudaEventDisableTiming));
+        CK(cudaMallocHost((void **) &J.x, sizeof(double) * 3 * N));
+        CK(cudaMallocHost((void **) &J.v, sizeof(double) * 3 * N));
+        CK(cudaMallocHost((void **) &J.scal, sizeof(double) * 4 * N));
+        CK(cudaMallocHost((void **) &J.type, sizeof(int) * N));
+        CK(cudaMallocHost((void **) &J.C, sizeof(double) * (Sc > 0 ? Sc : 1) * N));
+        CK(cudaMallocHost((void **) &J.xx, sizeof(unsigned) * (Sd > 0 ? Sd : 1) * N));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->writer = std::thread(writer_main, h);
+    return SSB_OK;
+}
+
+extern "C" int ssb_load_kernels(ssb_handle *h, const char *path) {
+    if (!h || !path) return SSB_ERR_ARG;
+    void *dl = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!dl) return fail(h, SSB_ERR_MODEL_UNIT, "dlopen(%s): %s", path, dlerror());
+    typedef const SsbModelUnit *(*getter)();
+    getter g = (getter) dlsym(dl, "ssbm_get_unit");
+    if (!g) { dlclose(dl); return fail(h, SSB_ERR_MODEL_UNIT, "%s does not export ssbm_get_unit", path); }
+    const SsbModelUnit *u = g();
+    if (!u || u->abi != SSB_UNIT_ABI) { dlclose(dl); return fail(h, SSB_ERR_MODEL_UNIT, "model unit ABI mismatch"); }
+    const SsbView &V = h->V;
+    if (u->Sc != V.Sc || u->Rc != V.Rc || u->Sd != V.Sd || u->Rd != V.Rd || u->ndf != V.ndf || u->ntypes != V.num_types) {
+        dlclose(dl);
+        return fail(h, SSB_ERR_MODEL_UNIT, "model unit compiled for (Sc=%d Rc=%d Sd=%d Rd=%d ndf=%d types=%d), model has (%d %d %d %d %d %d)",
+                    u->Sc, u->Rc, u->Sd, u->Rd, u->ndf, u->ntypes, V.Sc, V.Rc, V.Sd, V.Rd, V.ndf, V.num_types);
+    }
+    if (h->unit_dl) dlclose(h->unit_dl);
+    h->unit_dl = dl;
+    h->unit = u;
+    return SSB_OK;
+}
+
+static int drain_writer(ssb_handle *h) {
+    std::unique_lock<std::mutex> lk(h->mu);
+    h->cv.wait(lk, [&] { return !h->writer_pending[0] && !h->writer_pending[1]; });
+    int rc = h->writer_error;
+    h->writer_error = 0;
+    return rc;
+}
+
+extern "C" int ssb_destroy(ssb_handle *h) {
+    if (!h) return SSB_OK;
+    if (h->writer.joinable()) {
+        { std::lock_guard<std::mutex> lk(h->mu); h->writer_quit = 1; }
+        h->cv.notify_all();
+        h->writer.join();
+    }
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    for (int b = 0; b < 2; b++) {
+        OutputJob &J = h->jobs[b];
+        if (J.ready) cudaEventDestroy(J.ready);
+        cudaFreeHost(J.x); cudaFreeHost(J.v); cudaFreeHost(J.scal); cudaFreeHost(J.type); cudaFreeHost(J.C); cudaFreeHost(J.xx);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->unit_dl) dlclose(h->unit_dl);
+    delete h;
+    return SSB_OK;
+}
+
+extern "C" int ssb_cancel(ssb_handle *h) { if (h) h->cancel.store(1); return SSB_OK; }
+
+// ----------------------------------------------------------------------------------------------------
+// state reset (replaces init_all_particles + initialize_rdme, template:134-138)
+// ----------------------------------------------------------------------------------------------------
+extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
+    if (!h) return SSB_ERR_ARG;
+    if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
+    CK(cudaSetDevice(h->device));
+    SsbView &V = h->V;
+    const int N = h->N, Sc = V.Sc, Sd = V.Sd, S = h->S, ndf = V.ndf;
+    cudaStream_t st = h->stream;
+    std::vector<double> tmp((size_t) N);
+    for (int d = 0; d < 3; d++) {
+        for (int i = 0; i < N; i++) tmp[i] = h->hx[(size_t) i * 3 + d];
+        CK(cudaMemcpyAsync(V.x[d], tmp.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        // fields the reference leaves uninitialised are defined as 0 (particle.cpp:70-83)
+        CK(cudaMemsetAsync(V.v[d], 0, sizeof(double) * N, st));
+        CK(cudaMemsetAsync(V.vt[d], 0, sizeof(double) * N, st));
+        CK(cudaMemsetAsync(V.F[d], 0, sizeof(double) * N, st));
+        CK(cudaMemsetAsync(V.Fbp[d], 0, sizeof(double) * N, st));
+    }
+    CK(cudaMemcpyAsync(V.rho, h->hrho.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(V.mass, h->hmass.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(V.nu, h->hnu.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(V.type, h->htype.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(V.solid, h->hsolid.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(V.old_rho, 0, sizeof(double) * N, st));
+    CK(cudaMemsetAsync(V.Frho, 0, sizeof(double) * N, st));
+    CK(cudaMemsetAsync(V.bvf, 0, sizeof(double) * N, st));
+    CK(cudaMemsetAsync(V.rho_new, 0, sizeof(double) * N, st));
+    k_iota<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id);
+    // species: u0 is voxel-major [N][S] (solver.py:211-220); C starts as (double) u0 (template:77-81)
+    if (Sc > 0) {
+        for (int s = 0; s < Sc; s++) {
+            for (int i = 0; i < N; i++) tmp[i] = (double) h->hu0[(size_t) i * S + s];
+            CK(cudaMemcpyAsync(V.C + (size_t) s * N, tmp.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        }
+        CK(cudaMemsetAsync(V.Q, 0, sizeof(double) * Sc * N, st));
+    }
+    if (Sd > 0) {
+        std::vector<unsigned> ut((size_t) N);
+        for (int s = 0; s < Sd; s++) {
+            for (int i = 0; i < N; i++) ut[i] = h->hu0[(size_t) i * S + s];
+            CK(cudaMemcpyAsync(V.xx + (size_t) s * N, ut.data(), sizeof(unsigned) * N, cudaMemcpyHostToDevice, st));
+        }
+        CK(cudaMemsetAsync(V.inbox[0], 0, sizeof(unsigned) * Sd * N, st));
+        CK(cudaMemsetAsync(V.inbox[1], 0, sizeof(unsigned) * Sd * N, st));
+        CK(cudaMemsetAsync(V.inbox_src[0], 0, sizeof(int) * N, st));
+        CK(cudaMemsetAsync(V.inbox_src[1], 0, sizeof(int) * N, st));
+    }
+    if (ndf > 0) CK(cudaMemcpyAsync(V.data_fn, h->hdata_fn.data(), sizeof(double) * ndf * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(V.err_flag, 0, 16, st));
+    CK(cudaMemsetAsync(V.counters, 0, 32, st));
+    CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, st));
+    if (V.static_domain) for (int d = 0; d < 3; d++) V.x0[d] = V.x[d];
+    V.rho_search = V.rho;
+    CK(cudaStreamSynchronize(st));
+    h->current_step = 0;
+    h->rdme_initialized = 0;
+    h->seed = seed;
+    h->epoch = 0;
+    h->inbox_buf = 0;
+    h->nbr_valid = 0;
+    h->launches = 0;
+    h->windows = 0;
+    h->total_reactions = h->total_diffusion = 0;
+    h->step_seconds = 0.0;
+    h->cancel.store(0);
+    return SSB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K1: cell list build + permutation into cell-sorted storage order
+// ----------------------------------------------------------------------------------------------------
+static int build_cells(ssb_handle *h) {
+    SsbView &V = h->V;
+    const int N = h->N, nc = h->grid.ncells;
+    cudaStream_t st = h->stream;
+    CK(cudaMemsetAsync(h->d_cell_count, 0, sizeof(int) * (nc + 1), st));
+    CK(cudaMemsetAsync(h->d_cursor, 0, sizeof(int) * (nc + 1), st));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 2, st));
+    k_cell_keys<<<gridN(N), CORE_BLOCK, 0, st>>>(N, h->grid, V.x[0], V.x[1], V.x[2], h->d_key, h->d_cell_count);
+    const int ntiles = (nc + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<ntiles, 256, 0, st>>>(nc, h->d_cell_count, h->d_cell_start, h->d_tile_sums);
+    k_scan_sums<<<1, 256, 0, st>>>(ntiles, h->d_tile_sums, nullptr);
+    k_scan_add<<<gridN(nc), CORE_BLOCK, 0, st>>>(nc, h->d_cell_start, h->d_tile_sums);
+    k_scatter<<<gridN(N), CORE_BLOCK, 0, st>>>(N, h->d_key, h->d_cell_start, h->d_cursor, h->d_perm);
+    k_sort_cells<<<gridN(nc), CORE_BLOCK, 0, st>>>(nc, h->d_cell_start, N, h->d_perm, h->d_flags);
+    h->launches += 6;
+    int nonid = 0;
+    CK(cudaMemcpyAsync(&nonid, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!nonid) return SSB_OK;
+    // permute every per-particle field into the alternate buffers, then swap
+    PermTable T;
+    memset(&T, 0, sizeof(T));
+    size_t nf = h->f64_slots.size();
+    for (size_t f = 0; f < nf; f++) { T.src64[T.n64] = *h->f64_slots[f]; T.dst64[T.n64] = h->f64_alt[f]; T.n64++; }
+    double *blk_alt = h->f64_alt[nf];
+    const int Sc = V.Sc, Sd = V.Sd, ndf = V.ndf;
+    for (int s = 0; s < Sc; s++) { T.src64[T.n64] = V.C + (size_t) s * N; T.dst64[T.n64] = blk_alt + (size_t) s * N; T.n64++; }
+    for (int s = 0; s < Sc; s++) { T.src64[T.n64] = V.Q + (size_t) s * N; T.dst64[T.n64] = blk_alt + (size_t) (Sc + s) * N; T.n64++; }
+    for (int q = 0; q < ndf; q++) { T.src64[T.n64] = V.data_fn + (size_t) q * N; T.dst64[T.n64] = blk_alt + (size_t) (2 * Sc + q) * N; T.n64++; }
+    size_t ni = h->i32_slots.size();
+    for (size_t f = 0; f < ni; f++) { T.src32[T.n32] = *h->i32_slots[f]; T.dst32[T.n32] = h->i32_alt[f]; T.n32++; }
+    int *xx_alt = h->i32_alt[ni];
+    for (int s = 0; s < Sd; s++) { T.src32[T.n32] = (int *) V.xx + (size_t) s * N; T.dst32[T.n32] = xx_alt + (size_t) s * N; T.n32++; }
+    CK(cudaMemcpyAsync(h->d_permtable, &T, sizeof(T), cudaMemcpyHostToDevice, st));
+    k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, h->d_perm, h->d_permtable);
+    h->launches += 1;
+    CK(cudaStreamSynchronize(st));   // T lives on this stack frame
+    for (size_t f = 0; f < nf; f++) { double *cur = *h->f64_slots[f]; *h->f64_slots[f] = h->f64_alt[f]; h->f64_alt[f] = cur; }
+    for (size_t f = 0; f < ni; f++) { int *cur = *h->i32_slots[f]; *h->i32_slots[f] = h->i32_alt[f]; h->i32_alt[f] = cur; }
+    // species blocks: copy back (blocks keep their identity so C/Q/data_fn/xx stay contiguous)
+    if (2 * Sc + ndf > 0) {
+        if (Sc > 0) { CK(cudaMemcpyAsync(V.C, blk_alt, sizeof(double) * Sc * N, cudaMemcpyDeviceToDevice, st));
+                      CK(cudaMemcpyAsync(V.Q, blk_alt + (size_t) Sc * N, sizeof(double) * Sc * N, cudaMemcpyDeviceToDevice, st)); }
+        if (ndf > 0) CK(cudaMemcpyAsync(V.data_fn, blk_alt + (size_t) 2 * Sc * N, sizeof(double) * ndf * N, cudaMemcpyDeviceToDevice, st));
+    }
+    if (Sd > 0) CK(cudaMemcpyAsync(V.xx, xx_alt, sizeof(unsigned) * Sd * N, cudaMemcpyDeviceToDevice, st));
+    if (V.static_domain) for (int d = 0; d < 3; d++) V.x0[d] = V.x[d];
+    V.rho_search = V.rho;
+    return SSB_OK;
+}
+
+static int neighbour_search(ssb_handle *h) {
+    SsbView &V = h->V;
+    const int N = h->N;
+    cudaStream_t st = h->stream;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        if (V.nbr_cap == 0) {
+            // first build: size the ELL rows from an exact count pass (cap 0 stores nothing)
+        }
+        CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), st));
+        k_search<<<gridN(N), CORE_BLOCK, 0, st>>>(V, h->grid, h->d_cell_start, h->d_flags + 1);
+        h->launches += 1;
+        int mx = 0;
+        CK(cudaMemcpyAsync(&mx, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (mx <= V.nbr_cap) return SSB_OK;
+        // grow (with head-room on moving domains) and search again
+        int cap = V.static_domain ? mx : (mx + mx / 4 + 8);
+        int *nb = nullptr;
+        CK(cudaMalloc((void **) &nb, sizeof(int) * (size_t) cap * N));
+        if (V.nbr) { cudaFree(V.nbr); for (auto &p : h->allocs) if (p == V.nbr) p = nullptr; }
+        h->allocs.push_back(nb);
+        V.nbr = nb;
+        V.nbr_cap = cap;
+        if (V.static_domain && V.Sd > 0) {
+            double *dj = nullptr;
+            CK(cudaMalloc((void **) &dj, sizeof(double) * (size_t) cap * N));
+            if (V.Dij) { cudaFree(V.Dij); for (auto &p : h->allocs) if (p == V.Dij) p = nullptr; }
+            h->allocs.push_back(dj);
+            V.Dij = dj;
+        }
+    }
+    return fail(h, SSB_ERR_CUDA, "neighbour list capacity did not converge");
+}
+
+// ----------------------------------------------------------------------------------------------------
+// one engine step: simulate_threads.cpp:232-281 (three substeps, then the RDME)
+// ----------------------------------------------------------------------------------------------------
+static int check_device_error(ssb_handle *h) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->V.err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (flag == SSB_ERR_NAN) return fail(h, SSB_ERR_NAN, "ERROR: nan/inf detected!!! (step %u)", h->current_step);
+    if (flag == SSB_ERR_RDME) return fail(h, SSB_ERR_RDME, "RDME state error (negative population or propensity overflow) at step %u", h->current_step);
+    return SSB_OK;
+}
+
+static int rdme_step(ssb_handle *h) {
+    SsbView &V = h->V;
+    const SsbModelUnit *u = h->unit;
+    cudaStream_t st = h->stream;
+    if (V.Sd == 0) return SSB_OK;
+    const double t0 = V.dt * h->current_step;
+    if (!V.static_domain || !h->rdme_initialized) {      // simulate_rdme.cpp:54-65
+        CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+        if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
+        // propensities are (re)initialised at t = 0.0 in the reference (simulate_rdme.cpp:124)
+        if (u->rdme_init(&V, t0, 0.0, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
+        h->launches += 2;
+        unsigned long long bits = 0;
+        CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        double mx;
+        memcpy(&mx, &bits, sizeof(mx));
+        double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
+        h->tau = (mx > 0.0) ? eps / mx : V.dt;
+        h->rdme_initialized = 1;
+        h->inbox_buf = 0;
+    }
+    double nwin_d = ceil(V.dt / h->tau);
+    if (!(nwin_d >= 1.0)) nwin_d = 1.0;
+    if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
+    const long long nwin = (long long) nwin_d;
+    for (long long w = 0; w < nwin; w++) {
+        double lo = t0 + V.dt * ((double) w / (double) nwin);
+        double hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
+        if (u->rdme_window(&V, lo, hi, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+        h->inbox_buf ^= 1;
+        if ((w & 1023) == 1023 && h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
+    }
+    h->launches += nwin;
+    h->windows += nwin;
+    return SSB_OK;
+}
+
+static int engine_step(ssb_handle *h) {
+    SsbView &V = h->V;
+    const SsbModelUnit *u = h->unit;
+    cudaStream_t st = h->stream;
+    const unsigned step = h->current_step;
+    const bool moving = !V.static_domain;
+    int rc;
+    if (step == 0 || moving) { if ((rc = build_cells(h))) return rc; }     // buildKDTree (simulate_threads.cpp:80-108)
+    if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
+    h->launches++;
+    if (step == 0 || moving) {                                               // find_neighbors (simulate.cpp:61-63,121-123)
+        V.rho_search = V.rho;
+        if ((rc = neighbour_search(h))) return rc;
+    }
+    const bool full = moving || !(V.flags & SSB_FLAG_SKIP_STATIC_FORCES);
+    if (full || V.Sc > 0) {
+        if (u->force(&V, step, full ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
+        h->launches++;
+    }
+    if (moving) {
+        if (u->corrector(&V, step, st)) return fail(h, SSB_ERR_CUDA, "corrector launch failed");
+        h->launches++;
+    }
+    if (u->finish(&V, step, moving ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
+    h->launches++;
+    if (moving) {
+        // rho <- post-corrector density; the old buffer keeps the search-time density frozen into D_i_j
+        double *pre = V.rho;
+        V.rho = V.rho_new;
+        V.rho_new = pre;
+        V.rho_search = pre;
+        // keep the permutation table consistent: V.rho is a registered slot (swapped in place above)
+    }
+    if ((rc = rdme_step(h))) return rc;
+    h->current_step++;
+    return SSB_OK;
+}
+
+extern "C" int ssb_step(ssb_handle *h, uint32_t nsteps) {
+    if (!h) return SSB_ERR_ARG;
+    if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
+    CK(cudaSetDevice(h->device));
+    auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t s = 0; s < nsteps; s++) {
+        int rc = engine_step(h);
+        if (rc) return rc;
+        if ((s & 15) == 15 || s + 1 == nsteps) { if ((rc = check_device_error(h))) return rc; }
+        if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->step_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return SSB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// K8 output staging
+// ----------------------------------------------------------------------------------------------------
+static int stage_output(ssb_handle *h, const char *dir, unsigned file_index) {
+    SsbView &V = h->V;
+    const int N = h->N, Sc = V.Sc, Sd = V.Sd;
+    cudaStream_t st = h->stream;
+    const int b = h->job_cursor;
+    {   // the slot must have been written out before it is overwritten
+        std::unique_lock<std::mutex> lk(h->mu);
+        h->cv.wait(lk, [&] { return !h->writer_pending[b]; });
+        if (h->writer_error) { int rc = h->writer_error; h->writer_error = 0; return fail(h, rc, "could not write VTK output into %s", dir); }
+    }
+    OutputJob &J = h->jobs[b];
+    // device staging layout (id order): x[3N] v[3N] scal[4N] C[Sc*N] | type[N] xx[Sd*N]
+    double *sx = h->d_stage, *sv = sx + (size_t) 3 * N, *ss = sv + (size_t) 3 * N, *sC = ss + (size_t) 4 * N;
+    int *stype = (int *) (sC + (size_t) Sc * N);
+    int *sxx = stype + N;
+    for (int d = 0; d < 3; d++) {
+        k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.x[d], sx, 3, d);
+        k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.v[d], sv, 3, d);
+    }
+    const double *scal[4] = {V.rho, V.mass, V.bvf, V.nu};
+    for (int f = 0; f < 4; f++) k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, scal[f], ss + (size_t) f * N, 1, 0);
+    for (int s = 0; s < Sc; s++) k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.C + (size_t) s * N, sC + (size_t) s * N, 1, 0);
+    k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.type, stype, 1, 0);
+    for (int s = 0; s < Sd; s++) k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, (int *) V.xx + (size_t) s * N, sxx + (size_t) s * N, 1, 0);
+    h->launches += 11 + Sc + Sd;
+    CK(cudaMemcpyAsync(J.x, sx, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(J.v, sv, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(J.scal, ss, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, st));
+    if (Sc > 0) CK(cudaMemcpyAsync(J.C, sC, sizeof(double) * Sc * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(J.type, stype, sizeof(int) * N, cudaMemcpyDeviceToHost, st));
+    if (Sd > 0) CK(cudaMemcpyAsync(J.xx, sxx, sizeof(unsigned) * Sd * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(J.ready, st));
+    // d_stage is reused by the next snapshot: the copies above are stream-ordered before any later gather
+    J.step = h->current_step;
+    J.file_index = file_index;
+    J.rdme_initialized = h->rdme_initialized;
+    J.dir = dir;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->writer_pending[b] = 1;
+    }
+    h->cv.notify_all();
+    h->job_cursor ^= 1;
+    return SSB_OK;
+}
+
+extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t first_traj, const char *const *out_dirs,
+                       ssb_progress_cb cb, void *cb_user) {
+    if (!h || ntraj < 0) return SSB_ERR_ARG;
+    if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
+    const bool write_files = !(h->m.flags & SSB_FLAG_NO_VTK);
+    if (write_files && !out_dirs) return SSB_ERR_ARG;
+    const unsigned nt = h->m.nt;
+    for (int k = 0; k < ntraj; k++) {
+        int rc = ssb_reset(h, seed + (uint64_t) (first_traj + k));      // solver.py:558-559
+        if (rc) return rc;
+        auto t0 = std::chrono::steady_clock::now();
+        // output gate of run_simulation (simulate_threads.cpp:231-247): next_output_step starts at 0 and
+        // get_next_output() walks the table from its first entry, which yields the reference's file->step map.
+        unsigned next_output_step = 0;
+        size_t out_index = 0;
+        unsigned file_index = 0;
+        for (unsigned step = 0; step < nt; step++) {
+            if (step >= next_output_step) {
+                if (write_files && (rc = stage_output(h, out_dirs[k], file_index))) return rc;
+                file_index++;
+                next_output_step = (out_index < h->hout_steps.size()) ? h->hout_steps[out_index] : 0xffffffffu;
+                out_index++;
+            }
+            if ((rc = engine_step(h))) return rc;
+            if ((step & 15) == 15 || step + 1 == nt) { if ((rc = check_device_error(h))) return rc; }
+            if (h->cancel.load()) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled"); }
+            if (cb && cb(cb_user, step + 1, nt)) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled by callback"); }
+        }
+        if (write_files && (rc = stage_output(h, out_dirs[k], file_index))) return rc;   // final timepoint (:283-285)
+        CK(cudaStreamSynchronize(h->stream));
+        h->step_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        unsigned long long cnt[2] = {0, 0};
+        CK(cudaMemcpy(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+        h->total_reactions = (int64_t) cnt[0];
+        h->total_diffusion = (int64_t) cnt[1];
+        if ((rc = drain_writer(h))) return fail(h, rc, "could not write VTK output into %s", out_dirs[k]);
+    }
+    return SSB_OK;
+}
+
+extern "C" int ssb_counters(ssb_handle *h, int64_t *reactions, int64_t *diffusions, double *seconds, int64_t *windows) {
+    if (!h) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long cnt[2] = {0, 0};
+    CK(cudaMemcpy(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (reactions) *reactions = (int64_t) cnt[0];
+    if (diffusions) *diffusions = (int64_t) cnt[1];
+    if (seconds) *seconds = h->step_seconds;
+    if (windows) *windows = h->windows;
+    return SSB_OK;
+}
+
+extern "C" int ssb_launch_count(ssb_handle *h, int64_t *launches) {
+    if (!h || !launches) return SSB_ERR_ARG;
+    *launches = h->launches;
+    return SSB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// parity taps
+// ----------------------------------------------------------------------------------------------------
+extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t bytes) {
+    if (!h || !name || !dst) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    SsbView &V = h->V;
+    const int N = h->N;
+    cudaStream_t st = h->stream;
+    std::string n(name);
+    double **v3 = nullptr;
+    if (n == "x") v3 = V.x; else if (n == "v") v3 = V.v; else if (n == "vt") v3 = V.vt; else if (n == "F") v3 = V.F; else if (n == "Fbp") v3 = V.Fbp;
+    else if (n == "x0") v3 = V.x0;
+    if (v3) {
+        if (bytes != (int64_t) sizeof(double) * 3 * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * 3 * N);
+        for (int d = 0; d < 3; d++) k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, v3[d], h->d_stage, 3, d);
+        CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SSB_OK;
+    }
+    const double *s1 = nullptr;
+    if (n == "rho") s1 = V.rho; else if (n == "old_rho") s1 = V.old_rho; else if (n == "Frho") s1 = V.Frho; else if (n == "bvf_phi") s1 = V.bvf;
+    else if (n == "mass") s1 = V.mass; else if (n == "nu") s1 = V.nu; else if (n == "srrate") s1 = V.srrate; else if (n == "sdrate") s1 = V.sdrate;
+    else if (n == "tnext") s1 = V.tnext; else if (n == "rho_search") s1 = V.rho_search;
+    if (s1) {
+        if (bytes != (int64_t) sizeof(double) * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * N);
+        k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, s1, h->d_stage, 1, 0);
+        CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SSB_OK;
+    }
+    const int *i1 = nullptr;
+    if (n == "type") i1 = V.type; else if (n == "solid") i1 = V.solid; else if (n == "nbr_count") i1 = V.nbr_count; else if (n == "id") i1 = V.id;
+    if (i1) {
+        if (bytes != (int64_t) sizeof(int) * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(int) * N);
+        k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, i1, (int *) h->d_stage, 1, 0);
+        CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SSB_OK;
+    }
+    // species-major blocks -> voxel-major [N][K] on the host side
+    const double *blk = nullptr;
+    int K = 0;
+    if (n == "C") { blk = V.C; K = V.Sc; } else if (n == "Q") { blk = V.Q; K = V.Sc; } else if (n == "Ddiag") { blk = V.Ddiag; K = V.Sd; }
+    else if (n == "rrate") { blk = V.rrate; K = V.Rd; }
+    if (blk || n == "C" || n == "Q" || n == "Ddiag" || n == "rrate") {
+        if (bytes != (int64_t) sizeof(double) * K * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * K * N);
+        for (int s = 0; s < K; s++) k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, blk + (size_t) s * N, h->d_stage, K, s);
+        if (K > 0) CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SSB_OK;
+    }
+    if (n == "xx") {
+        K = V.Sd;
+        if (bytes != (int64_t) sizeof(unsigned) * K * N) return fail(h, SSB_ERR_ARG, "field xx needs %lld bytes", (long long) sizeof(unsigned) * K * N);
+        for (int s = 0; s < K; s++) k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, (int *) V.xx + (size_t) s * N, (int *) h->d_stage, K, s);
+        if (K > 0) CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SSB_OK;
+    }
+    return fail(h, SSB_ERR_ARG, "unknown field '%s'", name);
+}
+
+extern "C" int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, double *dist, double *dWdr, double *Dij, int64_t *nnz_out) {
+    if (!h || !nnz_out) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    SsbView &V = h->V;
+    const int N = h->N;
+    cudaStream_t st = h->stream;
+    std::vector<long long> cnt((size_t) N + 1, 0);
+    long long *d_cnt = nullptr;
+    CK(cudaMalloc((void **) &d_cnt, sizeof(long long) * (N + 1)));
+    k_nbr_count_by_id<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.nbr_count, d_cnt);
+    CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<long long> p((size_t) N + 1, 0);
+    for (int i = 0; i < N; i++) p[i + 1] = p[i] + cnt[i];
+    const long long nnz = p[N];
+    *nnz_out = nnz;
+    if (!idx) { cudaFree(d_cnt); return SSB_OK; }
+    if (!ptr || !dist || !dWdr || !Dij) { cudaFree(d_cnt); return SSB_ERR_ARG; }
+    for (int i = 0; i <= N; i++) ptr[i] = p[i];
+    CK(cudaMemcpyAsync(d_cnt, p.data(), sizeof(long long) * (N + 1), cudaMemcpyHostToDevice, st));
+    int *d_idx = nullptr;
+    double *d_a = nullptr;
+    CK(cudaMalloc((void **) &d_idx, sizeof(int) * (size_t) (nnz + 1)));
+    CK(cudaMalloc((void **) &d_a, sizeof(double) * 3 * (size_t) (nnz + 1)));
+    k_nbr_export<<<gridN(N), CORE_BLOCK, 0, st>>>(V, d_cnt, d_idx, d_a, d_a + nnz, d_a + 2 * nnz);
+    CK(cudaMemcpyAsync(idx, d_idx, sizeof(int) * nnz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(dist, d_a, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(dWdr, d_a + nnz, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(Dij, d_a + 2 * nnz, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_cnt); cudaFree(d_idx); cudaFree(d_a);
+    return SSB_OK;
+}

@@ -1,0 +1,640 @@
+// ssb_model_unit.cuh — the model-specialised kernels of the ssa_sdpd hot path (sm_100a).
+//
+// Included at the END of a generated model .cu (spatialpy_b200/codegen.py), after it has defined
+//   SSB_SC, SSB_RC, SSB_SD, SSB_RD, SSB_NDF, SSB_NTYPES, SSB_S, SSB_R            (compile-time sizes)
+//   namespace ssb_gen { parameters P<i>, type_<name> constants, rxn_<j>(), det_<j>(), N_dense[], dep graph,
+//                       struct Particle (BC proxy), applyBoundaryConditions(Particle*, const System*) }
+// so that species loops unroll and x[] / C[] / rrate[] live in registers (SURVEY.md §8b "device-function ABI").
+// The kernels restate, per substep, E/src/simulate.cpp (take_step1 / compute_forces / take_step2),
+// E/src/model.cpp (pairwiseForce / filterDensity / computeBoundaryVolumeFraction / applyBoundaryVolumeFraction)
+// and E/src/simulate_rdme.cpp (propensity init, NSM event execution) — citations at each block.
+// E = /root/reference/spatialpy/solvers/c_base/ssa_sdpd-c-simulation-engine.
+#pragma once
+#include <math.h>
+#include "ssb_device.cuh"
+#include "ssb_unit_abi.h"
+
+#ifndef SSB_BLOCK
+#define SSB_BLOCK 128
+#endif
+
+namespace ssb_unit {
+
+using ssb_gen::Particle;
+using ssb_gen::System;
+
+// ---------------------------------------------------------------------------------------------
+// Boundary-condition proxy: load a particle into registers, run the user text, store what it may assign
+// (v, nu, rho, C — spatialpy/core/boundarycondition.py:147-166).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bc_load(const SsbView &V, int i, Particle &p) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) { p.x[d] = V.x[d][i]; p.v[d] = V.v[d][i]; }
+    p.nu = V.nu[i]; p.rho = V.rho[i]; p.mass = V.mass[i]; p.type = V.type[i]; p.id = V.id[i];
+    p.solidTag = V.solid[i];
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) p.C[s] = V.C[(size_t) s * V.N + i];
+}
+
+__device__ __forceinline__ System make_system(const SsbView &V, unsigned step) {
+    System sys;
+    sys.dt = V.dt; sys.h = V.h; sys.rho0 = V.rho0; sys.c0 = V.c0; sys.P0 = V.P0;
+    sys.dimension = V.dim; sys.current_step = step; sys.static_domain = V.static_domain;
+    return sys;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  take_step1 (E/src/simulate.cpp:56-109) + check_particle_nan (E/src/particle.cpp:88-134)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned step) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    Particle p;
+    bc_load(V, i, p);
+    // NaN / Inf guard (particle.cpp:89-96) — the reference exit(1)s; we raise the device error flag.
+    bool bad = !isfinite(p.x[0]) || !isfinite(p.x[1]) || !isfinite(p.x[2]) ||
+               !isfinite(p.v[0]) || !isfinite(p.v[1]) || !isfinite(p.v[2]) || !isfinite(p.rho);
+    if (bad) atomicCAS(V.err_flag, 0, 1 /*SSB_ERR_NAN*/);
+    const double dt = V.dt;
+    if (!V.static_domain) {
+        // snapshot = what the kd-tree of this step holds (simulate_threads.cpp:100-104)
+#pragma unroll
+        for (int d = 0; d < 3; d++) V.x0[d][i] = p.x[d];
+    }
+    if (p.solidTag == 0 && V.static_domain == 0) {     // simulate.cpp:68-79
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            p.v[d] = p.v[d] + 0.5 * dt * V.F[d][i];
+            double vt = p.v[d] + 0.5 * dt * V.Fbp[d][i];
+            V.vt[d][i] = vt;
+            p.x[d] = p.x[d] + dt * vt;
+            V.x[d][i] = p.x[d];
+        }
+        p.rho = p.rho + 0.5 * dt * V.Frho[i];
+    }
+    if (step > 0) {                                     // simulate.cpp:81-85
+#pragma unroll
+        for (int s = 0; s < SSB_SC; s++) p.C[s] += V.Q[(size_t) s * V.N + i] * dt * 0.5;
+    }
+    System sys = make_system(V, step);
+    ssb_gen::applyBoundaryConditions(&p, &sys);         // simulate.cpp:88
+#pragma unroll
+    for (int d = 0; d < 3; d++) {                       // simulate.cpp:92-97
+        V.v[d][i] = p.v[d];
+        V.F[d][i] = V.gravity[d];
+        V.Fbp[d][i] = 0.0;
+    }
+    V.Frho[i] = 0.0;
+    V.nu[i] = p.nu;
+    V.rho[i] = p.rho;
+    V.old_rho[i] = p.rho;                               // simulate.cpp:106
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) {
+        V.C[(size_t) s * V.N + i] = p.C[s];
+        V.Q[(size_t) s * V.N + i] = 0.0;                // simulate.cpp:101-103
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  compute_forces -> pairwiseForce (E/src/model.cpp:39-191).  One thread per particle over its
+// index-only neighbour list; r and dWdr are recomputed from (live x_i, snapshot x0_j) exactly as
+// add_to_neighbor_list froze them (particle.cpp:160-178); dx, dv, rho, C are live (model.cpp:102-108).
+// FULL = false on static domains: only the chemistry flux Q is consumed there (simulate.cpp:68,137).
+// ---------------------------------------------------------------------------------------------
+template <bool FULL>
+__global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N, dim = V.dim;
+    const double h = V.h, rho0 = V.rho0, P0 = V.P0;
+    const double alpha = ssb_alpha(dim, h);
+    const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+    const double rho_i = V.rho[i], m_i = V.mass[i];
+    const int type_i = V.type[i];
+    double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1];
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) {
+        Ci[s] = V.C[(size_t) s * N + i];
+        Qi[s] = V.Q[(size_t) s * N + i];
+        // NOTE the reference indexes the species-major table as [S_c*(type-1)+s] (model.cpp:163) — mirrored,
+        // with a bounds guard (the read is in-bounds whenever S == num_types or D is type-independent).
+        int k = SSB_SC * (type_i - 1) + s;
+        Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
+    }
+    double vi[3], vti[3], nu_i = 0, Pi = 0, Fa[3], Fb[3], Frho = 0;
+    if (FULL) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) { vi[d] = V.v[d][i]; vti[d] = V.vt[d][i]; Fa[d] = V.F[d][i]; Fb[d] = V.Fbp[d][i]; }
+        nu_i = V.nu[i];
+        Pi = P0 * (rho_i / rho0 - 1.0);                 // model.cpp:55
+        Frho = V.Frho[i];
+    }
+    const int cnt = V.nbr_count[i];
+    for (int k = 0; k < cnt; k++) {
+        const int j = V.nbr[(size_t) k * N + i];
+        const double d2 = ssb_dist2(dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+        const double r = sqrt(d2);                      // n->dist (particle.cpp:160)
+        const double dWdr = ssb_dWdr(alpha, r, h);      // n->dWdr (particle.cpp:178)
+        const double rho_j = V.rho[j], m_j = V.mass[j];
+        double dx[3] = {0.0, 0.0, 0.0};
+        dx[0] = xi0 - V.x[0][j];
+        if (dim > 1) dx[1] = xi1 - V.x[1][j];
+        if (dim > 2) dx[2] = xi2 - V.x[2][j];
+        const double inv_reg = 1.0 / (r + 0.001 * h);
+        if (FULL) {
+            double dv[3] = {0.0, 0.0, 0.0}, vj[3], vtj[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) { vj[d] = V.v[d][j]; vtj[d] = V.vt[d][j]; }
+            double dv_dx = 0.0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) if (d < dim) { dv[d] = vi[d] - vj[d]; dv_dx += dv[d] * dx[d]; }
+            const double nu_j = V.nu[j];
+            const double Pj = P0 * (rho_j / rho0 - 1.0);                        // model.cpp:108
+            double pg = Pi / (rho_i * rho_i) + Pj / (rho_j * rho_j);            // model.cpp:111
+            if (pg < 0) pg = -Pi / (rho_i * rho_i) + Pj / (rho_j * rho_j);      // model.cpp:112
+            const double fp = -1.0 * m_j * pg * dWdr / (r + 0.001 * h);         // model.cpp:115
+            const double fv = m_j * (2.0 * (nu_i * nu_j) / (nu_i + nu_j)) * inv_reg * dWdr / ((rho_i * rho_j));  // :118
+            const double voli = m_i / rho_i, volj = m_j / rho_j;
+            const double vv = voli * voli + volj * volj;                        // pow(.,2)+pow(.,2)
+            const double fbp = -10.0 * P0 * (1.0 / m_i) * vv * dWdr / (r + 0.001 * h);   // model.cpp:121
+            double ft[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {                                       // model.cpp:124-132
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    double T = 0.5 * ((rho_i * vi[a] * (vti[b] - vi[b])) + (rho_j * vj[a] * (vtj[b] - vj[b])));
+                    acc += T * dx[b];
+                }
+                ft[a] = (1.0 / m_i) * vv * acc * dWdr / (r + 0.001 * h);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) if (d < dim) {                          // model.cpp:135-138
+                Fa[d] += fp * dx[d] + fv * dv[d] + ft[d];
+                Fb[d] += fbp * dx[d];
+            }
+            // model.cpp:143-146 (the c0 term is multiplied by 0.0 in the reference and dropped here)
+            Frho = Frho + rho_i * volj * dv_dx * inv_reg * dWdr
+                   - volj * (rho_i * ((vi[0] - vti[0]) * dx[0] + (vi[1] - vti[1]) * dx[1] + (vi[2] - vti[2]) * dx[2])
+                             + rho_j * ((vj[0] - vtj[0]) * dx[0] + (vj[1] - vtj[1]) * dx[1] + (vj[2] - vtj[2]) * dx[2])) * inv_reg * dWdr;
+        }
+        if (SSB_SC > 0) {                                                       // model.cpp:152-170
+            const double wfd = inv_reg * dWdr;
+            const double dQc_base = 2.0 * ((m_i * m_j) / (m_i + m_j)) * ((rho_i + rho_j) / (rho_i * rho_j)) * (r * r) * wfd / ((r * r) + 0.01 * h * h);
+#pragma unroll
+            for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - V.C[(size_t) s * N + j]) * dQc_base;
+        }
+    }
+    if (FULL) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) { V.F[d][i] = Fa[d]; V.Fbp[d][i] = Fb[d]; }
+        V.Frho[i] = Frho;
+    }
+    if (SSB_SC > 0) {
+        // deterministic reaction right-hand side (model.cpp:181-189)
+        if (SSB_RC > 0) {
+            const double vol = m_i / rho_i;
+            const double cur_time = step * V.dt;
+            double df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+            for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
+            double flux[SSB_RC > 0 ? SSB_RC : 1];
+            ssb_gen::eval_det(Ci, cur_time, vol, df, type_i, flux);
+#pragma unroll
+            for (int rxn = 0; rxn < SSB_RC; rxn++) {
+#pragma unroll
+                for (int s = 0; s < SSB_SC; s++) {
+                    int nval;
+                    if (V.flags & 2u /*SSB_FLAG_CORRECTED_STOICH*/) {
+                        nval = ssb_gen::N_dense(s * SSB_R + rxn);
+                    } else {
+                        // reference: stoichiometric_matrix[num_chem_rxns*rxn + s] on the species x rxn row-major table
+                        // (model.cpp:186) — transposed, and out of bounds when rxn >= S; out-of-bounds reads are defined 0 here.
+                        int kk = SSB_RC * rxn + s;
+                        nval = (kk < SSB_S * SSB_R) ? ssb_gen::N_dense(kk) : 0;
+                    }
+                    Qi[s] += nval * flux[rxn];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SSB_SC; s++) V.Q[(size_t) s * N + i] = Qi[s];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  take_step2 part 1 (E/src/simulate.cpp:136-155): corrector + Shepard filter (model.cpp:194-233).
+// Writes the post-corrector density to rho_new so that the BVF sweep can serve `rho_j` with the
+// reference's serial Gauss–Seidel visibility (model.cpp:285-293).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSB_BLOCK) k_corrector(SsbView V, unsigned step) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N, dim = V.dim;
+    const double h = V.h, dt = V.dt;
+    const int solid = V.solid[i];
+    double rho = V.rho[i];
+    if (solid == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) V.v[d][i] = V.v[d][i] + 0.5 * dt * V.F[d][i];      // simulate.cpp:139-141
+    }
+    if (step % 20 == 0) {                               // filterDensity (model.cpp:194-233)
+        const double alpha = ssb_alpha(dim, h);
+        const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+        double num = 0.0, den = 0.0;
+        const int cnt = V.nbr_count[i];
+        for (int k = 0; k < cnt; k++) {
+            const int j = V.nbr[(size_t) k * N + i];
+            const double d2 = ssb_dist2(dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+            const double r = sqrt(d2);
+            const double Wij = ssb_W(alpha, r, h);
+            num += V.old_rho[j] * Wij;
+            den += Wij;
+        }
+        rho = num / den;
+    }
+    if (solid == 0) rho = rho + 0.5 * dt * V.Frho[i];   // simulate.cpp:147
+    // effect of the trailing applyBoundaryConditions (simulate.cpp:171) on rho, so later particles see it
+    Particle p;
+    bc_load(V, i, p);
+    p.rho = rho;
+    System sys = make_system(V, step);
+    ssb_gen::applyBoundaryConditions(&p, &sys);
+    V.rho_new[i] = p.rho;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5  take_step2 part 2 (E/src/simulate.cpp:158-171): boundary volume fraction (model.cpp:236-313),
+// bounce-back (model.cpp:316-329), chemistry half step, boundary conditions.
+// MOVING = false on static domains: only the C half step and the BCs remain.
+// ---------------------------------------------------------------------------------------------
+template <bool MOVING>
+__global__ void __launch_bounds__(SSB_BLOCK) k_finish(SsbView V, unsigned step) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N, dim = V.dim;
+    const double h = V.h, dt = V.dt;
+    Particle p;
+    bc_load(V, i, p);
+    if (MOVING) p.rho = V.rho_new[i];
+    if (MOVING && p.solidTag == 0) {
+        const double alpha = ssb_alpha(dim, h);
+        const int my_id = p.id;
+        double nw[3] = {0.0, 0.0, 0.0}, dx[3] = {0.0, 0.0, 0.0};
+        double vos = 0.0, vtot = 0.0;
+        const int cnt = V.nbr_count[i];
+        for (int k = 0; k < cnt; k++) {
+            const int j = V.nbr[(size_t) k * N + i];
+            const double d2 = ssb_dist2(dim, p.x[0], p.x[1], p.x[2], V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+            const double r = sqrt(d2);
+            const double Wij = ssb_W(alpha, r, h);
+            const double dWdr = ssb_dWdr(alpha, r, h);
+            dx[0] = p.x[0] - V.x[0][j];
+            if (dim > 1) dx[1] = p.x[1] - V.x[1][j];
+            if (dim > 2) dx[2] = p.x[2] - V.x[2][j];
+            // serial (-t 1) visibility: particles earlier in the vector already ran their corrector
+            const double rho_j = (V.id[j] <= my_id) ? V.rho_new[j] : V.rho[j];
+            const double volj = V.mass[j] / rho_j;
+            const double w2 = volj * volj * Wij;
+            const int solid_j = V.solid[j];
+            if (solid_j) vos += w2;
+            vtot += w2;
+            if (solid_j) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) nw[d] += volj * volj * dx[d] * dWdr / (r + 0.001 * h);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) nw[d] = nw[d] / vtot;
+        const double norm_nw = sqrt(nw[0] * nw[0] + nw[1] * nw[1] + nw[2] * nw[2]);
+        double normal[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) normal[d] = -nw[d] / norm_nw;
+        const double bvf = fabs(vos / vtot);            // fluid particle (model.cpp:309-312)
+        V.bvf[i] = bvf;
+#pragma unroll
+        for (int d = 0; d < 3; d++) if (d < dim) V.vt[d][i] = 0.0;              // model.cpp:257-260
+        // applyBoundaryVolumeFraction (model.cpp:316-329)
+        const double vdn = p.v[0] * normal[0] + p.v[1] * normal[1] + p.v[2] * normal[2];
+        if (bvf >= 0.5) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) if (d < dim) p.v[d] = -p.v[d] + 2.0 * fmax(0.0, vdn) * normal[d];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) p.C[s] += V.Q[(size_t) s * N + i] * dt * 0.5;   // simulate.cpp:167-169
+    System sys = make_system(V, step);
+    ssb_gen::applyBoundaryConditions(&p, &sys);         // simulate.cpp:171
+#pragma unroll
+    for (int d = 0; d < 3; d++) V.v[d][i] = p.v[d];
+    V.nu[i] = p.nu;
+    if (!MOVING) V.rho[i] = p.rho;   // moving: rho_new already carries the BC effect (k_corrector)
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) V.C[(size_t) s * N + i] = p.C[s];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6  diffusion-matrix assembly: D_i_j (particle.cpp:182-187) and Ddiag / sdrate
+// (E/src/simulate_rdme.cpp:131-152).  Caches D_i_j on static domains (V.Dij != nullptr).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pair_Dij(const SsbView &V, int i, int j, double xi0, double xi1, double xi2,
+                                           double m_i, double rho_i) {
+    const double d2 = ssb_dist2(V.dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+    const double r = sqrt(d2);
+    return ssb_Dij(d2, r, V.h, m_i, V.mass[j], rho_i, V.rho_search[j]);
+}
+
+__global__ void __launch_bounds__(SSB_BLOCK) k_diff_init(SsbView V, unsigned long long *max_ddiag_bits) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double mx = 0.0;
+    if (i < V.N) {
+        const int N = V.N;
+        const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+        const double m_i = V.mass[i], rho_i = V.rho_search[i];
+        double Dd[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) Dd[s] = 0.0;
+        const int cnt = V.nbr_count[i];
+        for (int k = 0; k < cnt; k++) {
+            const int j = V.nbr[(size_t) k * N + i];
+            const double Dij = pair_Dij(V, i, j, xi0, xi1, xi2, m_i, rho_i);
+            if (V.Dij) V.Dij[(size_t) k * N + i] = Dij;
+            const int tj = V.type[j] - 1;
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) Dd[s] += V.dmat[s * V.num_types + tj] * Dij;   // simulate_rdme.cpp:146-147
+        }
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) { V.Ddiag[(size_t) s * N + i] = Dd[s]; mx = fmax(mx, Dd[s]); }
+    }
+    // block max -> global max (positive doubles order like their bit patterns)
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7a  RDME (re)initialisation: reaction propensities (simulate_rdme.cpp:113-128), sdrate (:149),
+// first event time Exp(1)/(srrate+sdrate)+t0 (simulate_rdme.cpp:155-195, NRMConstant_v5.cpp:52-59).
+// ---------------------------------------------------------------------------------------------
+struct VoxelRates {
+    double rr[SSB_RD > 0 ? SSB_RD : 1];
+    double sr, sd;
+};
+
+__device__ __forceinline__ void eval_rates(const SsbView &V, int i, const int *xx, double t, double vol,
+                                           const double *df, int type, VoxelRates &R) {
+    ssb_gen::eval_propensities(xx, t, vol, df, type, R.rr);
+    double sr = 0.0;
+#pragma unroll
+    for (int r = 0; r < SSB_RD; r++) sr += R.rr[r];
+    double sd = 0.0;
+#pragma unroll
+    for (int s = 0; s < SSB_SD; s++) sd += V.Ddiag[(size_t) s * V.N + i] * xx[s];
+    R.sr = sr; R.sd = sd;
+}
+
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, double t_eval, uint64_t seed, uint64_t epoch) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N;
+    int xx[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+    for (int s = 0; s < SSB_SD; s++) xx[s] = (int) V.xx[(size_t) s * N + i];
+    double df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+    for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
+    const double vol = V.mass[i] / V.rho[i];
+    VoxelRates R;
+    eval_rates(V, i, xx, t_eval, vol, df, V.type[i], R);
+#pragma unroll
+    for (int r = 0; r < SSB_RD; r++) V.rrate[(size_t) r * N + i] = R.rr[r];
+    V.srrate[i] = R.sr;
+    V.sdrate[i] = R.sd;
+    const double tot = R.sr + R.sd;
+    double u0, u1;
+    philox_uniform2((uint32_t) V.id[i], 0u, epoch, seed, u0, u1);
+    V.tnext[i] = (tot > 0.0) ? t0 + (-log(u0)) / tot : INFINITY;
+#pragma unroll
+    for (int s = 0; s < SSB_SD; s++) { V.inbox[0][(size_t) s * N + i] = 0u; V.inbox[1][(size_t) s * N + i] = 0u; }
+    V.inbox_src[0][i] = 0; V.inbox_src[1][i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7b  one sSSA window [t_lo, t_hi] — one thread per voxel.
+// The reference's NSM (simulate_rdme.cpp:211-472) executes events in global time order, which is inherently
+// serial.  Here every voxel runs an exact SSA of ITS OWN channels (reactions + outgoing diffusion jumps) inside
+// the window; molecules that jump are delivered to the destination's inbox (integer atomicAdd: order-independent,
+// so results are bit-reproducible) and become visible at the start of the next window, when the destination
+// re-draws its next event time (memoryless, same as NRMConstant_v5::update redrawing Exp(1)/a + t,
+// NRMConstant_v5.cpp:98).  The splitting error is O(tau * jump rate) and is bounded by the window controller
+// (ssb_model.rdme_epsilon).  Event execution mirrors the reference branch by branch:
+//   channel draw  rand1 <= srrate/totrate ? reaction : diffusion                     (simulate_rdme.cpp:253-255)
+//   reaction pick rand1*srrate against the running sum of rrate[]                     (:260-261)  [reference rule]
+//   species pick  rand1*sdrate against the running sum of Ddiag[s]*xx[s]              (:317-321)  [reference rule]
+//   direction     r2*Ddiag[spec] against the running sum of D_i_j*D[spec,type(dest)]  (:353-367)
+// SSB_FLAG_CORRECTED_NSM_SELECT switches the two picks to the textbook rule (rand*totrate, subtract srrate).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, uint64_t seed,
+                                                          uint64_t epoch, int buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_rx = 0, n_df = 0;
+    if (i < V.N) {
+        const int N = V.N;
+        const unsigned *in_prev = V.inbox[buf ^ 1];
+        unsigned *out_box = V.inbox[buf];
+        double tnext = V.tnext[i];
+        bool arrived = false;
+        unsigned inc[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) { inc[s] = in_prev[(size_t) s * N + i]; arrived |= (inc[s] != 0u); }
+        if (arrived || tnext <= t_hi) {
+            int xx[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) xx[s] = (int) V.xx[(size_t) s * N + i];
+            double df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+            for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
+            const int type_i = V.type[i];
+            const double m_i = V.mass[i];
+            const double vol = m_i / V.rho[i];
+            const uint32_t vid = (uint32_t) V.id[i];
+            uint32_t draw = 0;
+            VoxelRates R;
+            if (arrived) {
+                // stored propensities; only the reactions that depend on an arrived species are re-evaluated
+                // (dependency graph columns [0,S), simulate_rdme.cpp:419-435)
+#pragma unroll
+                for (int r = 0; r < SSB_RD; r++) R.rr[r] = V.rrate[(size_t) r * N + i];
+                unsigned long long mask = 0ull;
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) {
+                    if (inc[s]) {
+                        xx[s] += (int) inc[s];
+                        ((unsigned *) in_prev)[(size_t) s * N + i] = 0u;     // nobody writes buf^1 during this window
+                        mask |= ssb_gen::dep_mask_species(s);
+                    }
+                }
+                // reference quirk: the destination's propensities are re-evaluated with the SOURCE voxel's vol
+                // (simulate_rdme.cpp:433) and stay that way until its next own event.
+                double vol_dest = vol;
+                const int src = V.inbox_src[buf ^ 1][i];
+                if (src > 0 && !(V.flags & 1u)) { vol_dest = V.mass[src - 1] / V.rho[src - 1]; }
+                V.inbox_src[buf ^ 1][i] = 0;
+                double tmp[SSB_RD > 0 ? SSB_RD : 1];
+                ssb_gen::eval_propensities(xx, t_lo, vol_dest, df, type_i, tmp);
+                double sr = 0.0, sd = 0.0;
+#pragma unroll
+                for (int r = 0; r < SSB_RD; r++) { if ((mask >> r) & 1ull) R.rr[r] = tmp[r]; sr += R.rr[r]; }
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) sd += V.Ddiag[(size_t) s * N + i] * xx[s];
+                R.sr = sr; R.sd = sd;
+                const double tot = R.sr + R.sd;
+                double u0, u1;
+                philox_uniform2(vid, draw++, epoch, seed, u0, u1);
+                tnext = (tot > 0.0) ? t_lo + (-log(u0)) / tot : INFINITY;
+            } else {
+                R.sr = V.srrate[i]; R.sd = V.sdrate[i];
+#pragma unroll
+                for (int r = 0; r < SSB_RD; r++) R.rr[r] = V.rrate[(size_t) r * N + i];
+            }
+            const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+            int guard = 0;
+            while (tnext <= t_hi) {
+                const double tt = tnext;
+                const double tot = R.sr + R.sd;
+                double rand1, rand2;
+                philox_uniform2(vid, draw++, epoch, seed, rand1, rand2);
+                bool is_rxn;
+                double pick;
+                if (V.flags & 1u /*SSB_FLAG_CORRECTED_NSM_SELECT*/) {
+                    pick = rand1 * tot;
+                    is_rxn = pick <= R.sr;
+                    if (!is_rxn) pick -= R.sr;
+                } else {
+                    is_rxn = rand1 <= R.sr / tot;
+                    pick = is_rxn ? rand1 * R.sr : rand1 * R.sd;
+                }
+                if (is_rxn) {
+                    int re = 0;
+                    double cum = R.rr[0];
+#pragma unroll
+                    for (int q = 1; q < SSB_RD; q++) { if (pick > cum) { re = q; cum += R.rr[q]; } else break; }
+                    // fell off the end with a zero-propensity tail: step back to the last live reaction (:262-281)
+                    while (re > 0 && R.rr[re] <= 0.0) re--;
+                    bool neg = false;
+                    ssb_gen::apply_stoich(re, xx, neg);                         // simulate_rdme.cpp:285-296
+                    if (neg) atomicCAS(V.err_flag, 0, 2 /*SSB_ERR_RDME*/);
+                    n_rx++;
+                } else {
+                    int spec = 0;
+                    double cum = V.Ddiag[i] * xx[0];
+#pragma unroll
+                    for (int q = 1; q < SSB_SD; q++) {
+                        if (pick > cum) { spec = q; cum += V.Ddiag[(size_t) q * N + i] * xx[q]; } else break;
+                    }
+                    while (spec > 0 && xx[spec] <= 0) spec--;                   // simulate_rdme.cpp:338-347
+                    if (xx[spec] <= 0) { atomicCAS(V.err_flag, 0, 2); break; }
+                    // direction (simulate_rdme.cpp:353-367)
+                    const double dd = V.Ddiag[(size_t) spec * N + i];
+                    const double target = rand2 * dd;
+                    const int cnt = V.nbr_count[i];
+                    const double rho_si = V.rho_search[i];
+                    double cum2 = 0.0;
+                    int dest = -1, last_ok = -1;
+                    for (int k = 0; k < cnt; k++) {
+                        const int j = V.nbr[(size_t) k * N + i];
+                        const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
+                        if (dc == 0.0) continue;
+                        const double Dij = V.Dij ? V.Dij[(size_t) k * N + i] : pair_Dij(V, i, j, xi0, xi1, xi2, m_i, rho_si);
+                        cum2 += Dij * dc;
+                        last_ok = j;
+                        if (cum2 > target) { dest = j; break; }
+                    }
+                    if (dest < 0) dest = last_ok;                               // round-off overflow (:368-380)
+                    if (dest < 0) { atomicCAS(V.err_flag, 0, 2); break; }
+                    xx[spec]--;
+                    if (dest == i) xx[spec]++;                                  // stale self-neighbour on moving domains
+                    else {
+                        atomicAdd(&out_box[(size_t) spec * N + dest], 1u);
+                        atomicMax(&V.inbox_src[buf][dest], i + 1);
+                    }
+                    n_df++;
+                }
+                eval_rates(V, i, xx, tt, vol, df, type_i, R);
+                const double tot2 = R.sr + R.sd;
+                double u0, u1;
+                philox_uniform2(vid, draw++, epoch, seed, u0, u1);
+                tnext = (tot2 > 0.0) ? tt + (-log(u0)) / tot2 : INFINITY;       // NRMConstant_v5.cpp:92-99
+                if (++guard > 100000000) { atomicCAS(V.err_flag, 0, 2); break; }
+            }
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) V.xx[(size_t) s * N + i] = (unsigned) xx[s];
+#pragma unroll
+            for (int r = 0; r < SSB_RD; r++) V.rrate[(size_t) r * N + i] = R.rr[r];
+            V.srrate[i] = R.sr;
+            V.sdrate[i] = R.sd;
+            V.tnext[i] = tnext;
+        }
+    }
+    // event counters (ParticleSystem::total_reactions / total_diffusion): warp reduce, one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        n_rx += __shfl_xor_sync(0xffffffffu, n_rx, o);
+        n_df += __shfl_xor_sync(0xffffffffu, n_df, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_rx) atomicAdd(&V.counters[0], (unsigned long long) n_rx);
+        if (n_df) atomicAdd(&V.counters[1], (unsigned long long) n_df);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers (the table the core library calls through)
+// ---------------------------------------------------------------------------------------------
+static inline unsigned grid_for(int n) { return (unsigned) ((n + SSB_BLOCK - 1) / SSB_BLOCK); }
+
+static int l_predictor(const SsbView *V, unsigned step, cudaStream_t st) {
+    k_predictor<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
+    return (int) cudaGetLastError();
+}
+static int l_force(const SsbView *V, unsigned step, int full, cudaStream_t st) {
+    if (full) k_force<true><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
+    else k_force<false><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
+    return (int) cudaGetLastError();
+}
+static int l_corrector(const SsbView *V, unsigned step, cudaStream_t st) {
+    k_corrector<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
+    return (int) cudaGetLastError();
+}
+static int l_finish(const SsbView *V, unsigned step, int moving, cudaStream_t st) {
+    if (moving) k_finish<true><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
+    else k_finish<false><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
+    return (int) cudaGetLastError();
+}
+static int l_diff_init(const SsbView *V, unsigned long long *max_bits, cudaStream_t st) {
+    k_diff_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, max_bits);
+    return (int) cudaGetLastError();
+}
+static int l_rdme_init(const SsbView *V, double t0, double t_eval, uint64_t seed, uint64_t epoch, cudaStream_t st) {
+    k_rdme_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t0, t_eval, seed, epoch);
+    return (int) cudaGetLastError();
+}
+static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
+    k_rdme_window<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, seed, epoch, buf);
+    return (int) cudaGetLastError();
+}
+
+}  // namespace ssb_unit
+
+extern "C" const SsbModelUnit *ssbm_get_unit() {
+    static SsbModelUnit u;
+    u.abi = SSB_UNIT_ABI;
+    u.Sc = SSB_SC; u.Rc = SSB_RC; u.Sd = SSB_SD; u.Rd = SSB_RD; u.ndf = SSB_NDF; u.ntypes = SSB_NTYPES;
+    u.S = SSB_S; u.R = SSB_R;
+    u.predictor = ssb_unit::l_predictor;
+    u.force = ssb_unit::l_force;
+    u.corrector = ssb_unit::l_corrector;
+    u.finish = ssb_unit::l_finish;
+    u.diff_init = ssb_unit::l_diff_init;
+    u.rdme_init = ssb_unit::l_rdme_init;
+    u.rdme_window = ssb_unit::l_rdme_window;
+    return &u;
+}

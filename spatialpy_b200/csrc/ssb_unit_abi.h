@@ -1,0 +1,25 @@
+// ssb_unit_abi.h — the table a compiled model unit (one .so per model, built by codegen.py with
+// nvcc -arch=sm_100a) hands to libssb_core.  Replaces the reference's function-pointer tables
+// ALLOC_propensities()/ALLOC_ChemRxnFun() and the generated applyBoundaryConditions()
+// (E/propensity_file_template.cpp:47-66,92-94; E/include/propensities.hpp:44-53).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+struct SsbView;
+
+#define SSB_UNIT_ABI 3
+
+struct SsbModelUnit {
+    int abi;
+    int Sc, Rc, Sd, Rd, ndf, ntypes, S, R;
+    int (*predictor)(const SsbView *, unsigned step, cudaStream_t);
+    int (*force)(const SsbView *, unsigned step, int full, cudaStream_t);
+    int (*corrector)(const SsbView *, unsigned step, cudaStream_t);
+    int (*finish)(const SsbView *, unsigned step, int moving, cudaStream_t);
+    int (*diff_init)(const SsbView *, unsigned long long *max_ddiag_bits, cudaStream_t);
+    int (*rdme_init)(const SsbView *, double t0, double t_eval, uint64_t seed, uint64_t epoch, cudaStream_t);
+    int (*rdme_window)(const SsbView *, double t_lo, double t_hi, uint64_t seed, uint64_t epoch, int buf, cudaStream_t);
+};
+
+extern "C" const SsbModelUnit *ssbm_get_unit();

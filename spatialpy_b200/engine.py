@@ -1,0 +1,233 @@
+"""ctypes binding of include/ssb.h — the thin layer between Python and the CUDA engine.
+
+There is no CPU fallback: constructing an `Engine` without libssb_core.so (or without a usable GPU) raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import codegen
+from .flatmodel import FlatModel
+
+SSB_ABI_VERSION = 1
+FLAG_CORRECTED_NSM_SELECT = 1
+FLAG_CORRECTED_STOICH = 2
+FLAG_NO_VTK = 4
+FLAG_SKIP_STATIC_FORCES = 8
+
+ERR_NAMES = {1: "SSB_ERR_NAN", 2: "SSB_ERR_RDME", 3: "SSB_ERR_CUDA", 4: "SSB_ERR_ARG", 5: "SSB_ERR_IO",
+             6: "SSB_ERR_CANCELLED", 7: "SSB_ERR_MODEL_UNIT"}
+
+# every symbol include/ssb.h declares (tests check the library exports exactly these)
+EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernels", "ssb_destroy", "ssb_run",
+           "ssb_reset", "ssb_step", "ssb_counters", "ssb_get_field", "ssb_get_neighbors", "ssb_cancel",
+           "ssb_last_error", "ssb_launch_count"]
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"Solver execution failed, return code = {code} ({ERR_NAMES.get(code, '?')}): {message}")
+        self.code = code
+        self.message = message
+
+
+class SsbModel(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("flags", C.c_uint32), ("n_particles", C.c_int64),
+        ("dimension", C.c_int32), ("static_domain", C.c_int32), ("num_types", C.c_int32),
+        ("num_chem_species", C.c_int32), ("num_chem_rxns", C.c_int32), ("num_stoch_species", C.c_int32),
+        ("num_stoch_rxns", C.c_int32), ("num_data_fn", C.c_int32),
+        ("dt", C.c_double), ("nt", C.c_uint32), ("n_output_steps", C.c_uint32),
+        ("output_steps", C.POINTER(C.c_uint32)),
+        ("h", C.c_double), ("rho0", C.c_double), ("c0", C.c_double), ("P0", C.c_double),
+        ("xlo", C.c_double), ("xhi", C.c_double), ("ylo", C.c_double), ("yhi", C.c_double),
+        ("zlo", C.c_double), ("zhi", C.c_double), ("gravity", C.c_double * 3),
+        ("x", C.POINTER(C.c_double)), ("type", C.POINTER(C.c_int32)),
+        ("nu", C.POINTER(C.c_double)), ("mass", C.POINTER(C.c_double)), ("c", C.POINTER(C.c_double)),
+        ("rho", C.POINTER(C.c_double)), ("solid", C.POINTER(C.c_int32)), ("u0", C.POINTER(C.c_uint32)),
+        ("data_fn", C.POINTER(C.c_double)), ("N_dense", C.POINTER(C.c_int32)),
+        ("irN", C.POINTER(C.c_int64)), ("jcN", C.POINTER(C.c_int64)), ("prN", C.POINTER(C.c_int32)),
+        ("irG", C.POINTER(C.c_int64)), ("jcG", C.POINTER(C.c_int64)),
+        ("diffusion_matrix", C.POINTER(C.c_double)), ("species_names", C.POINTER(C.c_char_p)),
+        ("rdme_epsilon", C.c_double), ("device", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+_LIB = None
+
+
+def load_library(path=None):
+    """dlopen libssb_core.so (built in-tree by __graft_entry__.build / codegen.build_core)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or codegen.CORE_LIB
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the B200 engine has no CPU fallback)")
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    H = C.c_void_p
+    lib.ssb_abi_version.restype = C.c_int
+    lib.ssb_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.ssb_create.argtypes = [C.POINTER(SsbModel), C.POINTER(H)]
+    lib.ssb_load_kernels.argtypes = [H, C.c_char_p]
+    lib.ssb_destroy.argtypes = [H]
+    lib.ssb_run.argtypes = [H, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p]
+    lib.ssb_reset.argtypes = [H, C.c_uint64]
+    lib.ssb_step.argtypes = [H, C.c_uint32]
+    lib.ssb_counters.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.ssb_get_field.argtypes = [H, C.c_char_p, C.c_void_p, C.c_int64]
+    lib.ssb_get_neighbors.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.ssb_cancel.argtypes = [H]
+    lib.ssb_last_error.argtypes = [H]
+    lib.ssb_last_error.restype = C.c_char_p
+    lib.ssb_launch_count.argtypes = [H, C.POINTER(C.c_int64)]
+    for name in EXPORTS:
+        if getattr(lib, name).restype is None:
+            getattr(lib, name).restype = C.c_int
+    if path == codegen.CORE_LIB:
+        _LIB = lib
+    return lib
+
+
+def device_count():
+    n = C.c_int(0)
+    load_library().ssb_device_count(C.byref(n))
+    return n.value
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Engine:
+    """One engine handle = one model on one GPU (include/ssb.h ssb_handle)."""
+
+    _FIELDS = {  # name -> (dtype, columns or key)
+        "x": (np.float64, 3), "v": (np.float64, 3), "vt": (np.float64, 3), "F": (np.float64, 3), "Fbp": (np.float64, 3),
+        "x0": (np.float64, 3),
+        "rho": (np.float64, 1), "old_rho": (np.float64, 1), "Frho": (np.float64, 1), "bvf_phi": (np.float64, 1),
+        "mass": (np.float64, 1), "nu": (np.float64, 1), "srrate": (np.float64, 1), "sdrate": (np.float64, 1),
+        "tnext": (np.float64, 1), "rho_search": (np.float64, 1),
+        "type": (np.int32, 1), "solid": (np.int32, 1), "nbr_count": (np.int32, 1), "id": (np.int32, 1),
+        "C": (np.float64, "Sc"), "Q": (np.float64, "Sc"), "Ddiag": (np.float64, "Sd"), "rrate": (np.float64, "Rd"),
+        "xx": (np.uint32, "Sd"),
+    }
+
+    def __init__(self, fm: FlatModel, device=0, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, unit_path=None,
+                 unit_flags=()):
+        self.lib = load_library()
+        self.fm = fm.finalize()
+        self._h = C.c_void_p(None)
+        m = SsbModel()
+        self._keep = []
+        m.abi_version = SSB_ABI_VERSION
+        m.flags = int(flags)
+        m.n_particles = fm.num_particles
+        m.dimension = int(fm.dimension)
+        m.static_domain = int(bool(fm.static_domain))
+        m.num_types = int(fm.num_types)
+        m.num_chem_species, m.num_chem_rxns = fm.num_chem_species, fm.num_chem_rxns
+        m.num_stoch_species, m.num_stoch_rxns = fm.num_stoch_species, fm.num_stoch_rxns
+        m.num_data_fn = fm.num_data_fn
+        m.dt, m.nt = float(fm.dt), int(fm.nt)
+        m.n_output_steps = int(fm.output_steps.shape[0])
+        m.output_steps = _ptr(fm.output_steps, C.c_uint32)
+        m.h, m.rho0, m.c0, m.P0 = float(fm.h), float(fm.rho0), float(fm.c0), float(fm.P0)
+        m.xlo, m.xhi = fm.xlim
+        m.ylo, m.yhi = fm.ylim
+        m.zlo, m.zhi = fm.zlim
+        m.gravity = (C.c_double * 3)(*fm.gravity)
+        m.x = _ptr(fm.x, C.c_double)
+        m.type = _ptr(fm.type, C.c_int32)
+        m.nu, m.mass, m.c, m.rho = (_ptr(a, C.c_double) for a in (fm.nu, fm.mass, fm.c, fm.rho))
+        m.solid = _ptr(fm.solid, C.c_int32)
+        m.u0 = _ptr(fm.u0, C.c_uint32)
+        m.data_fn = _ptr(fm.data_fn, C.c_double)
+        m.N_dense = _ptr(fm.N_dense, C.c_int32)
+        m.irN, m.jcN, m.prN = _ptr(fm.irN, C.c_int64), _ptr(fm.jcN, C.c_int64), _ptr(fm.prN, C.c_int32)
+        m.irG, m.jcG = _ptr(fm.irG, C.c_int64), _ptr(fm.jcG, C.c_int64)
+        m.diffusion_matrix = _ptr(fm.diffusion_matrix, C.c_double)
+        names = (C.c_char_p * max(1, fm.num_species))(*[n.encode() for n in fm.species_names])
+        m.species_names = C.cast(names, C.POINTER(C.c_char_p))
+        m.rdme_epsilon = float(rdme_epsilon)
+        m.device = int(device)
+        self._check(self.lib.ssb_create(C.byref(m), C.byref(self._h)))
+        self.unit_path = unit_path or codegen.build_model_unit(fm, extra_flags=unit_flags)
+        self._check(self.lib.ssb_load_kernels(self._h, self.unit_path.encode()))
+        self.N = fm.num_particles
+        self._sizes = {"Sc": fm.num_chem_species, "Sd": fm.num_stoch_species, "Rd": fm.num_stoch_rxns}
+
+    # ------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.ssb_last_error(self._h) if self._h else b""
+            raise EngineError(rc, (msg or b"").decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.ssb_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ------------------------------------------------------------------
+    def reset(self, seed):
+        self._check(self.lib.ssb_reset(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def step(self, n=1):
+        self._check(self.lib.ssb_step(self._h, int(n)))
+
+    def run(self, seed, out_dirs, first_traj=0):
+        """Run len(out_dirs) trajectories (seed+first_traj+k each), writing VTK files into out_dirs[k]."""
+        n = len(out_dirs)
+        arr = (C.c_char_p * max(1, n))(*[os.fsencode(d) for d in out_dirs])
+        self._check(self.lib.ssb_run(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, n, int(first_traj),
+                                     C.cast(arr, C.POINTER(C.c_char_p)), None, None))
+
+    def run_no_files(self, seed, ntraj=1, first_traj=0):
+        self._check(self.lib.ssb_run(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(ntraj), int(first_traj), None, None, None))
+
+    def cancel(self):
+        self.lib.ssb_cancel(self._h)
+
+    def counters(self):
+        r, d, w = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        s = C.c_double(0)
+        self._check(self.lib.ssb_counters(self._h, C.byref(r), C.byref(d), C.byref(s), C.byref(w)))
+        return {"reactions": r.value, "diffusions": d.value, "seconds": s.value, "windows": w.value}
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        self._check(self.lib.ssb_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def get(self, name):
+        dtype, cols = self._FIELDS[name]
+        k = self._sizes[cols] if isinstance(cols, str) else cols
+        out = np.empty((self.N, k) if (k != 1 or isinstance(cols, str)) else (self.N,), dtype=dtype)
+        self._check(self.lib.ssb_get_field(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def neighbors(self):
+        """Neighbour lists in id space: (ptr[N+1], idx, dist, dWdr, Dij) — same shape as oracle dumps."""
+        nnz = C.c_int64(0)
+        self._check(self.lib.ssb_get_neighbors(self._h, None, None, None, None, None, C.byref(nnz)))
+        n = nnz.value
+        ptr = np.empty(self.N + 1, np.int64)
+        idx = np.empty(n, np.int32)
+        dist, dWdr, Dij = (np.empty(n, np.float64) for _ in range(3))
+        self._check(self.lib.ssb_get_neighbors(self._h, ptr.ctypes.data, idx.ctypes.data, dist.ctypes.data,
+                                               dWdr.ctypes.data, Dij.ctypes.data, C.byref(nnz)))
+        return ptr, idx, dist, dWdr, Dij

@@ -1,0 +1,121 @@
+"""Generate the committed parity fixtures from the UNMODIFIED reference engine (dev container only).
+
+    python tests/golden/make_golden.py [names...]
+
+For every model in tests/golden/models.py this
+  1. flattens the spatialpy.Model with FlatModel.from_spatialpy  -> tests/golden/<name>.model.npz
+     (the exact inputs both engines consume; same Python process => same type indices),
+  2. builds oracle/_ref/<name>/parity_dump/ssa_sdpd.exe (reference sources + oracle/ref_dump_output.cpp),
+  3. runs it with `-t 1 -s <seed>` and stores selected full-precision taps -> tests/golden/<name>.ref.npz,
+  4. for stochastic models runs an ensemble and stores per-trajectory observables -> tests/golden/<name>.ens.npz.
+The GPU box never runs this script (no /root/reference there); it only reads the .npz files.
+"""
+import os
+import shutil
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, HERE)
+
+import build_ref  # noqa: E402
+import ref_dump  # noqa: E402
+
+build_ref.add_reference_to_path()
+import models  # noqa: E402
+from spatialpy_b200 import FlatModel  # noqa: E402
+
+SEED = 1000
+TAP_FIELDS = ("x", "v", "vt", "F", "Fbp", "rho", "old_rho", "Frho", "bvf_phi", "C", "Q", "xx")
+NBR_FIELDS = ("nbr_ptr", "nbr_idx", "nbr_dist", "nbr_dWdr", "nbr_Dij")
+RDME_FIELDS = ("srrate", "sdrate", "Ddiag", "rrate")
+
+# which dump steps to keep per model (dump k = state at the top of step k = after k completed steps)
+TAPS = {
+    "birth_death": [0, 1],
+    "diffusion3d": [0, 1, 2, 10],
+    "cavity2d": [0, 1, 2, 3, 20, 21, 22, 45],
+    "tank3d": [0, 1, 2, 21, 25],
+    "cylinder": [0, 1],
+}
+ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000}
+XBINS = 8
+
+
+def coarse_bins(fm):
+    """voxel -> coarse bin along x (observables for the KS tests)."""
+    x = fm.x[:, 0]
+    lo, hi = x.min(), x.max()
+    b = np.minimum(((x - lo) / max(hi - lo, 1e-300) * XBINS).astype(int), XBINS - 1)
+    return b
+
+
+def run_one(exe, seed):
+    d = tempfile.mkdtemp(prefix="ssb_golden_")
+    try:
+        build_ref.run_exe(exe, d, seed, threads=1)
+        steps = sorted(int(f[5:11]) for f in os.listdir(d) if f.startswith("dump_"))
+        dumps = {s: ref_dump.read_dump(os.path.join(d, f"dump_{s:06d}.bin")) for s in steps}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return dumps
+
+
+def make(name):
+    model = models.BUILDERS[name]()
+    fm = FlatModel.from_spatialpy(model)
+    fm.save(os.path.join(HERE, f"{name}.model.npz"))
+    exe = build_ref.build_model(model, name, variant="parity", dump=True, h=fm.h)
+    dumps = run_one(exe, SEED)
+    out = {"steps": np.array(TAPS[name]), "seed": np.array(SEED)}
+    for s in TAPS[name]:
+        d = dumps[s]
+        for f in TAP_FIELDS:
+            out[f"s{s}_{f}"] = d[f]
+        if s <= 1 or not fm.static_domain:
+            for f in NBR_FIELDS:
+                out[f"s{s}_{f}"] = d[f]
+        if d["initialized"]:
+            for f in RDME_FIELDS:
+                out[f"s{s}_{f}"] = d[f]
+        out[f"s{s}_events"] = np.array([d["total_reactions"], d["total_diffusion"]])
+    np.savez_compressed(os.path.join(HERE, f"{name}.ref.npz"), **out)
+    print(f"{name}: N={fm.num_particles} taps={TAPS[name]} final events={dumps[max(dumps)]['total_reactions']}/{dumps[max(dumps)]['total_diffusion']}")
+    if name in ENSEMBLES:
+        ntraj = ENSEMBLES[name]
+        bins = coarse_bins(fm)
+        last = max(dumps)
+        mid = sorted(dumps)[len(dumps) // 2]
+
+        def obs(k):
+            dd = run_one(exe, SEED + k)
+            res = []
+            for s in (mid, last):
+                xx = dd[s]["xx"].astype(np.int64)                       # [N, S]
+                binned = np.stack([np.bincount(bins, weights=xx[:, j], minlength=XBINS) for j in range(xx.shape[1])])
+                res.append((xx.sum(axis=0), binned, xx))
+            return res, (dd[last]["total_reactions"], dd[last]["total_diffusion"])
+        with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+            results = list(ex.map(obs, range(ntraj)))
+        ens = {"ntraj": np.array(ntraj), "seed0": np.array(SEED), "steps": np.array([mid, last]), "bins": bins}
+        for ti, s in enumerate((mid, last)):
+            ens[f"t{ti}_totals"] = np.array([r[0][ti][0] for r in results])                 # [ntraj, S]
+            ens[f"t{ti}_binned"] = np.array([r[0][ti][1] for r in results])                 # [ntraj, S, XBINS]
+            allxx = np.array([r[0][ti][2] for r in results], dtype=np.float64)              # [ntraj, N, S]
+            ens[f"t{ti}_vox_mean"] = allxx.mean(axis=0)
+            ens[f"t{ti}_vox_var"] = allxx.var(axis=0, ddof=1)
+        ens["events"] = np.array([r[1] for r in results])
+        np.savez_compressed(os.path.join(HERE, f"{name}.ens.npz"), **ens)
+        print(f"{name}: ensemble of {ntraj}: mean totals at last = {ens['t1_totals'].mean(axis=0)}, events/traj = {ens['events'].mean(axis=0)}")
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(models.BUILDERS)
+    for n in names:
+        make(n)
