@@ -950,7 +950,14 @@ static int rdme_step(ssb_handle *h) {
         h->inbox_buf ^= 1;
         if ((w & 1023) == 1023 && h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
     }
-    h->launches += nwin;
+    // zero-length closing window: delivers the molecules still in flight in the inbox so that the state read at
+    // the step boundary (output, taps, the next step's re-initialisation) conserves molecules
+    {
+        const double te = t0 + V.dt;
+        if (u->rdme_window(&V, te, te, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+        h->inbox_buf ^= 1;
+    }
+    h->launches += nwin + 1;
     h->windows += nwin;
     return SSB_OK;
 }

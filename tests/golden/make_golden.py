@@ -69,8 +69,12 @@ def run_one(exe, seed):
 
 def make(name):
     model = models.BUILDERS[name]()
+    # compile_prep() re-applies the (random) scatter initial conditions every time it is called
+    # (model.py:178-185), and both flattenings call it: re-seed so the two engines get the same u0.
+    np.random.seed(12345)
     fm = FlatModel.from_spatialpy(model)
     fm.save(os.path.join(HERE, f"{name}.model.npz"))
+    np.random.seed(12345)
     exe = build_ref.build_model(model, name, variant="parity", dump=True, h=fm.h)
     dumps = run_one(exe, SEED)
     out = {"steps": np.array(TAPS[name]), "seed": np.array(SEED)}
