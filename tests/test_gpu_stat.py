@@ -1,0 +1,102 @@
+"""Statistical parity of the sSSA against ensembles of the UNMODIFIED reference NSM (tests/golden/*.ens.npz,
+>= 1000 reference trajectories each).  BASELINE.json: per-voxel mean and variance within 3 sigma, KS p > 0.01."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from util import load_ens, load_model
+
+pytestmark = pytest.mark.gpu
+
+XBINS = 8
+
+
+def gpu_ensemble(name, ntraj, steps, seed0=50_000, **kw):
+    from spatialpy_b200.engine import Engine
+    fm = load_model(name)
+    out = {s: [] for s in steps}
+    with Engine(fm, **kw) as eng:
+        for k in range(ntraj):
+            eng.reset(seed0 + k)
+            done = 0
+            for s in steps:
+                eng.step(s - done)
+                done = s
+                out[s].append(eng.get("xx").astype(np.int64))
+    return {s: np.array(v) for s, v in out.items()}       # [ntraj, N, S]
+
+
+def check_against_reference(name, ntraj):
+    ens = load_ens(name)
+    steps = [int(s) for s in ens["steps"]]
+    bins = ens["bins"]
+    g = gpu_ensemble(name, ntraj, steps)
+    nref = int(ens["ntraj"])
+    report = []
+    for ti, s in enumerate(steps):
+        xx = g[s]                                           # [ntraj, N, S]
+        S = xx.shape[2]
+        # (1) KS on the total population of every species
+        tot = xx.sum(axis=1)
+        for j in range(S):
+            ref_tot = ens[f"t{ti}_totals"][:, j]
+            if ref_tot.std() == 0 and tot[:, j].std() == 0:
+                assert ref_tot[0] == tot[0, j]
+                continue
+            p = stats.ks_2samp(tot[:, j], ref_tot).pvalue
+            report.append((f"step {s} total[{j}]", p))
+            assert p > 0.01, f"{name} step {s} species {j}: KS p={p:.4f} on totals"
+        # (2) KS on coarse spatial bins (Bonferroni over the family)
+        binned = np.stack([np.stack([np.bincount(bins, weights=xx[k, :, j], minlength=XBINS) for j in range(S)])
+                           for k in range(xx.shape[0])])    # [ntraj, S, XBINS]
+        ps = []
+        for j in range(S):
+            for b in range(XBINS):
+                a, r = binned[:, j, b], ens[f"t{ti}_binned"][:, j, b]
+                if a.std() == 0 and r.std() == 0:
+                    continue
+                ps.append(stats.ks_2samp(a, r).pvalue)
+        if ps:
+            assert min(ps) > 0.01 / len(ps), f"{name} step {s}: min binned KS p={min(ps):.2e} over {len(ps)} tests"
+        # (3) per-voxel mean and variance within 3 sigma (a 1% outlier allowance for the multiplicity, none beyond 4.5)
+        mean_g, var_g = xx.mean(axis=0), xx.var(axis=0, ddof=1)
+        mean_r, var_r = ens[f"t{ti}_vox_mean"], ens[f"t{ti}_vox_var"]
+        se_mean = np.sqrt(var_g / ntraj + var_r / nref)
+        ok = se_mean > 0
+        z = np.abs(mean_g - mean_r)[ok] / se_mean[ok]
+        assert (z > 3).mean() <= 0.01 and z.max() < 4.5, f"{name} step {s}: mean z max {z.max():.2f}, frac>3 {(z > 3).mean():.4f}"
+        m4 = ((xx - mean_g) ** 4).mean(axis=0)
+        se_var = np.sqrt(np.maximum(m4 - var_g ** 2, 0) * (1.0 / ntraj + 1.0 / nref))
+        okv = se_var > 0
+        zv = np.abs(var_g - var_r)[okv] / se_var[okv]
+        assert (zv > 3).mean() <= 0.02 and zv.max() < 5.5, f"{name} step {s}: var z max {zv.max():.2f}, frac>3 {(zv > 3).mean():.4f}"
+    return report
+
+
+def test_birth_death_ensemble_matches_reference():
+    """BASELINE config 1 — note the reference's channel pick makes `death` unreachable (simulate_rdme.cpp:260):
+    the population GROWS (100 -> ~480 in 10 s); parity mode reproduces that law."""
+    check_against_reference("birth_death", 1000)
+
+
+def test_cylinder_ensemble_matches_reference():
+    """BASELINE config 2a — shipped cylinder mesh, A+B annihilation with sources at both ends, unequal voxel volumes."""
+    check_against_reference("cylinder", 1000)
+
+
+def test_pure_diffusion_ensemble_matches_reference():
+    check_against_reference("diffusion3d", 1000)
+
+
+def test_corrected_mode_birth_death_is_poisson():
+    """SSB_FLAG_CORRECTED_NSM_SELECT: textbook NSM; stationary law is Poisson(k_birth*vol/k_death = 1) per voxel,
+    so total over 121 voxels ~ Poisson(121) once relaxed (t = 10 s is one death time constant: mean
+    100*e^-1 + 121*(1-e^-1))."""
+    from spatialpy_b200.engine import FLAG_CORRECTED_NSM_SELECT, FLAG_SKIP_STATIC_FORCES
+    g = gpu_ensemble("birth_death", 300, [10], flags=FLAG_CORRECTED_NSM_SELECT | FLAG_SKIP_STATIC_FORCES)
+    tot = g[10].sum(axis=(1, 2))
+    expect = 100 * np.exp(-1.0) + 121 * (1 - np.exp(-1.0))
+    # variance of the total: survivors Binomial(100, e^-1) + Poisson(121(1-e^-1))
+    var = 100 * np.exp(-1.0) * (1 - np.exp(-1.0)) + 121 * (1 - np.exp(-1.0))
+    z = abs(tot.mean() - expect) / np.sqrt(var / len(tot))
+    assert z < 4, (tot.mean(), expect, z)
