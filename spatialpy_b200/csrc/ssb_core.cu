@@ -310,6 +310,7 @@ struct ssb_handle {
     uint64_t seed = 0, epoch = 0;
     int inbox_buf = 0;
     double tau = 0.0;
+    long long nwin = 1;
     int nbr_valid = 0;
     int64_t launches = 0, windows = 0;
     int64_t total_reactions = 0, total_diffusion = 0;
@@ -926,27 +927,31 @@ static int rdme_step(ssb_handle *h) {
     if (!V.static_domain || !h->rdme_initialized) {      // simulate_rdme.cpp:54-65
         CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
         if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
-        // propensities are (re)initialised at t = 0.0 in the reference (simulate_rdme.cpp:124)
-        if (u->rdme_init(&V, t0, 0.0, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
-        h->launches += 2;
+        h->launches += 1;
         unsigned long long bits = 0;
         CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         double mx;
         memcpy(&mx, &bits, sizeof(mx));
+        // window controller: tau * (largest per-molecule jump rate) <= rdme_epsilon, and an integer number of windows per step
         double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
-        h->tau = (mx > 0.0) ? eps / mx : V.dt;
+        double tau = (mx > 0.0) ? eps / mx : V.dt;
+        double nwin_d = ceil(V.dt / tau);
+        if (!(nwin_d >= 1.0)) nwin_d = 1.0;
+        if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
+        h->nwin = (long long) nwin_d;
+        h->tau = V.dt / (double) h->nwin;
+        // propensities are (re)initialised at t = 0.0 in the reference (simulate_rdme.cpp:124)
+        if (u->rdme_init(&V, t0, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
+        h->launches += 1;
         h->rdme_initialized = 1;
         h->inbox_buf = 0;
     }
-    double nwin_d = ceil(V.dt / h->tau);
-    if (!(nwin_d >= 1.0)) nwin_d = 1.0;
-    if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
-    const long long nwin = (long long) nwin_d;
+    const long long nwin = h->nwin;
     for (long long w = 0; w < nwin; w++) {
         double lo = t0 + V.dt * ((double) w / (double) nwin);
         double hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
-        if (u->rdme_window(&V, lo, hi, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+        if (u->rdme_window(&V, lo, hi, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
         h->inbox_buf ^= 1;
         if ((w & 1023) == 1023 && h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
     }
@@ -954,7 +959,7 @@ static int rdme_step(ssb_handle *h) {
     // the step boundary (output, taps, the next step's re-initialisation) conserves molecules
     {
         const double te = t0 + V.dt;
-        if (u->rdme_window(&V, te, te, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+        if (u->rdme_window(&V, te, te, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
         h->inbox_buf ^= 1;
     }
     h->launches += nwin + 1;

@@ -380,19 +380,27 @@ struct VoxelRates {
     double sr, sd;
 };
 
-__device__ __forceinline__ void eval_rates(const SsbView &V, int i, const int *xx, double t, double vol,
-                                           const double *df, int type, VoxelRates &R) {
-    ssb_gen::eval_propensities(xx, t, vol, df, type, R.rr);
+// lag compensation of the windowed scheme: a molecule that jumps inside a window only becomes mobile again at the
+// window end (mean lag tau/2), so its jump cadence would be 1/d + tau/2; using d' = d / (1 - d tau/2) restores 1/d.
+__device__ __forceinline__ double lag_comp(double d, double tau) {
+    const double q = fmin(0.5 * d * tau, 0.5);
+    return d / (1.0 - q);
+}
+
+// xr = molecules that can REACT here (present + departing), xx = molecules that can still JUMP (present)
+__device__ __forceinline__ void eval_rates(const SsbView &V, int i, const int *xr, const int *xx, double t, double vol,
+                                           const double *df, int type, double tau, VoxelRates &R) {
+    ssb_gen::eval_propensities(xr, t, vol, df, type, R.rr);
     double sr = 0.0;
 #pragma unroll
     for (int r = 0; r < SSB_RD; r++) sr += R.rr[r];
     double sd = 0.0;
 #pragma unroll
-    for (int s = 0; s < SSB_SD; s++) sd += V.Ddiag[(size_t) s * V.N + i] * xx[s];
+    for (int s = 0; s < SSB_SD; s++) sd += lag_comp(V.Ddiag[(size_t) s * V.N + i], tau) * xx[s];
     R.sr = sr; R.sd = sd;
 }
 
-__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, double t_eval, uint64_t seed, uint64_t epoch) {
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, double t_eval, double tau, uint64_t seed, uint64_t epoch) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V.N) return;
     const int N = V.N;
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
     for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
     const double vol = V.mass[i] / V.rho[i];
     VoxelRates R;
-    eval_rates(V, i, xx, t_eval, vol, df, V.type[i], R);
+    eval_rates(V, i, xx, xx, t_eval, vol, df, V.type[i], tau, R);
 #pragma unroll
     for (int r = 0; r < SSB_RD; r++) V.rrate[(size_t) r * N + i] = R.rr[r];
     V.srrate[i] = R.sr;
@@ -422,18 +430,21 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
 // K7b  one sSSA window [t_lo, t_hi] — one thread per voxel.
 // The reference's NSM (simulate_rdme.cpp:211-472) executes events in global time order, which is inherently
 // serial.  Here every voxel runs an exact SSA of ITS OWN channels (reactions + outgoing diffusion jumps) inside
-// the window; molecules that jump are delivered to the destination's inbox (integer atomicAdd: order-independent,
-// so results are bit-reproducible) and become visible at the start of the next window, when the destination
-// re-draws its next event time (memoryless, same as NRMConstant_v5::update redrawing Exp(1)/a + t,
-// NRMConstant_v5.cpp:98).  The splitting error is O(tau * jump rate) and is bounded by the window controller
-// (ssb_model.rdme_epsilon).  Event execution mirrors the reference branch by branch:
+// the window.  A molecule that jumps is posted to the destination's inbox (integer atomicAdd: order-independent, so
+// results are bit-reproducible) and is picked up by the destination at the start of the next window, when the
+// destination re-draws its next event time (memoryless, exactly what NRMConstant_v5::update does:
+// Exp(1)/a + t, NRMConstant_v5.cpp:98).  Until the window closes the jumped molecule stays REACTIVE in its source
+// voxel (`dep`), so no molecule is ever invisible to the reaction channels, and the jump propensities carry the
+// lag compensation above; what remains is an O((tau * jump rate)^2) splitting error bounded by the window
+// controller (ssb_model.rdme_epsilon = tau * max jump rate).
+// Event execution mirrors the reference branch by branch:
 //   channel draw  rand1 <= srrate/totrate ? reaction : diffusion                     (simulate_rdme.cpp:253-255)
 //   reaction pick rand1*srrate against the running sum of rrate[]                     (:260-261)  [reference rule]
 //   species pick  rand1*sdrate against the running sum of Ddiag[s]*xx[s]              (:317-321)  [reference rule]
 //   direction     r2*Ddiag[spec] against the running sum of D_i_j*D[spec,type(dest)]  (:353-367)
 // SSB_FLAG_CORRECTED_NSM_SELECT switches the two picks to the textbook rule (rand*totrate, subtract srrate).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, uint64_t seed,
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, double tau, uint64_t seed,
                                                           uint64_t epoch, int buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned n_rx = 0, n_df = 0;
@@ -447,9 +458,14 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
 #pragma unroll
         for (int s = 0; s < SSB_SD; s++) { inc[s] = in_prev[(size_t) s * N + i]; arrived |= (inc[s] != 0u); }
         if (arrived || tnext <= t_hi) {
-            int xx[SSB_SD > 0 ? SSB_SD : 1];
+            int xx[SSB_SD > 0 ? SSB_SD : 1];     // present: may react and jump
+            int xr[SSB_SD > 0 ? SSB_SD : 1];     // present + departing: may react
+            double Dd[SSB_SD > 0 ? SSB_SD : 1];  // lag-compensated jump propensity per molecule
 #pragma unroll
-            for (int s = 0; s < SSB_SD; s++) xx[s] = (int) V.xx[(size_t) s * N + i];
+            for (int s = 0; s < SSB_SD; s++) {
+                xx[s] = (int) V.xx[(size_t) s * N + i];
+                Dd[s] = lag_comp(V.Ddiag[(size_t) s * N + i], tau);
+            }
             double df[SSB_NDF > 0 ? SSB_NDF : 1];
 #pragma unroll
             for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
 #pragma unroll
                 for (int r = 0; r < SSB_RD; r++) { if ((mask >> r) & 1ull) R.rr[r] = tmp[r]; sr += R.rr[r]; }
 #pragma unroll
-                for (int s = 0; s < SSB_SD; s++) sd += V.Ddiag[(size_t) s * N + i] * xx[s];
+                for (int s = 0; s < SSB_SD; s++) sd += Dd[s] * xx[s];
                 R.sr = sr; R.sd = sd;
                 const double tot = R.sr + R.sd;
                 double u0, u1;
@@ -496,6 +512,8 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
 #pragma unroll
                 for (int r = 0; r < SSB_RD; r++) R.rr[r] = V.rrate[(size_t) r * N + i];
             }
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) xr[s] = xx[s];
             const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
             int guard = 0;
             while (tnext <= t_hi) {
@@ -520,16 +538,29 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
                     for (int q = 1; q < SSB_RD; q++) { if (pick > cum) { re = q; cum += R.rr[q]; } else break; }
                     // fell off the end with a zero-propensity tail: step back to the last live reaction (:262-281)
                     while (re > 0 && R.rr[re] <= 0.0) re--;
+                    // the reaction acts on the reactive population; consumption is taken from the present molecules.
+                    int xn[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+                    for (int s = 0; s < SSB_SD; s++) xn[s] = xr[s];
                     bool neg = false;
-                    ssb_gen::apply_stoich(re, xx, neg);                         // simulate_rdme.cpp:285-296
+                    ssb_gen::apply_stoich(re, xn, neg);                         // simulate_rdme.cpp:285-296
                     if (neg) atomicCAS(V.err_flag, 0, 2 /*SSB_ERR_RDME*/);
-                    n_rx++;
+                    bool feasible = true;
+#pragma unroll
+                    for (int s = 0; s < SSB_SD; s++) feasible &= (xx[s] + (xn[s] - xr[s]) >= 0);
+                    if (feasible) {
+#pragma unroll
+                        for (int s = 0; s < SSB_SD; s++) { xx[s] += xn[s] - xr[s]; xr[s] = xn[s]; }
+                        n_rx++;
+                    }
+                    // else: every present reactant already departed in this window — the event is dropped
+                    // (second order in tau; keeps posted jumps final and the result deterministic)
                 } else {
                     int spec = 0;
-                    double cum = V.Ddiag[i] * xx[0];
+                    double cum = Dd[0] * xx[0];
 #pragma unroll
                     for (int q = 1; q < SSB_SD; q++) {
-                        if (pick > cum) { spec = q; cum += V.Ddiag[(size_t) q * N + i] * xx[q]; } else break;
+                        if (pick > cum) { spec = q; cum += Dd[q] * xx[q]; } else break;
                     }
                     while (spec > 0 && xx[spec] <= 0) spec--;                   // simulate_rdme.cpp:338-347
                     if (xx[spec] <= 0) { atomicCAS(V.err_flag, 0, 2); break; }
@@ -551,20 +582,30 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
                     }
                     if (dest < 0) dest = last_ok;                               // round-off overflow (:368-380)
                     if (dest < 0) { atomicCAS(V.err_flag, 0, 2); break; }
-                    xx[spec]--;
-                    if (dest == i) xx[spec]++;                                  // stale self-neighbour on moving domains
-                    else {
+                    if (dest != i) {                                            // (dest == i: stale self-neighbour on moving domains)
+                        xx[spec]--;                                             // no longer mobile here, still reactive (xr) until the window closes
                         atomicAdd(&out_box[(size_t) spec * N + dest], 1u);
                         atomicMax(&V.inbox_src[buf][dest], i + 1);
                     }
                     n_df++;
                 }
-                eval_rates(V, i, xx, tt, vol, df, type_i, R);
+                eval_rates(V, i, xr, xx, tt, vol, df, type_i, tau, R);
                 const double tot2 = R.sr + R.sd;
                 double u0, u1;
                 philox_uniform2(vid, draw++, epoch, seed, u0, u1);
                 tnext = (tot2 > 0.0) ? tt + (-log(u0)) / tot2 : INFINITY;       // NRMConstant_v5.cpp:92-99
                 if (++guard > 100000000) { atomicCAS(V.err_flag, 0, 2); break; }
+            }
+            // window closes: departed molecules leave the reactive population; rates for the next window
+            bool departed = false;
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) departed |= (xr[s] != xx[s]);
+            if (departed) {
+                eval_rates(V, i, xx, xx, t_hi, vol, df, type_i, tau, R);
+                const double tot3 = R.sr + R.sd;
+                double u0, u1;
+                philox_uniform2(vid, draw++, epoch, seed, u0, u1);
+                tnext = (tot3 > 0.0) ? t_hi + (-log(u0)) / tot3 : INFINITY;
             }
 #pragma unroll
             for (int s = 0; s < SSB_SD; s++) V.xx[(size_t) s * N + i] = (unsigned) xx[s];
@@ -613,12 +654,12 @@ static int l_diff_init(const SsbView *V, unsigned long long *max_bits, cudaStrea
     k_diff_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, max_bits);
     return (int) cudaGetLastError();
 }
-static int l_rdme_init(const SsbView *V, double t0, double t_eval, uint64_t seed, uint64_t epoch, cudaStream_t st) {
-    k_rdme_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t0, t_eval, seed, epoch);
+static int l_rdme_init(const SsbView *V, double t0, double t_eval, double tau, uint64_t seed, uint64_t epoch, cudaStream_t st) {
+    k_rdme_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t0, t_eval, tau, seed, epoch);
     return (int) cudaGetLastError();
 }
-static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
-    k_rdme_window<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, seed, epoch, buf);
+static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
+    k_rdme_window<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
     return (int) cudaGetLastError();
 }
 

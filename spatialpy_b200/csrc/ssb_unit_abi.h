@@ -8,7 +8,7 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 3
+#define SSB_UNIT_ABI 4
 
 struct SsbModelUnit {
     int abi;
@@ -18,8 +18,8 @@ struct SsbModelUnit {
     int (*corrector)(const SsbView *, unsigned step, cudaStream_t);
     int (*finish)(const SsbView *, unsigned step, int moving, cudaStream_t);
     int (*diff_init)(const SsbView *, unsigned long long *max_ddiag_bits, cudaStream_t);
-    int (*rdme_init)(const SsbView *, double t0, double t_eval, uint64_t seed, uint64_t epoch, cudaStream_t);
-    int (*rdme_window)(const SsbView *, double t_lo, double t_hi, uint64_t seed, uint64_t epoch, int buf, cudaStream_t);
+    int (*rdme_init)(const SsbView *, double t0, double t_eval, double tau, uint64_t seed, uint64_t epoch, cudaStream_t);
+    int (*rdme_window)(const SsbView *, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t);
 };
 
 extern "C" const SsbModelUnit *ssbm_get_unit();
