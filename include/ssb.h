@@ -128,6 +128,16 @@ const char *ssb_last_error(ssb_handle *h);     /* message for the last non-zero 
 /* Kernel accounting for bench.py: number of engine kernels launched since the last ssb_reset/ssb_run start. */
 int ssb_launch_count(ssb_handle *h, int64_t *launches);
 
+/* Measurement hooks (bench.py).  ssb_step_timed = ssb_step bracketed by CUDA events on the engine's own stream.
+ * ssb_profile(1) brackets every launch group with event pairs; categories:
+ * 0 cell list  1 predictor  2 neighbour search  3 force sweep  4 corrector  5 finish/BVF  6 diffusion matrix
+ * 7 RDME init  8 sSSA windows  9 output staging.  ssb_io_bytes = bytes copied H2D at reset / D2H by output staging. */
+int ssb_step_timed(ssb_handle *h, uint32_t nsteps, double *device_ms);
+int ssb_profile(ssb_handle *h, int enable);
+int ssb_profile_read(ssb_handle *h, int category, double *ms_total, int64_t *launches);
+int ssb_io_bytes(ssb_handle *h, int64_t *h2d, int64_t *d2h);
+int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,34 @@ def build_model(model, name, variant="parity", dump=False, debug_level=0, h=None
     return exe
 
 
+def build_flat(fm, name, variant="parity", dump=False, debug_level=0, model_opt=None):
+    """Same as build_model, for a FlatModel (synthetic configs): the reference's own template is filled by
+    oracle/emit_ref_model.py with the substitutions of solver.py:135-153."""
+    import emit_ref_model
+    lib = build_core(variant, dump)
+    mdir = os.path.join(OUT, name, f"{variant}{'_dump' if dump else ''}")
+    os.makedirs(mdir, exist_ok=True)
+    src = os.path.join(mdir, "model.cpp")
+    exe = os.path.join(mdir, "ssa_sdpd.exe")
+    emit_ref_model.emit(fm, src + ".new", os.path.join(ENGINE, "propensity_file_template.cpp"), debug_level)
+    with open(src + ".new", "rb") as f:
+        new_hash = hashlib.sha256(f.read()).hexdigest()
+    stamp = os.path.join(mdir, "model.sha256")
+    if os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read() == new_hash:
+        os.remove(src + ".new")
+        return exe
+    os.replace(src + ".new", src)
+    flags = list(FLAGS[variant])
+    if model_opt is not None:
+        flags = [f for f in flags if not f.startswith("-O")] + [model_opt]
+    inc = ["-I", os.path.join(ENGINE, "include"), "-I", os.path.join(ENGINE, "external/ANN/include")]
+    _run(["g++"] + flags + inc + [src, lib, "-lpthread", "-o", exe])
+    os.remove(src)      # the literal-laden TU can be hundreds of MB; the stamp identifies it
+    with open(stamp, "w") as f:
+        f.write(new_hash)
+    return exe
+
+
 def run_exe(exe, out_dir, seed, threads=1, timeout=None):
     """`exe -t T -s SEED` with cwd = out_dir (the reference's process contract, solver.py:553-569)."""
     os.makedirs(out_dir, exist_ok=True)

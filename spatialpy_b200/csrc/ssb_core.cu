@@ -34,6 +34,8 @@
 #include "ssb_unit_abi.h"
 
 #define CORE_BLOCK 256
+#define SSB_NCAT 10
+enum { CAT_CELLS = 0, CAT_PREDICTOR, CAT_SEARCH, CAT_FORCE, CAT_CORRECTOR, CAT_FINISH, CAT_DIFF_INIT, CAT_RDME_INIT, CAT_RDME_WINDOW, CAT_OUTPUT };
 
 // =====================================================================================================
 // device kernels
@@ -262,6 +264,7 @@ struct OutputJob {
     unsigned step = 0;
     unsigned file_index = 0;
     int rdme_initialized = 0;
+    int write_file = 1;
     std::string dir;
     cudaEvent_t ready = nullptr;
     // pinned staging (id order)
@@ -312,11 +315,17 @@ struct ssb_handle {
     double tau = 0.0;
     long long nwin = 1;
     int nbr_valid = 0;
-    int64_t launches = 0, windows = 0;
+    int64_t launches = 0, windows = 0, h2d_bytes = 0, d2h_bytes = 0;
     int64_t total_reactions = 0, total_diffusion = 0;
     double step_seconds = 0.0;
     std::atomic<int> cancel{0};
     std::string err;
+    // per-category device timing (ssb_profile): CUDA event pairs on the engine stream around each launch group
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_a, ev_b;
+    std::vector<int> ev_cat;
+    double cat_ms[SSB_NCAT] = {0};
+    int64_t cat_launches[SSB_NCAT] = {0};
     // output
     OutputJob jobs[2];
     int job_cursor = 0;
@@ -353,6 +362,32 @@ static cudaError_t dalloc(ssb_handle *h, T **p, size_t count) {
 }
 
 static inline unsigned gridN(int n) { return (unsigned) ((n + CORE_BLOCK - 1) / CORE_BLOCK); }
+
+// ---- per-category device timing -------------------------------------------------------------------------
+static void prof_harvest(ssb_handle *h) {
+    if (h->ev_cat.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (size_t k = 0; k < h->ev_cat.size(); k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_a[k], h->ev_b[k]) == cudaSuccess) h->cat_ms[h->ev_cat[k]] += ms;
+    }
+    h->ev_cat.clear();
+}
+static int prof_begin(ssb_handle *h, int cat, int nlaunch) {
+    if (!h->profile) return -1;
+    if (h->ev_cat.size() >= 4096) prof_harvest(h);
+    size_t k = h->ev_cat.size();
+    if (k >= h->ev_a.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        h->ev_a.push_back(a); h->ev_b.push_back(b);
+    }
+    h->ev_cat.push_back(cat);
+    h->cat_launches[cat] += nlaunch;
+    cudaEventRecord(h->ev_a[k], h->stream);
+    return (int) k;
+}
+static void prof_end(ssb_handle *h, int slot) { if (slot >= 0) cudaEventRecord(h->ev_b[slot], h->stream); }
 
 // ----------------------------------------------------------------------------------------------------
 // VTK writer (host thread) — byte format of E/src/output.cpp:104-229
@@ -515,7 +550,7 @@ static void writer_main(ssb_handle *h) {
         }
         OutputJob &J = h->jobs[next];
         cudaEventSynchronize(J.ready);
-        int rc = write_vtk(h, J);
+        int rc = J.write_file ? write_vtk(h, J) : 0;
         {
             std::lock_guard<std::mutex> lk(h->mu);
             if (rc) h->writer_error = rc;
@@ -812,6 +847,8 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     h->nbr_valid = 0;
     h->launches = 0;
     h->windows = 0;
+    h->h2d_bytes = (int64_t) N * (3 * 8 + 3 * 8 + 2 * 4 + 8 * Sc + 4 * Sd + 8 * ndf);
+    h->d2h_bytes = 0;
     h->total_reactions = h->total_diffusion = 0;
     h->step_seconds = 0.0;
     h->cancel.store(0);
@@ -926,7 +963,9 @@ static int rdme_step(ssb_handle *h) {
     const double t0 = V.dt * h->current_step;
     if (!V.static_domain || !h->rdme_initialized) {      // simulate_rdme.cpp:54-65
         CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+        int ps0 = prof_begin(h, CAT_DIFF_INIT, 1);
         if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
+        prof_end(h, ps0);
         h->launches += 1;
         unsigned long long bits = 0;
         CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
@@ -942,12 +981,15 @@ static int rdme_step(ssb_handle *h) {
         h->nwin = (long long) nwin_d;
         h->tau = V.dt / (double) h->nwin;
         // propensities are (re)initialised at t = 0.0 in the reference (simulate_rdme.cpp:124)
+        int ps1 = prof_begin(h, CAT_RDME_INIT, 1);
         if (u->rdme_init(&V, t0, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
+        prof_end(h, ps1);
         h->launches += 1;
         h->rdme_initialized = 1;
         h->inbox_buf = 0;
     }
     const long long nwin = h->nwin;
+    int psw = prof_begin(h, CAT_RDME_WINDOW, (int) nwin + 1);
     for (long long w = 0; w < nwin; w++) {
         double lo = t0 + V.dt * ((double) w / (double) nwin);
         double hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
@@ -962,6 +1004,7 @@ static int rdme_step(ssb_handle *h) {
         if (u->rdme_window(&V, te, te, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
         h->inbox_buf ^= 1;
     }
+    prof_end(h, psw);
     h->launches += nwin + 1;
     h->windows += nwin;
     return SSB_OK;
@@ -974,23 +1017,40 @@ static int engine_step(ssb_handle *h) {
     const unsigned step = h->current_step;
     const bool moving = !V.static_domain;
     int rc;
-    if (step == 0 || moving) { if ((rc = build_cells(h))) return rc; }     // buildKDTree (simulate_threads.cpp:80-108)
+    int ps;
+    if (step == 0 || moving) {                                               // buildKDTree (simulate_threads.cpp:80-108)
+        ps = prof_begin(h, CAT_CELLS, 7);
+        rc = build_cells(h);
+        prof_end(h, ps);
+        if (rc) return rc;
+    }
+    ps = prof_begin(h, CAT_PREDICTOR, 1);
     if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
+    prof_end(h, ps);
     h->launches++;
     if (step == 0 || moving) {                                               // find_neighbors (simulate.cpp:61-63,121-123)
         V.rho_search = V.rho;
-        if ((rc = neighbour_search(h))) return rc;
+        ps = prof_begin(h, CAT_SEARCH, 1);
+        rc = neighbour_search(h);
+        prof_end(h, ps);
+        if (rc) return rc;
     }
     const bool full = moving || !(V.flags & SSB_FLAG_SKIP_STATIC_FORCES);
     if (full || V.Sc > 0) {
+        ps = prof_begin(h, CAT_FORCE, 1);
         if (u->force(&V, step, full ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
+        prof_end(h, ps);
         h->launches++;
     }
     if (moving) {
+        ps = prof_begin(h, CAT_CORRECTOR, 1);
         if (u->corrector(&V, step, st)) return fail(h, SSB_ERR_CUDA, "corrector launch failed");
+        prof_end(h, ps);
         h->launches++;
     }
+    ps = prof_begin(h, CAT_FINISH, 1);
     if (u->finish(&V, step, moving ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
+    prof_end(h, ps);
     h->launches++;
     if (moving) {
         // rho <- post-corrector density; the old buffer keeps the search-time density frozen into D_i_j
@@ -1032,7 +1092,7 @@ static int stage_output(ssb_handle *h, const char *dir, unsigned file_index) {
     {   // the slot must have been written out before it is overwritten
         std::unique_lock<std::mutex> lk(h->mu);
         h->cv.wait(lk, [&] { return !h->writer_pending[b]; });
-        if (h->writer_error) { int rc = h->writer_error; h->writer_error = 0; return fail(h, rc, "could not write VTK output into %s", dir); }
+        if (h->writer_error) { int rc = h->writer_error; h->writer_error = 0; return fail(h, rc, "could not write VTK output into %s", dir ? dir : "(none)"); }
     }
     OutputJob &J = h->jobs[b];
     // device staging layout (id order): x[3N] v[3N] scal[4N] C[Sc*N] | type[N] xx[Sd*N]
@@ -1049,6 +1109,7 @@ static int stage_output(ssb_handle *h, const char *dir, unsigned file_index) {
     k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.type, stype, 1, 0);
     for (int s = 0; s < Sd; s++) k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, (int *) V.xx + (size_t) s * N, sxx + (size_t) s * N, 1, 0);
     h->launches += 11 + Sc + Sd;
+    h->d2h_bytes += (int64_t) N * (3 * 8 * 2 + 4 * 8 + 4 + 8 * Sc + 4 * Sd);
     CK(cudaMemcpyAsync(J.x, sx, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(J.v, sv, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(J.scal, ss, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, st));
@@ -1060,7 +1121,8 @@ static int stage_output(ssb_handle *h, const char *dir, unsigned file_index) {
     J.step = h->current_step;
     J.file_index = file_index;
     J.rdme_initialized = h->rdme_initialized;
-    J.dir = dir;
+    J.write_file = (h->m.flags & SSB_FLAG_NO_VTK) ? 0 : 1;
+    J.dir = dir ? dir : "";
     {
         std::lock_guard<std::mutex> lk(h->mu);
         h->writer_pending[b] = 1;
@@ -1088,7 +1150,7 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
         unsigned file_index = 0;
         for (unsigned step = 0; step < nt; step++) {
             if (step >= next_output_step) {
-                if (write_files && (rc = stage_output(h, out_dirs[k], file_index))) return rc;
+                if ((rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;
                 file_index++;
                 next_output_step = (out_index < h->hout_steps.size()) ? h->hout_steps[out_index] : 0xffffffffu;
                 out_index++;
@@ -1098,14 +1160,14 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
             if (h->cancel.load()) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled"); }
             if (cb && cb(cb_user, step + 1, nt)) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled by callback"); }
         }
-        if (write_files && (rc = stage_output(h, out_dirs[k], file_index))) return rc;   // final timepoint (:283-285)
+        if ((rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;   // final timepoint (:283-285)
         CK(cudaStreamSynchronize(h->stream));
         h->step_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         unsigned long long cnt[2] = {0, 0};
         CK(cudaMemcpy(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
         h->total_reactions = (int64_t) cnt[0];
         h->total_diffusion = (int64_t) cnt[1];
-        if ((rc = drain_writer(h))) return fail(h, rc, "could not write VTK output into %s", out_dirs[k]);
+        if ((rc = drain_writer(h))) return fail(h, rc, "could not write VTK output into %s", write_files ? out_dirs[k] : "(none)");
     }
     return SSB_OK;
 }
@@ -1223,5 +1285,66 @@ extern "C" int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, doub
     CK(cudaMemcpyAsync(Dij, d_a + 2 * nnz, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_cnt); cudaFree(d_idx); cudaFree(d_a);
+    return SSB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// measurement hooks (bench.py): device-timed stepping and per-kernel-category timers
+// ----------------------------------------------------------------------------------------------------
+extern "C" int ssb_step_timed(ssb_handle *h, uint32_t nsteps, double *device_ms) {
+    if (!h || !device_ms) return SSB_ERR_ARG;
+    if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(a, h->stream));
+    int rc = SSB_OK;
+    for (uint32_t s = 0; s < nsteps && !rc; s++) rc = engine_step(h);
+    CK(cudaEventRecord(b, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *device_ms = ms;
+    if (rc) return rc;
+    if (h->profile) prof_harvest(h);
+    return check_device_error(h);
+}
+
+extern "C" int ssb_profile(ssb_handle *h, int enable) {
+    if (!h) return SSB_ERR_ARG;
+    prof_harvest(h);
+    h->profile = enable ? 1 : 0;
+    for (int c = 0; c < SSB_NCAT; c++) { h->cat_ms[c] = 0.0; h->cat_launches[c] = 0; }
+    return SSB_OK;
+}
+
+extern "C" int ssb_profile_read(ssb_handle *h, int category, double *ms_total, int64_t *launches) {
+    if (!h || category < 0 || category >= SSB_NCAT) return SSB_ERR_ARG;
+    prof_harvest(h);
+    if (ms_total) *ms_total = h->cat_ms[category];
+    if (launches) *launches = h->cat_launches[category];
+    return SSB_OK;
+}
+
+extern "C" int ssb_io_bytes(ssb_handle *h, int64_t *h2d, int64_t *d2h) {
+    if (!h) return SSB_ERR_ARG;
+    if (h2d) *h2d = h->h2d_bytes;
+    if (d2h) *d2h = h->d2h_bytes;
+    return SSB_OK;
+}
+
+extern "C" int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total) {
+    if (!h) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (capacity) *capacity = h->V.nbr_cap;
+    if (total) {
+        std::vector<int> c((size_t) h->N);
+        CK(cudaMemcpy(c.data(), h->V.nbr_count, sizeof(int) * h->N, cudaMemcpyDeviceToHost));
+        long long t = 0;
+        for (int v : c) t += v;
+        *total = t;
+    }
     return SSB_OK;
 }

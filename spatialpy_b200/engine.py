@@ -22,7 +22,11 @@ ERR_NAMES = {1: "SSB_ERR_NAN", 2: "SSB_ERR_RDME", 3: "SSB_ERR_CUDA", 4: "SSB_ERR
 # every symbol include/ssb.h declares (tests check the library exports exactly these)
 EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernels", "ssb_destroy", "ssb_run",
            "ssb_reset", "ssb_step", "ssb_counters", "ssb_get_field", "ssb_get_neighbors", "ssb_cancel",
-           "ssb_last_error", "ssb_launch_count"]
+           "ssb_last_error", "ssb_launch_count", "ssb_step_timed", "ssb_profile", "ssb_profile_read", "ssb_io_bytes",
+           "ssb_nbr_stats"]
+
+PROFILE_CATEGORIES = ["cells", "predictor", "search", "force", "corrector", "finish", "diff_init", "rdme_init",
+                      "rdme_window", "output"]
 
 
 class EngineError(RuntimeError):
@@ -83,6 +87,11 @@ def load_library(path=None):
     lib.ssb_last_error.argtypes = [H]
     lib.ssb_last_error.restype = C.c_char_p
     lib.ssb_launch_count.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.ssb_step_timed.argtypes = [H, C.c_uint32, C.POINTER(C.c_double)]
+    lib.ssb_profile.argtypes = [H, C.c_int]
+    lib.ssb_profile_read.argtypes = [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.ssb_io_bytes.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ssb_nbr_stats.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     for name in EXPORTS:
         if getattr(lib, name).restype is None:
             getattr(lib, name).restype = C.c_int
@@ -212,6 +221,33 @@ class Engine:
         n = C.c_int64(0)
         self._check(self.lib.ssb_launch_count(self._h, C.byref(n)))
         return n.value
+
+    def step_timed(self, n=1):
+        """n engine steps; returns the device time in ms (CUDA events on the engine stream)."""
+        ms = C.c_double(0)
+        self._check(self.lib.ssb_step_timed(self._h, int(n), C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        self._check(self.lib.ssb_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        out = {}
+        for k, name in enumerate(PROFILE_CATEGORIES):
+            ms, n = C.c_double(0), C.c_int64(0)
+            self._check(self.lib.ssb_profile_read(self._h, k, C.byref(ms), C.byref(n)))
+            out[name] = {"ms": ms.value, "launches": n.value}
+        return out
+
+    def io_bytes(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.ssb_io_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def nbr_stats(self):
+        cap, tot = C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.ssb_nbr_stats(self._h, C.byref(cap), C.byref(tot)))
+        return cap.value, tot.value
 
     def get(self, name):
         dtype, cols = self._FIELDS[name]
