@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — the ssa_sdpd hot path on B200, measured as BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cylinder|tank|box]
+
+Workload at N=1 (default): BASELINE configs[1] — the 3D_Cylinder_Demo static-domain RDME + PDE model refined to
+~1.0 M fixed particles (spatialpy_b200/configs.py:cylinder_rdme).  One bench "step" = SPS
+engine timesteps (each: predictor, chemistry-flux sweep over the neighbour lists, corrector, and the sSSA windows)
+of one trajectory.  `value` = particle-steps/s with the model resident in HBM, timed with CUDA events on the engine's
+stream; `e2e` = the same metric through the public call a user makes (ssb_run: upload of the initial state from host
+memory, stepping, output snapshots copied back to pinned host memory) timed on the host clock.
+N>1: trajectories are independent units (solver.py:547-605) — each rank runs its own trajectory of the same model,
+no data-path collective, `scaling: weak`.
+
+`--impl reference` times the UNMODIFIED reference engine (oracle/_ref/bench_*/fast/ssa_sdpd.exe, built from
+/root/reference by oracle/oracle_build.py) on the host cores, on a bounded instance of the same workload (the
+reference cannot be compiled at 1 M particles: one C++ source line per particle).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/s (SDPD+sSSA)"
+UNIT = "particle-steps/s"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------
+def make_workload(name, scale):
+    from spatialpy_b200 import configs
+    if name == "cylinder":
+        delta = 0.03155 if scale >= 1.0 else 0.03155 / scale ** (1.0 / 3.0)
+        fm = configs.cylinder_rdme(delta=delta, nt=1000, output_every=100, dt=1e-3)
+        desc = f"BASELINE configs[1]: 3D_Cylinder_Demo static RDME+PDE, A+B->0 with end-cap sources, jittered lattice delta={delta:.5f}"
+    elif name == "tank":
+        n = max(12, int(round(120 * scale ** (1.0 / 3.0))))
+        fm = configs.tank_sdpd(n=n, nt=1000, output_every=100, dt=1e-5)
+        desc = f"BASELINE configs[2] stand-in: 3-D SDPD tank {n}^3 lattice under gravity with one advected reacting species"
+    elif name == "box":
+        n = max(16, int(round(200 * scale ** (1.0 / 3.0))))
+        fm = configs.box_sdpd_rdme(n, n, n, nt=100, output_every=100, dt=1e-5)
+        desc = f"BASELINE configs[4] per-GPU unit: synthetic 3-D SDPD+sSSA box {n}^3"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return fm, desc
+
+
+def algorithmic_bytes(fm, moving):
+    """SURVEY.md §8(d) contract figures, per particle-step and per RDME event."""
+    Sc, Sd, R = fm.num_chem_species, fm.num_stoch_species, fm.num_stoch_rxns
+    per_step = (698 + 64 * Sc) + (68 + 12 * Sd + 8 * R if Sd else 0) if moving else (48 + 40 * Sc)
+    return per_step
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    name = {"cylinder": "bench_cylinder", "tank": "bench_tank", "box": "bench_tank"}[args.workload]
+    base = os.path.join(ROOT, "oracle", "_ref", name)
+    exe = os.path.join(base, "fast", "ssa_sdpd.exe")
+    if not os.path.exists(exe):
+        print(json.dumps({"impl": "reference", "unavailable": f"{exe} not built (oracle/oracle_build.py needs /root/reference)"}))
+        return
+    meta = json.load(open(os.path.join(base, "meta.json")))
+    cores = os.cpu_count() or 1
+    threads = cores
+    times = []
+    for it in range(args.warmup + args.steps):
+        d = tempfile.mkdtemp(prefix="ssb_ref_")
+        t0 = time.perf_counter()
+        subprocess.run([exe, "-t", str(threads), "-s", str(1000 + it)], cwd=d, stdout=subprocess.DEVNULL, check=True)
+        dt = time.perf_counter() - t0
+        subprocess.run(["rm", "-rf", d])
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = meta["N"] * meta["nt"] / (ms / 1e3)
+    sample = (f"unmodified reference engine (g++ -O3), {meta['builder']}{meta['kwargs']}: N={meta['N']} particles x {meta['nt']} steps per run, "
+              f"-t {threads}; wall clock of the whole executable (includes particle construction and VTK output)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} (bounded CPU instance of the GPU workload)", "particles": meta["N"], "engine_steps_per_step": meta["nt"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(workload):
+    """Bounded sample of the reference on the host cores (rank 0, N=1 only)."""
+    name = {"cylinder": "bench_cylinder", "tank": "bench_tank", "box": "bench_tank"}[workload]
+    base = os.path.join(ROOT, "oracle", "_ref", name)
+    exe = os.path.join(base, "fast", "ssa_sdpd.exe")
+    if not os.path.exists(exe):
+        return None
+    meta = json.load(open(os.path.join(base, "meta.json")))
+    cores = os.cpu_count() or 1
+    d = tempfile.mkdtemp(prefix="ssb_ref_")
+    t0 = time.perf_counter()
+    subprocess.run([exe, "-t", str(cores), "-s", "1000"], cwd=d, stdout=subprocess.DEVNULL, check=True)
+    dt = time.perf_counter() - t0
+    subprocess.run(["rm", "-rf", d])
+    return {"value": meta["N"] * meta["nt"] / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"unmodified reference engine (g++ -O3) on {meta['builder']}{meta['kwargs']}: N={meta['N']} x {meta['nt']} steps, -t {cores}, {dt:.2f} s wall"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    from spatialpy_b200.engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fm, desc = make_workload(args.workload, args.scale)
+    moving = not fm.static_domain
+    N, SPS = fm.num_particles, args.sps
+    eng = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def allmax(v):
+        if not use_dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if not use_dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident run: model uploaded once, W warm-up steps, K timed steps ---------------------------
+    eng.reset(1000 + rank)
+    for _ in range(args.warmup):
+        eng.step_timed(SPS)
+    ev0 = eng.counters()
+    launches0 = eng.launch_count()
+    eng.profile(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += eng.step_timed(SPS)          # CUDA events on the engine stream, synchronised on both sides
+    barrier()
+    clk = clocks.stop()
+    prof = eng.profile_read()
+    eng.profile(False)
+    ev1 = eng.counters()
+    launches = eng.launch_count() - launches0
+    dev_ms = allmax(dev_ms)
+    events = allsum(float((ev1["reactions"] + ev1["diffusions"]) - (ev0["reactions"] + ev0["diffusions"])))
+    ms_per_step = dev_ms / args.steps
+    value = world * N * SPS * args.steps / (dev_ms / 1e3)
+    events_per_s = events / (dev_ms / 1e3)
+    cap, nnz = eng.nbr_stats()
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations over the timed region) ----------------------
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    Sc, Sd, R = fm.num_chem_species, fm.num_stoch_species, fm.num_stoch_rxns
+    kernel_bytes = {   # algorithmic bytes per particle per launch
+        "force": (104 + 8 * Sc + 56 + 8 * Sc) if moving else (48 + 16 * Sc),
+        "rdme_window": 8 + 4 * Sd,
+        "finish": (80 + 16 * Sc + 56 + 8 * Sc) if moving else (24 * Sc + 8),
+        "predictor": (116 + 16 * Sc + 88 + 8 * Sc) if moving else (24 * Sc + 8),
+        "cells": 96, "search": 24 + 24 + 4, "corrector": 70 + 32, "diff_init": 68 + 12 * Sd, "rdme_init": 4 * Sd + 8 * R + 24,
+        "output": 0,
+    }
+    dn = max(prof[dom]["launches"], 1)
+    dom_ms = prof[dom]["ms"] / dn
+    achieved = kernel_bytes[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms, "launches": prof[dom]["launches"],
+                "share_of_step": prof[dom]["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-30),
+                "algorithmic_bytes_per_particle": kernel_bytes[dom],
+                "whole_step_frac": (algorithmic_bytes(fm, moving) * value / world) / (peak * 1e9),
+                "kernels_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}}
+
+    # ---- end to end: the public call, host buffers in, host buffers out ------------------------------------------
+    fm_e2e = fm
+    fm_e2e.nt = SPS
+    fm_e2e.output_steps = __import__("numpy").array([0, SPS], dtype="uint32")
+    eng.close()
+    t_create0 = time.perf_counter()
+    eng2 = Engine(fm_e2e, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK)
+    create_s = time.perf_counter() - t_create0
+    eng2.run_no_files(2000 + rank, 1)           # warm-up trajectory
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        eng2.run_no_files(3000 + rank + 17 * k, 1)   # reset (H2D of the initial state) + SPS steps + 2 output snapshots (D2H)
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    h2d, d2h = eng2.io_bytes()
+    e2e_value = world * N * SPS * args.steps / e2e_s
+    eng2.close()
+
+    cpu = cpu_baseline_sample(args.workload) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "particles_per_gpu": N, "engine_steps_per_step": SPS, "static_domain": not moving,
+                       "species": fm.num_species, "reactions": fm.num_reactions, "mean_neighbours": nnz / N,
+                       "sssa_windows_per_engine_step": (ev1["windows"] - ev0["windows"]) / max(SPS * args.steps, 1),
+                       "parallelism": f"ensemble: one trajectory per GPU x {world}",
+                       "l2": "working set (neighbour lists + cached D_ij + state) exceeds the 126 MB L2; no explicit flush"},
+            "rdme_events_per_s": events_per_s,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "includes": "ssb_run: H2D of the initial state, stepping, output snapshots D2H into pinned memory (no VTK text)",
+                    "engine_create_s": create_s},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
+    ap.add_argument("--sps", type=int, default=20, help="engine timesteps per bench step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    args = ap.parse_args()
+    rank, local_rank, world = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
