@@ -1,0 +1,195 @@
+"""Drop-in replacement for `spatialpy.Solver` (spatialpy/solvers/solver.py:46) backed by the CUDA engine.
+
+Same class contract: `Solver(model, debug_level=0)`, attributes `model, is_compiled, debug_level, model_name, build_dir,
+propfilename, prop_file_name, executable_name, h` (solver.py:63-71), `compile(debug=False, profile=False)` (solver.py:443),
+`run(number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False, verbose=True)`
+(solver.py:510) returning a Result whose `listOfResultObjects` holds one Result per trajectory (solver.py:602-607), each
+with a `result_dir` of `output%u.vtk` files the reference's VTKReader parses (the file contract).
+What changed underneath: no generated C++ / SCons / subprocess — the model is flattened to arrays (flatmodel.py), the
+propensities / BCs are compiled into a CUDA model unit (codegen.py) and trajectories run in-process through the C-ABI
+(engine.py).  Additive keywords (not in the reference): `devices=[...]` to spread an ensemble over GPUs, `flags`,
+`rdme_epsilon`.
+
+`install()` adds the `solver=` keyword that the reference's README promises but `Model.run` never implemented
+(model.py:1021-1056): `model.run(solver=spatialpy_b200.Solver, number_of_trajectories=..., seed=...)`.
+"""
+import os
+import tempfile
+import threading
+import time
+
+from . import codegen
+from .flatmodel import FlatModel
+
+try:  # reuse the reference's exception / result types when the front-end is importable
+    from spatialpy.core.spatialpyerror import SimulationError, ModelError
+except Exception:  # pragma: no cover - GPU box: no spatialpy
+    class SimulationError(Exception):
+        """Same name and meaning as spatialpy.core.spatialpyerror.SimulationError."""
+
+    class ModelError(Exception):
+        pass
+
+
+class FlatResult:
+    """Minimal Result for FlatModel runs where spatialpy is not importable: list-like ensemble + read_step()."""
+
+    def __init__(self, model=None, result_dir=None):
+        self.model = model
+        self.success = False
+        self.timeout = False
+        self.result_dir = result_dir
+        self.listOfResultObjects = [self]
+
+    def __len__(self):
+        return len(self.listOfResultObjects)
+
+    def __getitem__(self, i):
+        return self.listOfResultObjects[i]
+
+    def append(self, item):
+        self.listOfResultObjects.append(item)
+
+    def read_step(self, step_num, debug=False):
+        from .vtk import read_vtk
+        return read_vtk(os.path.join(self.result_dir, f"output{step_num}.vtk"))
+
+    def get_species(self, species, timepoints=None, concentration=False, deterministic=False):
+        import numpy as np
+        name = species if isinstance(species, str) else species.name
+        key = f"C[{name}]" if (deterministic or concentration) else f"D[{name}]"
+        n_out = len([f for f in os.listdir(self.result_dir) if f.startswith("output") and "bounding" not in f])
+        steps = range(n_out) if timepoints is None else ([timepoints] if isinstance(timepoints, int) else timepoints)
+        out = np.array([self.read_step(s)[1][key] for s in steps])
+        return out[0] if isinstance(timepoints, int) else out
+
+
+class Solver:
+    def __init__(self, model, debug_level=0):
+        if not (isinstance(model, FlatModel) or type(model).__name__ == "Model"):
+            raise SimulationError("Model must be of type spatialpy.Model.")   # solver.py:58-59
+        self.model = model
+        self.is_compiled = False
+        self.debug_level = debug_level
+        self.model_name = model.name
+        self.build_dir = None
+        self.propfilename = None
+        self.prop_file_name = None
+        self.executable_name = "libssb_core.so"
+        self.h = None  # basis function width (solver.py:71); may be overridden before compile (solver.py:391-395)
+        self.flat = None
+        self.unit_path = None
+
+    # -- pickling: no live handles are held between calls (test_solver.py:167-195 pickles Solver)
+    def __getstate__(self):
+        return dict(self.__dict__)
+
+    def compile(self, debug=False, profile=False):
+        """Flatten + code-generate + nvcc the model unit (replaces solver.py:443-508)."""
+        if isinstance(self.model, FlatModel):
+            self.flat = self.model.finalize()
+            if self.h is not None:
+                self.flat.h = float(self.h)
+        else:
+            self.flat = FlatModel.from_spatialpy(self.model, h=self.h)
+        self.h = self.flat.h
+        if self.h == 0.0:
+            raise ModelError("h (basis function width) can not be zero.")     # solver.py:393-394
+        codegen.build_core()
+        try:
+            self.unit_path = codegen.build_model_unit(self.flat)
+        except codegen.BuildError as err:
+            raise SimulationError(f"Compilation of solver failed, return_code=1\n{err}") from err   # solver.py:496-500
+        self.build_dir = os.path.dirname(self.unit_path)
+        self.prop_file_name = self.propfilename = self.unit_path[:-3] + ".cu"
+        self.is_compiled = True
+
+    def _new_result(self, outdir):
+        if isinstance(self.model, FlatModel):
+            return FlatResult(self.model, outdir)
+        from spatialpy.core.result import Result
+        return Result(self.model, outdir)
+
+    def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False,
+            verbose=True, devices=None, flags=None, rdme_epsilon=0.0):
+        from .engine import Engine, EngineError, FLAG_SKIP_STATIC_FORCES
+        if not self.is_compiled:
+            self.compile(debug=debug, profile=profile)
+        if seed is None:                      # template:127 std::random_device
+            seed = int.from_bytes(os.urandom(4), "little")
+        devices = list(devices) if devices else [0]
+        flags = FLAG_SKIP_STATIC_FORCES if flags is None else flags
+        results = []
+        for _ in range(number_of_trajectories):
+            outdir = tempfile.mkdtemp(prefix="spatialpy_result_", dir=os.environ.get("SPATIALPY_TMPDIR"))   # solver.py:548
+            results.append(self._new_result(outdir))
+        errors, engines, lock = [], [], threading.Lock()
+        start = time.monotonic()
+
+        def worker(rank):
+            # trajectory k -> GPU k mod G; trajectory k always uses seed + k (solver.py:558-559)
+            mine = [k for k in range(number_of_trajectories) if k % len(devices) == rank]
+            if not mine:
+                return
+            try:
+                eng = Engine(self.flat, device=devices[rank], flags=flags, rdme_epsilon=rdme_epsilon, unit_path=self.unit_path)
+                with lock:
+                    engines.append(eng)
+                try:
+                    for k in mine:
+                        eng.run(seed, [results[k].result_dir], first_traj=k)
+                        results[k].success = True
+                finally:
+                    eng.close()
+            except EngineError as err:
+                errors.append(err)
+
+        threads = [threading.Thread(target=worker, args=(r,)) for r in range(len(devices))]
+        for t in threads:
+            t.start()
+        timed_out = False
+        for t in threads:
+            if timeout is None:
+                t.join()
+            else:
+                t.join(max(0.0, timeout - (time.monotonic() - start)))
+                if t.is_alive():               # solver.py:583-586: SIGINT on timeout, result.timeout = True
+                    timed_out = True
+                    with lock:
+                        for e in engines:
+                            e.cancel()
+                    t.join()
+        if self.debug_level >= 1:
+            print("Elapsed seconds: {:.2f}".format(time.monotonic() - start))
+        if timed_out:
+            for r in results:
+                if not r.success:
+                    r.timeout = True
+        else:
+            for err in errors:
+                raise SimulationError(f"Solver execution failed, return code = {err.code}") from err   # solver.py:595-597
+        first = results[0]
+        for r in results[1:]:
+            first.append(r)
+        return first
+
+
+def install():
+    """Add `solver=` to spatialpy.Model.run without forking model.py (additive hook)."""
+    import spatialpy
+    from spatialpy.core.model import Model
+    if getattr(Model.run, "_ssb_patched", False):
+        return
+    orig = Model.run
+
+    def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug_level=0, debug=False,
+            profile=False, solver=None, **kw):
+        if solver is None:
+            return orig(self, number_of_trajectories=number_of_trajectories, seed=seed, timeout=timeout,
+                        number_of_threads=number_of_threads, debug_level=debug_level, debug=debug, profile=profile)
+        sol = solver(self, debug_level=debug_level) if isinstance(solver, type) else solver
+        return sol.run(number_of_trajectories=number_of_trajectories, seed=seed, timeout=timeout,
+                       number_of_threads=number_of_threads, debug=debug, profile=profile, **kw)
+    run._ssb_patched = True
+    Model.run = run
+    spatialpy.B200Solver = Solver

@@ -120,6 +120,32 @@ def make(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(models.BUILDERS)
+    names = [a for a in sys.argv[1:] if a != "vtk"] or (list(models.BUILDERS) if len(sys.argv) == 1 else [])
     for n in names:
         make(n)
+
+
+def make_vtk(name="diffusion3d", keep=(0, 1, 10)):
+    """Reference VTK byte-format fixtures (E/src/output.cpp:104-229) from the unmodified engine incl. its own output.cpp."""
+    import gzip
+    model = models.BUILDERS[name]()
+    np.random.seed(12345)
+    fm = FlatModel.from_spatialpy(model)
+    np.random.seed(12345)
+    exe = build_ref.build_model(model, name, variant="parity", dump=False, h=fm.h)
+    d = tempfile.mkdtemp(prefix="ssb_golden_vtk_")
+    build_ref.run_exe(exe, d, SEED, threads=1)
+    out = os.path.join(HERE, f"vtk_{name}")
+    os.makedirs(out, exist_ok=True)
+    files = sorted(os.listdir(d))
+    with open(os.path.join(out, "listing.txt"), "w") as f:
+        f.write("\n".join(files) + "\n")
+    for fn in ["output0_boundingBox.vtk"] + [f"output{k}.vtk" for k in keep]:
+        with open(os.path.join(d, fn), "rb") as src, gzip.open(os.path.join(out, fn + ".gz"), "wb") as dst:
+            dst.write(src.read())
+    shutil.rmtree(d, ignore_errors=True)
+    print(f"vtk fixtures for {name}: {files}")
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or "vtk" in sys.argv[1:]):
+    make_vtk()

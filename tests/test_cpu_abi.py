@@ -1,0 +1,125 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/ssb.h declares, fails loudly without a GPU,
+the code generator emits what the reference's would, and the host-side mirror keeps the reference's surface."""
+import ctypes
+import inspect
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_reference
+from util import load_model
+
+
+def _lib():
+    from spatialpy_b200 import codegen
+    return codegen.build_core()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ssb.h")).read()
+    declared = sorted(set(re.findall(r"\b(ssb_[a-z_]+)\s*\(", hdr)) - {"ssb_progress_cb"})
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_lib())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ssb.h but not exported"
+    from spatialpy_b200 import engine
+    assert sorted(engine.EXPORTS) == declared
+    assert lib.ssb_abi_version() == engine.SSB_ABI_VERSION
+
+
+def test_only_sm100a_code_in_the_library():
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
+def test_no_cpu_fallback_fails_loudly():
+    from spatialpy_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError) as ei:
+        Engine(load_model("birth_death"))
+    assert ei.value.code == 3 and "no CPU fallback" in str(ei.value)
+
+
+def test_flatmodel_roundtrip(tmp_path):
+    from spatialpy_b200 import FlatModel
+    fm = load_model("cylinder")
+    p = str(tmp_path / "m.npz")
+    fm.save(p)
+    fm2 = FlatModel.load(p)
+    for k in FlatModel._ARRAYS:
+        np.testing.assert_array_equal(getattr(fm, k), getattr(fm2, k))
+    assert [r.propensity for r in fm.reactions] == [r.propensity for r in fm2.reactions]
+    assert fm2.h == fm.h and fm2.type_constants == fm.type_constants
+
+
+def test_codegen_emits_reference_propensity_text():
+    from spatialpy_b200 import codegen
+    fm = load_model("cylinder")
+    src = codegen.generate_unit_source(fm)
+    assert "return (((P0*x[0])*x[1])/vol);" in src                      # mass-action text from the reference's converter
+    assert "if(sd == type_Edge1){" in src and "return 0.0;}" in src       # restrict_to wrapper (solver.py:356-368)
+    assert "#define SSB_SD 2" in src and "#define SSB_RD 3" in src
+    fm = load_model("cavity2d")
+    assert "me->v[0]=1.0;" in codegen.generate_unit_source(fm)           # BC text passes through unmodified
+
+
+def test_model_unit_builds_for_sm100a_and_exports_the_table():
+    from spatialpy_b200 import codegen
+    so = codegen.build_model_unit(load_model("birth_death"))
+    lib = ctypes.CDLL(so)
+    assert hasattr(lib, "ssbm_get_unit")
+    sass = subprocess.run(["cuobjdump", "--list-elf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+
+
+def test_solver_surface_and_pickle():
+    from spatialpy_b200 import Solver, SimulationError
+    with pytest.raises(SimulationError):
+        Solver(object())
+    sol = Solver(load_model("birth_death"), debug_level=0)
+    for attr in ("model", "is_compiled", "debug_level", "model_name", "build_dir", "propfilename", "prop_file_name",
+                 "executable_name", "h"):
+        assert hasattr(sol, attr)
+    sol.compile()
+    assert sol.is_compiled and abs(sol.h - 0.24444444444444458) < 1e-15
+    sol2 = pickle.loads(pickle.dumps(sol))
+    assert sol2.is_compiled and sol2.unit_path == sol.unit_path
+    run_params = list(inspect.signature(Solver.run).parameters)
+    assert run_params[:8] == ["self", "number_of_trajectories", "seed", "timeout", "number_of_threads", "debug", "profile", "verbose"]
+
+
+def test_ensemble_sharding_partitions_trajectories():
+    from spatialpy_b200.ensemble import shard_trajectories
+    for n in (0, 1, 7, 1024):
+        for world in (1, 2, 8):
+            shards = [shard_trajectories(n, r, world) for r in range(world)]
+            assert sorted(sum(shards, [])) == list(range(n))
+            assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not has_reference(), reason="needs /root/reference")
+def test_flattening_matches_reference_codegen_inputs():
+    """FlatModel.from_spatialpy reproduces the committed fixture, and the reference's Solver has the surface we mirror."""
+    import build_ref
+    build_ref.add_reference_to_path()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import models
+    from spatialpy_b200 import FlatModel, Solver
+    m = models.cavity2d()
+    np.random.seed(12345)
+    fm = FlatModel.from_spatialpy(m)
+    ref = load_model("cavity2d")
+    for k in ("x", "type", "nu", "mass", "rho", "solid", "output_steps"):
+        np.testing.assert_array_equal(getattr(fm, k), getattr(ref, k))
+    assert fm.bc_source == ref.bc_source and fm.h == ref.h and fm.nt == ref.nt
+    from spatialpy.solvers.solver import Solver as RefSolver
+    ref_params = list(inspect.signature(RefSolver.run).parameters)
+    assert list(inspect.signature(Solver.run).parameters)[:len(ref_params)] == ref_params
+    assert list(inspect.signature(Solver.__init__).parameters) == list(inspect.signature(RefSolver.__init__).parameters)
+    assert list(inspect.signature(Solver.compile).parameters) == list(inspect.signature(RefSolver.compile).parameters)

@@ -1,0 +1,123 @@
+"""GPU tier: the CUDA engine against the CPU oracle restatement (oracle/sdpd_oracle.py, oracle/nsm_oracle.cpp — both
+pinned to the unmodified reference by tests/test_cpu_oracle.py) on seeded inputs that have no golden fixture, and
+size-independent properties at the BASELINE sizes."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from util import RTOL_STEP, RTOL_TRAJ, csr_sorted, rel_err
+
+import sdpd_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _jitter(fm, seed, amp):
+    rng = np.random.default_rng(seed)
+    fm.x = fm.x + rng.uniform(-amp, amp, size=fm.x.shape) * (np.arange(3) < fm.dimension)
+    return fm
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_moving_tank_matches_oracle(seed):
+    """Ragged (jittered) 3-D tank: neighbour sets bit-exact, every field within tolerance over 22 steps (Shepard at 0 and 20)."""
+    from spatialpy_b200 import configs
+    from spatialpy_b200.engine import Engine
+    fm = _jitter(configs.tank_sdpd(n=11, nt=30, output_every=30, dt=2e-5), seed, 0.012)
+    o = sdpd_oracle.SdpdOracle(fm)
+    with Engine(fm) as eng:
+        eng.reset(1)
+        for s in (1, 2, 21, 22):
+            while o.step_no < s:
+                o.step()
+            eng.step(s - (s - 1 if s in (2, 22) else 0 if s == 1 else 2))
+            ptr, idx, dist, dWdr, Dij = eng.neighbors()
+            np.testing.assert_array_equal(ptr, o.nbr["ptr"])
+            gi, gd = csr_sorted(ptr, idx, dist)
+            ri, rd = csr_sorted(o.nbr["ptr"], o.nbr["j"].astype(np.int32), o.nbr["dist"])
+            np.testing.assert_array_equal(gi, ri)
+            tol = RTOL_STEP if s == 1 else RTOL_TRAJ
+            for f, a in (("x", o.x), ("v", o.v), ("rho", o.rho), ("F", o.F), ("Fbp", o.Fbp), ("Frho", o.Frho),
+                         ("bvf_phi", o.bvf), ("C", o.C)):
+                err = rel_err(eng.get(f), a)
+                assert err <= tol, f"seed {seed} step {s} {f}: {err:.3e}"
+
+
+def test_edge_cases_isolated_particle_and_1d():
+    """A particle with no neighbour inside h (empty list) and a 1-D domain (alpha = `5/4*h` == h, particle.cpp:174)."""
+    from spatialpy_b200 import FlatModel
+    from spatialpy_b200.engine import Engine
+    N = 12
+    x = np.zeros((N, 3))
+    x[:, 0] = np.arange(N) * 0.1
+    x[-1, 0] = 5.0                                     # isolated: no neighbour
+    fm = FlatModel(name="line1d", x=x, type=np.ones(N, np.int32), nu=np.ones(N), mass=np.ones(N), c=np.zeros(N),
+                   rho=np.ones(N), solid=np.ones(N, np.int32), static_domain=True, dt=0.01, nt=2,
+                   output_steps=np.array([0, 1, 2], np.uint32), h=0.25, dimension=1, xlim=(0, 5), ylim=(0, 0), zlim=(0, 0)).finalize()
+    o = sdpd_oracle.SdpdOracle(fm)
+    nb = o.find_neighbors(o.x, o.x)
+    with Engine(fm, flags=0) as eng:
+        eng.reset(1)
+        eng.step(1)
+        ptr, idx, dist, dWdr, Dij = eng.neighbors()
+        np.testing.assert_array_equal(ptr, nb["ptr"])
+        assert ptr[-1] - ptr[-2] == 0
+        gi, gw = csr_sorted(ptr, idx, dWdr)
+        ri, rw = csr_sorted(nb["ptr"], nb["j"].astype(np.int32), nb["dWdr"])
+        np.testing.assert_array_equal(gi, ri)
+        assert rel_err(gw, rw) <= RTOL_STEP
+
+
+def test_small_cylinder_rdme_matches_nsm_oracle():
+    """Synthetic config 2b geometry at oracle size: sSSA ensemble vs the serial NSM restatement, KS p > 0.01."""
+    import nsm_oracle
+    from spatialpy_b200 import configs
+    from spatialpy_b200.engine import Engine
+    fm = configs.cylinder_rdme(delta=0.25, nt=40, output_every=40, dt=0.05, enable_pde=False)
+    o = sdpd_oracle.SdpdOracle(fm)
+    nb = o.find_neighbors(o.x, o.x)
+    lib = nsm_oracle.build(fm)
+    ntraj = 400
+    ref = np.array([nsm_oracle.run(lib, fm, nb, 9000 + k, fm.nt * fm.dt)[0] for k in range(ntraj)]).astype(np.int64)
+    got = []
+    with Engine(fm) as eng:
+        for k in range(ntraj):
+            eng.reset(100 + k)
+            eng.step(fm.nt)
+            got.append(eng.get("xx").astype(np.int64))
+    got = np.array(got)
+    for j in range(2):
+        p = stats.ks_2samp(got[:, :, j].sum(axis=1), ref[:, :, j].sum(axis=1)).pvalue
+        assert p > 0.01, f"species {j}: KS p={p:.4f}"
+    mg, mr = got.mean(axis=0), ref.mean(axis=0)
+    se = np.sqrt(got.var(axis=0, ddof=1) / ntraj + ref.var(axis=0, ddof=1) / ntraj)
+    ok = se > 0
+    z = np.abs(mg - mr)[ok] / se[ok]
+    assert (z > 3).mean() <= 0.01 and z.max() < 4.5, (z.max(), (z > 3).mean())
+
+
+def test_full_size_static_cylinder_properties():
+    """BASELINE configs[1] at full size (~1.0 M voxels): molecule balance = u0 + creations - 2*annihilations is checked through
+    the counters, neighbour relation is symmetric in count, C stays finite, same seed => identical state."""
+    from spatialpy_b200 import configs
+    from spatialpy_b200.engine import Engine
+    fm = configs.cylinder_rdme(nt=20, output_every=20)
+    with Engine(fm) as eng:
+        outs = []
+        for rep in range(2):
+            eng.reset(77)
+            eng.step(10)
+            outs.append((eng.get("xx").copy(), eng.get("C").copy()))
+        np.testing.assert_array_equal(outs[0][0], outs[1][0])
+        np.testing.assert_array_equal(outs[0][1], outs[1][1])
+        xx = outs[0][0].astype(np.int64)
+        c = eng.counters()
+        # A and B are created one at a time and annihilated in pairs: #A - #B changes only by creations, and
+        # reactions >= |#A - #B| ; diffusion conserves both
+        assert c["reactions"] >= abs(int(xx[:, 0].sum()) - int(xx[:, 1].sum()))
+        assert np.isfinite(outs[0][1]).all()
+        cnt = eng.get("nbr_count")
+        cap, total = eng.nbr_stats()
+        assert total == int(cnt.sum()) and total % 2 == 0          # j in N(i) <=> i in N(j) on a static domain
+        # species restriction: A never enters Edge2 voxels, B never enters Edge1 voxels (diffusion matrix zeros)
+        assert xx[fm.type == 1, 0].sum() == 0 and xx[fm.type == 2, 1].sum() == 0
