@@ -207,6 +207,33 @@ class SdpdOracle:
                 k = self.Sc * (self.type[i] - 1) + s          # model.cpp:163 (transposed index, mirrored)
                 Dk = np.where(k < dm.size, dm[np.minimum(k, dm.size - 1)], 0.0)
                 np.add.at(self.Q[:, s], i, Dk * (self.C[i, s] - self.C[j, s]) * base)
+            self.det_reactions()
+
+    def det_reactions(self, corrected=False):
+        """model.cpp:181-189: Q[s] += stoichiometric_matrix[num_chem_rxns*rxn + s] * det_rxn(C, t, vol, data_fn, type).
+        The index is the reference's (transposed on the species x rxn row-major table; out-of-bounds reads defined 0)."""
+        fm = self.fm
+        Rc, Sc, S, R = fm.num_chem_rxns, self.Sc, fm.num_species, fm.num_reactions
+        if Rc == 0:
+            return
+        dense = fm.N_dense.reshape(-1)
+        vol = self.mass / self.rho
+        t = self.step_no * self.dt
+        env = {k: v for k, v in fm.parameters.items()}
+        env.update({k: v for k, v in fm.type_constants.items()})
+        env.update(vol=vol, t=t, pow=np.power, exp=np.exp, log=np.log, sqrt=np.sqrt, sin=np.sin, cos=np.cos,
+                   x=[self.C[:, q] for q in range(Sc)], data_fn=[fm.data_fn[q] for q in range(fm.num_data_fn)])
+        for rxn, r in enumerate(fm.reactions):
+            flux = eval(r.ode_propensity, {"__builtins__": {}}, env) * np.ones(self.N)     # C arithmetic text == Python text here
+            if r.restrict_to:
+                ok = np.zeros(self.N, bool)
+                for tname in r.restrict_to:
+                    ok |= self.type == (fm.type_constants[tname] if not str(tname).isdigit() else int(tname))
+                flux = np.where(ok, flux, 0.0)
+            for s_ in range(Sc):
+                k = (s_ * R + rxn) if corrected else (Rc * rxn + s_)
+                nval = dense[k] if k < S * R else 0
+                self.Q[:, s_] += nval * flux
 
     def _W(self, r):
         R = r / self.h

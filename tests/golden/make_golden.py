@@ -14,6 +14,10 @@ import os
 import shutil
 import sys
 import tempfile
+
+if os.environ.get("PYTHONHASHSEED") != "0":     # type indices come from iterating a Python set (domain.py:141-146):
+    os.environ["PYTHONHASHSEED"] = "0"           # pin the hash seed so every fixture of a model agrees on them
+    os.execv(sys.executable, [sys.executable] + sys.argv)
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
