@@ -39,6 +39,8 @@ extern "C" {
 #define SSB_FLAG_CORRECTED_STOICH 2u       /* index the dense stoichiometry as N[s][rxn] instead of the reference's transposed/out-of-bounds
                                               read (E/src/model.cpp:186-187) */
 #define SSB_FLAG_NO_VTK 4u                 /* stage outputs (ssb_get_output) but do not write outputN.vtk files */
+#define SSB_FLAG_LITERAL_KERNELS 16u       /* evaluate every pair expression in the reference's literal order (k_force<true>, separate diffusion-matrix
+                                              sweep) instead of the restructured sweeps; slower, used by the parity tests as a cross-check */
 #define SSB_FLAG_SKIP_STATIC_FORCES 8u     /* static domains: skip F/Fbp/Frho (never consumed when static, simulate.cpp:68,137); default on via Python */
 
 /* Flat model description.  Replaces the generated-literal inputs of solver.py:100-419. */

@@ -315,6 +315,7 @@ struct ssb_handle {
     double tau = 0.0;
     long long nwin = 1;
     int nbr_valid = 0;
+    int ddiag_fresh = 0;
     int64_t launches = 0, windows = 0, h2d_bytes = 0, d2h_bytes = 0;
     int64_t total_reactions = 0, total_diffusion = 0;
     double step_seconds = 0.0;
@@ -684,12 +685,18 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     if (V.static_domain) { for (int d = 0; d < 3; d++) V.x0[d] = nullptr; }   // aliased to x after allocation (below)
     else { for (int d = 0; d < 3; d++) CK(dalloc(h, &V.x0[d], (size_t) N)); }
     CK(dalloc(h, &V.rho_new, (size_t) N));
+    if (!V.static_domain) { CK(dalloc(h, &V.rec, (size_t) 16 * N)); CK(dalloc(h, &V.rec2, (size_t) 4 * N)); }
+    if (V.static_domain && Sc > 0) { CK(dalloc(h, &V.Cpre[0], (size_t) Sc * N)); CK(dalloc(h, &V.Cpre[1], (size_t) Sc * N)); }
     CK(dalloc(h, &V.nbr_count, (size_t) N));
     CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, h->stream));
     CK(dalloc(h, &V.rrate, (size_t) Rd * N)); CK(dalloc(h, &V.srrate, (size_t) N)); CK(dalloc(h, &V.sdrate, (size_t) N));
     CK(dalloc(h, &V.tnext, (size_t) N)); CK(dalloc(h, &V.Ddiag, (size_t) Sd * N));
     CK(dalloc(h, &V.inbox[0], (size_t) Sd * N)); CK(dalloc(h, &V.inbox[1], (size_t) Sd * N));
     CK(dalloc(h, &V.inbox_src[0], (size_t) N)); CK(dalloc(h, &V.inbox_src[1], (size_t) N));
+    {
+        const size_t nblk = (size_t) (N + 31) / 32 + 1;     // enough for any model-unit block size >= 32
+        CK(dalloc(h, &V.blk_tmin, nblk)); CK(dalloc(h, &V.blk_mail[0], nblk)); CK(dalloc(h, &V.blk_mail[1], nblk));
+    }
     CK(dalloc(h, &V.err_flag, 4)); CK(dalloc(h, &V.counters, 4));
     CK(dalloc(h, &h->d_dmat, (size_t) S * m->num_types));
     if (S > 0) CK(cudaMemcpyAsync(h->d_dmat, h->hdmat.data(), sizeof(double) * S * m->num_types, cudaMemcpyHostToDevice, h->stream));
@@ -845,6 +852,7 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     h->epoch = 0;
     h->inbox_buf = 0;
     h->nbr_valid = 0;
+    h->ddiag_fresh = 0;
     h->launches = 0;
     h->windows = 0;
     h->h2d_bytes = (int64_t) N * (3 * 8 + 3 * 8 + 2 * 4 + 8 * Sc + 4 * Sd + 8 * ndf);
@@ -932,6 +940,13 @@ static int neighbour_search(ssb_handle *h) {
         h->allocs.push_back(nb);
         V.nbr = nb;
         V.nbr_cap = cap;
+        if (V.static_domain && V.Sc > 0) {
+            double *cf = nullptr;
+            CK(cudaMalloc((void **) &cf, sizeof(double) * (size_t) cap * N));
+            if (V.coef) { cudaFree(V.coef); for (auto &p : h->allocs) if (p == V.coef) p = nullptr; }
+            h->allocs.push_back(cf);
+            V.coef = cf;
+        }
         if (V.static_domain && V.Sd > 0) {
             double *dj = nullptr;
             CK(cudaMalloc((void **) &dj, sizeof(double) * (size_t) cap * N));
@@ -962,11 +977,14 @@ static int rdme_step(ssb_handle *h) {
     if (V.Sd == 0) return SSB_OK;
     const double t0 = V.dt * h->current_step;
     if (!V.static_domain || !h->rdme_initialized) {      // simulate_rdme.cpp:54-65
-        CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
-        int ps0 = prof_begin(h, CAT_DIFF_INIT, 1);
-        if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
-        prof_end(h, ps0);
-        h->launches += 1;
+        if (!h->ddiag_fresh) {     // the optimised moving-domain force sweep already assembled Ddiag and its maximum
+            CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+            int ps0 = prof_begin(h, CAT_DIFF_INIT, 1);
+            if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
+            prof_end(h, ps0);
+            h->launches += 1;
+        }
+        h->ddiag_fresh = 0;
         unsigned long long bits = 0;
         CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1018,6 +1036,20 @@ static int engine_step(ssb_handle *h) {
     const bool moving = !V.static_domain;
     int rc;
     int ps;
+    // static-domain fast path: one fused chemistry kernel per step (k_static_step); with no continuous species a static
+    // step has no SDPD work at all after step 0 (boundary conditions are idempotent assignments)
+    const bool fast_static = !moving && (V.flags & SSB_FLAG_SKIP_STATIC_FORCES) && !u->bc_touches_rho;
+    if (fast_static && step > 0) {
+        if (V.Sc > 0) {
+            ps = prof_begin(h, CAT_FORCE, 1);
+            if (u->static_step(&V, step, (int) ((step + 1) & 1), st)) return fail(h, SSB_ERR_CUDA, "static_step launch failed");
+            prof_end(h, ps);
+            h->launches++;
+        }
+        if ((rc = rdme_step(h))) return rc;
+        h->current_step++;
+        return SSB_OK;
+    }
     if (step == 0 || moving) {                                               // buildKDTree (simulate_threads.cpp:80-108)
         ps = prof_begin(h, CAT_CELLS, 7);
         rc = build_cells(h);
@@ -1035,8 +1067,30 @@ static int engine_step(ssb_handle *h) {
         prof_end(h, ps);
         if (rc) return rc;
     }
+    if (fast_static) {
+        // step 0 of the fast path: cache the pair coefficients, then run the fused kernel from a copy of C
+        if (V.Sc > 0) {
+            if (u->static_coef(&V, st)) return fail(h, SSB_ERR_CUDA, "static_coef launch failed");
+            CK(cudaMemcpyAsync(V.Cpre[1], V.C, sizeof(double) * (size_t) V.Sc * V.N, cudaMemcpyDeviceToDevice, st));
+            ps = prof_begin(h, CAT_FORCE, 1);
+            if (u->static_step(&V, step, 1, st)) return fail(h, SSB_ERR_CUDA, "static_step launch failed");
+            prof_end(h, ps);
+            h->launches += 2;
+        }
+        if ((rc = rdme_step(h))) return rc;
+        h->current_step++;
+        return SSB_OK;
+    }
     const bool full = moving || !(V.flags & SSB_FLAG_SKIP_STATIC_FORCES);
-    if (full || V.Sc > 0) {
+    if (moving && !(V.flags & SSB_FLAG_LITERAL_KERNELS)) {
+        // optimised moving-domain sweep; also produces Ddiag + its maximum for the sSSA window controller
+        if (V.Sd > 0) CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+        ps = prof_begin(h, CAT_FORCE, 1);
+        if (u->force_mv(&V, step, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
+        prof_end(h, ps);
+        h->launches++;
+        h->ddiag_fresh = 1;
+    } else if (full || V.Sc > 0) {
         ps = prof_begin(h, CAT_FORCE, 1);
         if (u->force(&V, step, full ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
         prof_end(h, ps);

@@ -40,12 +40,24 @@ struct SsbView {
     int nbr_cap;
     double *Dij;        // [cap*N] cached D_i_j (static domains) or nullptr
     double *rho_search; // density at neighbour-search time (frozen into D_i_j, particle.cpp:187)
+    // moving-domain gather records (written by k_predictor, read by the neighbour sweeps): one 128-byte line per particle
+    //   rec[16*j + 0..2] x0   3..5 x   6..8 v   9..11 vt   12 rho   13 mass   14 nu   15 bits(id:32 | type:16 | solid:16)
+    //   rec2[4*j + 0] 1/rho   1 P/rho^2   2 mass/rho   3 (spare)
+    double *rec, *rec2;
+    // static-domain fast path: cached chemistry pair coefficient dQc_base (model.cpp:155) and the double-buffered
+    // half-stepped concentrations the next sweep reads (see k_static_step)
+    double *coef;       // [cap*N] or nullptr
+    double *Cpre[2];    // [Sc*N] each
     // RDME
     double *rrate;      // [Rd*N]
     double *srrate, *sdrate, *tnext;
     double *Ddiag;      // [Sd*N]
     unsigned *inbox[2]; // [Sd*N] each, double-buffered arrivals
     int *inbox_src[2];  // [N] id of one arriving source voxel (+1), 0 = none  (dest-propensity vol quirk, simulate_rdme.cpp:433)
+    // block summaries (one entry per SSB_BLOCK consecutive voxels): earliest tnext in the block, and whether any voxel of
+    // the block has mail in inbox[b]; lets a whole block leave an sSSA window after two loads when nothing is due.
+    double *blk_tmin;   // [ceil(N/SSB_BLOCK)]
+    int *blk_mail[2];   // [ceil(N/SSB_BLOCK)] each
     const double *dmat; // [S*num_types]
     // error / counters (device)
     int *err_flag;      // 0 ok, SSB_ERR_*

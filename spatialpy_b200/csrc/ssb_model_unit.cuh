@@ -88,6 +88,23 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
     V.nu[i] = p.nu;
     V.rho[i] = p.rho;
     V.old_rho[i] = p.rho;                               // simulate.cpp:106
+    if (!V.static_domain && V.rec) {
+        double2 *r2 = reinterpret_cast<double2 *>(V.rec + (size_t) i * 16);
+        const long long bits = ((long long) (unsigned) p.id) | ((long long) (p.type & 0xffff) << 32) | ((long long) (p.solidTag & 0xffff) << 48);
+        r2[0] = make_double2(V.x0[0][i], V.x0[1][i]);
+        r2[1] = make_double2(V.x0[2][i], p.x[0]);
+        r2[2] = make_double2(p.x[1], p.x[2]);
+        r2[3] = make_double2(p.v[0], p.v[1]);
+        r2[4] = make_double2(p.v[2], V.vt[0][i]);
+        r2[5] = make_double2(V.vt[1][i], V.vt[2][i]);
+        r2[6] = make_double2(p.rho, p.mass);
+        r2[7] = make_double2(p.nu, __longlong_as_double(bits));
+        const double inv_rho = 1.0 / p.rho;
+        const double Pp = V.P0 * (p.rho / V.rho0 - 1.0);
+        double2 *q2 = reinterpret_cast<double2 *>(V.rec2 + (size_t) i * 4);
+        q2[0] = make_double2(inv_rho, Pp * inv_rho * inv_rho);
+        q2[1] = make_double2(p.mass * inv_rho, 0.0);
+    }
 #pragma unroll
     for (int s = 0; s < SSB_SC; s++) {
         V.C[(size_t) s * V.N + i] = p.C[s];
@@ -220,6 +237,246 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
 #pragma unroll
         for (int s = 0; s < SSB_SC; s++) V.Q[(size_t) s * N + i] = Qi[s];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 (moving domains, optimised form of k_force<true>): same physics as model.cpp:39-191, restructured for B200:
+//   * neighbour data comes from ONE 128-byte record + one 32-byte record per neighbour (5 sectors instead of 17 scattered
+//     8-byte gathers);
+//   * per-particle quantities (1/rho, P/rho^2, m/rho) are precomputed once in k_predictor instead of once per pair;
+//   * the three per-pair reciprocals 1/(r+0.001h), 1/(nu_i+nu_j), 1/((m_i+m_j)(r^2+0.01h^2)) share ONE division;
+//   * the 3x3 transport tensor contraction T.dx is factorised as 0.5*(rho_i v_i (w_i.dx) + rho_j v_j (w_j.dx)), w = vt - v;
+//   * K6 (D_i_j, Ddiag, max for the window controller; simulate_rdme.cpp:131-152) is fused in — it shares r and the
+//     (m, rho, r^2) factor with the chemistry flux.
+// Results differ from the literal evaluation order by a few ulp per pair (parity gate: 1e-12 of the field scale).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSB_BLOCK) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double mx = 0.0;
+    if (i < V.N) {
+        const int N = V.N, dim = V.dim;
+        const double h = V.h, P0 = V.P0;
+        const double inv_h = 1.0 / h;
+        const double c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
+        const double eps_r = 0.001 * h, eps2 = 0.01 * h * h;
+        const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
+        const double2 *ri = reinterpret_cast<const double2 *>(V.rec + (size_t) i * 16);
+        const double2 a1 = ri[1], a2 = ri[2], a3 = ri[3], a4 = ri[4], a5 = ri[5], a6 = ri[6], a7 = ri[7];
+        const double xi0 = a1.y, xi1 = a2.x, xi2 = a2.y;
+        const double vi0 = a3.x, vi1 = a3.y, vi2 = a4.x;
+        const double wi0 = a4.y - vi0, wi1 = a5.x - vi1, wi2 = a5.y - vi2;
+        const double rho_i = a6.x, m_i = a6.y, nu_i = a7.x;
+        const double2 b0 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) i * 4)[0];
+        const double2 b1 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) i * 4)[1];
+        const double inv_rho_i = b0.x, aP_i = b0.y, vol_i = b1.x;
+        const double volsq_i = vol_i * vol_i, inv_m_i = 1.0 / m_i;
+        const double rv0 = rho_i * vi0, rv1 = rho_i * vi1, rv2 = rho_i * vi2;
+        const int type_i = (int) ((__double_as_longlong(a7.y) >> 32) & 0xffff);
+        double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1], Dd[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+        for (int s = 0; s < SSB_SC; s++) {
+            Ci[s] = V.C[(size_t) s * N + i];
+            Qi[s] = V.Q[(size_t) s * N + i];
+            int k = SSB_SC * (type_i - 1) + s;
+            Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) Dd[s] = 0.0;
+        double F0 = V.F[0][i], F1 = V.F[1][i], F2 = V.F[2][i];
+        double B0 = V.Fbp[0][i], B1 = V.Fbp[1][i], B2 = V.Fbp[2][i];
+        double Frho = V.Frho[i];
+        const int cnt = V.nbr_count[i];
+        for (int k = 0; k < cnt; k++) {
+            const int j = V.nbr[(size_t) k * N + i];
+            const double2 *rj = reinterpret_cast<const double2 *>(V.rec + (size_t) j * 16);
+            const double2 c0 = rj[0], c1 = rj[1], c2 = rj[2], c3 = rj[3], c4 = rj[4], c5 = rj[5], c6 = rj[6], c7 = rj[7];
+            const double2 e0 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) j * 4)[0];
+            const double2 e1 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) j * 4)[1];
+            const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.x, c0.y, c1.x);      // live x_i vs snapshot x0_j (particle.cpp:160)
+            const double r = sqrt(d2);
+            double dx0 = xi0 - c1.y, dx1 = 0.0, dx2 = 0.0;
+            if (dim > 1) dx1 = xi1 - c2.x;
+            if (dim > 2) dx2 = xi2 - c2.y;
+            const double vj0 = c3.x, vj1 = c3.y, vj2 = c4.x;
+            const double wj0 = c4.y - vj0, wj1 = c5.x - vj1, wj2 = c5.y - vj2;
+            const double rho_j = c6.x, m_j = c6.y, nu_j = c7.x;
+            const double inv_rho_j = e0.x, aP_j = e0.y, vol_j = e1.x;
+            // one division for three reciprocals
+            const double reg = r + eps_r, nusum = nu_i + nu_j, r2 = r * r;
+            const double md = (m_i + m_j) * (r2 + eps2);
+            const double rn = reg * nusum;
+            const double q = 1.0 / (rn * md);
+            const double inv_reg = q * (nusum * md), inv_nusum = q * (reg * md), inv_md = q * rn;
+            const double R = r * inv_h, omR = 1.0 - R;
+            const double dWdr = c12 * r * (omR * omR);                           // particle.cpp:178
+            const double wr = dWdr * inv_reg;                                    // dWdr / (r + 0.001 h)
+            double dv0 = vi0 - vj0, dv1 = 0.0, dv2 = 0.0;
+            if (dim > 1) dv1 = vi1 - vj1;
+            if (dim > 2) dv2 = vi2 - vj2;
+            const double dv_dx = dv0 * dx0 + dv1 * dx1 + dv2 * dx2;
+            double pg = aP_i + aP_j;                                             // model.cpp:111
+            if (pg < 0) pg = -aP_i + aP_j;                                       // model.cpp:112
+            const double fp = -m_j * pg * wr;                                    // model.cpp:115
+            const double fv = m_j * (2.0 * (nu_i * nu_j) * inv_nusum) * wr * (inv_rho_i * inv_rho_j);   // model.cpp:118
+            const double vv = volsq_i + vol_j * vol_j;
+            const double fbp = -10.0 * P0 * inv_m_i * vv * wr;                   // model.cpp:121
+            const double widx = wi0 * dx0 + wi1 * dx1 + wi2 * dx2;
+            const double wjdx = wj0 * dx0 + wj1 * dx1 + wj2 * dx2;
+            const double ftc = 0.5 * inv_m_i * vv * wr;                          // model.cpp:124-132
+            const double rj_w = rho_j * wjdx;
+            const double ft0 = ftc * (rv0 * widx + vj0 * rj_w);
+            const double ft1 = ftc * (rv1 * widx + vj1 * rj_w);
+            const double ft2 = ftc * (rv2 * widx + vj2 * rj_w);
+            F0 += fp * dx0 + fv * dv0 + ft0;                                     // model.cpp:135-138
+            B0 += fbp * dx0;
+            if (dim > 1) { F1 += fp * dx1 + fv * dv1 + ft1; B1 += fbp * dx1; }
+            if (dim > 2) { F2 += fp * dx2 + fv * dv2 + ft2; B2 += fbp * dx2; }
+            Frho += wr * vol_j * (rho_i * dv_dx + rho_i * widx + rj_w);          // model.cpp:143-146
+            if (SSB_SC > 0 || SSB_SD > 0) {
+                const double G = 2.0 * (m_i * m_j) * (inv_rho_i + inv_rho_j) * r2 * inv_md;   // shared by model.cpp:155 and particle.cpp:187
+                if (SSB_SC > 0) {
+                    const double base = G * wr;
+#pragma unroll
+                    for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - V.C[(size_t) s * N + j]) * base;
+                }
+                if (SSB_SD > 0) {
+                    const double hr = h - r;
+                    const double Dij = G * (ih7c * hr * hr);                     // particle.cpp:182-187 (sign folded)
+                    const int tj = (int) ((__double_as_longlong(c7.y) >> 32) & 0xffff) - 1;
+#pragma unroll
+                    for (int s = 0; s < SSB_SD; s++) Dd[s] += V.dmat[s * V.num_types + tj] * Dij;
+                }
+            }
+        }
+        V.F[0][i] = F0; V.F[1][i] = F1; V.F[2][i] = F2;
+        V.Fbp[0][i] = B0; V.Fbp[1][i] = B1; V.Fbp[2][i] = B2;
+        V.Frho[i] = Frho;
+        if (SSB_SC > 0) {
+            if (SSB_RC > 0) {                                                    // model.cpp:181-189
+                const double vol = m_i / rho_i;
+                const double cur_time = step * V.dt;
+                double df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+                for (int qd = 0; qd < SSB_NDF; qd++) df[qd] = V.data_fn[(size_t) qd * N + i];
+                double flux[SSB_RC > 0 ? SSB_RC : 1];
+                ssb_gen::eval_det(Ci, cur_time, vol, df, type_i, flux);
+#pragma unroll
+                for (int rxn = 0; rxn < SSB_RC; rxn++) {
+#pragma unroll
+                    for (int s = 0; s < SSB_SC; s++) {
+                        int nval;
+                        if (V.flags & 2u) nval = ssb_gen::N_dense(s * SSB_R + rxn);
+                        else { int kk = SSB_RC * rxn + s; nval = (kk < SSB_S * SSB_R) ? ssb_gen::N_dense(kk) : 0; }
+                        Qi[s] += nval * flux[rxn];
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SSB_SC; s++) V.Q[(size_t) s * N + i] = Qi[s];
+        }
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) { V.Ddiag[(size_t) s * N + i] = Dd[s]; mx = fmax(mx, Dd[s]); }
+    }
+    if (SSB_SD > 0) {
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Static-domain fast path (positions, masses and densities never change: simulate.cpp:68,137 skip the integrator).
+//   k_static_coef  once: the chemistry pair coefficient dQc_base of model.cpp:155 per ELL entry.
+//   k_static_step  one launch per engine step, fusing  [compute_forces: Q = sweep(C)]  [take_step2: C += dt/2 Q; BC]
+//                  with the NEXT step's [take_step1: C += dt/2 Q; BC; Q = 0]  — legal because the RDME that runs in between
+//                  never touches C.  Reads the half-stepped concentrations of all particles from Cpre[in], writes the
+//                  state after this step to C (what outputs and taps see), Q, and the next half-step to Cpre[in^1].
+// Per particle-step the kernel streams 12 B per neighbour (index + coefficient) and gathers C_j from L2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SSB_BLOCK) k_static_coef(SsbView V) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N, dim = V.dim;
+    const double h = V.h;
+    const double alpha = ssb_alpha(dim, h);
+    const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+    const double rho_i = V.rho[i], m_i = V.mass[i];
+    const int cnt = V.nbr_count[i];
+    for (int k = 0; k < cnt; k++) {
+        const int j = V.nbr[(size_t) k * N + i];
+        const double d2 = ssb_dist2(dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+        const double r = sqrt(d2);
+        const double dWdr = ssb_dWdr(alpha, r, h);
+        const double rho_j = V.rho[j], m_j = V.mass[j];
+        const double inv_reg = 1.0 / (r + 0.001 * h);
+        const double wfd = inv_reg * dWdr;
+        V.coef[(size_t) k * N + i] = 2.0 * ((m_i * m_j) / (m_i + m_j)) * ((rho_i + rho_j) / (rho_i * rho_j)) * (r * r) * wfd / ((r * r) + 0.01 * h * h);
+    }
+}
+
+__global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned step, int in_buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+    const int N = V.N;
+    const double dt = V.dt;
+    const double *Cin = V.Cpre[in_buf];
+    double *Cnext = V.Cpre[in_buf ^ 1];
+    const int type_i = V.type[i];
+    double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1];
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) {
+        Ci[s] = Cin[(size_t) s * N + i];
+        Qi[s] = 0.0;
+        int k = SSB_SC * (type_i - 1) + s;                                  // model.cpp:163 (mirrored index)
+        Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
+    }
+    const int cnt = V.nbr_count[i];
+    for (int k = 0; k < cnt; k++) {
+        const int j = V.nbr[(size_t) k * N + i];
+        const double cf = V.coef[(size_t) k * N + i];
+#pragma unroll
+        for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cin[(size_t) s * N + j]) * cf;
+    }
+    if (SSB_RC > 0) {                                                       // model.cpp:181-189
+        const double vol = V.mass[i] / V.rho[i];
+        const double cur_time = step * dt;
+        double df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+        for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
+        double flux[SSB_RC > 0 ? SSB_RC : 1];
+        ssb_gen::eval_det(Ci, cur_time, vol, df, type_i, flux);
+#pragma unroll
+        for (int rxn = 0; rxn < SSB_RC; rxn++) {
+#pragma unroll
+            for (int s = 0; s < SSB_SC; s++) {
+                int nval;
+                if (V.flags & 2u) nval = ssb_gen::N_dense(s * SSB_R + rxn);
+                else { int kk = SSB_RC * rxn + s; nval = (kk < SSB_S * SSB_R) ? ssb_gen::N_dense(kk) : 0; }
+                Qi[s] += nval * flux[rxn];
+            }
+        }
+    }
+    Particle p;
+#if SSB_HAS_BC
+    bc_load(V, i, p);
+    System sys = make_system(V, step);
+#endif
+    // take_step2 of this step: C += dt/2 Q; BC      (simulate.cpp:167-171)
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) p.C[s] = Ci[s] + Qi[s] * dt * 0.5;
+#if SSB_HAS_BC
+    ssb_gen::applyBoundaryConditions(&p, &sys);
+#endif
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) { V.C[(size_t) s * N + i] = p.C[s]; V.Q[(size_t) s * N + i] = Qi[s]; }
+    // take_step1 of the next step: C += dt/2 Q; BC   (simulate.cpp:81-88)
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) p.C[s] += Qi[s] * dt * 0.5;
+#if SSB_HAS_BC
+    sys.current_step = step + 1;
+    ssb_gen::applyBoundaryConditions(&p, &sys);
+#endif
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) Cnext[(size_t) s * N + i] = p.C[s];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -375,6 +632,20 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_diff_init(SsbView V, unsigned lon
 // K7a  RDME (re)initialisation: reaction propensities (simulate_rdme.cpp:113-128), sdrate (:149),
 // first event time Exp(1)/(srrate+sdrate)+t0 (simulate_rdme.cpp:155-195, NRMConstant_v5.cpp:52-59).
 // ---------------------------------------------------------------------------------------------
+// minimum over the block (all threads must call); result valid in thread 0
+__device__ __forceinline__ double block_min(double v) {
+    __shared__ double sh_min[SSB_BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sh_min[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double w = (threadIdx.x < SSB_BLOCK / 32) ? sh_min[threadIdx.x] : INFINITY;
+        for (int o = 16; o > 0; o >>= 1) w = fmin(w, __shfl_xor_sync(0xffffffffu, w, o));
+        v = w;
+    }
+    return v;
+}
+
 struct VoxelRates {
     double rr[SSB_RD > 0 ? SSB_RD : 1];
     double sr, sd;
@@ -402,28 +673,33 @@ __device__ __forceinline__ void eval_rates(const SsbView &V, int i, const int *x
 
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, double t_eval, double tau, uint64_t seed, uint64_t epoch) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V.N) return;
-    const int N = V.N;
-    int xx[SSB_SD > 0 ? SSB_SD : 1];
+    double tn = INFINITY;
+    if (i < V.N) {
+        const int N = V.N;
+        int xx[SSB_SD > 0 ? SSB_SD : 1];
 #pragma unroll
-    for (int s = 0; s < SSB_SD; s++) xx[s] = (int) V.xx[(size_t) s * N + i];
-    double df[SSB_NDF > 0 ? SSB_NDF : 1];
+        for (int s = 0; s < SSB_SD; s++) xx[s] = (int) V.xx[(size_t) s * N + i];
+        double df[SSB_NDF > 0 ? SSB_NDF : 1];
 #pragma unroll
-    for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
-    const double vol = V.mass[i] / V.rho[i];
-    VoxelRates R;
-    eval_rates(V, i, xx, xx, t_eval, vol, df, V.type[i], tau, R);
+        for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
+        const double vol = V.mass[i] / V.rho[i];
+        VoxelRates R;
+        eval_rates(V, i, xx, xx, t_eval, vol, df, V.type[i], tau, R);
 #pragma unroll
-    for (int r = 0; r < SSB_RD; r++) V.rrate[(size_t) r * N + i] = R.rr[r];
-    V.srrate[i] = R.sr;
-    V.sdrate[i] = R.sd;
-    const double tot = R.sr + R.sd;
-    double u0, u1;
-    philox_uniform2((uint32_t) V.id[i], 0u, epoch, seed, u0, u1);
-    V.tnext[i] = (tot > 0.0) ? t0 + (-log(u0)) / tot : INFINITY;
+        for (int r = 0; r < SSB_RD; r++) V.rrate[(size_t) r * N + i] = R.rr[r];
+        V.srrate[i] = R.sr;
+        V.sdrate[i] = R.sd;
+        const double tot = R.sr + R.sd;
+        double u0, u1;
+        philox_uniform2((uint32_t) V.id[i], 0u, epoch, seed, u0, u1);
+        tn = (tot > 0.0) ? t0 + (-log(u0)) / tot : INFINITY;
+        V.tnext[i] = tn;
 #pragma unroll
-    for (int s = 0; s < SSB_SD; s++) { V.inbox[0][(size_t) s * N + i] = 0u; V.inbox[1][(size_t) s * N + i] = 0u; }
-    V.inbox_src[0][i] = 0; V.inbox_src[1][i] = 0;
+        for (int s = 0; s < SSB_SD; s++) { V.inbox[0][(size_t) s * N + i] = 0u; V.inbox[1][(size_t) s * N + i] = 0u; }
+        V.inbox_src[0][i] = 0; V.inbox_src[1][i] = 0;
+    }
+    tn = block_min(tn);
+    if (threadIdx.x == 0) { V.blk_tmin[blockIdx.x] = tn; V.blk_mail[0][blockIdx.x] = 0; V.blk_mail[1][blockIdx.x] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,7 +723,17 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, double tau, uint64_t seed,
                                                           uint64_t epoch, int buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // block triage: nothing due in this window and no mail for any voxel of the block -> the block leaves after two loads
+    __shared__ int sh_active;
+    if (threadIdx.x == 0) {
+        const int mail = V.blk_mail[buf ^ 1][blockIdx.x];
+        sh_active = (mail != 0) || (V.blk_tmin[blockIdx.x] <= t_hi);
+        if (mail) V.blk_mail[buf ^ 1][blockIdx.x] = 0;
+    }
+    __syncthreads();
+    if (!sh_active) return;
     unsigned n_rx = 0, n_df = 0;
+    double tn_final = INFINITY;
     if (i < V.N) {
         const int N = V.N;
         const unsigned *in_prev = V.inbox[buf ^ 1];
@@ -586,6 +872,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
                         xx[spec]--;                                             // no longer mobile here, still reactive (xr) until the window closes
                         atomicAdd(&out_box[(size_t) spec * N + dest], 1u);
                         atomicMax(&V.inbox_src[buf][dest], i + 1);
+                        V.blk_mail[buf][dest / SSB_BLOCK] = 1;
                     }
                     n_df++;
                 }
@@ -615,7 +902,10 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
             V.sdrate[i] = R.sd;
             V.tnext[i] = tnext;
         }
+        tn_final = tnext;
     }
+    tn_final = block_min(tn_final);
+    if (threadIdx.x == 0) V.blk_tmin[blockIdx.x] = tn_final;
     // event counters (ParticleSystem::total_reactions / total_diffusion): warp reduce, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
         n_rx += __shfl_xor_sync(0xffffffffu, n_rx, o);
@@ -641,6 +931,10 @@ static int l_force(const SsbView *V, unsigned step, int full, cudaStream_t st) {
     else k_force<false><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
     return (int) cudaGetLastError();
 }
+static int l_force_mv(const SsbView *V, unsigned step, unsigned long long *max_bits, cudaStream_t st) {
+    k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
+    return (int) cudaGetLastError();
+}
 static int l_corrector(const SsbView *V, unsigned step, cudaStream_t st) {
     k_corrector<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step);
     return (int) cudaGetLastError();
@@ -652,6 +946,14 @@ static int l_finish(const SsbView *V, unsigned step, int moving, cudaStream_t st
 }
 static int l_diff_init(const SsbView *V, unsigned long long *max_bits, cudaStream_t st) {
     k_diff_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, max_bits);
+    return (int) cudaGetLastError();
+}
+static int l_static_coef(const SsbView *V, cudaStream_t st) {
+    k_static_coef<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V);
+    return (int) cudaGetLastError();
+}
+static int l_static_step(const SsbView *V, unsigned step, int in_buf, cudaStream_t st) {
+    k_static_step<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, in_buf);
     return (int) cudaGetLastError();
 }
 static int l_rdme_init(const SsbView *V, double t0, double t_eval, double tau, uint64_t seed, uint64_t epoch, cudaStream_t st) {
@@ -672,9 +974,13 @@ extern "C" const SsbModelUnit *ssbm_get_unit() {
     u.S = SSB_S; u.R = SSB_R;
     u.predictor = ssb_unit::l_predictor;
     u.force = ssb_unit::l_force;
+    u.force_mv = ssb_unit::l_force_mv;
     u.corrector = ssb_unit::l_corrector;
     u.finish = ssb_unit::l_finish;
     u.diff_init = ssb_unit::l_diff_init;
+    u.has_bc = SSB_HAS_BC; u.bc_touches_rho = SSB_BC_TOUCHES_RHO;
+    u.static_coef = ssb_unit::l_static_coef;
+    u.static_step = ssb_unit::l_static_step;
     u.rdme_init = ssb_unit::l_rdme_init;
     u.rdme_window = ssb_unit::l_rdme_window;
     return &u;

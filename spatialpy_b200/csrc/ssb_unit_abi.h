@@ -8,17 +8,21 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 4
+#define SSB_UNIT_ABI 7
 
 struct SsbModelUnit {
     int abi;
     int Sc, Rc, Sd, Rd, ndf, ntypes, S, R;
+    int has_bc, bc_touches_rho;
     int (*predictor)(const SsbView *, unsigned step, cudaStream_t);
     int (*force)(const SsbView *, unsigned step, int full, cudaStream_t);
+    int (*force_mv)(const SsbView *, unsigned step, unsigned long long *max_ddiag_bits, cudaStream_t);
     int (*corrector)(const SsbView *, unsigned step, cudaStream_t);
     int (*finish)(const SsbView *, unsigned step, int moving, cudaStream_t);
     int (*diff_init)(const SsbView *, unsigned long long *max_ddiag_bits, cudaStream_t);
     int (*rdme_init)(const SsbView *, double t0, double t_eval, double tau, uint64_t seed, uint64_t epoch, cudaStream_t);
+    int (*static_coef)(const SsbView *, cudaStream_t);
+    int (*static_step)(const SsbView *, unsigned step, int in_buf, cudaStream_t);
     int (*rdme_window)(const SsbView *, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t);
 };
 
