@@ -303,6 +303,8 @@ struct ssb_handle {
     double *d_stage = nullptr;   // device staging for output/taps (id order)
     size_t stage_bytes = 0;
     double *d_dmat = nullptr;
+    double *init_f64 = nullptr;   // pinned
+    int *init_i32 = nullptr;      // pinned
     double *rho_buf[2] = {nullptr, nullptr};
     // model unit
     void *unit_dl = nullptr;
@@ -316,6 +318,9 @@ struct ssb_handle {
     long long nwin = 1;
     int nbr_valid = 0;
     int ddiag_fresh = 0;
+    int static_cached = 0;        // static domain: storage order, neighbour lists, coefficients and Ddiag survive ssb_reset
+    int *d_static_perm = nullptr; // slot -> particle id of the cached storage order
+    double max_ddiag_cached = 0.0;
     int64_t launches = 0, windows = 0, h2d_bytes = 0, d2h_bytes = 0;
     int64_t total_reactions = 0, total_diffusion = 0;
     double step_seconds = 0.0;
@@ -732,6 +737,19 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
         CK(cudaMallocHost((void **) &J.C, sizeof(double) * (Sc > 0 ? Sc : 1) * N));
         CK(cudaMallocHost((void **) &J.xx, sizeof(unsigned) * (Sd > 0 ? Sd : 1) * N));
     }
+    {   // pinned SoA image of the initial condition (device layout), uploaded by every ssb_reset
+        const size_t nd = (size_t) (6 + Sc + ndf) * N, ni = (size_t) (2 + Sd) * N;
+        CK(cudaMallocHost((void **) &h->init_f64, sizeof(double) * (nd > 0 ? nd : 1)));
+        CK(cudaMallocHost((void **) &h->init_i32, sizeof(int) * (ni > 0 ? ni : 1)));
+        double *pd = h->init_f64;
+        for (int d = 0; d < 3; d++) for (int i = 0; i < N; i++) pd[(size_t) d * N + i] = h->hx[(size_t) i * 3 + d];
+        for (int i = 0; i < N; i++) { pd[(size_t) 3 * N + i] = h->hrho[i]; pd[(size_t) 4 * N + i] = h->hmass[i]; pd[(size_t) 5 * N + i] = h->hnu[i]; }
+        for (int sp = 0; sp < Sc; sp++) for (int i = 0; i < N; i++) pd[(size_t) (6 + sp) * N + i] = (double) h->hu0[(size_t) i * S + sp];
+        for (size_t k = 0; k < (size_t) ndf * N; k++) pd[(size_t) (6 + Sc) * N + k] = h->hdata_fn[k];
+        int *pi = h->init_i32;
+        for (int i = 0; i < N; i++) { pi[i] = h->htype[i]; pi[(size_t) N + i] = h->hsolid[i]; }
+        for (int sp = 0; sp < Sd; sp++) for (int i = 0; i < N; i++) pi[(size_t) (2 + sp) * N + i] = (int) h->hu0[(size_t) i * S + sp];
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->writer = std::thread(writer_main, h);
     return SSB_OK;
@@ -781,6 +799,8 @@ extern "C" int ssb_destroy(ssb_handle *h) {
         if (J.ready) cudaEventDestroy(J.ready);
         cudaFreeHost(J.x); cudaFreeHost(J.v); cudaFreeHost(J.scal); cudaFreeHost(J.type); cudaFreeHost(J.C); cudaFreeHost(J.xx);
     }
+    if (h->init_f64) cudaFreeHost(h->init_f64);
+    if (h->init_i32) cudaFreeHost(h->init_i32);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->unit_dl) dlclose(h->unit_dl);
@@ -793,6 +813,8 @@ extern "C" int ssb_cancel(ssb_handle *h) { if (h) h->cancel.store(1); return SSB
 // ----------------------------------------------------------------------------------------------------
 // state reset (replaces init_all_particles + initialize_rdme, template:134-138)
 // ----------------------------------------------------------------------------------------------------
+static int apply_permutation(ssb_handle *h, const int *d_perm);
+
 extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     if (!h) return SSB_ERR_ARG;
     if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
@@ -800,52 +822,51 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     SsbView &V = h->V;
     const int N = h->N, Sc = V.Sc, Sd = V.Sd, S = h->S, ndf = V.ndf;
     cudaStream_t st = h->stream;
-    std::vector<double> tmp((size_t) N);
-    for (int d = 0; d < 3; d++) {
-        for (int i = 0; i < N; i++) tmp[i] = h->hx[(size_t) i * 3 + d];
-        CK(cudaMemcpyAsync(V.x[d], tmp.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
-        // fields the reference leaves uninitialised are defined as 0 (particle.cpp:70-83)
-        CK(cudaMemsetAsync(V.v[d], 0, sizeof(double) * N, st));
-        CK(cudaMemsetAsync(V.vt[d], 0, sizeof(double) * N, st));
-        CK(cudaMemsetAsync(V.F[d], 0, sizeof(double) * N, st));
-        CK(cudaMemsetAsync(V.Fbp[d], 0, sizeof(double) * N, st));
+    // the initial condition lives in one pinned SoA block built once by ssb_create: reset = a handful of async H2D copies
+    {
+        const double *pd = h->init_f64;
+        for (int d = 0; d < 3; d++) {
+            CK(cudaMemcpyAsync(V.x[d], pd + (size_t) d * N, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+            // fields the reference leaves uninitialised are defined as 0 (particle.cpp:70-83)
+            CK(cudaMemsetAsync(V.v[d], 0, sizeof(double) * N, st));
+            CK(cudaMemsetAsync(V.vt[d], 0, sizeof(double) * N, st));
+            CK(cudaMemsetAsync(V.F[d], 0, sizeof(double) * N, st));
+            CK(cudaMemsetAsync(V.Fbp[d], 0, sizeof(double) * N, st));
+        }
+        CK(cudaMemcpyAsync(V.rho, pd + (size_t) 3 * N, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(V.mass, pd + (size_t) 4 * N, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(V.nu, pd + (size_t) 5 * N, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+        // species: u0 is voxel-major [N][S] (solver.py:211-220); C starts as (double) u0 (template:77-81)
+        if (Sc > 0) CK(cudaMemcpyAsync(V.C, pd + (size_t) 6 * N, sizeof(double) * Sc * N, cudaMemcpyHostToDevice, st));
+        if (ndf > 0) CK(cudaMemcpyAsync(V.data_fn, pd + (size_t) (6 + Sc) * N, sizeof(double) * ndf * N, cudaMemcpyHostToDevice, st));
+        const int *pi = h->init_i32;
+        CK(cudaMemcpyAsync(V.type, pi, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(V.solid, pi + (size_t) N, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+        if (Sd > 0) CK(cudaMemcpyAsync(V.xx, pi + (size_t) 2 * N, sizeof(unsigned) * Sd * N, cudaMemcpyHostToDevice, st));
     }
-    CK(cudaMemcpyAsync(V.rho, h->hrho.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(V.mass, h->hmass.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(V.nu, h->hnu.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(V.type, h->htype.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(V.solid, h->hsolid.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(V.old_rho, 0, sizeof(double) * N, st));
     CK(cudaMemsetAsync(V.Frho, 0, sizeof(double) * N, st));
     CK(cudaMemsetAsync(V.bvf, 0, sizeof(double) * N, st));
     CK(cudaMemsetAsync(V.rho_new, 0, sizeof(double) * N, st));
     k_iota<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id);
-    // species: u0 is voxel-major [N][S] (solver.py:211-220); C starts as (double) u0 (template:77-81)
-    if (Sc > 0) {
-        for (int s = 0; s < Sc; s++) {
-            for (int i = 0; i < N; i++) tmp[i] = (double) h->hu0[(size_t) i * S + s];
-            CK(cudaMemcpyAsync(V.C + (size_t) s * N, tmp.data(), sizeof(double) * N, cudaMemcpyHostToDevice, st));
-        }
-        CK(cudaMemsetAsync(V.Q, 0, sizeof(double) * Sc * N, st));
-    }
+    if (Sc > 0) CK(cudaMemsetAsync(V.Q, 0, sizeof(double) * Sc * N, st));
     if (Sd > 0) {
-        std::vector<unsigned> ut((size_t) N);
-        for (int s = 0; s < Sd; s++) {
-            for (int i = 0; i < N; i++) ut[i] = h->hu0[(size_t) i * S + s];
-            CK(cudaMemcpyAsync(V.xx + (size_t) s * N, ut.data(), sizeof(unsigned) * N, cudaMemcpyHostToDevice, st));
-        }
         CK(cudaMemsetAsync(V.inbox[0], 0, sizeof(unsigned) * Sd * N, st));
         CK(cudaMemsetAsync(V.inbox[1], 0, sizeof(unsigned) * Sd * N, st));
         CK(cudaMemsetAsync(V.inbox_src[0], 0, sizeof(int) * N, st));
         CK(cudaMemsetAsync(V.inbox_src[1], 0, sizeof(int) * N, st));
     }
-    if (ndf > 0) CK(cudaMemcpyAsync(V.data_fn, h->hdata_fn.data(), sizeof(double) * ndf * N, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(V.err_flag, 0, 16, st));
     CK(cudaMemsetAsync(V.counters, 0, 32, st));
-    CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, st));
+    if (!h->static_cached) CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, st));
     if (V.static_domain) for (int d = 0; d < 3; d++) V.x0[d] = V.x[d];
     V.rho_search = V.rho;
     CK(cudaStreamSynchronize(st));
+    if (h->static_cached) {      // put the freshly uploaded (id-ordered) state into the cached storage order
+        int rcp = apply_permutation(h, h->d_static_perm);
+        if (rcp) return rcp;
+        CK(cudaStreamSynchronize(st));
+    }
     h->current_step = 0;
     h->rdme_initialized = 0;
     h->seed = seed;
@@ -885,7 +906,14 @@ static int build_cells(ssb_handle *h) {
     CK(cudaMemcpyAsync(&nonid, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (!nonid) return SSB_OK;
-    // permute every per-particle field into the alternate buffers, then swap
+    return apply_permutation(h, h->d_perm);
+}
+
+// dst[p] = src[perm[p]] for every per-particle field (alternate buffers, then swap)
+static int apply_permutation(ssb_handle *h, const int *d_perm) {
+    SsbView &V = h->V;
+    const int N = h->N;
+    cudaStream_t st = h->stream;
     PermTable T;
     memset(&T, 0, sizeof(T));
     size_t nf = h->f64_slots.size();
@@ -900,7 +928,7 @@ static int build_cells(ssb_handle *h) {
     int *xx_alt = h->i32_alt[ni];
     for (int s = 0; s < Sd; s++) { T.src32[T.n32] = (int *) V.xx + (size_t) s * N; T.dst32[T.n32] = xx_alt + (size_t) s * N; T.n32++; }
     CK(cudaMemcpyAsync(h->d_permtable, &T, sizeof(T), cudaMemcpyHostToDevice, st));
-    k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, h->d_perm, h->d_permtable);
+    k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, d_perm, h->d_permtable);
     h->launches += 1;
     CK(cudaStreamSynchronize(st));   // T lives on this stack frame
     for (size_t f = 0; f < nf; f++) { double *cur = *h->f64_slots[f]; *h->f64_slots[f] = h->f64_alt[f]; h->f64_alt[f] = cur; }
@@ -977,6 +1005,7 @@ static int rdme_step(ssb_handle *h) {
     if (V.Sd == 0) return SSB_OK;
     const double t0 = V.dt * h->current_step;
     if (!V.static_domain || !h->rdme_initialized) {      // simulate_rdme.cpp:54-65
+        if (h->static_cached && V.static_domain) h->ddiag_fresh = 2;   // Ddiag, D_ij, tau from the first trajectory are still valid
         if (!h->ddiag_fresh) {     // the optimised moving-domain force sweep already assembled Ddiag and its maximum
             CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
             int ps0 = prof_begin(h, CAT_DIFF_INIT, 1);
@@ -984,12 +1013,17 @@ static int rdme_step(ssb_handle *h) {
             prof_end(h, ps0);
             h->launches += 1;
         }
-        h->ddiag_fresh = 0;
         unsigned long long bits = 0;
-        CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if (h->ddiag_fresh == 2) {
+            memcpy(&bits, &h->max_ddiag_cached, sizeof(bits));
+        } else {
+            CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        h->ddiag_fresh = 0;
         double mx;
         memcpy(&mx, &bits, sizeof(mx));
+        h->max_ddiag_cached = mx;
         // window controller: tau * (largest per-molecule jump rate) <= rdme_epsilon, and an integer number of windows per step
         double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
         double tau = (mx > 0.0) ? eps / mx : V.dt;
@@ -1050,7 +1084,8 @@ static int engine_step(ssb_handle *h) {
         h->current_step++;
         return SSB_OK;
     }
-    if (step == 0 || moving) {                                               // buildKDTree (simulate_threads.cpp:80-108)
+    const bool reuse = !moving && h->static_cached;                          // geometry work of step 0 already done by an earlier trajectory
+    if ((step == 0 && !reuse) || moving) {                                   // buildKDTree (simulate_threads.cpp:80-108)
         ps = prof_begin(h, CAT_CELLS, 7);
         rc = build_cells(h);
         prof_end(h, ps);
@@ -1060,7 +1095,7 @@ static int engine_step(ssb_handle *h) {
     if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
     prof_end(h, ps);
     h->launches++;
-    if (step == 0 || moving) {                                               // find_neighbors (simulate.cpp:61-63,121-123)
+    if ((step == 0 && !reuse) || moving) {                                   // find_neighbors (simulate.cpp:61-63,121-123)
         V.rho_search = V.rho;
         ps = prof_begin(h, CAT_SEARCH, 1);
         rc = neighbour_search(h);
@@ -1070,7 +1105,7 @@ static int engine_step(ssb_handle *h) {
     if (fast_static) {
         // step 0 of the fast path: cache the pair coefficients, then run the fused kernel from a copy of C
         if (V.Sc > 0) {
-            if (u->static_coef(&V, st)) return fail(h, SSB_ERR_CUDA, "static_coef launch failed");
+            if (!reuse && u->static_coef(&V, st)) return fail(h, SSB_ERR_CUDA, "static_coef launch failed");
             CK(cudaMemcpyAsync(V.Cpre[1], V.C, sizeof(double) * (size_t) V.Sc * V.N, cudaMemcpyDeviceToDevice, st));
             ps = prof_begin(h, CAT_FORCE, 1);
             if (u->static_step(&V, step, 1, st)) return fail(h, SSB_ERR_CUDA, "static_step launch failed");
@@ -1078,6 +1113,11 @@ static int engine_step(ssb_handle *h) {
             h->launches += 2;
         }
         if ((rc = rdme_step(h))) return rc;
+        if (!reuse) {             // remember the storage order so later trajectories skip the geometry work
+            if (!h->d_static_perm) CK(dalloc(h, &h->d_static_perm, (size_t) V.N));
+            CK(cudaMemcpyAsync(h->d_static_perm, V.id, sizeof(int) * V.N, cudaMemcpyDeviceToDevice, st));
+            h->static_cached = 1;
+        }
         h->current_step++;
         return SSB_OK;
     }

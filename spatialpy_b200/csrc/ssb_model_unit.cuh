@@ -722,17 +722,29 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, double tau, uint64_t seed,
                                                           uint64_t epoch, int buf) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // block triage: nothing due in this window and no mail for any voxel of the block -> the block leaves after two loads
-    __shared__ int sh_active;
-    if (threadIdx.x == 0) {
-        const int mail = V.blk_mail[buf ^ 1][blockIdx.x];
-        sh_active = (mail != 0) || (V.blk_tmin[blockIdx.x] <= t_hi);
-        if (mail) V.blk_mail[buf ^ 1][blockIdx.x] = 0;
+    // Persistent grid: each CTA owns the chunks c = blockIdx.x + t*gridDim.x (a chunk = SSB_BLOCK consecutive voxels).
+    // Parallel triage first — thread t inspects chunk t's summary (earliest tnext, mail flag) — so a window in which
+    // nothing is due costs two loads per chunk instead of a block dispatch per chunk; then only the active chunks run.
+    // The order of the active list depends on atomics, the result does not (chunks are independent in a window).
+    __shared__ int sh_act[SSB_BLOCK];
+    __shared__ int sh_nact;
+    const int nchunks = (V.N + SSB_BLOCK - 1) / SSB_BLOCK;
+    if (threadIdx.x == 0) sh_nact = 0;
+    __syncthreads();
+    {
+        const int c = blockIdx.x + threadIdx.x * gridDim.x;     // launcher guarantees chunks per CTA <= SSB_BLOCK
+        if (c < nchunks) {
+            const int mail = V.blk_mail[buf ^ 1][c];
+            if (mail) V.blk_mail[buf ^ 1][c] = 0;
+            if (mail != 0 || V.blk_tmin[c] <= t_hi) sh_act[atomicAdd(&sh_nact, 1)] = c;
+        }
     }
     __syncthreads();
-    if (!sh_active) return;
+    const int nact = sh_nact;
     unsigned n_rx = 0, n_df = 0;
+    for (int a = 0; a < nact; a++) {
+    const int chunk = sh_act[a];
+    const int i = chunk * SSB_BLOCK + threadIdx.x;
     double tn_final = INFINITY;
     if (i < V.N) {
         const int N = V.N;
@@ -905,7 +917,9 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
         tn_final = tnext;
     }
     tn_final = block_min(tn_final);
-    if (threadIdx.x == 0) V.blk_tmin[blockIdx.x] = tn_final;
+    if (threadIdx.x == 0) V.blk_tmin[chunk] = tn_final;
+    __syncthreads();                 // block_min's shared scratch is reused by the next chunk
+    }
     // event counters (ParticleSystem::total_reactions / total_diffusion): warp reduce, one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
         n_rx += __shfl_xor_sync(0xffffffffu, n_rx, o);
@@ -961,7 +975,13 @@ static int l_rdme_init(const SsbView *V, double t0, double t_eval, double tau, u
     return (int) cudaGetLastError();
 }
 static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
-    k_rdme_window<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
+    // persistent grid: a multiple of the 148 SMs, grown only when a CTA would own more than SSB_BLOCK chunks
+    const unsigned nchunks = grid_for(V->N);
+    unsigned grid = 148u * 8u;
+    if (grid > nchunks) grid = nchunks;
+    const unsigned need = (nchunks + SSB_BLOCK - 1) / SSB_BLOCK;
+    if (grid < need) grid = need;
+    k_rdme_window<<<grid, SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
     return (int) cudaGetLastError();
 }
 
