@@ -1042,22 +1042,15 @@ static int rdme_step(ssb_handle *h) {
     }
     const long long nwin = h->nwin;
     int psw = prof_begin(h, CAT_RDME_WINDOW, (int) nwin + 1);
-    for (long long w = 0; w < nwin; w++) {
-        double lo = t0 + V.dt * ((double) w / (double) nwin);
-        double hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
-        if (u->rdme_window(&V, lo, hi, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
-        h->inbox_buf ^= 1;
-        if ((w & 1023) == 1023 && h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
-    }
-    // zero-length closing window: delivers the molecules still in flight in the inbox so that the state read at
-    // the step boundary (output, taps, the next step's re-initialisation) conserves molecules
-    {
-        const double te = t0 + V.dt;
-        if (u->rdme_window(&V, te, te, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
-        h->inbox_buf ^= 1;
-    }
+    // all windows of the step plus the zero-length closing window (delivers in-flight molecules so that the state read at
+    // the step boundary conserves molecules) — one cooperative launch when the device supports it
+    int nl = 0;
+    if (u->rdme_windows(&V, t0, V.dt, nwin, h->tau, h->seed, h->epoch, h->inbox_buf, &nl, st)) return fail(h, SSB_ERR_CUDA, "rdme_windows launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    h->epoch += (uint64_t) nwin + 1;
+    h->inbox_buf ^= (int) ((nwin + 1) & 1);
     prof_end(h, psw);
-    h->launches += nwin + 1;
+    h->launches += nl;
+    if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
     h->windows += nwin;
     return SSB_OK;
 }

@@ -11,6 +11,7 @@
 // E = /root/reference/spatialpy/solvers/c_base/ssa_sdpd-c-simulation-engine.
 #pragma once
 #include <math.h>
+#include <cooperative_groups.h>
 #include "ssb_device.cuh"
 #include "ssb_unit_abi.h"
 
@@ -720,8 +721,8 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
 //   direction     r2*Ddiag[spec] against the running sum of D_i_j*D[spec,type(dest)]  (:353-367)
 // SSB_FLAG_CORRECTED_NSM_SELECT switches the two picks to the textbook rule (rand*totrate, subtract srrate).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, double tau, uint64_t seed,
-                                                          uint64_t epoch, int buf) {
+__device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, double t_hi, double tau, uint64_t seed,
+                                                 uint64_t epoch, int buf, unsigned &n_rx, unsigned &n_df) {
     // Persistent grid: each CTA owns the chunks c = blockIdx.x + t*gridDim.x (a chunk = SSB_BLOCK consecutive voxels).
     // Parallel triage first — thread t inspects chunk t's summary (earliest tnext, mail flag) — so a window in which
     // nothing is due costs two loads per chunk instead of a block dispatch per chunk; then only the active chunks run.
@@ -729,19 +730,20 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
     __shared__ int sh_act[SSB_BLOCK];
     __shared__ int sh_nact;
     const int nchunks = (V.N + SSB_BLOCK - 1) / SSB_BLOCK;
+    for (int round0 = 0; blockIdx.x + (long long) round0 * gridDim.x < nchunks; round0 += SSB_BLOCK) {
+    __syncthreads();
     if (threadIdx.x == 0) sh_nact = 0;
     __syncthreads();
     {
-        const int c = blockIdx.x + threadIdx.x * gridDim.x;     // launcher guarantees chunks per CTA <= SSB_BLOCK
+        const long long c = blockIdx.x + (long long) (round0 + threadIdx.x) * gridDim.x;
         if (c < nchunks) {
-            const int mail = V.blk_mail[buf ^ 1][c];
+            const int mail = __ldcg(&V.blk_mail[buf ^ 1][c]);      // written by other CTAs: read through L2
             if (mail) V.blk_mail[buf ^ 1][c] = 0;
-            if (mail != 0 || V.blk_tmin[c] <= t_hi) sh_act[atomicAdd(&sh_nact, 1)] = c;
+            if (mail != 0 || V.blk_tmin[c] <= t_hi) sh_act[atomicAdd(&sh_nact, 1)] = (int) c;
         }
     }
     __syncthreads();
     const int nact = sh_nact;
-    unsigned n_rx = 0, n_df = 0;
     for (int a = 0; a < nact; a++) {
     const int chunk = sh_act[a];
     const int i = chunk * SSB_BLOCK + threadIdx.x;
@@ -754,7 +756,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
         bool arrived = false;
         unsigned inc[SSB_SD > 0 ? SSB_SD : 1];
 #pragma unroll
-        for (int s = 0; s < SSB_SD; s++) { inc[s] = in_prev[(size_t) s * N + i]; arrived |= (inc[s] != 0u); }
+        for (int s = 0; s < SSB_SD; s++) { inc[s] = __ldcg(&in_prev[(size_t) s * N + i]); arrived |= (inc[s] != 0u); }   // written by other CTAs
         if (arrived || tnext <= t_hi) {
             int xx[SSB_SD > 0 ? SSB_SD : 1];     // present: may react and jump
             int xr[SSB_SD > 0 ? SSB_SD : 1];     // present + departing: may react
@@ -790,7 +792,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
                 // reference quirk: the destination's propensities are re-evaluated with the SOURCE voxel's vol
                 // (simulate_rdme.cpp:433) and stay that way until its next own event.
                 double vol_dest = vol;
-                const int src = V.inbox_src[buf ^ 1][i];
+                const int src = __ldcg(&V.inbox_src[buf ^ 1][i]);
                 if (src > 0 && !(V.flags & 1u)) { vol_dest = V.mass[src - 1] / V.rho[src - 1]; }
                 V.inbox_src[buf ^ 1][i] = 0;
                 double tmp[SSB_RD > 0 ? SSB_RD : 1];
@@ -920,7 +922,11 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
     if (threadIdx.x == 0) V.blk_tmin[chunk] = tn_final;
     __syncthreads();                 // block_min's shared scratch is reused by the next chunk
     }
-    // event counters (ParticleSystem::total_reactions / total_diffusion): warp reduce, one atomic per warp
+    }
+}
+
+// event counters (ParticleSystem::total_reactions / total_diffusion): warp reduce, one atomic per warp
+__device__ __forceinline__ void flush_event_counters(const SsbView &V, unsigned n_rx, unsigned n_df) {
     for (int o = 16; o > 0; o >>= 1) {
         n_rx += __shfl_xor_sync(0xffffffffu, n_rx, o);
         n_df += __shfl_xor_sync(0xffffffffu, n_df, o);
@@ -929,6 +935,35 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
         if (n_rx) atomicAdd(&V.counters[0], (unsigned long long) n_rx);
         if (n_df) atomicAdd(&V.counters[1], (unsigned long long) n_df);
     }
+}
+
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, double tau, uint64_t seed,
+                                                          uint64_t epoch, int buf) {
+    unsigned n_rx = 0, n_df = 0;
+    rdme_window_body(V, t_lo, t_hi, tau, seed, epoch, buf, n_rx, n_df);
+    flush_event_counters(V, n_rx, n_df);
+}
+
+// All sSSA windows of one engine step in ONE cooperative launch: windows w = 0..nwin-1 of [t0, t0+dt], then the
+// zero-length closing window that delivers in-flight molecules; a grid-wide barrier separates consecutive windows
+// (a window's inbox writes must be complete before the next window reads them).  Removes the per-window launch
+// latency that dominates small systems (config 1: ~1900 windows per step) and idle windows of large ones.
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, double t0, double dt, long long nwin, double tau,
+                                                                uint64_t seed, uint64_t epoch0, int buf0) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    unsigned n_rx = 0, n_df = 0;
+    int buf = buf0;
+    for (long long w = 0; w <= nwin; w++) {
+        double lo, hi;
+        if (w < nwin) {
+            lo = t0 + dt * ((double) w / (double) nwin);
+            hi = (w + 1 == nwin) ? t0 + dt : t0 + dt * ((double) (w + 1) / (double) nwin);
+        } else { lo = hi = t0 + dt; }
+        rdme_window_body(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
+        buf ^= 1;
+        if (w < nwin) grid.sync();
+    }
+    flush_event_counters(V, n_rx, n_df);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -974,13 +1009,44 @@ static int l_rdme_init(const SsbView *V, double t0, double t_eval, double tau, u
     k_rdme_init<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, t0, t_eval, tau, seed, epoch);
     return (int) cudaGetLastError();
 }
-static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
-    // persistent grid: a multiple of the 148 SMs, grown only when a CTA would own more than SSB_BLOCK chunks
+// all windows of a step; returns the number of kernel launches used through *launches
+static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin, double tau, uint64_t seed, uint64_t epoch0,
+                          int buf0, int *launches, cudaStream_t st) {
+    static int coop_blocks = -1;       // co-resident CTAs of the cooperative kernel on this device (0 = unsupported)
+    if (coop_blocks < 0) {
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop, SSB_BLOCK, 0);
+        coop_blocks = coop ? sms * per_sm : 0;
+    }
     const unsigned nchunks = grid_for(V->N);
+    if (coop_blocks > 0) {
+        unsigned grid = (unsigned) coop_blocks;
+        if (grid > nchunks) grid = nchunks;
+        SsbView view = *V;
+        void *args[] = {&view, &t0, &dt, &nwin, &tau, &seed, &epoch0, &buf0};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_rdme_windows_coop, dim3(grid), dim3(SSB_BLOCK), args, 0, st);
+        if (launches) *launches = 1;
+        return (int) e;
+    }
+    int buf = buf0;
     unsigned grid = 148u * 8u;
     if (grid > nchunks) grid = nchunks;
-    const unsigned need = (nchunks + SSB_BLOCK - 1) / SSB_BLOCK;
-    if (grid < need) grid = need;
+    for (long long w = 0; w <= nwin; w++) {
+        double lo = (w < nwin) ? t0 + dt * ((double) w / (double) nwin) : t0 + dt;
+        double hi = (w < nwin) ? ((w + 1 == nwin) ? t0 + dt : t0 + dt * ((double) (w + 1) / (double) nwin)) : t0 + dt;
+        k_rdme_window<<<grid, SSB_BLOCK, 0, st>>>(*V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf);
+        buf ^= 1;
+    }
+    if (launches) *launches = (int) (nwin + 1);
+    return (int) cudaGetLastError();
+}
+static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
+    const unsigned nchunks = grid_for(V->N);
+    unsigned grid = 148u * 8u;         // persistent grid: a multiple of the 148 SMs
+    if (grid > nchunks) grid = nchunks;
     k_rdme_window<<<grid, SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
     return (int) cudaGetLastError();
 }
@@ -1003,5 +1069,6 @@ extern "C" const SsbModelUnit *ssbm_get_unit() {
     u.static_step = ssb_unit::l_static_step;
     u.rdme_init = ssb_unit::l_rdme_init;
     u.rdme_window = ssb_unit::l_rdme_window;
+    u.rdme_windows = ssb_unit::l_rdme_windows;
     return &u;
 }

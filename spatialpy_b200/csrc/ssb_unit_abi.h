@@ -8,7 +8,7 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 7
+#define SSB_UNIT_ABI 8
 
 struct SsbModelUnit {
     int abi;
@@ -24,6 +24,8 @@ struct SsbModelUnit {
     int (*static_coef)(const SsbView *, cudaStream_t);
     int (*static_step)(const SsbView *, unsigned step, int in_buf, cudaStream_t);
     int (*rdme_window)(const SsbView *, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t);
+    int (*rdme_windows)(const SsbView *, double t0, double dt, long long nwin, double tau, uint64_t seed, uint64_t epoch0, int buf0,
+                        int *launches, cudaStream_t);
 };
 
 extern "C" const SsbModelUnit *ssbm_get_unit();
