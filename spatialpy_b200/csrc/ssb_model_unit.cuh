@@ -721,15 +721,58 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
 //   direction     r2*Ddiag[spec] against the running sum of D_i_j*D[spec,type(dest)]  (:353-367)
 // SSB_FLAG_CORRECTED_NSM_SELECT switches the two picks to the textbook rule (rand*totrate, subtract srrate).
 // ---------------------------------------------------------------------------------------------
+// warp-cooperative direction pick (simulate_rdme.cpp:353-380) for the voxel `il` of one lane: the 32 lanes evaluate 32
+// neighbours' weights D_i_j * D[spec, type(dest)] at once, a shuffle prefix sum forms the running sums, and the first
+// neighbour whose running sum exceeds `target` is the destination.  Returns -1 when no neighbour accepts the species.
+__device__ __forceinline__ int coop_pick_direction(const SsbView &V, int il, int spec, double target) {
+    const int N = V.N, lane = threadIdx.x & 31;
+    const int cnt = V.nbr_count[il];
+    const bool cached = V.Dij != nullptr;
+    double xl0 = 0, xl1 = 0, xl2 = 0, m_l = 0, rho_l = 0;
+    if (!cached) { xl0 = V.x[0][il]; xl1 = V.x[1][il]; xl2 = V.x[2][il]; m_l = V.mass[il]; rho_l = V.rho_search[il]; }
+    double base = 0.0;
+    int dest = -1, last_ok = -1;
+    for (int k0 = 0; k0 < cnt; k0 += 32) {
+        const int k = k0 + lane;
+        int j = -1;
+        double w = 0.0;
+        bool ok = false;
+        if (k < cnt) {
+            j = V.nbr[(size_t) k * N + il];
+            const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
+            if (dc != 0.0) {
+                ok = true;
+                const double Dij = cached ? V.Dij[(size_t) k * N + il] : pair_Dij(V, il, j, xl0, xl1, xl2, m_l, rho_l);
+                w = Dij * dc;
+            }
+        }
+        double incl = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        incl += base;
+        const unsigned hit = __ballot_sync(0xffffffffu, ok && incl > target);
+        const unsigned oks = __ballot_sync(0xffffffffu, ok);
+        if (hit) { dest = __shfl_sync(0xffffffffu, j, __ffs(hit) - 1); break; }
+        if (oks) last_ok = __shfl_sync(0xffffffffu, j, 31 - __clz(oks));
+        base = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return dest >= 0 ? dest : last_ok;                                          // round-off overflow (:368-380)
+}
+
 __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, double t_hi, double tau, uint64_t seed,
                                                  uint64_t epoch, int buf, unsigned &n_rx, unsigned &n_df) {
     // Persistent grid: each CTA owns the chunks c = blockIdx.x + t*gridDim.x (a chunk = SSB_BLOCK consecutive voxels).
     // Parallel triage first — thread t inspects chunk t's summary (earliest tnext, mail flag) — so a window in which
     // nothing is due costs two loads per chunk instead of a block dispatch per chunk; then only the active chunks run.
     // The order of the active list depends on atomics, the result does not (chunks are independent in a window).
+    // Inside a chunk the event loop is warp-synchronous: every lane runs the SSA of its own voxel, and the one long
+    // operation of an event — the scan of the neighbour row for the jump direction — is done by the whole warp for one
+    // lane at a time (coop_pick_direction), so an event costs a few memory round trips instead of one per neighbour.
     __shared__ int sh_act[SSB_BLOCK];
     __shared__ int sh_nact;
-    const int nchunks = (V.N + SSB_BLOCK - 1) / SSB_BLOCK;
+    const int N = V.N;
+    const int nchunks = (N + SSB_BLOCK - 1) / SSB_BLOCK;
+    const int lane = threadIdx.x & 31;
     for (int round0 = 0; blockIdx.x + (long long) round0 * gridDim.x < nchunks; round0 += SSB_BLOCK) {
     __syncthreads();
     if (threadIdx.x == 0) sh_nact = 0;
@@ -745,36 +788,38 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
     __syncthreads();
     const int nact = sh_nact;
     for (int a = 0; a < nact; a++) {
-    const int chunk = sh_act[a];
-    const int i = chunk * SSB_BLOCK + threadIdx.x;
-    double tn_final = INFINITY;
-    if (i < V.N) {
-        const int N = V.N;
+        const int chunk = sh_act[a];
+        const int i = chunk * SSB_BLOCK + threadIdx.x;
+        const bool valid = i < N;
+        const int ii = valid ? i : N - 1;                          // clamp so idle lanes can run the same code path
         const unsigned *in_prev = V.inbox[buf ^ 1];
         unsigned *out_box = V.inbox[buf];
-        double tnext = V.tnext[i];
+        double tnext = valid ? V.tnext[ii] : INFINITY;
         bool arrived = false;
         unsigned inc[SSB_SD > 0 ? SSB_SD : 1];
 #pragma unroll
-        for (int s = 0; s < SSB_SD; s++) { inc[s] = __ldcg(&in_prev[(size_t) s * N + i]); arrived |= (inc[s] != 0u); }   // written by other CTAs
-        if (arrived || tnext <= t_hi) {
-            int xx[SSB_SD > 0 ? SSB_SD : 1];     // present: may react and jump
-            int xr[SSB_SD > 0 ? SSB_SD : 1];     // present + departing: may react
-            double Dd[SSB_SD > 0 ? SSB_SD : 1];  // lag-compensated jump propensity per molecule
+        for (int s = 0; s < SSB_SD; s++) { inc[s] = valid ? __ldcg(&in_prev[(size_t) s * N + ii]) : 0u; arrived |= (inc[s] != 0u); }
+        const bool touched = valid && (arrived || tnext <= t_hi);
+        int xx[SSB_SD > 0 ? SSB_SD : 1];     // present: may react and jump
+        int xr[SSB_SD > 0 ? SSB_SD : 1];     // present + departing: may react
+        double Dd[SSB_SD > 0 ? SSB_SD : 1];  // lag-compensated jump propensity per molecule
+        double df[SSB_NDF > 0 ? SSB_NDF : 1];
+        VoxelRates R;
+        R.sr = 0.0; R.sd = 0.0;
+        int type_i = 1;
+        double vol = 1.0;
+        uint32_t vid = 0, draw = 0;
+        if (touched) {
 #pragma unroll
             for (int s = 0; s < SSB_SD; s++) {
                 xx[s] = (int) V.xx[(size_t) s * N + i];
                 Dd[s] = lag_comp(V.Ddiag[(size_t) s * N + i], tau);
             }
-            double df[SSB_NDF > 0 ? SSB_NDF : 1];
 #pragma unroll
             for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
-            const int type_i = V.type[i];
-            const double m_i = V.mass[i];
-            const double vol = m_i / V.rho[i];
-            const uint32_t vid = (uint32_t) V.id[i];
-            uint32_t draw = 0;
-            VoxelRates R;
+            type_i = V.type[i];
+            vol = V.mass[i] / V.rho[i];
+            vid = (uint32_t) V.id[i];
             if (arrived) {
                 // stored propensities; only the reactions that depend on an arrived species are re-evaluated
                 // (dependency graph columns [0,S), simulate_rdme.cpp:419-435)
@@ -814,23 +859,53 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
             }
 #pragma unroll
             for (int s = 0; s < SSB_SD; s++) xr[s] = xx[s];
-            const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
-            int guard = 0;
-            while (tnext <= t_hi) {
-                const double tt = tnext;
+        }
+        int guard = 0;
+        bool failed = false;
+        // ---- warp-synchronous event loop ------------------------------------------------------------------------
+        for (;;) {
+            const bool ev = touched && !failed && tnext <= t_hi;
+            if (!__any_sync(0xffffffffu, ev)) break;
+            double tt = tnext, rand2 = 0.0, pick = 0.0;
+            bool is_rxn = false;
+            int spec = 0;
+            if (ev) {
                 const double tot = R.sr + R.sd;
-                double rand1, rand2;
+                double rand1;
                 philox_uniform2(vid, draw++, epoch, seed, rand1, rand2);
-                bool is_rxn;
-                double pick;
                 if (V.flags & 1u /*SSB_FLAG_CORRECTED_NSM_SELECT*/) {
                     pick = rand1 * tot;
                     is_rxn = pick <= R.sr;
                     if (!is_rxn) pick -= R.sr;
                 } else {
-                    is_rxn = rand1 <= R.sr / tot;
-                    pick = is_rxn ? rand1 * R.sr : rand1 * R.sd;
+                    is_rxn = rand1 <= R.sr / tot;                               // simulate_rdme.cpp:253-255
+                    pick = is_rxn ? rand1 * R.sr : rand1 * R.sd;                // :260, :317
                 }
+                if (!is_rxn) {
+                    double cum = Dd[0] * xx[0];
+#pragma unroll
+                    for (int q = 1; q < SSB_SD; q++) {
+                        if (pick > cum) { spec = q; cum += Dd[q] * xx[q]; } else break;
+                    }
+                    while (spec > 0 && xx[spec] <= 0) spec--;                   // simulate_rdme.cpp:338-347
+                    if (xx[spec] <= 0) { atomicCAS(V.err_flag, 0, 2); failed = true; }
+                }
+            }
+            // the warp serves, one lane at a time, every lane that needs a jump direction
+            const bool need_dir = ev && !is_rxn && !failed;
+            int dest = -1;
+            unsigned todo = __ballot_sync(0xffffffffu, need_dir);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int il = __shfl_sync(0xffffffffu, ii, leader);
+                const int sl = __shfl_sync(0xffffffffu, spec, leader);
+                const double dd_l = V.Ddiag[(size_t) sl * N + il];
+                const double target = __shfl_sync(0xffffffffu, rand2, leader) * dd_l;     // simulate_rdme.cpp:353-354
+                const int d = coop_pick_direction(V, il, sl, target);
+                if (lane == leader) dest = d;
+            }
+            if (ev && !failed) {
                 if (is_rxn) {
                     int re = 0;
                     double cum = R.rr[0];
@@ -855,48 +930,31 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
                     }
                     // else: every present reactant already departed in this window — the event is dropped
                     // (second order in tau; keeps posted jumps final and the result deterministic)
+                } else if (dest < 0) {
+                    atomicCAS(V.err_flag, 0, 2);
+                    failed = true;
                 } else {
-                    int spec = 0;
-                    double cum = Dd[0] * xx[0];
-#pragma unroll
-                    for (int q = 1; q < SSB_SD; q++) {
-                        if (pick > cum) { spec = q; cum += Dd[q] * xx[q]; } else break;
-                    }
-                    while (spec > 0 && xx[spec] <= 0) spec--;                   // simulate_rdme.cpp:338-347
-                    if (xx[spec] <= 0) { atomicCAS(V.err_flag, 0, 2); break; }
-                    // direction (simulate_rdme.cpp:353-367)
-                    const double dd = V.Ddiag[(size_t) spec * N + i];
-                    const double target = rand2 * dd;
-                    const int cnt = V.nbr_count[i];
-                    const double rho_si = V.rho_search[i];
-                    double cum2 = 0.0;
-                    int dest = -1, last_ok = -1;
-                    for (int k = 0; k < cnt; k++) {
-                        const int j = V.nbr[(size_t) k * N + i];
-                        const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
-                        if (dc == 0.0) continue;
-                        const double Dij = V.Dij ? V.Dij[(size_t) k * N + i] : pair_Dij(V, i, j, xi0, xi1, xi2, m_i, rho_si);
-                        cum2 += Dij * dc;
-                        last_ok = j;
-                        if (cum2 > target) { dest = j; break; }
-                    }
-                    if (dest < 0) dest = last_ok;                               // round-off overflow (:368-380)
-                    if (dest < 0) { atomicCAS(V.err_flag, 0, 2); break; }
                     if (dest != i) {                                            // (dest == i: stale self-neighbour on moving domains)
-                        xx[spec]--;                                             // no longer mobile here, still reactive (xr) until the window closes
+                        // no longer mobile here, still reactive (xr) until the window closes
+#pragma unroll
+                        for (int s = 0; s < SSB_SD; s++) if (s == spec) xx[s]--;
                         atomicAdd(&out_box[(size_t) spec * N + dest], 1u);
                         atomicMax(&V.inbox_src[buf][dest], i + 1);
                         V.blk_mail[buf][dest / SSB_BLOCK] = 1;
                     }
                     n_df++;
                 }
-                eval_rates(V, i, xr, xx, tt, vol, df, type_i, tau, R);
-                const double tot2 = R.sr + R.sd;
-                double u0, u1;
-                philox_uniform2(vid, draw++, epoch, seed, u0, u1);
-                tnext = (tot2 > 0.0) ? tt + (-log(u0)) / tot2 : INFINITY;       // NRMConstant_v5.cpp:92-99
-                if (++guard > 100000000) { atomicCAS(V.err_flag, 0, 2); break; }
+                if (!failed) {
+                    eval_rates(V, i, xr, xx, tt, vol, df, type_i, tau, R);
+                    const double tot2 = R.sr + R.sd;
+                    double u0, u1;
+                    philox_uniform2(vid, draw++, epoch, seed, u0, u1);
+                    tnext = (tot2 > 0.0) ? tt + (-log(u0)) / tot2 : INFINITY;   // NRMConstant_v5.cpp:92-99
+                    if (++guard > 100000000) { atomicCAS(V.err_flag, 0, 2); failed = true; }
+                }
             }
+        }
+        if (touched) {
             // window closes: departed molecules leave the reactive population; rates for the next window
             bool departed = false;
 #pragma unroll
@@ -916,11 +974,9 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
             V.sdrate[i] = R.sd;
             V.tnext[i] = tnext;
         }
-        tn_final = tnext;
-    }
-    tn_final = block_min(tn_final);
-    if (threadIdx.x == 0) V.blk_tmin[chunk] = tn_final;
-    __syncthreads();                 // block_min's shared scratch is reused by the next chunk
+        const double tn_final = block_min(valid ? tnext : INFINITY);
+        if (threadIdx.x == 0) V.blk_tmin[chunk] = tn_final;
+        __syncthreads();                 // block_min's shared scratch is reused by the next chunk
     }
     }
 }
