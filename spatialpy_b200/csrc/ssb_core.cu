@@ -1099,7 +1099,6 @@ static int engine_step(ssb_handle *h) {
         // step 0 of the fast path: cache the pair coefficients, then run the fused kernel from a copy of C
         if (V.Sc > 0) {
             if (!reuse && u->static_coef(&V, st)) return fail(h, SSB_ERR_CUDA, "static_coef launch failed");
-            CK(cudaMemcpyAsync(V.Cpre[1], V.C, sizeof(double) * (size_t) V.Sc * V.N, cudaMemcpyDeviceToDevice, st));
             ps = prof_begin(h, CAT_FORCE, 1);
             if (u->static_step(&V, step, 1, st)) return fail(h, SSB_ERR_CUDA, "static_step launch failed");
             prof_end(h, ps);

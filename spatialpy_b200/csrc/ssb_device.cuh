@@ -114,6 +114,14 @@ __host__ __device__ __forceinline__ void philox_uniform2(uint32_t vox, uint32_t 
     u1 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+// 256-bit read-only global load (sm_100a LDG.E.256): one instruction per 32-byte sector of a gather record.
+struct ssb_d4 { double a, b, c, d; };
+__device__ __forceinline__ ssb_d4 ssb_ld256(const double *p) {
+    ssb_d4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pair arithmetic — restates E/src/particle.cpp:150-210 (add_to_neighbor_list) in registers.
 // ------------------------------------------------------------------------------------------------

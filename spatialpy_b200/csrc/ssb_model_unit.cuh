@@ -261,18 +261,17 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force_mv(SsbView V, unsigned step
         const double c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
         const double eps_r = 0.001 * h, eps2 = 0.01 * h * h;
         const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
-        const double2 *ri = reinterpret_cast<const double2 *>(V.rec + (size_t) i * 16);
-        const double2 a1 = ri[1], a2 = ri[2], a3 = ri[3], a4 = ri[4], a5 = ri[5], a6 = ri[6], a7 = ri[7];
-        const double xi0 = a1.y, xi1 = a2.x, xi2 = a2.y;
-        const double vi0 = a3.x, vi1 = a3.y, vi2 = a4.x;
-        const double wi0 = a4.y - vi0, wi1 = a5.x - vi1, wi2 = a5.y - vi2;
-        const double rho_i = a6.x, m_i = a6.y, nu_i = a7.x;
-        const double2 b0 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) i * 4)[0];
-        const double2 b1 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) i * 4)[1];
-        const double inv_rho_i = b0.x, aP_i = b0.y, vol_i = b1.x;
+        const double *ri = V.rec + (size_t) i * 16;
+        const ssb_d4 a0 = ssb_ld256(ri), a1 = ssb_ld256(ri + 4), a2 = ssb_ld256(ri + 8), a3 = ssb_ld256(ri + 12);
+        const ssb_d4 b0 = ssb_ld256(V.rec2 + (size_t) i * 4);
+        const double xi0 = a0.d, xi1 = a1.a, xi2 = a1.b;
+        const double vi0 = a1.c, vi1 = a1.d, vi2 = a2.a;
+        const double wi0 = a2.b - vi0, wi1 = a2.c - vi1, wi2 = a2.d - vi2;
+        const double rho_i = a3.a, m_i = a3.b, nu_i = a3.c;
+        const double inv_rho_i = b0.a, aP_i = b0.b, vol_i = b0.c;
         const double volsq_i = vol_i * vol_i, inv_m_i = 1.0 / m_i;
         const double rv0 = rho_i * vi0, rv1 = rho_i * vi1, rv2 = rho_i * vi2;
-        const int type_i = (int) ((__double_as_longlong(a7.y) >> 32) & 0xffff);
+        const int type_i = (int) ((__double_as_longlong(a3.d) >> 32) & 0xffff);
         double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1], Dd[SSB_SD > 0 ? SSB_SD : 1];
 #pragma unroll
         for (int s = 0; s < SSB_SC; s++) {
@@ -289,19 +288,18 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force_mv(SsbView V, unsigned step
         const int cnt = V.nbr_count[i];
         for (int k = 0; k < cnt; k++) {
             const int j = V.nbr[(size_t) k * N + i];
-            const double2 *rj = reinterpret_cast<const double2 *>(V.rec + (size_t) j * 16);
-            const double2 c0 = rj[0], c1 = rj[1], c2 = rj[2], c3 = rj[3], c4 = rj[4], c5 = rj[5], c6 = rj[6], c7 = rj[7];
-            const double2 e0 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) j * 4)[0];
-            const double2 e1 = reinterpret_cast<const double2 *>(V.rec2 + (size_t) j * 4)[1];
-            const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.x, c0.y, c1.x);      // live x_i vs snapshot x0_j (particle.cpp:160)
+            const double *rj = V.rec + (size_t) j * 16;
+            const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
+            const ssb_d4 e0 = ssb_ld256(V.rec2 + (size_t) j * 4);
+            const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
             const double r = sqrt(d2);
-            double dx0 = xi0 - c1.y, dx1 = 0.0, dx2 = 0.0;
-            if (dim > 1) dx1 = xi1 - c2.x;
-            if (dim > 2) dx2 = xi2 - c2.y;
-            const double vj0 = c3.x, vj1 = c3.y, vj2 = c4.x;
-            const double wj0 = c4.y - vj0, wj1 = c5.x - vj1, wj2 = c5.y - vj2;
-            const double rho_j = c6.x, m_j = c6.y, nu_j = c7.x;
-            const double inv_rho_j = e0.x, aP_j = e0.y, vol_j = e1.x;
+            double dx0 = xi0 - c0.d, dx1 = 0.0, dx2 = 0.0;
+            if (dim > 1) dx1 = xi1 - c1.a;
+            if (dim > 2) dx2 = xi2 - c1.b;
+            const double vj0 = c1.c, vj1 = c1.d, vj2 = c2.a;
+            const double wj0 = c2.b - vj0, wj1 = c2.c - vj1, wj2 = c2.d - vj2;
+            const double rho_j = c3.a, m_j = c3.b, nu_j = c3.c;
+            const double inv_rho_j = e0.a, aP_j = e0.b, vol_j = e0.c;
             // one division for three reciprocals
             const double reg = r + eps_r, nusum = nu_i + nu_j, r2 = r * r;
             const double md = (m_i + m_j) * (r2 + eps2);
@@ -343,7 +341,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force_mv(SsbView V, unsigned step
                 if (SSB_SD > 0) {
                     const double hr = h - r;
                     const double Dij = G * (ih7c * hr * hr);                     // particle.cpp:182-187 (sign folded)
-                    const int tj = (int) ((__double_as_longlong(c7.y) >> 32) & 0xffff) - 1;
+                    const int tj = (int) ((__double_as_longlong(c3.d) >> 32) & 0xffff) - 1;
 #pragma unroll
                     for (int s = 0; s < SSB_SD; s++) Dd[s] += V.dmat[s * V.num_types + tj] * Dij;
                 }
@@ -414,6 +412,24 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_static_coef(SsbView V) {
     }
 }
 
+// Cpre is voxel-major ([j*S_c + s]) so that a neighbour's concentrations arrive with ONE gather (one 16-byte load for S_c = 2)
+__global__ void __launch_bounds__(SSB_BLOCK) k_static_seed(SsbView V, int buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V.N) return;
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) V.Cpre[buf][(size_t) i * SSB_SC + s] = V.C[(size_t) s * V.N + i];
+}
+
+__device__ __forceinline__ void load_cvec(const double *base, size_t j, double *out) {
+    if (SSB_SC == 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(base + j * 2);
+        out[0] = v.x; out[SSB_SC > 1 ? 1 : 0] = v.y;
+    } else {
+#pragma unroll
+        for (int s = 0; s < SSB_SC; s++) out[s] = base[j * SSB_SC + s];
+    }
+}
+
 __global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned step, int in_buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V.N) return;
@@ -423,9 +439,9 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned s
     double *Cnext = V.Cpre[in_buf ^ 1];
     const int type_i = V.type[i];
     double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1];
+    load_cvec(Cin, (size_t) i, Ci);
 #pragma unroll
     for (int s = 0; s < SSB_SC; s++) {
-        Ci[s] = Cin[(size_t) s * N + i];
         Qi[s] = 0.0;
         int k = SSB_SC * (type_i - 1) + s;                                  // model.cpp:163 (mirrored index)
         Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
@@ -434,8 +450,10 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned s
     for (int k = 0; k < cnt; k++) {
         const int j = V.nbr[(size_t) k * N + i];
         const double cf = V.coef[(size_t) k * N + i];
+        double Cj[SSB_SC > 0 ? SSB_SC : 1];
+        load_cvec(Cin, (size_t) j, Cj);
 #pragma unroll
-        for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cin[(size_t) s * N + j]) * cf;
+        for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cj[s]) * cf;
     }
     if (SSB_RC > 0) {                                                       // model.cpp:181-189
         const double vol = V.mass[i] / V.rho[i];
@@ -477,7 +495,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned s
     ssb_gen::applyBoundaryConditions(&p, &sys);
 #endif
 #pragma unroll
-    for (int s = 0; s < SSB_SC; s++) Cnext[(size_t) s * N + i] = p.C[s];
+    for (int s = 0; s < SSB_SC; s++) Cnext[(size_t) i * SSB_SC + s] = p.C[s];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,28 +556,45 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_finish(SsbView V, unsigned step) 
     if (MOVING && p.solidTag == 0) {
         const double alpha = ssb_alpha(dim, h);
         const int my_id = p.id;
-        double nw[3] = {0.0, 0.0, 0.0}, dx[3] = {0.0, 0.0, 0.0};
+        const double inv_h = 1.0 / h;
+        double nw[3] = {0.0, 0.0, 0.0};
         double vos = 0.0, vtot = 0.0;
         const int cnt = V.nbr_count[i];
+        const bool use_rec = (V.rec != nullptr) && !(V.flags & 16u /*SSB_FLAG_LITERAL_KERNELS*/);
         for (int k = 0; k < cnt; k++) {
             const int j = V.nbr[(size_t) k * N + i];
-            const double d2 = ssb_dist2(dim, p.x[0], p.x[1], p.x[2], V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+            double x0j0, x0j1, x0j2, xj0, xj1, xj2, m_j, rho_pre_j;
+            int id_j, solid_j;
+            if (use_rec) {      // one 128-byte gather record per neighbour (3 of its 4 sectors are needed here)
+                const double *rj = V.rec + (size_t) j * 16;
+                const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c3 = ssb_ld256(rj + 12);
+                x0j0 = c0.a; x0j1 = c0.b; x0j2 = c0.c; xj0 = c0.d; xj1 = c1.a; xj2 = c1.b;
+                rho_pre_j = c3.a; m_j = c3.b;
+                const long long bits = __double_as_longlong(c3.d);
+                id_j = (int) (bits & 0xffffffffll);
+                solid_j = (int) ((bits >> 48) & 0xffff);
+            } else {
+                x0j0 = V.x0[0][j]; x0j1 = V.x0[1][j]; x0j2 = V.x0[2][j];
+                xj0 = V.x[0][j]; xj1 = V.x[1][j]; xj2 = V.x[2][j];
+                rho_pre_j = V.rho[j]; m_j = V.mass[j]; id_j = V.id[j]; solid_j = V.solid[j];
+            }
+            const double d2 = ssb_dist2(dim, p.x[0], p.x[1], p.x[2], x0j0, x0j1, x0j2);
             const double r = sqrt(d2);
-            const double Wij = ssb_W(alpha, r, h);
-            const double dWdr = ssb_dWdr(alpha, r, h);
-            dx[0] = p.x[0] - V.x[0][j];
-            if (dim > 1) dx[1] = p.x[1] - V.x[1][j];
-            if (dim > 2) dx[2] = p.x[2] - V.x[2][j];
+            const double R = use_rec ? r * inv_h : r / h;
+            const double q1 = 1 - R;
+            const double Wij = alpha * ((1 + 3 * R) * (q1 * q1 * q1));         // model.cpp:275
             // serial (-t 1) visibility: particles earlier in the vector already ran their corrector
-            const double rho_j = (V.id[j] <= my_id) ? V.rho_new[j] : V.rho[j];
-            const double volj = V.mass[j] / rho_j;
+            const double rho_j = (id_j <= my_id) ? V.rho_new[j] : rho_pre_j;
+            const double volj = m_j / rho_j;
             const double w2 = volj * volj * Wij;
-            const int solid_j = V.solid[j];
             if (solid_j) vos += w2;
             vtot += w2;
             if (solid_j) {
-#pragma unroll
-                for (int d = 0; d < 3; d++) nw[d] += volj * volj * dx[d] * dWdr / (r + 0.001 * h);
+                const double dWdr = ssb_dWdr(alpha, r, h);
+                const double f = volj * volj * dWdr / (r + 0.001 * h);
+                nw[0] += f * (p.x[0] - xj0);
+                if (dim > 1) nw[1] += f * (p.x[1] - xj1);
+                if (dim > 2) nw[2] += f * (p.x[2] - xj2);
             }
         }
 #pragma unroll
@@ -1058,6 +1093,7 @@ static int l_static_coef(const SsbView *V, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 static int l_static_step(const SsbView *V, unsigned step, int in_buf, cudaStream_t st) {
+    if (step == 0) k_static_seed<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, in_buf);     // C (species-major) -> Cpre[in] (voxel-major)
     k_static_step<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, in_buf);
     return (int) cudaGetLastError();
 }
