@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
 //     (m, rho, r^2) factor with the chemistry flux.
 // Results differ from the literal evaluation order by a few ulp per pair (parity gate: 1e-12 of the field scale).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSB_BLOCK) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
+__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double mx = 0.0;
     if (i < V.N) {
@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force_mv(SsbView V, unsigned step
         double B0 = V.Fbp[0][i], B1 = V.Fbp[1][i], B2 = V.Fbp[2][i];
         double Frho = V.Frho[i];
         const int cnt = V.nbr_count[i];
+#pragma unroll 2
         for (int k = 0; k < cnt; k++) {
             const int j = V.nbr[(size_t) k * N + i];
             const double *rj = V.rec + (size_t) j * 16;
@@ -447,7 +448,23 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned s
         Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
     }
     const int cnt = V.nbr_count[i];
-    for (int k = 0; k < cnt; k++) {
+    int k = 0;
+    // four neighbours per trip: the index/coefficient streams and the four gathers are issued before any arithmetic, so
+    // every thread keeps 12 loads in flight (the sweep is latency bound otherwise); accumulation order is unchanged
+    for (; k + 4 <= cnt; k += 4) {
+        int jq[4];
+        double cq[4], Cj[4][SSB_SC > 0 ? SSB_SC : 1];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { jq[q] = V.nbr[(size_t) (k + q) * N + i]; cq[q] = V.coef[(size_t) (k + q) * N + i]; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) load_cvec(Cin, (size_t) jq[q], Cj[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cj[q][s]) * cq[q];
+        }
+    }
+    for (; k < cnt; k++) {
         const int j = V.nbr[(size_t) k * N + i];
         const double cf = V.coef[(size_t) k * N + i];
         double Cj[SSB_SC > 0 ? SSB_SC : 1];
