@@ -237,11 +237,24 @@ def run_ours(args, rank, local_rank, world):
         "cells": 96, "search": 24 + 24 + 4, "corrector": 70 + 32, "diff_init": 68 + 12 * Sd, "rdme_init": 4 * Sd + 8 * R + 24,
         "output": 0,
     }
+    # DRAM traffic of the dominant kernel, bytes per particle per launch, from the committed `ncu --set full` captures
+    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_prof_cyl_r1b_metrics.csv, profiles/r1_prof_tank_r1b_metrics.csv)
+    ncu_traffic = {("cylinder", "force"): 862.6e6 / 1001382, ("tank", "force"): 420.9e6 / 987228}
+    # bytes the kernel must stream given the stored index-only neighbour lists: 4 B index per pair
+    # (+ 8 B cached coefficient per pair on the static fast path) on top of the SURVEY figure
+    mean_nbr = nnz / N
+    stream_bytes = dict(kernel_bytes)
+    stream_bytes["force"] = kernel_bytes["force"] + (12.0 if not moving else 4.0) * mean_nbr
     dn = max(prof[dom]["launches"], 1)
     dom_ms = prof[dom]["ms"] / dn
     achieved = kernel_bytes[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms, "launches": prof[dom]["launches"],
+                "traffic": (ncu_traffic.get((args.workload, dom)) * N if ncu_traffic.get((args.workload, dom)) else None),
+                "traffic_note": "bytes per launch of the dominant kernel, ncu --set full (profiles/), scaled to this N",
+                "stream_achieved": (stream_bytes[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0),
+                "stream_frac": (stream_bytes[dom] * N / (dom_ms / 1e3) / 1e9 / peak if dom_ms > 0 else 0.0),
+                "stream_note": "algorithmic bytes + the stored neighbour-list stream (4 B/pair index, +8 B/pair cached coefficient when static)",
+                "peak_source": peak_src, "avg_launch_ms": dom_ms, "launches": prof[dom]["launches"],
                 "share_of_step": prof[dom]["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-30),
                 "algorithmic_bytes_per_particle": kernel_bytes[dom],
                 "whole_step_frac": (algorithmic_bytes(fm, moving) * value / world) / (peak * 1e9),

@@ -187,7 +187,7 @@ __global__ void k_permute(int N, const int *perm, const PermTable *T) {
 
 // neighbour search: query = live x_i, data = snapshot x0 (cell-sorted).  One thread per particle; the three
 // x-adjacent cells of a (cy,cz) row form one contiguous particle range.
-__global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_count) {
+__global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_count, unsigned long long *total_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (i < V.N) {
@@ -205,9 +205,10 @@ __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_
                 const int e = (row + x_hi + 1 < g.ncells) ? cell_start[row + x_hi + 1] : N;
                 for (int j = b; j < e; j++) {
                     const double d2 = ssb_dist2(dim, qx, qy, qz, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
-                    if (d2 <= h2 && d2 != 0.0) {        // kd_fix_rad_search.cpp:168-176 (ANN_ALLOW_SELF_MATCH = false)
-                        const double r = sqrt(d2);
-                        if (r > h) continue;            // particle.cpp:160-162
+                    // exact lists: kd_fix_rad_search.cpp:168-176 (ANN_ALLOW_SELF_MATCH = false) + particle.cpp:160-162;
+                    // candidate lists (Verlet skin): everything within h*(1+skin), self included (the stale self-neighbour)
+                    const bool take = V.filter ? (d2 <= V.search_h2) : ssb_in_range(d2, h, h2);
+                    if (take) {
                         if (cnt < cap) V.nbr[(size_t) cnt * N + i] = j;
                         cnt++;
                     }
@@ -216,8 +217,9 @@ __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_
         }
         V.nbr_count[i] = min(cnt, cap);
     }
-    for (int o = 16; o > 0; o >>= 1) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
-    if ((threadIdx.x & 31) == 0 && cnt > 0) atomicMax(max_count, cnt);
+    int tot = cnt;
+    for (int o = 16; o > 0; o >>= 1) { cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o)); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
+    if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicMax(max_count, cnt); atomicAdd(total_count, (unsigned long long) tot); }
 }
 
 __global__ void k_iota(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
@@ -233,9 +235,20 @@ __global__ void k_unperm32(int N, const int *id, const int *src, int *dst, int s
     if (i < N) dst[(size_t) id[i] * stride + offset] = src[i];
 }
 // neighbour list taps in id space
-__global__ void k_nbr_count_by_id(int N, const int *id, const int *cnt, long long *out) {
+__global__ void k_nbr_count_by_id(SsbView V, long long *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) out[id[i]] = cnt[i];
+    if (i >= V.N) return;
+    int c = V.nbr_count[i];
+    if (V.filter) {     // candidate list -> exact count
+        const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+        int e = 0;
+        for (int k = 0; k < c; k++) {
+            int j = V.nbr[(size_t) k * V.N + i];
+            e += ssb_in_range(ssb_dist2(V.dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h)) ? 1 : 0;
+        }
+        c = e;
+    }
+    out[V.id[i]] = c;
 }
 __global__ void k_nbr_export(SsbView V, const long long *ptr, int *idx, double *dist, double *dWdr, double *Dij) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -244,15 +257,18 @@ __global__ void k_nbr_export(SsbView V, const long long *ptr, int *idx, double *
     const double alpha = ssb_alpha(V.dim, V.h);
     long long base = ptr[V.id[i]];
     const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
+    int o = 0;
     for (int k = 0; k < V.nbr_count[i]; k++) {
         int j = V.nbr[(size_t) k * N + i];
         double d2 = ssb_dist2(V.dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+        if (V.filter && !ssb_in_range(d2, V.h, __dmul_rn(V.h, V.h))) continue;
         double r = sqrt(d2);
-        idx[base + k] = V.id[j];
-        dist[base + k] = r;
-        dWdr[base + k] = ssb_dWdr(alpha, r, V.h);
-        Dij[base + k] = V.Dij ? V.Dij[(size_t) k * N + i]
+        idx[base + o] = V.id[j];
+        dist[base + o] = r;
+        dWdr[base + o] = ssb_dWdr(alpha, r, V.h);
+        Dij[base + o] = V.Dij ? V.Dij[(size_t) k * N + i]
                               : ssb_Dij(d2, r, V.h, V.mass[i], V.mass[j], V.rho_search[i], V.rho_search[j]);
+        o++;
     }
 }
 
@@ -318,6 +334,12 @@ struct ssb_handle {
     long long nwin = 1;
     int nbr_valid = 0;
     int ddiag_fresh = 0;
+    double skin = 0.0;            // Verlet skin as a fraction of h (moving domains; 0 = exact lists rebuilt every step)
+    int lists_valid = 0;          // candidate lists + storage order from an earlier step are still usable
+    double disp_prev = 0.0;       // max displacement from xref after the previous step
+    double step_disp_max = 0.0;   // largest single-step displacement seen in this trajectory
+    int64_t rebuilds = 0;
+    int skin_chosen = 0;
     int static_cached = 0;        // static domain: storage order, neighbour lists, coefficients and Ddiag survive ssb_reset
     int *d_static_perm = nullptr; // slot -> particle id of the cached storage order
     double max_ddiag_cached = 0.0;
@@ -578,7 +600,7 @@ static void setup_grid(ssb_handle *h) {
     CellGrid &g = h->grid;
     g.dim = h->m.dimension;
     long long total = 1;
-    const double hh = h->m.h;
+    const double hh = h->m.h * (1.0 + h->skin);       // cell edge >= candidate radius
     for (int d = 0; d < 3; d++) {
         double L = hi[d] - lo[d];
         int n = 1;
@@ -714,6 +736,13 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
         CK(dalloc(h, &ialt, (size_t) Sd * N)); h->i32_alt.push_back(ialt);
     }
     CK(dalloc(h, &h->d_permtable, 1));
+    // Verlet skin: moving domains keep candidate lists across steps unless the literal kernels are requested
+    h->skin = (!V.static_domain && !(m->flags & SSB_FLAG_LITERAL_KERNELS)) ? 0.1 : 0.0;
+    if (const char *e = getenv("SSB_SKIN")) { if (!V.static_domain && !(m->flags & SSB_FLAG_LITERAL_KERNELS)) { h->skin = atof(e); h->skin_chosen = 1; } }
+    V.filter = h->skin > 0.0 ? 1 : 0;
+    V.search_h2 = (m->h * (1.0 + h->skin)) * (m->h * (1.0 + h->skin));
+    if (V.filter) { for (int d = 0; d < 3; d++) CK(dalloc(h, &V.xref[d], (size_t) N)); }
+    CK(dalloc(h, &V.disp_bits, 2));
     // cell list
     setup_grid(h);
     CK(dalloc(h, &h->d_key, (size_t) N)); CK(dalloc(h, &h->d_perm, (size_t) N));
@@ -858,6 +887,7 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     }
     CK(cudaMemsetAsync(V.err_flag, 0, 16, st));
     CK(cudaMemsetAsync(V.counters, 0, 32, st));
+    CK(cudaMemsetAsync(V.disp_bits, 0, 16, st));
     if (!h->static_cached) CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, st));
     if (V.static_domain) for (int d = 0; d < 3; d++) V.x0[d] = V.x[d];
     V.rho_search = V.rho;
@@ -873,6 +903,9 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     h->epoch = 0;
     h->inbox_buf = 0;
     h->nbr_valid = 0;
+    h->lists_valid = 0;
+    h->disp_prev = 0.0;
+    h->step_disp_max = 0.0;
     h->ddiag_fresh = 0;
     h->launches = 0;
     h->windows = 0;
@@ -945,16 +978,58 @@ static int apply_permutation(ssb_handle *h, const int *d_perm) {
     return SSB_OK;
 }
 
+// count-only pass (capacity 0 stores nothing): total number of list entries the current (filter, search_h2) would produce
+static int count_candidates(ssb_handle *h, double *total) {
+    SsbView V = h->V;
+    V.nbr_cap = 0;
+    cudaStream_t st = h->stream;
+    CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(h->d_maxbits + 1, 0, sizeof(unsigned long long), st));
+    k_search<<<gridN(h->N), CORE_BLOCK, 0, st>>>(V, h->grid, h->d_cell_start, h->d_flags + 1, h->d_maxbits + 1);
+    unsigned long long t = 0;
+    CK(cudaMemcpyAsync(&t, h->d_maxbits + 1, sizeof(t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *total = (double) t;
+    h->launches += 1;
+    return SSB_OK;
+}
+
+// Verlet skin selection (first list build of a handle): the widest skin whose candidate lists are at most 15 % longer than
+// the exact lists.  On lattice-like clouds the neighbour shells make this a step function of the skin, so it is measured.
+static int choose_skin(ssb_handle *h) {
+    SsbView &V = h->V;
+    const double skin_max = h->skin;
+    int rc;
+    double exact = 0.0;
+    V.filter = 0;
+    if ((rc = count_candidates(h, &exact))) return rc;
+    V.filter = 1;
+    double pick = 0.0;
+    for (double sk = skin_max; sk >= 0.004; sk *= 0.5) {
+        V.search_h2 = (V.h * (1.0 + sk)) * (V.h * (1.0 + sk));
+        double cand = 0.0;
+        if ((rc = count_candidates(h, &cand))) return rc;
+        if (cand <= 1.15 * exact + (double) h->N) { pick = sk; break; }     // (+N: the self entry every particle carries)
+    }
+    h->skin = pick;
+    V.filter = pick > 0.0 ? 1 : 0;
+    V.search_h2 = (V.h * (1.0 + pick)) * (V.h * (1.0 + pick));
+    h->skin_chosen = 1;
+    return SSB_OK;
+}
+
 static int neighbour_search(ssb_handle *h) {
     SsbView &V = h->V;
     const int N = h->N;
     cudaStream_t st = h->stream;
+    if (V.filter && !h->skin_chosen) { int rcs = choose_skin(h); if (rcs) return rcs; }
     for (int attempt = 0; attempt < 8; attempt++) {
         if (V.nbr_cap == 0) {
             // first build: size the ELL rows from an exact count pass (cap 0 stores nothing)
         }
         CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), st));
-        k_search<<<gridN(N), CORE_BLOCK, 0, st>>>(V, h->grid, h->d_cell_start, h->d_flags + 1);
+        CK(cudaMemsetAsync(h->d_maxbits + 1, 0, sizeof(unsigned long long), st));
+        k_search<<<gridN(N), CORE_BLOCK, 0, st>>>(V, h->grid, h->d_cell_start, h->d_flags + 1, h->d_maxbits + 1);
         h->launches += 1;
         int mx = 0;
         CK(cudaMemcpyAsync(&mx, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1078,9 +1153,17 @@ static int engine_step(ssb_handle *h) {
         return SSB_OK;
     }
     const bool reuse = !moving && h->static_cached;                          // geometry work of step 0 already done by an earlier trajectory
-    if ((step == 0 && !reuse) || moving) {                                   // buildKDTree (simulate_threads.cpp:80-108)
+    // moving domains with a Verlet skin: storage order + candidate lists survive until particles have moved skin*h/2
+    const bool keep_lists = moving && V.filter && h->lists_valid;
+    if (moving && V.filter) CK(cudaMemsetAsync(V.disp_bits, 0, sizeof(unsigned long long), st));   // [0] recomputed each step, [1] running max
+    if ((step == 0 && !reuse) || (moving && !keep_lists)) {                  // buildKDTree (simulate_threads.cpp:80-108)
         ps = prof_begin(h, CAT_CELLS, 7);
         rc = build_cells(h);
+        if (!rc && moving && V.filter) {
+            for (int d = 0; d < 3; d++) CK(cudaMemcpyAsync(V.xref[d], V.x[d], sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
+            h->disp_prev = 0.0;
+            h->rebuilds++;
+        }
         prof_end(h, ps);
         if (rc) return rc;
     }
@@ -1088,12 +1171,30 @@ static int engine_step(ssb_handle *h) {
     if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
     prof_end(h, ps);
     h->launches++;
-    if ((step == 0 && !reuse) || moving) {                                   // find_neighbors (simulate.cpp:61-63,121-123)
+    if (moving) V.rho_search = V.rho;
+    if ((step == 0 && !reuse) || (moving && !keep_lists)) {                  // find_neighbors (simulate.cpp:61-63,121-123)
         V.rho_search = V.rho;
         ps = prof_begin(h, CAT_SEARCH, 1);
         rc = neighbour_search(h);
         prof_end(h, ps);
         if (rc) return rc;
+    }
+    if (moving && V.filter) {
+        // displacement bookkeeping of the skin: D = max |x - xref| after this predictor, s = largest single-step move so far.
+        // A pair within h now has |xref_i - xref_j| <= h + D_now + D_prev, so the lists are complete iff D_now + D_prev <= skin*h.
+        unsigned long long bits[2] = {0, 0};
+        CK(cudaMemcpyAsync(bits, V.disp_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        double d2now, s2;
+        memcpy(&d2now, &bits[0], 8); memcpy(&s2, &bits[1], 8);
+        const double Dnow = sqrt(d2now), budget = h->skin * V.h;
+        h->step_disp_max = sqrt(s2);
+        if (Dnow + h->disp_prev > budget)
+            return fail(h, SSB_ERR_ARG, "Verlet skin exceeded within one step (displacement %g + %g > %g): particles move more than skin*h per step; "
+                        "set SSB_SKIN=0 or reduce the time step", Dnow, h->disp_prev, budget);
+        // keep the lists for the next step only if even two more worst-case steps stay inside the budget
+        h->lists_valid = (2.0 * (Dnow + 2.0 * h->step_disp_max) <= budget) ? 1 : 0;
+        h->disp_prev = Dnow;
     }
     if (fast_static) {
         // step 0 of the fast path: cache the pair coefficients, then run the fused kernel from a copy of C
@@ -1349,7 +1450,7 @@ extern "C" int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, doub
     std::vector<long long> cnt((size_t) N + 1, 0);
     long long *d_cnt = nullptr;
     CK(cudaMalloc((void **) &d_cnt, sizeof(long long) * (N + 1)));
-    k_nbr_count_by_id<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, V.nbr_count, d_cnt);
+    k_nbr_count_by_id<<<gridN(N), CORE_BLOCK, 0, st>>>(V, d_cnt);
     CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * N, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     std::vector<long long> p((size_t) N + 1, 0);

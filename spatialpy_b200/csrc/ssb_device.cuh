@@ -38,6 +38,14 @@ struct SsbView {
     int *nbr;           // [cap*N]
     int *nbr_count;     // [N]
     int nbr_cap;
+    // Verlet-skin candidate lists (moving domains): nbr[] holds every particle within h*(1+skin) of the positions at the last
+    // list build; each sweep re-applies the reference's exact inclusion test against THIS step's snapshot (filter = 1), so the
+    // neighbour SETS are still exactly ANN's.  xref = positions at the last build; disp_bits[0] = max |x - xref|^2 since the build,
+    // disp_bits[1] = max squared displacement of a single step (both as the bit patterns of non-negative doubles).
+    int filter;
+    double search_h2;
+    double *xref[3];
+    unsigned long long *disp_bits;
     double *Dij;        // [cap*N] cached D_i_j (static domains) or nullptr
     double *rho_search; // density at neighbour-search time (frozen into D_i_j, particle.cpp:187)
     // moving-domain gather records (written by k_predictor, read by the neighbour sweeps): one 128-byte line per particle
@@ -147,6 +155,11 @@ __device__ __forceinline__ double ssb_dist2(int dim, double ax, double ay, doubl
     if (dim > 1) { t = __dsub_rn(ay, by); d = __dadd_rn(d, __dmul_rn(t, t)); }
     if (dim > 2) { t = __dsub_rn(az, bz); d = __dadd_rn(d, __dmul_rn(t, t)); }
     return d;
+}
+
+// the reference's neighbour rule: ANN's 0 < d2 <= h*h (kd_fix_rad_search.cpp:168-176) and particle.cpp:160-162's sqrt(d2) <= h
+__device__ __forceinline__ bool ssb_in_range(double d2, double h, double h2) {
+    return (d2 <= h2) && (d2 != 0.0) && !(sqrt(d2) > h);
 }
 
 // dWdr of the Wendland-type kernel, frozen at search time (particle.cpp:178)

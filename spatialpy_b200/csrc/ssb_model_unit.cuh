@@ -49,7 +49,8 @@ __device__ __forceinline__ System make_system(const SsbView &V, unsigned step) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned step) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= V.N) return;
+    double step2 = 0.0, ref2 = 0.0;        // Verlet-skin bookkeeping: squared displacement this step / since the list build
+    if (i < V.N) {
     Particle p;
     bc_load(V, i, p);
     // NaN / Inf guard (particle.cpp:89-96) — the reference exit(1)s; we raise the device error flag.
@@ -68,8 +69,10 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
             p.v[d] = p.v[d] + 0.5 * dt * V.F[d][i];
             double vt = p.v[d] + 0.5 * dt * V.Fbp[d][i];
             V.vt[d][i] = vt;
+            const double xo = p.x[d];
             p.x[d] = p.x[d] + dt * vt;
             V.x[d][i] = p.x[d];
+            if (V.filter) { const double a = p.x[d] - xo, b = p.x[d] - V.xref[d][i]; step2 += a * a; ref2 += b * b; }
         }
         p.rho = p.rho + 0.5 * dt * V.Frho[i];
     }
@@ -110,6 +113,17 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
     for (int s = 0; s < SSB_SC; s++) {
         V.C[(size_t) s * V.N + i] = p.C[s];
         V.Q[(size_t) s * V.N + i] = 0.0;                // simulate.cpp:101-103
+    }
+    }
+    if (V.filter) {     // one atomic pair per warp
+        for (int o = 16; o > 0; o >>= 1) {
+            ref2 = fmax(ref2, __shfl_xor_sync(0xffffffffu, ref2, o));
+            step2 = fmax(step2, __shfl_xor_sync(0xffffffffu, step2, o));
+        }
+        if ((threadIdx.x & 31) == 0 && step2 > 0.0) {
+            atomicMax(&V.disp_bits[0], (unsigned long long) __double_as_longlong(ref2));
+            atomicMax(&V.disp_bits[1], (unsigned long long) __double_as_longlong(step2));
+        }
     }
 }
 
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
         const double inv_h = 1.0 / h;
         const double c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
         const double eps_r = 0.001 * h, eps2 = 0.01 * h * h;
+        const double h2x = __dmul_rn(h, h);
         const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
         const double *ri = V.rec + (size_t) i * 16;
         const ssb_d4 a0 = ssb_ld256(ri), a1 = ssb_ld256(ri + 4), a2 = ssb_ld256(ri + 8), a3 = ssb_ld256(ri + 12);
@@ -294,6 +309,9 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
             const ssb_d4 e0 = ssb_ld256(V.rec2 + (size_t) j * 4);
             const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
             const double r = sqrt(d2);
+            // candidate list -> ANN's exact set (the record loads above are issued before this test on purpose: a rejected
+            // candidate wastes 4 sectors, a dependent second round trip per accepted neighbour would cost far more)
+            if (V.filter && !((d2 <= h2x) && (d2 != 0.0) && !(r > h))) continue;
             double dx0 = xi0 - c0.d, dx1 = 0.0, dx2 = 0.0;
             if (dim > 1) dx1 = xi1 - c1.a;
             if (dim > 2) dx2 = xi2 - c1.b;
@@ -539,6 +557,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_corrector(SsbView V, unsigned ste
         for (int k = 0; k < cnt; k++) {
             const int j = V.nbr[(size_t) k * N + i];
             const double d2 = ssb_dist2(dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
+            if (V.filter && !ssb_in_range(d2, h, __dmul_rn(h, h))) continue;
             const double r = sqrt(d2);
             const double Wij = ssb_W(alpha, r, h);
             num += V.old_rho[j] * Wij;
@@ -596,6 +615,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_finish(SsbView V, unsigned step) 
                 rho_pre_j = V.rho[j]; m_j = V.mass[j]; id_j = V.id[j]; solid_j = V.solid[j];
             }
             const double d2 = ssb_dist2(dim, p.x[0], p.x[1], p.x[2], x0j0, x0j1, x0j2);
+            if (V.filter && !ssb_in_range(d2, h, __dmul_rn(h, h))) continue;
             const double r = sqrt(d2);
             const double R = use_rec ? r * inv_h : r / h;
             const double q1 = 1 - R;
@@ -667,6 +687,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_diff_init(SsbView V, unsigned lon
         const int cnt = V.nbr_count[i];
         for (int k = 0; k < cnt; k++) {
             const int j = V.nbr[(size_t) k * N + i];
+            if (V.filter && !ssb_in_range(ssb_dist2(V.dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h))) continue;
             const double Dij = pair_Dij(V, i, j, xi0, xi1, xi2, m_i, rho_i);
             if (V.Dij) V.Dij[(size_t) k * N + i] = Dij;
             const int tj = V.type[j] - 1;
@@ -792,7 +813,9 @@ __device__ __forceinline__ int coop_pick_direction(const SsbView &V, int il, int
         if (k < cnt) {
             j = V.nbr[(size_t) k * N + il];
             const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
-            if (dc != 0.0) {
+            bool in = true;
+            if (V.filter) in = ssb_in_range(ssb_dist2(V.dim, xl0, xl1, xl2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h));
+            if (dc != 0.0 && in) {
                 ok = true;
                 const double Dij = cached ? V.Dij[(size_t) k * N + il] : pair_Dij(V, il, j, xl0, xl1, xl2, m_l, rho_l);
                 w = Dij * dc;
