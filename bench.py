@@ -172,6 +172,8 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     fm, desc = make_workload(args.workload, args.scale)
     moving = not fm.static_domain
+    if args.sps is None:
+        args.sps = 50 if moving else 200
     N, SPS = fm.num_particles, args.sps
     eng = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK)
 
@@ -307,12 +309,12 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
-    ap.add_argument("--sps", type=int, default=20, help="engine timesteps per bench step")
+    ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
