@@ -306,6 +306,86 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# slab-decomposed arm: ONE domain split over the ranks (BASELINE configs[4]: weak scaling, fixed particles per GPU)
+# ---------------------------------------------------------------------------------------------------------
+def run_slab(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from spatialpy_b200 import configs
+    from spatialpy_b200.slab import SlabEngine
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = max(16, int(round(200 * args.scale ** (1.0 / 3.0))))
+    part = configs.box_slab(rank, world, nx_per_rank=n, ny=n, nz=n)
+    se = SlabEngine(part, rank, world, device=local_rank)
+    SPS = args.sps or 10
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def allred(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    se.reset(1000)
+    for _ in range(args.warmup):
+        se.step(SPS)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0, c0 = se.eng.launch_count(), se.eng.counters()
+    barrier()
+    t0 = time.perf_counter()
+    se.eng.mark(0)
+    for _ in range(args.steps):
+        se.step(SPS)
+    se.eng.mark(1)
+    dev_ms = se.eng.mark_elapsed_ms()           # CUDA events on the engine stream (includes the waits for the halo exchanges)
+    barrier()
+    wall_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    c1 = se.eng.counters()
+    dev_ms = allred(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
+    wall_s = allred(wall_s, dist.ReduceOp.MAX if world > 1 else None)
+    owned_total = allred(float(part.n_owned), dist.ReduceOp.SUM if world > 1 else None)
+    events = allred(float(c1["reactions"] + c1["diffusions"] - c0["reactions"] - c0["diffusions"]), dist.ReduceOp.SUM if world > 1 else None)
+    nsteps = SPS * args.steps
+    value = owned_total * nsteps / (dev_ms / 1e3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    fm = part.local
+    per_step_bytes = algorithmic_bytes(fm, True)
+    ghosts = fm.num_particles - part.n_owned
+    halo_bytes = sum(len(v) for v in part.send_ids.values()) * 8 * (7 + fm.num_chem_species + 1 + 4)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: synthetic 3-D SDPD+sSSA box, {n}^3 owned particles per GPU, slab-decomposed along x",
+                       "particles_per_gpu": part.n_owned, "ghosts_per_gpu": ghosts, "engine_steps_per_step": SPS,
+                       "parallelism": f"spatial slabs x {world}, NCCL send/recv halo exchange (3 field groups + sSSA inboxes per step)",
+                       "halo_bytes_sent_per_engine_step_per_rank": halo_bytes,
+                       "l2": "working set exceeds the 126 MB L2; no explicit flush"},
+            "rdme_events_per_s": events / (dev_ms / 1e3),
+            "roofline": {"bound": "hbm", "kernel": "whole step (SURVEY 8d byte model)", "achieved": per_step_bytes * value / world / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": per_step_bytes * value / world / 1e9 / peak, "traffic": None},
+            "cpu_baseline": None,
+            "e2e": {"value": owned_total * nsteps / wall_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "includes": "host wall clock of the same stepping loop incl. Python orchestration and NCCL halo exchanges (state resident)"},
+            "gpu_launches": int(se.eng.launch_count() - l0), "clocks": clk}))
+    se.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,10 +396,15 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
     ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--decomp", default="ensemble", choices=["ensemble", "slab"],
+                    help="N>1: independent trajectories per GPU (default) or ONE box domain split into slabs (BASELINE configs[4])")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.decomp == "slab":
+        run_slab(args, rank, local_rank, world)
         return
     run_ours(args, rank, local_rank, world)
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 1
+#define SSB_ABI_VERSION 2
 
 /* error codes */
 #define SSB_OK 0
@@ -80,6 +80,11 @@ typedef struct ssb_model {
     double rdme_epsilon;
     int32_t device;                 /* CUDA device ordinal */
     int32_t reserved;
+    /* spatial slab decomposition (NULL on a single GPU): owned[i] = 1 if this rank integrates particle i, 0 if it is a
+     * ghost copy of a particle owned by a neighbouring slab; rng_id[i] = global particle id used as the Philox counter
+     * and as the serial order of the reference's particle vector (BVF sweep), so results do not depend on the partition */
+    const int32_t *owned;
+    const int32_t *rng_id;
 } ssb_model;
 
 typedef struct ssb_handle ssb_handle;
@@ -139,6 +144,25 @@ int ssb_profile(ssb_handle *h, int enable);
 int ssb_profile_read(ssb_handle *h, int category, double *ms_total, int64_t *launches);
 int ssb_io_bytes(ssb_handle *h, int64_t *h2d, int64_t *d2h);
 int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total);
+
+/* Spatial slab decomposition (one process per GPU; spatialpy_b200/slab.py does the NCCL send/recv between the phases).
+ * ssb_step_phase runs one piece of an engine step (phases: 0 PRE = cell list + predictor + search + force sweep,
+ * 1 CORRECTOR, 2 FINISH, 3 RDME_PREP -> *out = local max Ddiag, 4 RDME_INIT (arg = global max) -> *out = windows per step,
+ * 5 RDME_WINDOW (arg = window index), 6 RDME_CLOSE, 7 END).  ssb_halo_pack / ssb_halo_unpack move the field group that a
+ * phase produced between storage and a caller-owned DEVICE buffer for the particle ids listed in dev_ids (group 0: F[3]
+ * Fbp[3] Frho Q[S_c]; 1: rho_new; 2: v[3] bvf_phi; 3: rho); ssb_halo_inbox_pack reads-and-clears the molecules that jumped
+ * into ghost voxels in the last sSSA window, ssb_halo_inbox_add delivers them to the owner.  ssb_mark/ssb_mark_elapsed_ms
+ * record CUDA events on the engine's stream. */
+int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out);
+int ssb_halo_pack(ssb_handle *h, int group, const int32_t *dev_ids, int32_t n, double *dev_out);
+int ssb_halo_unpack(ssb_handle *h, int group, const int32_t *dev_ids, int32_t n, const double *dev_in);
+int ssb_halo_inbox_pack(ssb_handle *h, const int32_t *dev_ids, int32_t n, uint32_t *dev_out);
+int ssb_halo_inbox_add(ssb_handle *h, const int32_t *dev_ids, int32_t n, const uint32_t *dev_in);
+int ssb_halo_width(ssb_handle *h, int group, int32_t *width);
+/* Verlet-skin bookkeeping of moving domains: chosen skin (fraction of h), largest single-step displacement seen, list rebuilds */
+int ssb_skin_stats(ssb_handle *h, double *skin, double *step_disp_max, int64_t *rebuilds);
+int ssb_mark(ssb_handle *h, int which);
+int ssb_mark_elapsed_ms(ssb_handle *h, double *ms);
 
 #ifdef __cplusplus
 }

@@ -151,3 +151,52 @@ def box_sdpd_rdme(nx=200, ny=200, nz=200, nt=100, output_every=100, dt=1e-5, see
         xlim=(float(x[:, 0].min()), float(x[:, 0].max())), ylim=(float(x[:, 1].min()), float(x[:, 1].max())),
         zlim=(float(x[:, 2].min()), float(x[:, 2].max())), dimension=3, gravity=(0.0, 0.0, -1.0))
     return fm.finalize()
+
+
+def box_slab(rank, world, nx_per_rank=200, ny=200, nz=200, ghost_cols=5, nt=100, dt=1e-5, seed=5):
+    """Rank-local piece of the BASELINE config-5 box (box_sdpd_rdme) for a slab-decomposed run: the rank's own x-columns plus
+    `ghost_cols` ghost columns on each interior face, generated without ever materialising the global model.  Jitter is drawn
+    per x-plane from a generator seeded by (seed, plane), so neighbouring ranks agree on the shared columns.
+    Returns a spatialpy_b200.slab.SlabPartition."""
+    from .slab import SlabPartition
+    delta = 0.01
+    nx = nx_per_rank * world
+    i0, i1 = rank * nx_per_rank, (rank + 1) * nx_per_rank
+    lo, hi = max(0, i0 - ghost_cols), min(nx, i1 + ghost_cols)
+    cols = np.arange(lo, hi)
+    J, K = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+    xs = []
+    for i in cols:
+        rng = np.random.default_rng([seed, int(i)])
+        plane = np.stack([np.full(J.size, i * delta), J.ravel() * delta, K.ravel() * delta], axis=1)
+        plane += rng.uniform(-0.05 * delta, 0.05 * delta, size=plane.shape)
+        xs.append(plane)
+    x = np.concatenate(xs)
+    col_of = np.repeat(cols, ny * nz)
+    kk = np.tile(K.ravel(), len(cols))
+    gid = (col_of.astype(np.int64) * ny * nz + np.tile((J * nz + K).ravel(), len(cols)))
+    owned = ((col_of >= i0) & (col_of < i1)).astype(np.int32)
+    order = np.argsort(1 - owned, kind="stable")          # owned first, each group already sorted by global id
+    x, col_of, kk, gid, owned = x[order], col_of[order], kk[order], gid[order], owned[order]
+    N = x.shape[0]
+    solid = ((kk < 3) | (kk >= nz - 3)).astype(np.int32)
+    base = box_sdpd_rdme(2, 2, 8, nt=nt, output_every=nt, dt=dt)       # reactions / parameters / tables of the workload
+    fm = FlatModel(
+        name=f"box_slab_r{rank}of{world}", x=x, type=np.where(solid == 1, 1, 2).astype(np.int32), nu=np.full(N, 0.1),
+        mass=np.full(N, delta ** 3), c=np.zeros(N), rho=np.full(N, 1.0), solid=solid, species_names=list(base.species_names),
+        reactions=list(base.reactions), parameters=dict(base.parameters), type_constants=dict(base.type_constants),
+        u0=np.full((N, 2), 10, np.uint32), N_dense=base.N_dense, irG=base.irG, jcG=base.jcG, diffusion_matrix=base.diffusion_matrix,
+        enable_pde=True, enable_rdme=True, static_domain=False, dt=dt, nt=nt, output_steps=_output_steps(nt, nt),
+        h=base.h, rho0=1.0, c0=10.0, P0=100.0, xlim=(0.0, nx * delta), ylim=(0.0, ny * delta), zlim=(0.0, nz * delta),
+        dimension=3, gravity=(0.0, 0.0, -1.0)).finalize()
+    send_ids, recv_ids = {}, {}
+    n_own = int(owned.sum())
+    loc = np.arange(N)
+    if rank > 0:
+        send_ids[rank - 1] = loc[(owned == 1) & (col_of < i0 + ghost_cols)].astype(np.int32)
+        recv_ids[rank - 1] = loc[(owned == 0) & (col_of < i0)].astype(np.int32)
+    if rank < world - 1:
+        send_ids[rank + 1] = loc[(owned == 1) & (col_of >= i1 - ghost_cols)].astype(np.int32)
+        recv_ids[rank + 1] = loc[(owned == 0) & (col_of >= i1)].astype(np.int32)
+    assert n_own == nx_per_rank * ny * nz
+    return SlabPartition(fm, gid, owned, send_ids, recv_ids, (i0 * delta, i1 * delta), ghost_cols * delta)

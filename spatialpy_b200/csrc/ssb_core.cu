@@ -272,6 +272,77 @@ __global__ void k_nbr_export(SsbView V, const long long *ptr, int *idx, double *
     }
 }
 
+// ---- slab decomposition: halo pack / unpack (ids are particle ids of THIS rank's model; slot_of_id maps to storage) ----
+__global__ void k_slot_of_id(int N, const int *id, int *slot_of_id) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) slot_of_id[id[p]] = p;
+}
+// group 0 (after the force sweep): F[3] Fbp[3] Frho Q[Sc]   group 1 (after the corrector): rho_new
+// group 2 (after the BVF sweep): v[3] bvf_phi                group 3 (initial consistency): rho
+__device__ __forceinline__ int halo_width(int group, int Sc) { return group == 0 ? 7 + Sc : (group == 2 ? 4 : 1); }
+__global__ void k_halo_pack(SsbView V, int group, const int *ids, int n, const int *slot_of_id, double *out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = slot_of_id[ids[t]];
+    const int W = halo_width(group, V.Sc);
+    double *o = out + (size_t) t * W;
+    if (group == 0) {
+        for (int d = 0; d < 3; d++) { o[d] = V.F[d][p]; o[3 + d] = V.Fbp[d][p]; }
+        o[6] = V.Frho[p];
+        for (int s = 0; s < V.Sc; s++) o[7 + s] = V.Q[(size_t) s * V.N + p];
+    } else if (group == 1) {
+        o[0] = V.rho_new[p];
+    } else if (group == 2) {
+        for (int d = 0; d < 3; d++) o[d] = V.v[d][p];
+        o[3] = V.bvf[p];
+    } else {
+        o[0] = V.rho[p];
+    }
+}
+__global__ void k_halo_unpack(SsbView V, int group, const int *ids, int n, const int *slot_of_id, const double *in) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = slot_of_id[ids[t]];
+    const int W = halo_width(group, V.Sc);
+    const double *o = in + (size_t) t * W;
+    if (group == 0) {
+        for (int d = 0; d < 3; d++) { V.F[d][p] = o[d]; V.Fbp[d][p] = o[3 + d]; }
+        V.Frho[p] = o[6];
+        for (int s = 0; s < V.Sc; s++) V.Q[(size_t) s * V.N + p] = o[7 + s];
+    } else if (group == 1) {
+        V.rho_new[p] = o[0];
+    } else if (group == 2) {
+        for (int d = 0; d < 3; d++) V.v[d][p] = o[d];
+        V.bvf[p] = o[3];
+    } else {
+        V.rho[p] = o[0];
+    }
+}
+// molecules that jumped into ghost voxels during the last sSSA window: read-and-clear on the sender ...
+__global__ void k_inbox_pack(SsbView V, int buf, const int *ids, int n, const int *slot_of_id, unsigned *out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = slot_of_id[ids[t]];
+    for (int s = 0; s < V.Sd; s++) {
+        unsigned *q = &V.inbox[buf][(size_t) s * V.N + p];
+        out[(size_t) t * V.Sd + s] = *q;
+        *q = 0u;
+    }
+    V.inbox_src[buf][p] = 0;
+}
+// ... and add on the owner, which sees them as ordinary mail at the start of its next window
+__global__ void k_inbox_add(SsbView V, int buf, const int *ids, int n, const int *slot_of_id, const unsigned *in, int block) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int p = slot_of_id[ids[t]];
+    bool any = false;
+    for (int s = 0; s < V.Sd; s++) {
+        const unsigned v = in[(size_t) t * V.Sd + s];
+        if (v) { atomicAdd(&V.inbox[buf][(size_t) s * V.N + p], v); any = true; }
+    }
+    if (any) V.blk_mail[buf][p / block] = 1;
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -297,7 +368,7 @@ struct ssb_handle {
     int N = 0, S = 0, R = 0;
     // host copies of the initial condition
     std::vector<double> hx, hnu, hmass, hrho, hdata_fn, hdmat;
-    std::vector<int> htype, hsolid;
+    std::vector<int> htype, hsolid, howned, hgid;
     std::vector<unsigned> hu0, hout_steps;
     std::vector<std::string> species_names;
     // device
@@ -340,6 +411,10 @@ struct ssb_handle {
     double step_disp_max = 0.0;   // largest single-step displacement seen in this trajectory
     int64_t rebuilds = 0;
     int skin_chosen = 0;
+    // slab decomposition support
+    int *d_slot_of_id = nullptr;  // particle id -> storage slot (rebuilt lazily after a permutation)
+    int slot_dirty = 1;
+    cudaEvent_t mark_a = nullptr, mark_b = nullptr;
     int static_cached = 0;        // static domain: storage order, neighbour lists, coefficients and Ddiag survive ssb_reset
     int *d_static_perm = nullptr; // slot -> particle id of the cached storage order
     double max_ddiag_cached = 0.0;
@@ -667,6 +742,8 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     h->hmass.assign(m->mass, m->mass + N);
     h->hrho.assign(m->rho, m->rho + N);
     h->hsolid.assign(m->solid, m->solid + N);
+    if (m->owned) h->howned.assign(m->owned, m->owned + N); else h->howned.assign((size_t) N, 1);
+    if (m->rng_id) h->hgid.assign(m->rng_id, m->rng_id + N); else { h->hgid.resize((size_t) N); for (int i = 0; i < N; i++) h->hgid[i] = i; }
     if (S > 0) h->hu0.assign(m->u0, m->u0 + (size_t) N * S);
     if (ndf > 0) h->hdata_fn.assign(m->data_fn, m->data_fn + (size_t) N * ndf);
     if (S > 0) h->hdmat.assign(m->diffusion_matrix, m->diffusion_matrix + (size_t) S * m->num_types);
@@ -677,6 +754,7 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     h->m.x = nullptr; h->m.type = nullptr; h->m.nu = h->m.mass = h->m.c = h->m.rho = nullptr; h->m.solid = nullptr;
     h->m.u0 = nullptr; h->m.data_fn = nullptr; h->m.N_dense = nullptr; h->m.irN = h->m.jcN = nullptr; h->m.prN = nullptr;
     h->m.irG = h->m.jcG = nullptr; h->m.diffusion_matrix = nullptr; h->m.species_names = nullptr; h->m.output_steps = nullptr;
+    h->m.owned = nullptr; h->m.rng_id = nullptr;
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -704,7 +782,7 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     // species-major blocks are permuted row by row; allocate as blocks and register rows through shadow pointers
     CK(dalloc(h, &V.C, (size_t) Sc * N)); CK(dalloc(h, &V.Q, (size_t) Sc * N));
     CK(dalloc(h, &V.xx, (size_t) Sd * N)); CK(dalloc(h, &V.data_fn, (size_t) ndf * N));
-    register_i32(h, &V.type); register_i32(h, &V.solid); register_i32(h, &V.id);
+    register_i32(h, &V.type); register_i32(h, &V.solid); register_i32(h, &V.id); register_i32(h, &V.owned); register_i32(h, &V.gid);
     for (auto slot : h->i32_slots) { CK(dalloc(h, slot, (size_t) N)); int *alt; CK(dalloc(h, &alt, (size_t) N)); h->i32_alt.push_back(alt); }
     if ((size_t) (2 * Sc + ndf) + h->f64_slots.size() > PERM_MAX64 || (size_t) Sd + h->i32_slots.size() > PERM_MAX32)
         return fail(h, SSB_ERR_ARG, "too many species for the permutation table");
@@ -767,7 +845,7 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
         CK(cudaMallocHost((void **) &J.xx, sizeof(unsigned) * (Sd > 0 ? Sd : 1) * N));
     }
     {   // pinned SoA image of the initial condition (device layout), uploaded by every ssb_reset
-        const size_t nd = (size_t) (6 + Sc + ndf) * N, ni = (size_t) (2 + Sd) * N;
+        const size_t nd = (size_t) (6 + Sc + ndf) * N, ni = (size_t) (4 + Sd) * N;
         CK(cudaMallocHost((void **) &h->init_f64, sizeof(double) * (nd > 0 ? nd : 1)));
         CK(cudaMallocHost((void **) &h->init_i32, sizeof(int) * (ni > 0 ? ni : 1)));
         double *pd = h->init_f64;
@@ -776,8 +854,8 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
         for (int sp = 0; sp < Sc; sp++) for (int i = 0; i < N; i++) pd[(size_t) (6 + sp) * N + i] = (double) h->hu0[(size_t) i * S + sp];
         for (size_t k = 0; k < (size_t) ndf * N; k++) pd[(size_t) (6 + Sc) * N + k] = h->hdata_fn[k];
         int *pi = h->init_i32;
-        for (int i = 0; i < N; i++) { pi[i] = h->htype[i]; pi[(size_t) N + i] = h->hsolid[i]; }
-        for (int sp = 0; sp < Sd; sp++) for (int i = 0; i < N; i++) pi[(size_t) (2 + sp) * N + i] = (int) h->hu0[(size_t) i * S + sp];
+        for (int i = 0; i < N; i++) { pi[i] = h->htype[i]; pi[(size_t) N + i] = h->hsolid[i]; pi[(size_t) 2 * N + i] = h->howned[i]; pi[(size_t) 3 * N + i] = h->hgid[i]; }
+        for (int sp = 0; sp < Sd; sp++) for (int i = 0; i < N; i++) pi[(size_t) (4 + sp) * N + i] = (int) h->hu0[(size_t) i * S + sp];
     }
     CK(cudaStreamSynchronize(h->stream));
     h->writer = std::thread(writer_main, h);
@@ -828,6 +906,9 @@ extern "C" int ssb_destroy(ssb_handle *h) {
         if (J.ready) cudaEventDestroy(J.ready);
         cudaFreeHost(J.x); cudaFreeHost(J.v); cudaFreeHost(J.scal); cudaFreeHost(J.type); cudaFreeHost(J.C); cudaFreeHost(J.xx);
     }
+    if (h->mark_a) { cudaEventDestroy(h->mark_a); cudaEventDestroy(h->mark_b); }
+    for (auto e : h->ev_a) cudaEventDestroy(e);
+    for (auto e : h->ev_b) cudaEventDestroy(e);
     if (h->init_f64) cudaFreeHost(h->init_f64);
     if (h->init_i32) cudaFreeHost(h->init_i32);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -871,7 +952,9 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
         const int *pi = h->init_i32;
         CK(cudaMemcpyAsync(V.type, pi, sizeof(int) * N, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(V.solid, pi + (size_t) N, sizeof(int) * N, cudaMemcpyHostToDevice, st));
-        if (Sd > 0) CK(cudaMemcpyAsync(V.xx, pi + (size_t) 2 * N, sizeof(unsigned) * Sd * N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(V.owned, pi + (size_t) 2 * N, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(V.gid, pi + (size_t) 3 * N, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+        if (Sd > 0) CK(cudaMemcpyAsync(V.xx, pi + (size_t) 4 * N, sizeof(unsigned) * Sd * N, cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemsetAsync(V.old_rho, 0, sizeof(double) * N, st));
     CK(cudaMemsetAsync(V.Frho, 0, sizeof(double) * N, st));
@@ -909,7 +992,8 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     h->ddiag_fresh = 0;
     h->launches = 0;
     h->windows = 0;
-    h->h2d_bytes = (int64_t) N * (3 * 8 + 3 * 8 + 2 * 4 + 8 * Sc + 4 * Sd + 8 * ndf);
+    h->h2d_bytes = (int64_t) N * (3 * 8 + 3 * 8 + 4 * 4 + 8 * Sc + 4 * Sd + 8 * ndf);
+    h->slot_dirty = 1;
     h->d2h_bytes = 0;
     h->total_reactions = h->total_diffusion = 0;
     h->step_seconds = 0.0;
@@ -962,6 +1046,7 @@ static int apply_permutation(ssb_handle *h, const int *d_perm) {
     for (int s = 0; s < Sd; s++) { T.src32[T.n32] = (int *) V.xx + (size_t) s * N; T.dst32[T.n32] = xx_alt + (size_t) s * N; T.n32++; }
     CK(cudaMemcpyAsync(h->d_permtable, &T, sizeof(T), cudaMemcpyHostToDevice, st));
     k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, d_perm, h->d_permtable);
+    h->slot_dirty = 1;
     h->launches += 1;
     CK(cudaStreamSynchronize(st));   // T lives on this stack frame
     for (size_t f = 0; f < nf; f++) { double *cur = *h->f64_slots[f]; *h->f64_slots[f] = h->f64_alt[f]; h->f64_alt[f] = cur; }
@@ -1533,5 +1618,209 @@ extern "C" int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total) {
         for (int v : c) t += v;
         *total = t;
     }
+    return SSB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Slab decomposition support (spatialpy_b200/slab.py drives these; NCCL send/recv happens between the phases).
+// A rank's model = its owned particles + ghost copies (ssb_model.owned).  Ghosts run the same per-particle kernels as
+// everyone else (predictor / corrector updates are deterministic functions of synced inputs), but their neighbour sweeps
+// are skipped; after each sweep the owner's results overwrite the ghost copies:
+//     phase PRE        cell list (if due) + predictor + neighbour search (if due) + force sweep   -> exchange group 0
+//     phase CORRECTOR  corrector (+ Shepard filter)                                               -> exchange group 1
+//     phase FINISH     BVF sweep, bounce-back, chemistry half step, BCs                           -> exchange group 2
+//     phase RDME_PREP  -> local max Ddiag (all-reduced by the caller)   phase RDME_INIT (global max) -> number of windows
+//     phase RDME_WINDOW / RDME_CLOSE one sSSA window each               -> inbox exchange (ssb_halo_inbox_*)
+//     phase END        step counter
+// ----------------------------------------------------------------------------------------------------
+enum { PH_PRE = 0, PH_CORRECTOR = 1, PH_FINISH = 2, PH_RDME_PREP = 3, PH_RDME_INIT = 4, PH_RDME_WINDOW = 5, PH_RDME_CLOSE = 6, PH_END = 7 };
+
+static int ensure_slot_map(ssb_handle *h) {
+    if (!h->d_slot_of_id) CK(dalloc(h, &h->d_slot_of_id, (size_t) h->N));
+    if (h->slot_dirty) {
+        k_slot_of_id<<<gridN(h->N), CORE_BLOCK, 0, h->stream>>>(h->N, h->V.id, h->d_slot_of_id);
+        h->slot_dirty = 0;
+    }
+    return SSB_OK;
+}
+
+extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out) {
+    if (!h) return SSB_ERR_ARG;
+    if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
+    CK(cudaSetDevice(h->device));
+    SsbView &V = h->V;
+    const SsbModelUnit *u = h->unit;
+    cudaStream_t st = h->stream;
+    const unsigned step = h->current_step;
+    if (V.static_domain) return fail(h, SSB_ERR_ARG, "phase stepping (slab decomposition) is implemented for moving domains");
+    int rc;
+    switch (phase) {
+    case PH_PRE: {
+        const bool keep_lists = V.filter && h->lists_valid;
+        if (V.filter) CK(cudaMemsetAsync(V.disp_bits, 0, sizeof(unsigned long long), st));
+        if (!keep_lists) {
+            if ((rc = build_cells(h))) return rc;
+            if (V.filter) {
+                for (int d = 0; d < 3; d++) CK(cudaMemcpyAsync(V.xref[d], V.x[d], sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
+                h->disp_prev = 0.0;
+                h->rebuilds++;
+            }
+        }
+        if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
+        h->launches++;
+        V.rho_search = V.rho;
+        if (!keep_lists) { if ((rc = neighbour_search(h))) return rc; }
+        if (V.filter) {
+            unsigned long long bits[2] = {0, 0};
+            CK(cudaMemcpyAsync(bits, V.disp_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            double d2now, s2;
+            memcpy(&d2now, &bits[0], 8); memcpy(&s2, &bits[1], 8);
+            const double Dnow = sqrt(d2now), budget = h->skin * V.h;
+            h->step_disp_max = sqrt(s2);
+            if (Dnow + h->disp_prev > budget) return fail(h, SSB_ERR_ARG, "Verlet skin exceeded within one step");
+            h->lists_valid = (2.0 * (Dnow + 2.0 * h->step_disp_max) <= budget) ? 1 : 0;
+            h->disp_prev = Dnow;
+        }
+        if (V.Sd > 0) CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+        if (u->force_mv(&V, step, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
+        h->launches++;
+        h->ddiag_fresh = 1;
+        break;
+    }
+    case PH_CORRECTOR:
+        if (u->corrector(&V, step, st)) return fail(h, SSB_ERR_CUDA, "corrector launch failed");
+        h->launches++;
+        break;
+    case PH_FINISH: {
+        if (u->finish(&V, step, 1, st)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
+        h->launches++;
+        double *pre = V.rho;
+        V.rho = V.rho_new;
+        V.rho_new = pre;
+        V.rho_search = pre;
+        break;
+    }
+    case PH_RDME_PREP: {
+        unsigned long long bits = 0;
+        CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        double mx;
+        memcpy(&mx, &bits, sizeof(mx));
+        if (out) *out = mx;
+        break;
+    }
+    case PH_RDME_INIT: {
+        const double mx = arg;       // GLOBAL max Ddiag: every rank must use the same windows
+        const double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
+        const double tau = (mx > 0.0) ? eps / mx : V.dt;
+        double nwin_d = ceil(V.dt / tau);
+        if (!(nwin_d >= 1.0)) nwin_d = 1.0;
+        if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
+        h->nwin = (long long) nwin_d;
+        h->tau = V.dt / (double) h->nwin;
+        h->ddiag_fresh = 0;
+        if (u->rdme_init(&V, V.dt * step, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
+        h->launches++;
+        h->rdme_initialized = 1;
+        h->inbox_buf = 0;
+        if (out) *out = (double) h->nwin;
+        break;
+    }
+    case PH_RDME_WINDOW:
+    case PH_RDME_CLOSE: {
+        const double t0 = V.dt * step;
+        const long long nwin = h->nwin, w = (long long) arg;
+        double lo, hi;
+        if (phase == PH_RDME_WINDOW) {
+            lo = t0 + V.dt * ((double) w / (double) nwin);
+            hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
+            h->windows++;
+        } else { lo = hi = t0 + V.dt; }
+        if (u->rdme_window(&V, lo, hi, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+        h->inbox_buf ^= 1;
+        h->launches++;
+        break;
+    }
+    case PH_END:
+        h->current_step++;
+        return check_device_error(h);
+    default:
+        return fail(h, SSB_ERR_ARG, "unknown phase %d", phase);
+    }
+    return SSB_OK;
+}
+
+// pack `n` particles (ids = particle ids of this rank's model, device array) of field group `group` into dev_out
+// (n * width doubles, device memory owned by the caller, e.g. a torch tensor); synchronises the engine stream.
+extern "C" int ssb_halo_pack(ssb_handle *h, int group, const int32_t *dev_ids, int32_t n, double *dev_out) {
+    if (!h || group < 0 || group > 3) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_slot_map(h);
+    if (rc) return rc;
+    if (n > 0) k_halo_pack<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, group, dev_ids, n, h->d_slot_of_id, dev_out);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return SSB_OK;
+}
+extern "C" int ssb_halo_unpack(ssb_handle *h, int group, const int32_t *dev_ids, int32_t n, const double *dev_in) {
+    if (!h || group < 0 || group > 3) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_slot_map(h);
+    if (rc) return rc;
+    if (n > 0) k_halo_unpack<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, group, dev_ids, n, h->d_slot_of_id, dev_in);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return SSB_OK;
+}
+// inbox of the sSSA window that just ran (the buffer the next window will read)
+extern "C" int ssb_halo_inbox_pack(ssb_handle *h, const int32_t *dev_ids, int32_t n, uint32_t *dev_out) {
+    if (!h) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_slot_map(h);
+    if (rc) return rc;
+    if (n > 0 && h->V.Sd > 0) k_inbox_pack<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, h->inbox_buf ^ 1, dev_ids, n, h->d_slot_of_id, dev_out);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return SSB_OK;
+}
+extern "C" int ssb_halo_inbox_add(ssb_handle *h, const int32_t *dev_ids, int32_t n, const uint32_t *dev_in) {
+    if (!h) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_slot_map(h);
+    if (rc) return rc;
+    if (n > 0 && h->V.Sd > 0) k_inbox_add<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, h->inbox_buf ^ 1, dev_ids, n, h->d_slot_of_id, dev_in, h->unit->block);
+    h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    return SSB_OK;
+}
+extern "C" int ssb_halo_width(ssb_handle *h, int group, int32_t *width) {
+    if (!h || !width) return SSB_ERR_ARG;
+    *width = group == 0 ? 7 + h->V.Sc : (group == 2 ? 4 : 1);
+    return SSB_OK;
+}
+
+// CUDA-event markers on the engine stream (device timing of a phased step loop)
+extern "C" int ssb_mark(ssb_handle *h, int which) {
+    if (!h) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->mark_a) { CK(cudaEventCreate(&h->mark_a)); CK(cudaEventCreate(&h->mark_b)); }
+    CK(cudaEventRecord(which == 0 ? h->mark_a : h->mark_b, h->stream));
+    return SSB_OK;
+}
+extern "C" int ssb_mark_elapsed_ms(ssb_handle *h, double *ms) {
+    if (!h || !ms || !h->mark_a) return SSB_ERR_ARG;
+    CK(cudaEventSynchronize(h->mark_b));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->mark_a, h->mark_b));
+    *ms = f;
+    return SSB_OK;
+}
+
+extern "C" int ssb_skin_stats(ssb_handle *h, double *skin, double *step_disp_max, int64_t *rebuilds) {
+    if (!h) return SSB_ERR_ARG;
+    if (skin) *skin = h->skin;
+    if (step_disp_max) *step_disp_max = h->step_disp_max;
+    if (rebuilds) *rebuilds = h->rebuilds;
     return SSB_OK;
 }

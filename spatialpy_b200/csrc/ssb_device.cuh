@@ -31,6 +31,8 @@ struct SsbView {
     double *rho_new;    // density after the corrector (+BC), seen by later particles in the BVF sweep (model.cpp:285-293)
     double *old_rho, *Frho, *bvf, *mass, *nu;
     int *type, *solid, *id;
+    int *owned;         // 1 = this rank integrates the particle, 0 = ghost copy of a particle owned by a neighbouring slab
+    int *gid;           // global particle id (Philox counter), == id on a single GPU
     double *C, *Q;      // [Sc*N]
     unsigned *xx;       // [Sd*N]
     double *data_fn;    // [ndf*N]

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
     V.old_rho[i] = p.rho;                               // simulate.cpp:106
     if (!V.static_domain && V.rec) {
         double2 *r2 = reinterpret_cast<double2 *>(V.rec + (size_t) i * 16);
-        const long long bits = ((long long) (unsigned) p.id) | ((long long) (p.type & 0xffff) << 32) | ((long long) (p.solidTag & 0xffff) << 48);
+        const long long bits = ((long long) (unsigned) V.gid[i]) | ((long long) (p.type & 0xffff) << 32) | ((long long) (p.solidTag & 0xffff) << 48);
         r2[0] = make_double2(V.x0[0][i], V.x0[1][i]);
         r2[1] = make_double2(V.x0[2][i], p.x[0]);
         r2[2] = make_double2(p.x[1], p.x[2]);
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
         double F0 = V.F[0][i], F1 = V.F[1][i], F2 = V.F[2][i];
         double B0 = V.Fbp[0][i], B1 = V.Fbp[1][i], B2 = V.Fbp[2][i];
         double Frho = V.Frho[i];
-        const int cnt = V.nbr_count[i];
+        const int cnt = V.owned[i] ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
 #pragma unroll 2
         for (int k = 0; k < cnt; k++) {
             const int j = V.nbr[(size_t) k * N + i];
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_corrector(SsbView V, unsigned ste
 #pragma unroll
         for (int d = 0; d < 3; d++) V.v[d][i] = V.v[d][i] + 0.5 * dt * V.F[d][i];      // simulate.cpp:139-141
     }
-    if (step % 20 == 0) {                               // filterDensity (model.cpp:194-233)
+    if (step % 20 == 0 && V.owned[i]) {                 // filterDensity (model.cpp:194-233); ghosts receive rho_new from their owner
         const double alpha = ssb_alpha(dim, h);
         const double xi0 = V.x[0][i], xi1 = V.x[1][i], xi2 = V.x[2][i];
         double num = 0.0, den = 0.0;
@@ -589,9 +589,9 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_finish(SsbView V, unsigned step) 
     Particle p;
     bc_load(V, i, p);
     if (MOVING) p.rho = V.rho_new[i];
-    if (MOVING && p.solidTag == 0) {
+    if (MOVING && p.solidTag == 0 && V.owned[i]) {      // ghosts receive v and bvf_phi from their owner
         const double alpha = ssb_alpha(dim, h);
-        const int my_id = p.id;
+        const int my_id = V.gid[i];
         const double inv_h = 1.0 / h;
         double nw[3] = {0.0, 0.0, 0.0};
         double vos = 0.0, vtot = 0.0;
@@ -607,12 +607,12 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_finish(SsbView V, unsigned step) 
                 x0j0 = c0.a; x0j1 = c0.b; x0j2 = c0.c; xj0 = c0.d; xj1 = c1.a; xj2 = c1.b;
                 rho_pre_j = c3.a; m_j = c3.b;
                 const long long bits = __double_as_longlong(c3.d);
-                id_j = (int) (bits & 0xffffffffll);
+                id_j = (int) (bits & 0xffffffffll);                       // global particle id
                 solid_j = (int) ((bits >> 48) & 0xffff);
             } else {
                 x0j0 = V.x0[0][j]; x0j1 = V.x0[1][j]; x0j2 = V.x0[2][j];
                 xj0 = V.x[0][j]; xj1 = V.x[1][j]; xj2 = V.x[2][j];
-                rho_pre_j = V.rho[j]; m_j = V.mass[j]; id_j = V.id[j]; solid_j = V.solid[j];
+                rho_pre_j = V.rho[j]; m_j = V.mass[j]; id_j = V.gid[j]; solid_j = V.solid[j];
             }
             const double d2 = ssb_dist2(dim, p.x[0], p.x[1], p.x[2], x0j0, x0j1, x0j2);
             if (V.filter && !ssb_in_range(d2, h, __dmul_rn(h, h))) continue;
@@ -765,8 +765,8 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
         V.sdrate[i] = R.sd;
         const double tot = R.sr + R.sd;
         double u0, u1;
-        philox_uniform2((uint32_t) V.id[i], 0u, epoch, seed, u0, u1);
-        tn = (tot > 0.0) ? t0 + (-log(u0)) / tot : INFINITY;
+        philox_uniform2((uint32_t) V.gid[i], 0u, epoch, seed, u0, u1);
+        tn = (tot > 0.0 && V.owned[i]) ? t0 + (-log(u0)) / tot : INFINITY;      // ghost voxels are simulated by their owner
         V.tnext[i] = tn;
 #pragma unroll
         for (int s = 0; s < SSB_SD; s++) { V.inbox[0][(size_t) s * N + i] = 0u; V.inbox[1][(size_t) s * N + i] = 0u; }
@@ -869,12 +869,13 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
         const int ii = valid ? i : N - 1;                          // clamp so idle lanes can run the same code path
         const unsigned *in_prev = V.inbox[buf ^ 1];
         unsigned *out_box = V.inbox[buf];
-        double tnext = valid ? V.tnext[ii] : INFINITY;
+        const bool mine = valid && V.owned[ii];                    // mail addressed to ghost voxels stays in the inbox for the halo exchange
+        double tnext = mine ? V.tnext[ii] : INFINITY;
         bool arrived = false;
         unsigned inc[SSB_SD > 0 ? SSB_SD : 1];
 #pragma unroll
-        for (int s = 0; s < SSB_SD; s++) { inc[s] = valid ? __ldcg(&in_prev[(size_t) s * N + ii]) : 0u; arrived |= (inc[s] != 0u); }
-        const bool touched = valid && (arrived || tnext <= t_hi);
+        for (int s = 0; s < SSB_SD; s++) { inc[s] = mine ? __ldcg(&in_prev[(size_t) s * N + ii]) : 0u; arrived |= (inc[s] != 0u); }
+        const bool touched = mine && (arrived || tnext <= t_hi);
         int xx[SSB_SD > 0 ? SSB_SD : 1];     // present: may react and jump
         int xr[SSB_SD > 0 ? SSB_SD : 1];     // present + departing: may react
         double Dd[SSB_SD > 0 ? SSB_SD : 1];  // lag-compensated jump propensity per molecule
@@ -894,7 +895,7 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
             for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
             type_i = V.type[i];
             vol = V.mass[i] / V.rho[i];
-            vid = (uint32_t) V.id[i];
+            vid = (uint32_t) V.gid[i];
             if (arrived) {
                 // stored propensities; only the reactions that depend on an arrived species are re-evaluated
                 // (dependency graph columns [0,S), simulate_rdme.cpp:419-435)
@@ -1200,6 +1201,7 @@ extern "C" const SsbModelUnit *ssbm_get_unit() {
     u.static_coef = ssb_unit::l_static_coef;
     u.static_step = ssb_unit::l_static_step;
     u.rdme_init = ssb_unit::l_rdme_init;
+    u.block = SSB_BLOCK;
     u.rdme_window = ssb_unit::l_rdme_window;
     u.rdme_windows = ssb_unit::l_rdme_windows;
     return &u;

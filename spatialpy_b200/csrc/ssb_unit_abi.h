@@ -8,12 +8,13 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 8
+#define SSB_UNIT_ABI 9
 
 struct SsbModelUnit {
     int abi;
     int Sc, Rc, Sd, Rd, ndf, ntypes, S, R;
     int has_bc, bc_touches_rho;
+    int block;                 // voxels per sSSA chunk (index unit of blk_tmin / blk_mail)
     int (*predictor)(const SsbView *, unsigned step, cudaStream_t);
     int (*force)(const SsbView *, unsigned step, int full, cudaStream_t);
     int (*force_mv)(const SsbView *, unsigned step, unsigned long long *max_ddiag_bits, cudaStream_t);

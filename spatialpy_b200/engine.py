@@ -10,7 +10,7 @@ import numpy as np
 from . import codegen
 from .flatmodel import FlatModel
 
-SSB_ABI_VERSION = 1
+SSB_ABI_VERSION = 2
 FLAG_CORRECTED_NSM_SELECT = 1
 FLAG_CORRECTED_STOICH = 2
 FLAG_NO_VTK = 4
@@ -24,7 +24,10 @@ ERR_NAMES = {1: "SSB_ERR_NAN", 2: "SSB_ERR_RDME", 3: "SSB_ERR_CUDA", 4: "SSB_ERR
 EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernels", "ssb_destroy", "ssb_run",
            "ssb_reset", "ssb_step", "ssb_counters", "ssb_get_field", "ssb_get_neighbors", "ssb_cancel",
            "ssb_last_error", "ssb_launch_count", "ssb_step_timed", "ssb_profile", "ssb_profile_read", "ssb_io_bytes",
-           "ssb_nbr_stats"]
+           "ssb_nbr_stats", "ssb_step_phase", "ssb_halo_pack", "ssb_halo_unpack", "ssb_halo_inbox_pack", "ssb_halo_inbox_add",
+           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats"]
+
+PH_PRE, PH_CORRECTOR, PH_FINISH, PH_RDME_PREP, PH_RDME_INIT, PH_RDME_WINDOW, PH_RDME_CLOSE, PH_END = range(8)
 
 PROFILE_CATEGORIES = ["cells", "predictor", "search", "force", "corrector", "finish", "diff_init", "rdme_init",
                       "rdme_window", "output"]
@@ -56,6 +59,7 @@ class SsbModel(C.Structure):
         ("irG", C.POINTER(C.c_int64)), ("jcG", C.POINTER(C.c_int64)),
         ("diffusion_matrix", C.POINTER(C.c_double)), ("species_names", C.POINTER(C.c_char_p)),
         ("rdme_epsilon", C.c_double), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("owned", C.POINTER(C.c_int32)), ("rng_id", C.POINTER(C.c_int32)),
     ]
 
 
@@ -93,6 +97,15 @@ def load_library(path=None):
     lib.ssb_profile_read.argtypes = [H, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.ssb_io_bytes.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.ssb_nbr_stats.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    lib.ssb_step_phase.argtypes = [H, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    lib.ssb_halo_pack.argtypes = [H, C.c_int, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ssb_halo_unpack.argtypes = [H, C.c_int, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ssb_halo_inbox_pack.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ssb_halo_inbox_add.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ssb_halo_width.argtypes = [H, C.c_int, C.POINTER(C.c_int32)]
+    lib.ssb_skin_stats.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.ssb_mark.argtypes = [H, C.c_int]
+    lib.ssb_mark_elapsed_ms.argtypes = [H, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if getattr(lib, name).restype is None:
             getattr(lib, name).restype = C.c_int
@@ -126,7 +139,7 @@ class Engine:
     }
 
     def __init__(self, fm: FlatModel, device=0, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, unit_path=None,
-                 unit_flags=()):
+                 unit_flags=(), owned=None, rng_id=None):
         self.lib = load_library()
         self.fm = fm.finalize()
         self._h = C.c_void_p(None)
@@ -163,6 +176,10 @@ class Engine:
         m.species_names = C.cast(names, C.POINTER(C.c_char_p))
         m.rdme_epsilon = float(rdme_epsilon)
         m.device = int(device)
+        self._owned = None if owned is None else np.ascontiguousarray(owned, dtype=np.int32)
+        self._rng_id = None if rng_id is None else np.ascontiguousarray(rng_id, dtype=np.int32)
+        m.owned = None if self._owned is None else _ptr(self._owned, C.c_int32)
+        m.rng_id = None if self._rng_id is None else _ptr(self._rng_id, C.c_int32)
         self._check(self.lib.ssb_create(C.byref(m), C.byref(self._h)))
         self.unit_path = unit_path or codegen.build_model_unit(fm, extra_flags=unit_flags)
         self._check(self.lib.ssb_load_kernels(self._h, self.unit_path.encode()))
@@ -249,6 +266,42 @@ class Engine:
         cap, tot = C.c_int32(0), C.c_int64(0)
         self._check(self.lib.ssb_nbr_stats(self._h, C.byref(cap), C.byref(tot)))
         return cap.value, tot.value
+
+    # -- slab decomposition primitives (spatialpy_b200/slab.py) ---------------------------------------------------
+    def phase(self, phase, arg=0.0):
+        out = C.c_double(0.0)
+        self._check(self.lib.ssb_step_phase(self._h, int(phase), float(arg), C.byref(out)))
+        return out.value
+
+    def halo_width(self, group):
+        w = C.c_int32(0)
+        self._check(self.lib.ssb_halo_width(self._h, int(group), C.byref(w)))
+        return w.value
+
+    def halo_pack(self, group, ids_ptr, n, out_ptr):
+        self._check(self.lib.ssb_halo_pack(self._h, int(group), ids_ptr, int(n), out_ptr))
+
+    def halo_unpack(self, group, ids_ptr, n, in_ptr):
+        self._check(self.lib.ssb_halo_unpack(self._h, int(group), ids_ptr, int(n), in_ptr))
+
+    def inbox_pack(self, ids_ptr, n, out_ptr):
+        self._check(self.lib.ssb_halo_inbox_pack(self._h, ids_ptr, int(n), out_ptr))
+
+    def inbox_add(self, ids_ptr, n, in_ptr):
+        self._check(self.lib.ssb_halo_inbox_add(self._h, ids_ptr, int(n), in_ptr))
+
+    def skin_stats(self):
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._check(self.lib.ssb_skin_stats(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return {"skin": a.value, "step_disp_max": b.value, "rebuilds": n.value}
+
+    def mark(self, which):
+        self._check(self.lib.ssb_mark(self._h, int(which)))
+
+    def mark_elapsed_ms(self):
+        ms = C.c_double(0.0)
+        self._check(self.lib.ssb_mark_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def get(self, name):
         dtype, cols = self._FIELDS[name]
