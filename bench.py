@@ -282,6 +282,18 @@ def run_ours(args, rank, local_rank, world):
     eng2.close()
 
     cpu = cpu_baseline_sample(args.workload) if (rank == 0 and world == 1 and not args.no_cpu) else None
+    # the other sharding mode, measured in the same run: ONE 8 M-particle-per-GPU SDPD+sSSA box split into slabs with NCCL
+    # halo exchange (BASELINE configs[4]); reported beside the headline so per-N lines carry both scaling modes
+    slab = None
+    if not args.no_slab:
+        try:
+            sl = slab_measure(args, rank, local_rank, world, 3, 2, 5)
+            slab = {k: sl[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "rdme_events_per_s")}
+            slab.update(workload=sl["config"]["workload"], particles_per_gpu=sl["config"]["particles_per_gpu"],
+                        ghosts_per_gpu=sl["config"]["ghosts_per_gpu"], parallelism=sl["config"]["parallelism"],
+                        engine_steps_per_step=sl["config"]["engine_steps_per_step"], scaling="weak")
+        except Exception as err:      # never lose the headline line to the secondary measurement
+            slab = {"error": f"{type(err).__name__}: {err}"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -300,6 +312,7 @@ def run_ours(args, rank, local_rank, world):
                     "engine_create_s": create_s},
             "gpu_launches": int(launches),
             "clocks": clk,
+            "spatial_slab": slab,
         }
         print(json.dumps(line))
     if use_dist:
@@ -312,15 +325,25 @@ def run_ours(args, rank, local_rank, world):
 def run_slab(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
-    from spatialpy_b200 import configs
-    from spatialpy_b200.slab import SlabEngine
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = slab_measure(args, rank, local_rank, world, args.steps, args.warmup, args.sps or 10)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def slab_measure(args, rank, local_rank, world, steps, warmup, SPS):
+    """One box domain of 200^3 * scale particles per GPU, slab-decomposed over the ranks; returns the bench line (dict)."""
+    import torch
+    import torch.distributed as dist
+    from spatialpy_b200 import configs
+    from spatialpy_b200.slab import SlabEngine
     n = max(16, int(round(200 * args.scale ** (1.0 / 3.0))))
     part = configs.box_slab(rank, world, nx_per_rank=n, ny=n, nz=n)
     se = SlabEngine(part, rank, world, device=local_rank)
-    SPS = args.sps or 10
 
     def barrier():
         torch.cuda.synchronize()
@@ -336,7 +359,7 @@ def run_slab(args, rank, local_rank, world):
         return float(t.item())
 
     se.reset(1000)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         se.step(SPS)
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -344,7 +367,7 @@ def run_slab(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
     se.eng.mark(0)
-    for _ in range(args.steps):
+    for _ in range(steps):
         se.step(SPS)
     se.eng.mark(1)
     dev_ms = se.eng.mark_elapsed_ms()           # CUDA events on the engine stream (includes the waits for the halo exchanges)
@@ -356,7 +379,7 @@ def run_slab(args, rank, local_rank, world):
     wall_s = allred(wall_s, dist.ReduceOp.MAX if world > 1 else None)
     owned_total = allred(float(part.n_owned), dist.ReduceOp.SUM if world > 1 else None)
     events = allred(float(c1["reactions"] + c1["diffusions"] - c0["reactions"] - c0["diffusions"]), dist.ReduceOp.SUM if world > 1 else None)
-    nsteps = SPS * args.steps
+    nsteps = SPS * steps
     value = owned_total * nsteps / (dev_ms / 1e3)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
@@ -364,10 +387,9 @@ def run_slab(args, rank, local_rank, world):
     per_step_bytes = algorithmic_bytes(fm, True)
     ghosts = fm.num_particles - part.n_owned
     halo_bytes = sum(len(v) for v in part.send_ids.values()) * 8 * (7 + fm.num_chem_species + 1 + 4)
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+    line = ({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"BASELINE configs[4]: synthetic 3-D SDPD+sSSA box, {n}^3 owned particles per GPU, slab-decomposed along x",
                        "particles_per_gpu": part.n_owned, "ghosts_per_gpu": ghosts, "engine_steps_per_step": SPS,
@@ -380,10 +402,9 @@ def run_slab(args, rank, local_rank, world):
             "cpu_baseline": None,
             "e2e": {"value": owned_total * nsteps / wall_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "includes": "host wall clock of the same stepping loop incl. Python orchestration and NCCL halo exchanges (state resident)"},
-            "gpu_launches": int(se.eng.launch_count() - l0), "clocks": clk}))
+            "gpu_launches": int(se.eng.launch_count() - l0), "clocks": clk})
     se.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def main():
@@ -396,6 +417,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
     ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--no-slab", action="store_true", help="skip the secondary slab-decomposed measurement")
     ap.add_argument("--decomp", default="ensemble", choices=["ensemble", "slab"],
                     help="N>1: independent trajectories per GPU (default) or ONE box domain split into slabs (BASELINE configs[4])")
     args = ap.parse_args()
