@@ -154,5 +154,80 @@ def cylinder(steps=5, dt=1.0):
     return model
 
 
+def cdc42(DX=12, end_time=0.05, steps=5):
+    """BASELINE config 4 (examples/Yeast_Polarization/Cdc42.ipynb cell 12, create_cdc42_model) on a coarse DX x DX lattice and a
+    short horizon so a >= 600-trajectory reference ensemble is affordable: 3 types with different masses (=> different voxel
+    volumes across the membrane/cytoplasm interface), 9 species restricted by type, 13 reactions (12 mass action + CR0 with a
+    custom propensity reading the data function GbgGradient), scatter initial conditions restricted by type."""
+    import math
+    import spatialpy
+    numpy.random.seed(6)
+
+    class Membrane(spatialpy.Geometry):
+        def inside(self, point, on_boundary):
+            r = numpy.sqrt(point[0] ** 2 + point[1] ** 2)
+            return 0.6 >= r >= 0.4
+
+    class Cytoplasm(spatialpy.Geometry):
+        def inside(self, point, on_boundary):
+            return numpy.sqrt(point[0] ** 2 + point[1] ** 2) < 0.4
+
+    class GbgGradient(spatialpy.DataFunction):
+        def __init__(self, Gbg_mid=5000, Gbg_slope=0.0, mem_vol=1.0):
+            spatialpy.DataFunction.__init__(self, name="GbgGradient")
+            self.Gbg_mid, self.Gbg_slope, self.mem_vol = Gbg_mid, Gbg_slope, mem_vol
+
+        def map(self, x):
+            return (self.Gbg_slope * x[1] + self.Gbg_mid) / self.mem_vol
+
+    model = spatialpy.Model("Cdc42_2D")
+    EXTRA, MEM, CYT = "Extra_Cellular", "Membrane", "Cytoplasm"
+    D_membrane, D_bulk = 0.0053, 10.0
+    domain = spatialpy.Domain.create_2D_domain(xlim=(-1, 1), ylim=(-1, 1), numx=DX, numy=DX, rho0=1.0, c0=10, P0=10, type_id=EXTRA)
+    domain.set_properties(Membrane(), type_id=MEM, mass=4.0, nu=1.0, fixed=False)
+    domain.set_properties(Cytoplasm(), type_id=CYT, mass=2.0, nu=1.0, fixed=False)
+    model.add_domain(domain)
+    S = spatialpy.Species
+    model.add_species([
+        S(name="Cdc24_m", diffusion_coefficient=D_membrane, restrict_to=MEM),
+        S(name="Cdc24_c", diffusion_coefficient=D_bulk, restrict_to=[MEM, CYT]),
+        S(name="Cdc42", diffusion_coefficient=D_membrane, restrict_to=MEM),
+        S(name="Cdc42_a", diffusion_coefficient=D_membrane, restrict_to=MEM),
+        S(name="Bem1_m", diffusion_coefficient=D_membrane, restrict_to=MEM),
+        S(name="Bem1_c", diffusion_coefficient=D_bulk, restrict_to=[MEM, CYT]),
+        S(name="Cla4", diffusion_coefficient=D_bulk, restrict_to=[MEM, CYT]),
+        S(name="Cla4_a", diffusion_coefficient=D_membrane, restrict_to=MEM),
+        S(name="Cdc42_c", diffusion_coefficient=D_bulk, restrict_to=[MEM, CYT])])
+    IC = spatialpy.ScatterInitialCondition
+    model.add_initial_condition([IC("Cdc42", 2700, [CYT]), IC("Cdc24_c", 1000, [MEM]), IC("Bem1_c", 3000, [MEM]),
+                                 IC("Cla4", 5000, [MEM]), IC("Cdc42_a", 300, [CYT])])
+    P = spatialpy.Parameter
+    model.add_parameter([P(name="k_42a", expression=0.2), P(name="k_42d", expression=1.0), P(name="k_24cm1", expression=0.00297),
+                         P(name="k_24mc", expression=0.35), P(name="k_B1mc", expression=0.35), P(name="k_B1cm", expression=0.2667),
+                         P(name="k_Cla4a", expression=0.006), P(name="k_Cla4d", expression=0.01), P(name="k_24d", expression=1.0 / 30000),
+                         P(name="beta1", expression=0.266), P(name="beta2", expression=0.28), P(name="beta3", expression=1.0),
+                         P(name="delta1_gbg", expression=0.00297)])
+    R = spatialpy.Reaction
+    model.add_reaction([
+        R(name="CR0", reactants={'Cdc24_c': 1}, products={'Cdc24_m': 1},
+          propensity_function="delta1_gbg * Cdc24_c * GbgGradient * vol", restrict_to=MEM),
+        R(name="CR1", reactants={'Cdc24_c': 1, 'Bem1_m': 1}, products={'Cdc24_m': 1, 'Bem1_m': 1}, rate='k_24cm1', restrict_to=MEM),
+        R(name="CR2", reactants={'Cdc24_m': 1}, products={'Cdc24_c': 1}, rate='k_24mc', restrict_to=MEM),
+        R(name="CR3", reactants={'Cdc24_m': 1, 'Cla4_a': 1}, products={'Cdc24_c': 1, 'Cla4_a': 1}, rate='k_24d', restrict_to=MEM),
+        R(name="CR4", reactants={'Cdc24_m': 1, 'Cdc42': 1}, products={'Cdc24_m': 1, 'Cdc42_a': 1}, rate='k_42a', restrict_to=MEM),
+        R(name="CR5", reactants={'Cdc42_a': 1}, products={'Cdc42': 1}, rate='k_42d', restrict_to=MEM),
+        R(name="CR6", reactants={'Cdc42_a': 1, 'Bem1_c': 1}, products={'Cdc42_a': 1, 'Bem1_m': 1}, rate='k_B1cm', restrict_to=MEM),
+        R(name="CR7", reactants={'Bem1_m': 1}, products={'Bem1_c': 1}, rate='k_B1mc', restrict_to=MEM),
+        R(name="CR8", reactants={'Cdc42_a': 1, 'Cla4': 1}, products={'Cdc42_a': 1, 'Cla4_a': 1}, rate='k_Cla4a', restrict_to=MEM),
+        R(name="CR9", reactants={'Cla4_a': 1}, products={'Cla4': 1}, rate='k_Cla4d', restrict_to=MEM),
+        R(name="CR10", reactants={'Cdc42_c': 1}, products={'Cdc42': 1}, rate='beta2', restrict_to=MEM),
+        R(name="CR11", reactants={'Cdc42': 1}, products={'Cdc42_c': 1}, rate='beta3', restrict_to=MEM),
+        R(name="CR12", reactants={'Cdc42_c': 1, 'Cdc24_m': 1}, products={'Cdc42_a': 1, 'Cdc24_m': 1}, rate='beta1', restrict_to=MEM)])
+    membrane_volume = sum(model.domain.vol[i] for i, t in enumerate(model.domain.type_id) if t == model.domain.get_type_def(MEM))
+    model.add_data_function(GbgGradient(Gbg_mid=5000.0, Gbg_slope=0.0, mem_vol=membrane_volume))
+    model.timespan(spatialpy.TimeSpan.linspace(t=end_time, num_points=steps + 1, timestep_size=end_time / steps))
+    return model
+
+
 BUILDERS = {"birth_death": birth_death, "diffusion3d": diffusion3d, "cavity2d": cavity2d, "tank3d": tank3d,
-            "cylinder": cylinder}
+            "cylinder": cylinder, "cdc42": cdc42}

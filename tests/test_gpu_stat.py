@@ -86,6 +86,12 @@ def test_cylinder_ensemble_matches_reference():
     check_against_reference("cylinder", 1000)
 
 
+def test_cdc42_ensemble_matches_reference():
+    """BASELINE config 4 (yeast polarisation, coarse lattice, short horizon): 9 type-restricted species, 13 reactions, a custom
+    propensity reading a data function, voxel volumes that differ across the membrane/cytoplasm interface."""
+    check_against_reference("cdc42", 600)
+
+
 def test_pure_diffusion_ensemble_matches_reference():
     check_against_reference("diffusion3d", 1000)
 
