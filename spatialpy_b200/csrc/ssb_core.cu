@@ -965,8 +965,8 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     if (Sd > 0) {
         CK(cudaMemsetAsync(V.inbox[0], 0, sizeof(unsigned) * Sd * N, st));
         CK(cudaMemsetAsync(V.inbox[1], 0, sizeof(unsigned) * Sd * N, st));
-        CK(cudaMemsetAsync(V.inbox_src[0], 0, sizeof(int) * N, st));
-        CK(cudaMemsetAsync(V.inbox_src[1], 0, sizeof(int) * N, st));
+        CK(cudaMemsetAsync(V.inbox_src[0], 0, sizeof(unsigned long long) * N, st));
+        CK(cudaMemsetAsync(V.inbox_src[1], 0, sizeof(unsigned long long) * N, st));
     }
     CK(cudaMemsetAsync(V.err_flag, 0, 16, st));
     CK(cudaMemsetAsync(V.counters, 0, 32, st));

@@ -63,7 +63,10 @@ struct SsbView {
     double *srrate, *sdrate, *tnext;
     double *Ddiag;      // [Sd*N]
     unsigned *inbox[2]; // [Sd*N] each, double-buffered arrivals
-    int *inbox_src[2];  // [N] id of one arriving source voxel (+1), 0 = none  (dest-propensity vol quirk, simulate_rdme.cpp:433)
+    // [N] (random priority << 32 | source slot + 1) of ONE arrival of the window, 0 = none.  The reference evaluates a destination's
+    // propensities with the vol of the voxel the LAST molecule came from (simulate_rdme.cpp:433); within a window the last arrival
+    // is a uniformly random one, which the atomicMax over random priorities reproduces deterministically.
+    unsigned long long *inbox_src[2];
     // block summaries (one entry per SSB_BLOCK consecutive voxels): earliest tnext in the block, and whether any voxel of
     // the block has mail in inbox[b]; lets a whole block leave an sSSA window after two loads when nothing is due.
     double *blk_tmin;   // [ceil(N/SSB_BLOCK)]

@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
         V.tnext[i] = tn;
 #pragma unroll
         for (int s = 0; s < SSB_SD; s++) { V.inbox[0][(size_t) s * N + i] = 0u; V.inbox[1][(size_t) s * N + i] = 0u; }
-        V.inbox_src[0][i] = 0; V.inbox_src[1][i] = 0;
+        V.inbox_src[0][i] = 0ull; V.inbox_src[1][i] = 0ull;
     }
     tn = block_min(tn);
     if (threadIdx.x == 0) { V.blk_tmin[blockIdx.x] = tn; V.blk_mail[0][blockIdx.x] = 0; V.blk_mail[1][blockIdx.x] = 0; }
@@ -913,9 +913,9 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
                 // reference quirk: the destination's propensities are re-evaluated with the SOURCE voxel's vol
                 // (simulate_rdme.cpp:433) and stay that way until its next own event.
                 double vol_dest = vol;
-                const int src = __ldcg(&V.inbox_src[buf ^ 1][i]);
+                const int src = (int) (__ldcg(&V.inbox_src[buf ^ 1][i]) & 0xffffffffull);
                 if (src > 0 && !(V.flags & 1u)) { vol_dest = V.mass[src - 1] / V.rho[src - 1]; }
-                V.inbox_src[buf ^ 1][i] = 0;
+                V.inbox_src[buf ^ 1][i] = 0ull;
                 double tmp[SSB_RD > 0 ? SSB_RD : 1];
                 ssb_gen::eval_propensities(xx, t_lo, vol_dest, df, type_i, tmp);
                 double sr = 0.0, sd = 0.0;
@@ -944,7 +944,7 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
             if (!__any_sync(0xffffffffu, ev)) break;
             double tt = tnext, rand2 = 0.0, pick = 0.0;
             bool is_rxn = false;
-            int spec = 0;
+            int spec = 0, ev_re = 0;
             if (ev) {
                 const double tot = R.sr + R.sd;
                 double rand1;
@@ -989,6 +989,7 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
                     for (int q = 1; q < SSB_RD; q++) { if (pick > cum) { re = q; cum += R.rr[q]; } else break; }
                     // fell off the end with a zero-propensity tail: step back to the last live reaction (:262-281)
                     while (re > 0 && R.rr[re] <= 0.0) re--;
+                    ev_re = re;
                     // the reaction acts on the reactive population; consumption is taken from the present molecules.
                     int xn[SSB_SD > 0 ? SSB_SD : 1];
 #pragma unroll
@@ -1015,13 +1016,31 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
 #pragma unroll
                         for (int s = 0; s < SSB_SD; s++) if (s == spec) xx[s]--;
                         atomicAdd(&out_box[(size_t) spec * N + dest], 1u);
-                        atomicMax(&V.inbox_src[buf][dest], i + 1);
+                        {   // random priority from this voxel's Philox stream (bits of rand2 not used by the direction pick)
+                            const unsigned long long pri = (unsigned long long) (__double_as_longlong(rand2 * 4294967296.0 * 4096.0) & 0xffffffffll);
+                            atomicMax(&V.inbox_src[buf][dest], (pri << 32) | (unsigned long long) (unsigned) (i + 1));
+                        }
                         V.blk_mail[buf][dest / SSB_BLOCK] = 1;
                     }
                     n_df++;
                 }
                 if (!failed) {
-                    eval_rates(V, i, xr, xx, tt, vol, df, type_i, tau, R);
+                    if (V.flags & 1u) {
+                        eval_rates(V, i, xr, xx, tt, vol, df, type_i, tau, R);      // textbook mode: everything fresh, own vol
+                    } else {
+                        // reference: only the reactions the dependency graph lists for this event are re-evaluated
+                        // (simulate_rdme.cpp:299-308 after a reaction, :419-437 after a jump); the others keep their stored
+                        // value — including one computed with a neighbour's vol on arrival (:433)
+                        const unsigned long long mask = is_rxn ? ssb_gen::dep_mask_reaction(ev_re) : ssb_gen::dep_mask_species(spec);
+                        double tmp[SSB_RD > 0 ? SSB_RD : 1];
+                        ssb_gen::eval_propensities(xr, tt, vol, df, type_i, tmp);
+                        double sr = 0.0, sd = 0.0;
+#pragma unroll
+                        for (int r = 0; r < SSB_RD; r++) { if ((mask >> r) & 1ull) R.rr[r] = tmp[r]; sr += R.rr[r]; }
+#pragma unroll
+                        for (int s = 0; s < SSB_SD; s++) sd += Dd[s] * xx[s];
+                        R.sr = sr; R.sd = sd;
+                    }
                     const double tot2 = R.sr + R.sd;
                     double u0, u1;
                     philox_uniform2(vid, draw++, epoch, seed, u0, u1);

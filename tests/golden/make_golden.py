@@ -47,7 +47,7 @@ TAPS = {
     "cavity2d": [0, 1, 2, 3, 20, 21, 22, 45],
     "tank3d": [0, 1, 2, 21, 25],
     "cylinder": [0, 1],
-    "cdc42": [0, 1],
+    "cdc42": [0, 1, 2],
 }
 ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000, "cdc42": 600}
 XBINS = 8

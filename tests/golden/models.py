@@ -154,7 +154,7 @@ def cylinder(steps=5, dt=1.0):
     return model
 
 
-def cdc42(DX=12, end_time=0.05, steps=5):
+def cdc42(DX=12, end_time=0.02, steps=2):
     """BASELINE config 4 (examples/Yeast_Polarization/Cdc42.ipynb cell 12, create_cdc42_model) on a coarse DX x DX lattice and a
     short horizon so a >= 600-trajectory reference ensemble is affordable: 3 types with different masses (=> different voxel
     volumes across the membrane/cytoplasm interface), 9 species restricted by type, 13 reactions (12 mass action + CR0 with a

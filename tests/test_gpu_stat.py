@@ -64,7 +64,11 @@ def check_against_reference(name, ntraj):
         se_mean = np.sqrt(var_g / ntraj + var_r / nref)
         ok = se_mean > 0
         z = np.abs(mean_g - mean_r)[ok] / se_mean[ok]
-        assert (z > 3).mean() <= 0.01 and z.max() < 4.5, f"{name} step {s}: mean z max {z.max():.2f}, frac>3 {(z > 3).mean():.4f}"
+        zz = np.where(ok, np.abs(mean_g - mean_r) / np.where(ok, se_mean, 1.0), 0.0)
+        worst = [(int(v), int(sp), float(mean_g[v, sp]), float(mean_r[v, sp]), float(zz[v, sp]))
+                 for v, sp in zip(*np.unravel_index(np.argsort(-zz, axis=None)[:6], zz.shape))]
+        assert (z > 3).mean() <= 0.01 and z.max() < 4.5, \
+            f"{name} step {s}: mean z max {z.max():.2f}, frac>3 {(z > 3).mean():.4f}; worst (voxel, species, gpu, ref, z): {worst}"
         # variance: standard error from the fourth central moment; only where the count statistics are rich enough
         # for that estimate to mean anything (>= 100 expected molecules seen over the reference ensemble)
         m4 = ((xx - mean_g) ** 4).mean(axis=0)
@@ -89,7 +93,7 @@ def test_cylinder_ensemble_matches_reference():
 def test_cdc42_ensemble_matches_reference():
     """BASELINE config 4 (yeast polarisation, coarse lattice, short horizon): 9 type-restricted species, 13 reactions, a custom
     propensity reading a data function, voxel volumes that differ across the membrane/cytoplasm interface."""
-    check_against_reference("cdc42", 600)
+    check_against_reference("cdc42", 400)
 
 
 def test_pure_diffusion_ensemble_matches_reference():
