@@ -414,13 +414,66 @@ def slab_measure(args, rank, local_rank, world, steps, warmup, SPS):
     return line
 
 
+# ---------------------------------------------------------------------------------------------------------
+# ensemble arm: many trajectories of a SMALL model (BASELINE configs[0] birth-death, configs[3] Cdc42), k mod G over the GPUs
+# and several concurrent engine handles per GPU
+# ---------------------------------------------------------------------------------------------------------
+def run_ensemble_bench(args, rank, local_rank, world):
+    import torch
+    from spatialpy_b200 import FlatModel
+    from spatialpy_b200.ensemble import default_lanes, run_ensemble
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    name = {"ens_birth_death": "birth_death", "ens_cdc42": "cdc42"}[args.workload]
+    fm = FlatModel.load(os.path.join(ROOT, "tests", "golden", f"{name}.model.npz"))
+    lanes = args.lanes or default_lanes(fm.num_particles)
+    per_gpu = args.trajectories
+    total = per_gpu * world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+
+    run_ensemble(fm, lanes * world, 1, devices=[local_rank], lanes=lanes, rank=rank, world_size=world)      # warm-up (JIT, contexts)
+    barrier()
+    t0 = time.perf_counter()
+    res = run_ensemble(fm, total, 1000, devices=[local_rank], lanes=lanes, rank=rank, world_size=world)
+    barrier()
+    dt = time.perf_counter() - t0
+    ev = float(sum(c["reactions"] + c["diffusions"] for c in res.values()))
+    if use_dist:
+        t = torch.tensor([dt, ev], dtype=torch.float64, device="cuda")
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, ev = float(tm[0].item()), float(t[1].item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": fm.num_particles * fm.nt * total / dt, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"ensemble of {total} trajectories of the {name} fixture model ({fm.num_particles} particles, {fm.nt} steps, "
+                                   f"{fm.num_species} species, {fm.num_reactions} reactions)", "trajectories_per_gpu": per_gpu,
+                       "concurrent_engine_handles_per_gpu": lanes, "parallelism": f"ensemble: trajectory k -> GPU k mod {world}"},
+            "trajectories_per_s": total / dt, "rdme_events_per_s": ev / dt,
+            "e2e": {"value": fm.num_particles * fm.nt * total / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "includes": "host wall clock of ssb_run per trajectory incl. state upload and output staging (no VTK text)"}}))
+    if use_dist:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box"])
+    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box", "ens_birth_death", "ens_cdc42"])
+    ap.add_argument("--trajectories", type=int, default=128, help="ensemble workloads: trajectories per GPU")
+    ap.add_argument("--lanes", type=int, default=0, help="ensemble workloads: concurrent engine handles per GPU (0 = auto)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
     ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
@@ -431,6 +484,9 @@ def main():
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload.startswith("ens_"):
+        run_ensemble_bench(args, rank, local_rank, world)
         return
     if args.decomp == "slab":
         run_slab(args, rank, local_rank, world)

@@ -18,3 +18,63 @@ def reduce_scalar(value, op="max", device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def default_lanes(num_particles):
+    """Concurrent engine handles per GPU: small models cannot fill a B200 with one trajectory (a 144-voxel model occupies two
+    CTAs), so several trajectories run side by side on separate streams; large models get the GPU to themselves."""
+    if num_particles >= 200_000:
+        return 1
+    if num_particles >= 20_000:
+        return 4
+    return 16
+
+
+def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out_dirs=None, flags=None, rdme_epsilon=0.0,
+                 unit_path=None, on_engine=None, rank=0, world_size=1):
+    """Run trajectories k = rank, rank+world_size, ... (seed + k each) on `devices`, `lanes` engine handles per device, each
+    driven by its own host thread (ctypes releases the GIL during ssb_run).  Returns {k: counters} for the local trajectories;
+    raises the first EngineError.  `out_dirs[k]` (optional) receives trajectory k's VTK files."""
+    import threading
+    from .engine import Engine, EngineError, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+    lanes = lanes or default_lanes(fm.num_particles)
+    if flags is None:
+        flags = FLAG_SKIP_STATIC_FORCES | (0 if out_dirs is not None else FLAG_NO_VTK)
+    mine = shard_trajectories(number_of_trajectories, rank, world_size)
+    workers = [(d, l) for l in range(lanes) for d in devices][:max(1, len(mine))]
+    results, errors, lock = {}, [], threading.Lock()
+
+    def work(w):
+        dev, _ = workers[w]
+        ks = mine[w::len(workers)]
+        if not ks:
+            return
+        try:
+            eng = Engine(fm, device=dev, flags=flags, rdme_epsilon=rdme_epsilon, unit_path=unit_path)
+            if on_engine:
+                on_engine(eng)
+            try:
+                for k in ks:
+                    if errors:
+                        break
+                    if out_dirs is not None:
+                        eng.run(seed, [out_dirs[k]], first_traj=k)
+                    else:
+                        eng.run_no_files(seed, 1, first_traj=k)
+                    c = eng.counters()
+                    with lock:
+                        results[k] = c
+            finally:
+                eng.close()
+        except EngineError as err:
+            with lock:
+                errors.append(err)
+
+    threads = [threading.Thread(target=work, args=(w,)) for w in range(len(workers))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results

@@ -111,7 +111,7 @@ class Solver:
         return Result(self.model, outdir)
 
     def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False,
-            verbose=True, devices=None, flags=None, rdme_epsilon=0.0):
+            verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None):
         from .engine import Engine, EngineError, FLAG_SKIP_STATIC_FORCES
         if not self.is_compiled:
             self.compile(debug=debug, profile=profile)
@@ -123,51 +123,43 @@ class Solver:
         for _ in range(number_of_trajectories):
             outdir = tempfile.mkdtemp(prefix="spatialpy_result_", dir=os.environ.get("SPATIALPY_TMPDIR"))   # solver.py:548
             results.append(self._new_result(outdir))
-        errors, engines, lock = [], [], threading.Lock()
+        from .ensemble import run_ensemble
+        engines, lock = [], threading.Lock()
         start = time.monotonic()
+        state = {"error": None, "done": False}
+        out_dirs = [r.result_dir for r in results]
 
-        def worker(rank):
-            # trajectory k -> GPU k mod G; trajectory k always uses seed + k (solver.py:558-559)
-            mine = [k for k in range(number_of_trajectories) if k % len(devices) == rank]
-            if not mine:
-                return
+        def body():
             try:
-                eng = Engine(self.flat, device=devices[rank], flags=flags, rdme_epsilon=rdme_epsilon, unit_path=self.unit_path)
-                with lock:
-                    engines.append(eng)
-                try:
-                    for k in mine:
-                        eng.run(seed, [results[k].result_dir], first_traj=k)
-                        results[k].success = True
-                finally:
-                    eng.close()
+                done = run_ensemble(self.flat, number_of_trajectories, seed, devices=devices, lanes=lanes, out_dirs=out_dirs,
+                                    flags=flags, rdme_epsilon=rdme_epsilon, unit_path=self.unit_path,
+                                    on_engine=lambda e: (lock.acquire(), engines.append(e), lock.release()))
+                for k in done:
+                    results[k].success = True
             except EngineError as err:
-                errors.append(err)
+                state["error"] = err
+            state["done"] = True
 
-        threads = [threading.Thread(target=worker, args=(r,)) for r in range(len(devices))]
-        for t in threads:
-            t.start()
+        t = threading.Thread(target=body)
+        t.start()
         timed_out = False
-        for t in threads:
-            if timeout is None:
-                t.join()
-            else:
-                t.join(max(0.0, timeout - (time.monotonic() - start)))
-                if t.is_alive():               # solver.py:583-586: SIGINT on timeout, result.timeout = True
-                    timed_out = True
-                    with lock:
-                        for e in engines:
-                            e.cancel()
-                    t.join()
+        t.join(timeout)
+        if t.is_alive():                       # solver.py:583-586: SIGINT on timeout, result.timeout = True
+            timed_out = True
+            while t.is_alive():
+                with lock:
+                    for e in engines:
+                        e.cancel()
+                t.join(0.05)
         if self.debug_level >= 1:
             print("Elapsed seconds: {:.2f}".format(time.monotonic() - start))
         if timed_out:
             for r in results:
                 if not r.success:
                     r.timeout = True
-        else:
-            for err in errors:
-                raise SimulationError(f"Solver execution failed, return code = {err.code}") from err   # solver.py:595-597
+        elif state["error"] is not None:
+            err = state["error"]
+            raise SimulationError(f"Solver execution failed, return code = {err.code}") from err   # solver.py:595-597
         first = results[0]
         for r in results[1:]:
             first.append(r)
