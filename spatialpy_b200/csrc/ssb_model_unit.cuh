@@ -1099,9 +1099,11 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
 // zero-length closing window that delivers in-flight molecules; a grid-wide barrier separates consecutive windows
 // (a window's inbox writes must be complete before the next window reads them).  Removes the per-window launch
 // latency that dominates small systems (config 1: ~1900 windows per step) and idle windows of large ones.
+// SINGLE = true: the whole model fits the chunks of ONE CTA (small ensembles: birth-death, Cdc42): the barrier between windows is a
+// block barrier, the launch is an ordinary one, and many trajectories run side by side on separate streams.
+template <bool SINGLE>
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, double t0, double dt, long long nwin, double tau,
                                                                 uint64_t seed, uint64_t epoch0, int buf0) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     unsigned n_rx = 0, n_df = 0;
     int buf = buf0;
     for (long long w = 0; w <= nwin; w++) {
@@ -1112,7 +1114,10 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, doub
         } else { lo = hi = t0 + dt; }
         rdme_window_body(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
         buf ^= 1;
-        if (w < nwin) grid.sync();
+        if (w < nwin) {
+            if (SINGLE) { __threadfence(); __syncthreads(); }
+            else cooperative_groups::this_grid().sync();
+        }
     }
     flush_event_counters(V, n_rx, n_df);
 }
@@ -1170,16 +1175,21 @@ static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop, SSB_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop<false>, SSB_BLOCK, 0);
         coop_blocks = coop ? sms * per_sm : 0;
     }
     const unsigned nchunks = grid_for(V->N);
+    if (nchunks <= 8) {      // small model: one CTA walks all chunks; ordinary launch, block barrier between windows
+        k_rdme_windows_coop<true><<<1, SSB_BLOCK, 0, st>>>(*V, t0, dt, nwin, tau, seed, epoch0, buf0);
+        if (launches) *launches = 1;
+        return (int) cudaGetLastError();
+    }
     if (coop_blocks > 0) {
         unsigned grid = (unsigned) coop_blocks;
         if (grid > nchunks) grid = nchunks;
         SsbView view = *V;
         void *args[] = {&view, &t0, &dt, &nwin, &tau, &seed, &epoch0, &buf0};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_rdme_windows_coop, dim3(grid), dim3(SSB_BLOCK), args, 0, st);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_rdme_windows_coop<false>, dim3(grid), dim3(SSB_BLOCK), args, 0, st);
         if (launches) *launches = 1;
         return (int) e;
     }
