@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # see spatialpy_b200/engine.py (ensemble lanes)
 
 METRIC = "particle-steps/s (SDPD+sSSA)"
 UNIT = "particle-steps/s"

@@ -1,18 +1,24 @@
-import sys
+import sys, time, threading
 sys.path.insert(0,'tests'); sys.path.insert(0,'.')
-import numpy as np
-from util import *
-from spatialpy_b200.engine import Engine
-name='diffusion3d'
-fm=load_model(name); ref=load_ref(name)
-eng=Engine(fm, flags=0)
-eng.reset(1000); eng.step(1)
-for f in ('Q','C','F','Fbp','Frho','rho'):
-    a=eng.get(f); b=ref[f's1_{f}']
-    print(f, rel_err(a,b), a.shape)
-a=eng.get('Q'); b=ref['s1_Q']
-bad=np.where(np.abs(a-b).max(axis=1)>1e-9*np.abs(b).max())[0]
-print(len(bad), bad[:20])
-for i in bad[:5]:
-    print(i, fm.x[i], fm.type[i], a[i], b[i], eng.fm.u0[i])
-print('C0', ref['s0_C'][:3], 'Q0', ref['s0_Q'][:3])
+from util import load_model
+from spatialpy_b200.engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+fm=load_model('cdc42')
+def worker(k, out, ntraj, mode):
+    eng=Engine(fm, flags=FLAG_NO_VTK|FLAG_SKIP_STATIC_FORCES)
+    eng.run_no_files(1+k,1)
+    bar.wait()
+    t=time.perf_counter(); tr=0.0
+    for q in range(ntraj):
+        if mode==0:
+            t1=time.perf_counter(); eng.reset(100+k*10+q); tr+=time.perf_counter()-t1; eng.step(fm.nt)
+        else:
+            eng.run_no_files(100+k*10+q,1)
+    w=time.perf_counter()-t
+    out[k]=(w/ntraj*1e3, tr/ntraj*1e3)
+    eng.close()
+for mode in (0,1):
+  for T in (1,8,16):
+    out={}; bar=threading.Barrier(T)
+    th=[threading.Thread(target=worker,args=(k,out,4,mode)) for k in range(T)]
+    [t.start() for t in th]; [t.join() for t in th]
+    print('mode',mode,'threads',T, 'wall/traj ms', round(sum(v[0] for v in out.values())/T,1), 'reset ms', round(sum(v[1] for v in out.values())/T,2))

@@ -414,7 +414,7 @@ struct ssb_handle {
     // slab decomposition support
     int *d_slot_of_id = nullptr;  // particle id -> storage slot (rebuilt lazily after a permutation)
     int slot_dirty = 1;
-    cudaEvent_t mark_a = nullptr, mark_b = nullptr;
+    cudaEvent_t mark_a = nullptr, mark_b = nullptr, sync_ev = nullptr;
     int static_cached = 0;        // static domain: storage order, neighbour lists, coefficients and Ddiag survive ssb_reset
     int *d_static_perm = nullptr; // slot -> particle id of the cached storage order
     double max_ddiag_cached = 0.0;
@@ -466,10 +466,22 @@ static cudaError_t dalloc(ssb_handle *h, T **p, size_t count) {
 
 static inline unsigned gridN(int n) { return (unsigned) ((n + CORE_BLOCK - 1) / CORE_BLOCK); }
 
+// Host wait for the engine stream through a BLOCKING-SYNC event: the calling thread sleeps instead of spinning, so many
+// engine handles (ensemble lanes, one host thread each) do not fight over the host cores while their kernels run.
+static cudaError_t ssb_sync(ssb_handle *h) {
+    if (!h->sync_ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&h->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(h->sync_ev, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(h->sync_ev);
+}
+
 // ---- per-category device timing -------------------------------------------------------------------------
 static void prof_harvest(ssb_handle *h) {
     if (h->ev_cat.empty()) return;
-    cudaStreamSynchronize(h->stream);
+    ssb_sync(h);
     for (size_t k = 0; k < h->ev_cat.size(); k++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->ev_a[k], h->ev_b[k]) == cudaSuccess) h->cat_ms[h->ev_cat[k]] += ms;
@@ -836,7 +848,7 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     h->allocs.push_back(h->d_stage);
     for (int b = 0; b < 2; b++) {
         OutputJob &J = h->jobs[b];
-        CK(cudaEventCreateWithFlags(&J.ready, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&J.ready, cudaEventDisableTiming | cudaEventBlockingSync));
         CK(cudaMallocHost((void **) &J.x, sizeof(double) * 3 * N));
         CK(cudaMallocHost((void **) &J.v, sizeof(double) * 3 * N));
         CK(cudaMallocHost((void **) &J.scal, sizeof(double) * 4 * N));
@@ -857,7 +869,7 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
         for (int i = 0; i < N; i++) { pi[i] = h->htype[i]; pi[(size_t) N + i] = h->hsolid[i]; pi[(size_t) 2 * N + i] = h->howned[i]; pi[(size_t) 3 * N + i] = h->hgid[i]; }
         for (int sp = 0; sp < Sd; sp++) for (int i = 0; i < N; i++) pi[(size_t) (4 + sp) * N + i] = (int) h->hu0[(size_t) i * S + sp];
     }
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     h->writer = std::thread(writer_main, h);
     return SSB_OK;
 }
@@ -899,7 +911,7 @@ extern "C" int ssb_destroy(ssb_handle *h) {
         h->writer.join();
     }
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) ssb_sync(h);
     for (void *p : h->allocs) cudaFree(p);
     for (int b = 0; b < 2; b++) {
         OutputJob &J = h->jobs[b];
@@ -907,6 +919,7 @@ extern "C" int ssb_destroy(ssb_handle *h) {
         cudaFreeHost(J.x); cudaFreeHost(J.v); cudaFreeHost(J.scal); cudaFreeHost(J.type); cudaFreeHost(J.C); cudaFreeHost(J.xx);
     }
     if (h->mark_a) { cudaEventDestroy(h->mark_a); cudaEventDestroy(h->mark_b); }
+    if (h->sync_ev) cudaEventDestroy(h->sync_ev);
     for (auto e : h->ev_a) cudaEventDestroy(e);
     for (auto e : h->ev_b) cudaEventDestroy(e);
     if (h->init_f64) cudaFreeHost(h->init_f64);
@@ -974,11 +987,11 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     if (!h->static_cached) CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, st));
     if (V.static_domain) for (int d = 0; d < 3; d++) V.x0[d] = V.x[d];
     V.rho_search = V.rho;
-    CK(cudaStreamSynchronize(st));
+    CK(ssb_sync(h));
     if (h->static_cached) {      // put the freshly uploaded (id-ordered) state into the cached storage order
         int rcp = apply_permutation(h, h->d_static_perm);
         if (rcp) return rcp;
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
     }
     h->current_step = 0;
     h->rdme_initialized = 0;
@@ -1021,7 +1034,7 @@ static int build_cells(ssb_handle *h) {
     h->launches += 6;
     int nonid = 0;
     CK(cudaMemcpyAsync(&nonid, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(ssb_sync(h));
     if (!nonid) return SSB_OK;
     return apply_permutation(h, h->d_perm);
 }
@@ -1048,7 +1061,7 @@ static int apply_permutation(ssb_handle *h, const int *d_perm) {
     k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, d_perm, h->d_permtable);
     h->slot_dirty = 1;
     h->launches += 1;
-    CK(cudaStreamSynchronize(st));   // T lives on this stack frame
+    CK(ssb_sync(h));   // T lives on this stack frame
     for (size_t f = 0; f < nf; f++) { double *cur = *h->f64_slots[f]; *h->f64_slots[f] = h->f64_alt[f]; h->f64_alt[f] = cur; }
     for (size_t f = 0; f < ni; f++) { int *cur = *h->i32_slots[f]; *h->i32_slots[f] = h->i32_alt[f]; h->i32_alt[f] = cur; }
     // species blocks: copy back (blocks keep their identity so C/Q/data_fn/xx stay contiguous)
@@ -1073,7 +1086,7 @@ static int count_candidates(ssb_handle *h, double *total) {
     k_search<<<gridN(h->N), CORE_BLOCK, 0, st>>>(V, h->grid, h->d_cell_start, h->d_flags + 1, h->d_maxbits + 1);
     unsigned long long t = 0;
     CK(cudaMemcpyAsync(&t, h->d_maxbits + 1, sizeof(t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(ssb_sync(h));
     *total = (double) t;
     h->launches += 1;
     return SSB_OK;
@@ -1118,7 +1131,7 @@ static int neighbour_search(ssb_handle *h) {
         h->launches += 1;
         int mx = 0;
         CK(cudaMemcpyAsync(&mx, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         if (mx <= V.nbr_cap) return SSB_OK;
         // grow (with head-room on moving domains) and search again
         int cap = V.static_domain ? mx : (mx + mx / 4 + 8);
@@ -1152,7 +1165,7 @@ static int neighbour_search(ssb_handle *h) {
 static int check_device_error(ssb_handle *h) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, h->V.err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     if (flag == SSB_ERR_NAN) return fail(h, SSB_ERR_NAN, "ERROR: nan/inf detected!!! (step %u)", h->current_step);
     if (flag == SSB_ERR_RDME) return fail(h, SSB_ERR_RDME, "RDME state error (negative population or propensity overflow) at step %u", h->current_step);
     return SSB_OK;
@@ -1178,7 +1191,7 @@ static int rdme_step(ssb_handle *h) {
             memcpy(&bits, &h->max_ddiag_cached, sizeof(bits));
         } else {
             CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(ssb_sync(h));
         }
         h->ddiag_fresh = 0;
         double mx;
@@ -1269,7 +1282,7 @@ static int engine_step(ssb_handle *h) {
         // A pair within h now has |xref_i - xref_j| <= h + D_now + D_prev, so the lists are complete iff D_now + D_prev <= skin*h.
         unsigned long long bits[2] = {0, 0};
         CK(cudaMemcpyAsync(bits, V.disp_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         double d2now, s2;
         memcpy(&d2now, &bits[0], 8); memcpy(&s2, &bits[1], 8);
         const double Dnow = sqrt(d2now), budget = h->skin * V.h;
@@ -1348,7 +1361,7 @@ extern "C" int ssb_step(ssb_handle *h, uint32_t nsteps) {
         if ((s & 15) == 15 || s + 1 == nsteps) { if ((rc = check_device_error(h))) return rc; }
         if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
     }
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     h->step_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return SSB_OK;
 }
@@ -1433,10 +1446,11 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
             if (cb && cb(cb_user, step + 1, nt)) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled by callback"); }
         }
         if ((rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;   // final timepoint (:283-285)
-        CK(cudaStreamSynchronize(h->stream));
+        CK(ssb_sync(h));
         h->step_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         unsigned long long cnt[2] = {0, 0};
-        CK(cudaMemcpy(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+        CK(ssb_sync(h));
         h->total_reactions = (int64_t) cnt[0];
         h->total_diffusion = (int64_t) cnt[1];
         if ((rc = drain_writer(h))) return fail(h, rc, "could not write VTK output into %s", write_files ? out_dirs[k] : "(none)");
@@ -1447,9 +1461,10 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
 extern "C" int ssb_counters(ssb_handle *h, int64_t *reactions, int64_t *diffusions, double *seconds, int64_t *windows) {
     if (!h) return SSB_ERR_ARG;
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     unsigned long long cnt[2] = {0, 0};
-    CK(cudaMemcpy(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(cnt, h->V.counters, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream));
+    CK(ssb_sync(h));
     if (reactions) *reactions = (int64_t) cnt[0];
     if (diffusions) *diffusions = (int64_t) cnt[1];
     if (seconds) *seconds = h->step_seconds;
@@ -1480,7 +1495,7 @@ extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t
         if (bytes != (int64_t) sizeof(double) * 3 * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * 3 * N);
         for (int d = 0; d < 3; d++) k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, v3[d], h->d_stage, 3, d);
         CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         return SSB_OK;
     }
     const double *s1 = nullptr;
@@ -1491,7 +1506,7 @@ extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t
         if (bytes != (int64_t) sizeof(double) * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * N);
         k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, s1, h->d_stage, 1, 0);
         CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         return SSB_OK;
     }
     const int *i1 = nullptr;
@@ -1500,7 +1515,7 @@ extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t
         if (bytes != (int64_t) sizeof(int) * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(int) * N);
         k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, i1, (int *) h->d_stage, 1, 0);
         CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         return SSB_OK;
     }
     // species-major blocks -> voxel-major [N][K] on the host side
@@ -1512,7 +1527,7 @@ extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t
         if (bytes != (int64_t) sizeof(double) * K * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * K * N);
         for (int s = 0; s < K; s++) k_unperm64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, blk + (size_t) s * N, h->d_stage, K, s);
         if (K > 0) CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         return SSB_OK;
     }
     if (n == "xx") {
@@ -1520,7 +1535,7 @@ extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t
         if (bytes != (int64_t) sizeof(unsigned) * K * N) return fail(h, SSB_ERR_ARG, "field xx needs %lld bytes", (long long) sizeof(unsigned) * K * N);
         for (int s = 0; s < K; s++) k_unperm32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, (int *) V.xx + (size_t) s * N, (int *) h->d_stage, K, s);
         if (K > 0) CK(cudaMemcpyAsync(dst, h->d_stage, bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         return SSB_OK;
     }
     return fail(h, SSB_ERR_ARG, "unknown field '%s'", name);
@@ -1537,7 +1552,7 @@ extern "C" int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, doub
     CK(cudaMalloc((void **) &d_cnt, sizeof(long long) * (N + 1)));
     k_nbr_count_by_id<<<gridN(N), CORE_BLOCK, 0, st>>>(V, d_cnt);
     CK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(long long) * N, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(ssb_sync(h));
     std::vector<long long> p((size_t) N + 1, 0);
     for (int i = 0; i < N; i++) p[i + 1] = p[i] + cnt[i];
     const long long nnz = p[N];
@@ -1555,7 +1570,7 @@ extern "C" int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, doub
     CK(cudaMemcpyAsync(dist, d_a, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(dWdr, d_a + nnz, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(Dij, d_a + 2 * nnz, sizeof(double) * nnz, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(ssb_sync(h));
     cudaFree(d_cnt); cudaFree(d_idx); cudaFree(d_a);
     return SSB_OK;
 }
@@ -1568,13 +1583,13 @@ extern "C" int ssb_step_timed(ssb_handle *h, uint32_t nsteps, double *device_ms)
     if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
     CK(cudaSetDevice(h->device));
     cudaEvent_t a, b;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventCreateWithFlags(&a, cudaEventBlockingSync)); CK(cudaEventCreateWithFlags(&b, cudaEventBlockingSync));
+    CK(ssb_sync(h));
     CK(cudaEventRecord(a, h->stream));
     int rc = SSB_OK;
     for (uint32_t s = 0; s < nsteps && !rc; s++) rc = engine_step(h);
     CK(cudaEventRecord(b, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
@@ -1673,7 +1688,7 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
         if (V.filter) {
             unsigned long long bits[2] = {0, 0};
             CK(cudaMemcpyAsync(bits, V.disp_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(ssb_sync(h));
             double d2now, s2;
             memcpy(&d2now, &bits[0], 8); memcpy(&s2, &bits[1], 8);
             const double Dnow = sqrt(d2now), budget = h->skin * V.h;
@@ -1704,7 +1719,7 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
     case PH_RDME_PREP: {
         unsigned long long bits = 0;
         CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(ssb_sync(h));
         double mx;
         memcpy(&mx, &bits, sizeof(mx));
         if (out) *out = mx;
@@ -1760,7 +1775,7 @@ extern "C" int ssb_halo_pack(ssb_handle *h, int group, const int32_t *dev_ids, i
     if (rc) return rc;
     if (n > 0) k_halo_pack<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, group, dev_ids, n, h->d_slot_of_id, dev_out);
     h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     return SSB_OK;
 }
 extern "C" int ssb_halo_unpack(ssb_handle *h, int group, const int32_t *dev_ids, int32_t n, const double *dev_in) {
@@ -1770,7 +1785,7 @@ extern "C" int ssb_halo_unpack(ssb_handle *h, int group, const int32_t *dev_ids,
     if (rc) return rc;
     if (n > 0) k_halo_unpack<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, group, dev_ids, n, h->d_slot_of_id, dev_in);
     h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     return SSB_OK;
 }
 // inbox of the sSSA window that just ran (the buffer the next window will read)
@@ -1781,7 +1796,7 @@ extern "C" int ssb_halo_inbox_pack(ssb_handle *h, const int32_t *dev_ids, int32_
     if (rc) return rc;
     if (n > 0 && h->V.Sd > 0) k_inbox_pack<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, h->inbox_buf ^ 1, dev_ids, n, h->d_slot_of_id, dev_out);
     h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     return SSB_OK;
 }
 extern "C" int ssb_halo_inbox_add(ssb_handle *h, const int32_t *dev_ids, int32_t n, const uint32_t *dev_in) {
@@ -1791,7 +1806,7 @@ extern "C" int ssb_halo_inbox_add(ssb_handle *h, const int32_t *dev_ids, int32_t
     if (rc) return rc;
     if (n > 0 && h->V.Sd > 0) k_inbox_add<<<gridN(n), CORE_BLOCK, 0, h->stream>>>(h->V, h->inbox_buf ^ 1, dev_ids, n, h->d_slot_of_id, dev_in, h->unit->block);
     h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
+    CK(ssb_sync(h));
     return SSB_OK;
 }
 extern "C" int ssb_halo_width(ssb_handle *h, int group, int32_t *width) {

@@ -834,6 +834,29 @@ __device__ __forceinline__ int coop_pick_direction(const SsbView &V, int il, int
     return dest >= 0 ? dest : last_ok;                                          // round-off overflow (:368-380)
 }
 
+// the same pick done by ONE lane over its own neighbour row (serial running sum).  Used when several lanes of a warp need a
+// direction at once (crowded voxels): the lanes then work in parallel instead of queueing for the warp-cooperative pick.
+__device__ __forceinline__ int serial_pick_direction(const SsbView &V, int il, int spec, double target) {
+    const int N = V.N;
+    const int cnt = V.nbr_count[il];
+    const bool cached = V.Dij != nullptr;
+    double xl0 = 0, xl1 = 0, xl2 = 0, m_l = 0, rho_l = 0;
+    if (!cached) { xl0 = V.x[0][il]; xl1 = V.x[1][il]; xl2 = V.x[2][il]; m_l = V.mass[il]; rho_l = V.rho_search[il]; }
+    double cum = 0.0;
+    int last_ok = -1;
+    for (int k = 0; k < cnt; k++) {
+        const int j = V.nbr[(size_t) k * N + il];
+        const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
+        if (dc == 0.0) continue;
+        if (V.filter && !ssb_in_range(ssb_dist2(V.dim, xl0, xl1, xl2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h))) continue;
+        const double Dij = cached ? V.Dij[(size_t) k * N + il] : pair_Dij(V, il, j, xl0, xl1, xl2, m_l, rho_l);
+        cum += Dij * dc;
+        last_ok = j;
+        if (cum > target) return j;
+    }
+    return last_ok;
+}
+
 __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, double t_hi, double tau, uint64_t seed,
                                                  uint64_t epoch, int buf, unsigned &n_rx, unsigned &n_df) {
     // Persistent grid: each CTA owns the chunks c = blockIdx.x + t*gridDim.x (a chunk = SSB_BLOCK consecutive voxels).
@@ -971,6 +994,10 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
             const bool need_dir = ev && !is_rxn && !failed;
             int dest = -1;
             unsigned todo = __ballot_sync(0xffffffffu, need_dir);
+            if (__popc(todo) >= 4) {           // crowded: every lane scans its own row, all lanes in parallel
+                if (need_dir) dest = serial_pick_direction(V, ii, spec, rand2 * V.Ddiag[(size_t) spec * N + ii]);
+                todo = 0u;
+            }
             while (todo) {
                 const int leader = __ffs(todo) - 1;
                 todo &= todo - 1;
@@ -1115,7 +1142,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, doub
         rdme_window_body(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
         buf ^= 1;
         if (w < nwin) {
-            if (SINGLE) { __threadfence(); __syncthreads(); }
+            if (SINGLE) __syncthreads();       // one CTA: a block barrier orders the inbox traffic, and (unlike a device-scope fence) keeps L1 warm
             else cooperative_groups::this_grid().sync();
         }
     }

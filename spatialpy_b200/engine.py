@@ -5,6 +5,11 @@ There is no CPU fallback: constructing an `Engine` without libssb_core.so (or wi
 import ctypes as C
 import os
 
+# Ensemble lanes run one engine stream per concurrent trajectory.  With the default of 8 hardware work queues, more than 8
+# streams alias onto the same queue and serialise behind each other's long sSSA kernels (measured: 16 lanes ran 4x slower per
+# trajectory); 32 queues restore full concurrency.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 from . import codegen

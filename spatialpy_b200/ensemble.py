@@ -27,7 +27,7 @@ def default_lanes(num_particles):
         return 1
     if num_particles >= 20_000:
         return 4
-    return 16
+    return 24
 
 
 def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out_dirs=None, flags=None, rdme_epsilon=0.0,
