@@ -1,24 +1,11 @@
-import sys, time, threading
+import sys, time, threading, os
 sys.path.insert(0,'tests'); sys.path.insert(0,'.')
 from util import load_model
-from spatialpy_b200.engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+from spatialpy_b200.ensemble import run_ensemble
 fm=load_model('cdc42')
-def worker(k, out, ntraj, mode):
-    eng=Engine(fm, flags=FLAG_NO_VTK|FLAG_SKIP_STATIC_FORCES)
-    eng.run_no_files(1+k,1)
-    bar.wait()
-    t=time.perf_counter(); tr=0.0
-    for q in range(ntraj):
-        if mode==0:
-            t1=time.perf_counter(); eng.reset(100+k*10+q); tr+=time.perf_counter()-t1; eng.step(fm.nt)
-        else:
-            eng.run_no_files(100+k*10+q,1)
-    w=time.perf_counter()-t
-    out[k]=(w/ntraj*1e3, tr/ntraj*1e3)
-    eng.close()
-for mode in (0,1):
-  for T in (1,8,16):
-    out={}; bar=threading.Barrier(T)
-    th=[threading.Thread(target=worker,args=(k,out,4,mode)) for k in range(T)]
-    [t.start() for t in th]; [t.join() for t in th]
-    print('mode',mode,'threads',T, 'wall/traj ms', round(sum(v[0] for v in out.values())/T,1), 'reset ms', round(sum(v[1] for v in out.values())/T,2))
+if len(sys.argv)>2: import torch; torch.cuda.init(); torch.cuda.synchronize()
+lanes=int(sys.argv[1])
+run_ensemble(fm, lanes, 1, devices=[0], lanes=lanes)
+for T in (lanes*2, lanes*6):
+    t=time.perf_counter(); r=run_ensemble(fm, T, 1000, devices=[0], lanes=lanes); w=time.perf_counter()-t
+    print('lanes',lanes,'traj',T,'wall',round(w,2),'traj/s',round(T/w,1), 'torch' if len(sys.argv)>2 else '')
