@@ -1122,9 +1122,7 @@ static int neighbour_search(ssb_handle *h) {
     cudaStream_t st = h->stream;
     if (V.filter && !h->skin_chosen) { int rcs = choose_skin(h); if (rcs) return rcs; }
     for (int attempt = 0; attempt < 8; attempt++) {
-        if (V.nbr_cap == 0) {
-            // first build: size the ELL rows from an exact count pass (cap 0 stores nothing)
-        }
+        // (first build: the capacity is 0, so this pass only counts; the rows are then sized from the maximum)
         CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), st));
         CK(cudaMemsetAsync(h->d_maxbits + 1, 0, sizeof(unsigned long long), st));
         k_search<<<gridN(N), CORE_BLOCK, 0, st>>>(V, h->grid, h->d_cell_start, h->d_flags + 1, h->d_maxbits + 1);

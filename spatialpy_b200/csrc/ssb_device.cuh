@@ -81,11 +81,6 @@ struct SsbView {
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011).  key = (seed lo, seed hi);
 // counter = (voxel id, draw index, window lo, window hi) so every draw is addressable and no RNG state is stored.
 // ------------------------------------------------------------------------------------------------
-struct Philox {
-    uint32_t c[4];
-    uint32_t k[2];
-};
-
 __host__ __device__ __forceinline__ void philox_round(uint32_t c[4], const uint32_t k[2]) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #ifdef __CUDA_ARCH__
@@ -138,11 +133,6 @@ __device__ __forceinline__ ssb_d4 ssb_ld256(const double *p) {
 // ------------------------------------------------------------------------------------------------
 // Pair arithmetic — restates E/src/particle.cpp:150-210 (add_to_neighbor_list) in registers.
 // ------------------------------------------------------------------------------------------------
-struct SsbKernelConst {
-    double h, h2, alpha, inv_h;
-    double wfd_c;   // -25.066903536973515383 / h^7 factor pieces are applied in reference order below
-};
-
 // kernel normalisation alpha: 3-D 105/(16 pi h^3), 2-D 5/(pi h^2), 1-D `5 / 4 * h` == h (integer division!)
 // (particle.cpp:169-175, model.cpp:200-206,243-249)
 __host__ __device__ __forceinline__ double ssb_alpha(int dim, double h) {

@@ -121,3 +121,40 @@ def test_full_size_static_cylinder_properties():
         assert total == int(cnt.sum()) and total % 2 == 0          # j in N(i) <=> i in N(j) on a static domain
         # species restriction: A never enters Edge2 voxels, B never enters Edge1 voxels (diffusion matrix zeros)
         assert xx[fm.type == 1, 0].sum() == 0 and xx[fm.type == 2, 1].sum() == 0
+
+
+def test_full_size_moving_tank_properties():
+    """BASELINE configs[2] stand-in at full size (~1.0 M moving particles): same seed => identical state, walls never move,
+    the fluid stays finite and inside the tank, molecule bookkeeping balances, and the Verlet-skin candidate lists give the
+    same neighbour counts as exact per-step lists (SSB_SKIN=0)."""
+    import os
+    from spatialpy_b200 import configs
+    from spatialpy_b200.engine import Engine
+    fm = configs.tank_sdpd(n=120, nt=20, output_every=20)
+    fm.parameters = {"P0": 0.0, "P1": 0.0}            # reactions off: diffusion must conserve the molecule count exactly
+    outs = {}
+    for skin in ("auto", "0"):
+        if skin == "0":
+            os.environ["SSB_SKIN"] = "0"
+        try:
+            with Engine(fm) as eng:
+                eng.reset(5)
+                eng.step(6)
+                outs[skin] = dict(x=eng.get("x"), v=eng.get("v"), rho=eng.get("rho"), xx=eng.get("xx"), stats=eng.skin_stats(),
+                                  nbr=eng.neighbors()[0], counters=eng.counters())
+                if skin == "auto":
+                    eng.reset(5)
+                    eng.step(6)
+                    np.testing.assert_array_equal(eng.get("x"), outs[skin]["x"])       # bit-reproducible
+                    np.testing.assert_array_equal(eng.get("xx"), outs[skin]["xx"])
+        finally:
+            os.environ.pop("SSB_SKIN", None)
+    a, b = outs["auto"], outs["0"]
+    walls = fm.solid == 1
+    np.testing.assert_array_equal(a["x"][walls], fm.x[walls])
+    assert np.isfinite(a["x"]).all() and np.isfinite(a["v"]).all() and np.isfinite(a["rho"]).all()
+    assert a["x"].min() >= -1e-9 and a["x"].max() <= 1.0 + 1e-9
+    assert int(a["xx"].sum()) == int(fm.u0.sum()) and a["counters"]["reactions"] == 0 and a["counters"]["diffusions"] > 0
+    assert a["stats"]["skin"] > 0 and b["stats"]["skin"] == 0 and a["stats"]["rebuilds"] < b["stats"]["rebuilds"]
+    np.testing.assert_array_equal(a["nbr"], b["nbr"])                               # identical neighbour counts per particle
+    assert rel_err(a["x"], b["x"]) <= RTOL_TRAJ and rel_err(a["rho"], b["rho"]) <= RTOL_TRAJ
