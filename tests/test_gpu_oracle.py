@@ -155,6 +155,6 @@ def test_full_size_moving_tank_properties():
     assert np.isfinite(a["x"]).all() and np.isfinite(a["v"]).all() and np.isfinite(a["rho"]).all()
     assert a["x"].min() >= -1e-9 and a["x"].max() <= 1.0 + 1e-9
     assert int(a["xx"].sum()) == int(fm.u0.sum()) and a["counters"]["reactions"] == 0 and a["counters"]["diffusions"] > 0
-    assert a["stats"]["skin"] > 0 and b["stats"]["skin"] == 0 and a["stats"]["rebuilds"] < b["stats"]["rebuilds"]
+    assert a["stats"]["skin"] > 0 and b["stats"]["skin"] == 0 and a["stats"]["rebuilds"] == 1     # one list build served all 6 steps
     np.testing.assert_array_equal(a["nbr"], b["nbr"])                               # identical neighbour counts per particle
     assert rel_err(a["x"], b["x"]) <= RTOL_TRAJ and rel_err(a["rho"], b["rho"]) <= RTOL_TRAJ
