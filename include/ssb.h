@@ -41,6 +41,8 @@ extern "C" {
 #define SSB_FLAG_NO_VTK 4u                 /* stage outputs (ssb_get_output) but do not write outputN.vtk files */
 #define SSB_FLAG_LITERAL_KERNELS 16u       /* evaluate every pair expression in the reference's literal order (k_force<true>, separate diffusion-matrix
                                               sweep) instead of the restructured sweeps; slower, used by the parity tests as a cross-check */
+#define SSB_FLAG_LEAP_DIFFUSION 32u        /* sSSA: advance the diffusion channel per window (binomial jump counts, multinomial destinations)
+                                              instead of one event per jump; same law in the windowed scheme, O(1) per species and window */
 #define SSB_FLAG_SKIP_STATIC_FORCES 8u     /* static domains: skip F/Fbp/Frho (never consumed when static, simulate.cpp:68,137); default on via Python */
 
 /* Flat model description.  Replaces the generated-literal inputs of solver.py:100-419. */

@@ -767,6 +767,9 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_init(SsbView V, double t0, d
         double u0, u1;
         philox_uniform2((uint32_t) V.gid[i], 0u, epoch, seed, u0, u1);
         tn = (tot > 0.0 && V.owned[i]) ? t0 + (-log(u0)) / tot : INFINITY;      // ghost voxels are simulated by their owner
+        if ((V.flags & 32u) && V.owned[i]) {      // leap form: the stored clock is the REACTION clock; mobile molecules make a voxel due every window
+            tn = (R.sd > 0.0) ? -INFINITY : ((R.sr > 0.0) ? t0 + (-log(u0)) / R.sr : INFINITY);
+        }
         V.tnext[i] = tn;
 #pragma unroll
         for (int s = 0; s < SSB_SD; s++) { V.inbox[0][(size_t) s * N + i] = 0u; V.inbox[1][(size_t) s * N + i] = 0u; }
@@ -1103,6 +1106,292 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K7b, leap form (SSB_FLAG_LEAP_DIFFUSION): same windows, same inboxes, same reaction SSA — but the DIFFUSION channel of a
+// voxel is advanced per window instead of per jump: every molecule present at the window start jumps independently with
+// probability q = 1 - exp(-lambda' tau), so the number of jumpers of a species is Binomial(n, q) and their destinations are
+// multinomial over the neighbour weights D_i_j * D[spec, type(dest)].  In the windowed scheme a molecule jumps at most once per
+// window anyway (it sits in the destination's inbox until the window closes), so for the diffusion channel this is the same
+// law at O(1) work per species and window instead of O(jumps) — a voxel holding hundreds of molecules no longer serialises
+// hundreds of events.  The reference's channel-pick distortion (rand1*sdrate on (srrate/totrate, 1], simulate_rdme.cpp:317-321)
+// is carried over as the per-species effective propensity tot * |(p,1] ∩ (c_{s-1}/sd, c_s/sd]| evaluated at the window start.
+// ---------------------------------------------------------------------------------------------
+struct LeapRng {
+    uint32_t vid, draw;
+    uint64_t epoch, seed;
+    double spare;
+    bool has_spare;
+    __device__ __forceinline__ double next() {
+        if (has_spare) { has_spare = false; return spare; }
+        double a, b;
+        philox_uniform2(vid, draw++, epoch, seed, a, b);
+        spare = b; has_spare = true;
+        return a;
+    }
+};
+
+// Binomial(n, p): inversion (BINV) for small means, BTRS (Hormann 1993) otherwise; both exact up to fp rounding.
+__device__ int ssb_binomial(int n, double p, LeapRng &rng) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double pp = flip ? 1.0 - p : p;
+    int x;
+    if ((double) n * pp < 30.0 && (double) n * log1p(-pp) > -700.0) {
+        const double q = 1.0 - pp, s = pp / q, a = (n + 1) * s;
+        double r = exp((double) n * log(q)), u = rng.next();
+        x = 0;
+        while (u > r) {
+            u -= r;
+            x++;
+            if (x > n) { x = n; break; }
+            r *= (a / x - s);
+            if (r <= 0.0) break;
+        }
+    } else {
+        const double spq = sqrt((double) n * pp * (1.0 - pp));
+        const double b = 1.15 + 2.53 * spq, a = -0.0873 + 0.0248 * b + 0.01 * pp, c = n * pp + 0.5;
+        const double vr = 0.92 - 4.2 / b, alpha = (2.83 + 5.1 / b) * spq, lpq = log(pp / (1.0 - pp));
+        const int m = (int) floor((n + 1) * pp);
+        const double h = lgamma(m + 1.0) + lgamma(n - m + 1.0);
+        for (;;) {
+            double u = rng.next() - 0.5, v = rng.next();
+            const double us = 0.5 - fabs(u);
+            const double kd = floor((2.0 * a / us + b) * u + c);
+            if (kd < 0.0 || kd > (double) n) continue;
+            const int k = (int) kd;
+            if (us >= 0.07 && v <= vr) { x = k; break; }
+            v = log(v * alpha / (a / (us * us) + b));
+            if (v <= h - lgamma(k + 1.0) - lgamma(n - k + 1.0) + (k - m) * lpq) { x = k; break; }
+        }
+    }
+    return flip ? n - x : x;
+}
+
+__device__ __forceinline__ void rdme_window_body_leap(const SsbView &V, double t_lo, double t_hi, double tau, uint64_t seed,
+                                                      uint64_t epoch, int buf, unsigned &n_rx, unsigned &n_df) {
+    __shared__ int sh_act[SSB_BLOCK];
+    __shared__ int sh_nact;
+    const int N = V.N;
+    const int nchunks = (N + SSB_BLOCK - 1) / SSB_BLOCK;
+    const double tau_w = t_hi - t_lo;
+    for (int round0 = 0; blockIdx.x + (long long) round0 * gridDim.x < nchunks; round0 += SSB_BLOCK) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_nact = 0;
+    __syncthreads();
+    {
+        const long long c = blockIdx.x + (long long) (round0 + threadIdx.x) * gridDim.x;
+        if (c < nchunks) {
+            const int mail = __ldcg(&V.blk_mail[buf ^ 1][c]);
+            if (mail) V.blk_mail[buf ^ 1][c] = 0;
+            if (mail != 0 || V.blk_tmin[c] <= t_hi) sh_act[atomicAdd(&sh_nact, 1)] = (int) c;
+        }
+    }
+    __syncthreads();
+    const int nact = sh_nact;
+    for (int a = 0; a < nact; a++) {
+        const int chunk = sh_act[a];
+        const int i = chunk * SSB_BLOCK + threadIdx.x;
+        const bool valid = i < N;
+        const int ii = valid ? i : N - 1;
+        const unsigned *in_prev = V.inbox[buf ^ 1];
+        unsigned *out_box = V.inbox[buf];
+        const bool mine = valid && V.owned[ii];
+        double tnext = mine ? V.tnext[ii] : INFINITY;      // stored: next REACTION time of a voxel that was idle (-INF: has mobile molecules)
+        bool arrived = false;
+        unsigned inc[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) { inc[s] = mine ? __ldcg(&in_prev[(size_t) s * N + ii]) : 0u; arrived |= (inc[s] != 0u); }
+        const bool touched = mine && (arrived || tnext <= t_hi);
+        double tn_store = tnext;
+        if (touched) {
+            int xx[SSB_SD > 0 ? SSB_SD : 1], xr[SSB_SD > 0 ? SSB_SD : 1];
+            double Dd[SSB_SD > 0 ? SSB_SD : 1], df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) { xx[s] = (int) V.xx[(size_t) s * N + i]; Dd[s] = lag_comp(V.Ddiag[(size_t) s * N + i], tau); }
+#pragma unroll
+            for (int q = 0; q < SSB_NDF; q++) df[q] = V.data_fn[(size_t) q * N + i];
+            const int type_i = V.type[i];
+            const double vol = V.mass[i] / V.rho[i];
+            LeapRng rng;
+            rng.vid = (uint32_t) V.gid[i]; rng.draw = 0; rng.epoch = epoch; rng.seed = seed; rng.has_spare = false; rng.spare = 0.0;
+            VoxelRates R;
+#pragma unroll
+            for (int r = 0; r < SSB_RD; r++) R.rr[r] = V.rrate[(size_t) r * N + i];
+            // ---- arrivals (as in the event form): only dependents are re-evaluated, with the vol of a random arrival's source
+            unsigned long long amask = 0ull;
+            int n_arr = 0;
+            double vol_src = vol;
+            if (arrived) {
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) {
+                    if (inc[s]) {
+                        xx[s] += (int) inc[s];
+                        n_arr += (int) inc[s];
+                        ((unsigned *) in_prev)[(size_t) s * N + i] = 0u;
+                        amask |= ssb_gen::dep_mask_species(s);
+                    }
+                }
+                const int src = (int) (__ldcg(&V.inbox_src[buf ^ 1][i]) & 0xffffffffull);
+                if (src > 0 && !(V.flags & 1u)) vol_src = V.mass[src - 1] / V.rho[src - 1];
+                V.inbox_src[buf ^ 1][i] = 0ull;
+            }
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) xr[s] = xx[s];
+            // ---- diffusion leap --------------------------------------------------------------------------------------
+            double sr = 0.0, sd = 0.0;
+#pragma unroll
+            for (int r = 0; r < SSB_RD; r++) sr += R.rr[r];
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) sd += Dd[s] * xx[s];
+            unsigned long long dmask = 0ull;
+            int n_dep = 0;
+            if (tau_w > 0.0 && sd > 0.0) {
+                const double tot = sr + sd;
+                const double plo = (V.flags & 1u) ? 0.0 : (sr / tot) * sd;       // reference: species pick lives on (p*sd, sd]
+                double cum = 0.0;
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) {
+                    const double lo_s = cum;
+                    cum += Dd[s] * xx[s];
+                    if (xx[s] <= 0 || !(Dd[s] > 0.0)) continue;
+                    double a_eff;
+                    if (V.flags & 1u) a_eff = Dd[s] * xx[s];
+                    else { const double ov = fmax(0.0, cum - fmax(lo_s, plo)); a_eff = tot * ov / sd; }
+                    if (!(a_eff > 0.0)) continue;
+                    const double q = 1.0 - exp(-(a_eff / xx[s]) * tau_w);
+                    int nj = ssb_binomial(xx[s], q, rng);
+                    if (nj <= 0) continue;
+                    // destinations: one pass over the neighbour row, conditional binomials (multinomial), weights in list order
+                    const int cnt = V.nbr_count[i];
+                    const bool cached = V.Dij != nullptr;
+                    double xl0 = 0, xl1 = 0, xl2 = 0, m_l = 0, rho_l = 0;
+                    if (!cached) { xl0 = V.x[0][i]; xl1 = V.x[1][i]; xl2 = V.x[2][i]; m_l = V.mass[i]; rho_l = V.rho_search[i]; }
+                    double wrem = V.Ddiag[(size_t) s * N + i];
+                    int rem = nj, sent = 0, last_ok = -1;
+                    for (int k = 0; k < cnt && rem > 0; k++) {
+                        const int j = V.nbr[(size_t) k * N + i];
+                        const double dc = V.dmat[s * V.num_types + (V.type[j] - 1)];
+                        if (dc == 0.0) continue;
+                        if (V.filter && !ssb_in_range(ssb_dist2(V.dim, xl0, xl1, xl2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h))) continue;
+                        const double w = (cached ? V.Dij[(size_t) k * N + i] : pair_Dij(V, i, j, xl0, xl1, xl2, m_l, rho_l)) * dc;
+                        last_ok = j;
+                        const double pk = (wrem > w) ? w / wrem : 1.0;
+                        const int mk = (pk >= 1.0) ? rem : ssb_binomial(rem, pk, rng);
+                        wrem -= w;
+                        if (mk > 0) {
+                            rem -= mk;
+                            if (j != i) {
+                                sent += mk;
+                                atomicAdd(&out_box[(size_t) s * N + j], (unsigned) mk);
+                                const unsigned long long pri = (unsigned long long) (__double_as_longlong(rng.next() * 4294967296.0 * 4096.0) & 0xffffffffll);
+                                atomicMax(&V.inbox_src[buf][j], (pri << 32) | (unsigned long long) (unsigned) (i + 1));
+                                V.blk_mail[buf][j / SSB_BLOCK] = 1;
+                            }
+                        }
+                    }
+                    if (rem > 0 && last_ok >= 0 && last_ok != i) {               // round-off left-over goes to the last eligible neighbour
+                        sent += rem;
+                        atomicAdd(&out_box[(size_t) s * N + last_ok], (unsigned) rem);
+                        V.blk_mail[buf][last_ok / SSB_BLOCK] = 1;
+                    }
+                    xx[s] -= sent;                                              // gone for diffusion, still reactive (xr) until the window closes
+                    n_dep += nj;
+                    n_df += (unsigned) nj;
+                    dmask |= ssb_gen::dep_mask_species(s);
+                }
+            }
+            // ---- propensities after arrivals / departures: dependents only; arrival-dependents with a source vol with the
+            // probability that an arrival (not a departure) was the last event to touch them (simulate_rdme.cpp:419-437)
+            if ((amask | dmask) != 0ull || (V.flags & 1u)) {
+                double tmp_own[SSB_RD > 0 ? SSB_RD : 1], tmp_src[SSB_RD > 0 ? SSB_RD : 1];
+                ssb_gen::eval_propensities(xr, t_lo, vol, df, type_i, tmp_own);
+                bool use_src = false;
+                if (n_arr > 0 && vol_src != vol) use_src = rng.next() * (double) (n_arr + n_dep) < (double) n_arr;
+                if (use_src) ssb_gen::eval_propensities(xr, t_lo, vol_src, df, type_i, tmp_src);
+                const unsigned long long mask = (V.flags & 1u) ? ~0ull : (amask | dmask);
+#pragma unroll
+                for (int r = 0; r < SSB_RD; r++) {
+                    if ((mask >> r) & 1ull) R.rr[r] = (use_src && ((amask >> r) & 1ull)) ? tmp_src[r] : tmp_own[r];
+                }
+            }
+            sr = 0.0;
+#pragma unroll
+            for (int r = 0; r < SSB_RD; r++) sr += R.rr[r];
+            // ---- reaction SSA inside the window (clock re-drawn at the window start: memoryless) -------------------------
+            // a voxel that sat idle keeps the reaction clock it stored (its rates did not change); anything that changed the state in
+            // this window (arrivals, departures) makes a fresh draw from the window start valid by memorylessness
+            double tr;
+            if (tnext != -INFINITY && !arrived && n_dep == 0) tr = tnext;
+            else tr = (sr > 0.0 && tau_w > 0.0) ? t_lo + (-log(rng.next())) / sr : INFINITY;
+            int guard = 0;
+            while (tr <= t_hi) {
+                sd = 0.0;
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) sd += Dd[s] * xx[s];
+                double pick;
+                if (V.flags & 1u) pick = rng.next() * sr;
+                else pick = rng.next() * (sr / (sr + sd)) * sr;                  // rand1 <= srrate/totrate, then rand1*srrate (:253-261)
+                int re = 0;
+                double cum = R.rr[0];
+#pragma unroll
+                for (int q = 1; q < SSB_RD; q++) { if (pick > cum) { re = q; cum += R.rr[q]; } else break; }
+                while (re > 0 && R.rr[re] <= 0.0) re--;
+                int xn[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) xn[s] = xr[s];
+                bool neg = false;
+                ssb_gen::apply_stoich(re, xn, neg);
+                if (neg) atomicCAS(V.err_flag, 0, 2);
+                bool feasible = true;
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) feasible &= (xx[s] + (xn[s] - xr[s]) >= 0);
+                if (feasible) {
+#pragma unroll
+                    for (int s = 0; s < SSB_SD; s++) { xx[s] += xn[s] - xr[s]; xr[s] = xn[s]; }
+                    n_rx++;
+                }
+                double tmp[SSB_RD > 0 ? SSB_RD : 1];
+                ssb_gen::eval_propensities(xr, tr, vol, df, type_i, tmp);
+                const unsigned long long mask = (V.flags & 1u) ? ~0ull : ssb_gen::dep_mask_reaction(re);
+                sr = 0.0;
+#pragma unroll
+                for (int r = 0; r < SSB_RD; r++) { if ((mask >> r) & 1ull) R.rr[r] = tmp[r]; sr += R.rr[r]; }
+                tr = (sr > 0.0) ? tr + (-log(rng.next())) / sr : INFINITY;
+                if (++guard > 100000000) { atomicCAS(V.err_flag, 0, 2); break; }
+            }
+            // ---- window closes: departed molecules leave the reactive population ------------------------------------------
+            bool departed = false, mobile = false;
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) { departed |= (xr[s] != xx[s]); mobile |= (xx[s] > 0 && Dd[s] > 0.0); }
+            if (departed) {
+                double tmp[SSB_RD > 0 ? SSB_RD : 1];
+                ssb_gen::eval_propensities(xx, t_hi, vol, df, type_i, tmp);
+                const unsigned long long mask = (V.flags & 1u) ? ~0ull : dmask;
+                sr = 0.0;
+#pragma unroll
+                for (int r = 0; r < SSB_RD; r++) { if ((mask >> r) & 1ull) R.rr[r] = tmp[r]; sr += R.rr[r]; }
+            }
+            sd = 0.0;
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) sd += Dd[s] * xx[s];
+            // voxels with mobile molecules are due in every window; idle ones keep a reaction clock for the triage
+            tn_store = mobile ? -INFINITY : ((sr > 0.0) ? t_hi + (-log(rng.next())) / sr : INFINITY);
+#pragma unroll
+            for (int s = 0; s < SSB_SD; s++) V.xx[(size_t) s * N + i] = (unsigned) xx[s];
+#pragma unroll
+            for (int r = 0; r < SSB_RD; r++) V.rrate[(size_t) r * N + i] = R.rr[r];
+            V.srrate[i] = sr;
+            V.sdrate[i] = sd;
+            V.tnext[i] = tn_store;
+        }
+        const double tn_final = block_min(valid ? tn_store : INFINITY);
+        if (threadIdx.x == 0) V.blk_tmin[chunk] = tn_final;
+        __syncthreads();
+    }
+    }
+}
+
 // event counters (ParticleSystem::total_reactions / total_diffusion): warp reduce, one atomic per warp
 __device__ __forceinline__ void flush_event_counters(const SsbView &V, unsigned n_rx, unsigned n_df) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -1115,10 +1404,12 @@ __device__ __forceinline__ void flush_event_counters(const SsbView &V, unsigned 
     }
 }
 
+template <bool LEAP>
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_lo, double t_hi, double tau, uint64_t seed,
                                                           uint64_t epoch, int buf) {
     unsigned n_rx = 0, n_df = 0;
-    rdme_window_body(V, t_lo, t_hi, tau, seed, epoch, buf, n_rx, n_df);
+    if (LEAP) rdme_window_body_leap(V, t_lo, t_hi, tau, seed, epoch, buf, n_rx, n_df);
+    else rdme_window_body(V, t_lo, t_hi, tau, seed, epoch, buf, n_rx, n_df);
     flush_event_counters(V, n_rx, n_df);
 }
 
@@ -1128,7 +1419,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
 // latency that dominates small systems (config 1: ~1900 windows per step) and idle windows of large ones.
 // SINGLE = true: the whole model fits the chunks of ONE CTA (small ensembles: birth-death, Cdc42): the barrier between windows is a
 // block barrier, the launch is an ordinary one, and many trajectories run side by side on separate streams.
-template <bool SINGLE>
+template <bool SINGLE, bool LEAP>
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, double t0, double dt, long long nwin, double tau,
                                                                 uint64_t seed, uint64_t epoch0, int buf0) {
     unsigned n_rx = 0, n_df = 0;
@@ -1139,7 +1430,8 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, doub
             lo = t0 + dt * ((double) w / (double) nwin);
             hi = (w + 1 == nwin) ? t0 + dt : t0 + dt * ((double) (w + 1) / (double) nwin);
         } else { lo = hi = t0 + dt; }
-        rdme_window_body(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
+        if (LEAP) rdme_window_body_leap(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
+        else rdme_window_body(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
         buf ^= 1;
         if (w < nwin) {
             if (SINGLE) __syncthreads();       // one CTA: a block barrier orders the inbox traffic, and (unlike a device-scope fence) keeps L1 warm
@@ -1202,12 +1494,17 @@ static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop<false>, SSB_BLOCK, 0);
+        int per_sm_leap = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop<false, false>, SSB_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_leap, k_rdme_windows_coop<false, true>, SSB_BLOCK, 0);
+        if (per_sm_leap < per_sm) per_sm = per_sm_leap;
         coop_blocks = coop ? sms * per_sm : 0;
     }
+    const bool leap = (V->flags & 32u) != 0;
     const unsigned nchunks = grid_for(V->N);
     if (nchunks <= 8) {      // small model: one CTA walks all chunks; ordinary launch, block barrier between windows
-        k_rdme_windows_coop<true><<<1, SSB_BLOCK, 0, st>>>(*V, t0, dt, nwin, tau, seed, epoch0, buf0);
+        if (leap) k_rdme_windows_coop<true, true><<<1, SSB_BLOCK, 0, st>>>(*V, t0, dt, nwin, tau, seed, epoch0, buf0);
+        else k_rdme_windows_coop<true, false><<<1, SSB_BLOCK, 0, st>>>(*V, t0, dt, nwin, tau, seed, epoch0, buf0);
         if (launches) *launches = 1;
         return (int) cudaGetLastError();
     }
@@ -1216,7 +1513,7 @@ static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin
         if (grid > nchunks) grid = nchunks;
         SsbView view = *V;
         void *args[] = {&view, &t0, &dt, &nwin, &tau, &seed, &epoch0, &buf0};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *) k_rdme_windows_coop<false>, dim3(grid), dim3(SSB_BLOCK), args, 0, st);
+        cudaError_t e = cudaLaunchCooperativeKernel(leap ? (const void *) k_rdme_windows_coop<false, true> : (const void *) k_rdme_windows_coop<false, false>, dim3(grid), dim3(SSB_BLOCK), args, 0, st);
         if (launches) *launches = 1;
         return (int) e;
     }
@@ -1226,7 +1523,8 @@ static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin
     for (long long w = 0; w <= nwin; w++) {
         double lo = (w < nwin) ? t0 + dt * ((double) w / (double) nwin) : t0 + dt;
         double hi = (w < nwin) ? ((w + 1 == nwin) ? t0 + dt : t0 + dt * ((double) (w + 1) / (double) nwin)) : t0 + dt;
-        k_rdme_window<<<grid, SSB_BLOCK, 0, st>>>(*V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf);
+        if (leap) k_rdme_window<true><<<grid, SSB_BLOCK, 0, st>>>(*V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf);
+        else k_rdme_window<false><<<grid, SSB_BLOCK, 0, st>>>(*V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf);
         buf ^= 1;
     }
     if (launches) *launches = (int) (nwin + 1);
@@ -1236,7 +1534,8 @@ static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau,
     const unsigned nchunks = grid_for(V->N);
     unsigned grid = 148u * 8u;         // persistent grid: a multiple of the 148 SMs
     if (grid > nchunks) grid = nchunks;
-    k_rdme_window<<<grid, SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
+    if (V->flags & 32u) k_rdme_window<true><<<grid, SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
+    else k_rdme_window<false><<<grid, SSB_BLOCK, 0, st>>>(*V, t_lo, t_hi, tau, seed, epoch, buf);
     return (int) cudaGetLastError();
 }
 
