@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -589,28 +590,53 @@ static int write_vtk(ssb_handle *h, const OutputJob &J) {
     FILE *fp = fopen(filename, "w+");
     if (!fp) return SSB_ERR_IO;
     Buf b;
-    b.d.resize((size_t) np * 64 + 65536);
+    b.d.resize(65536);
     auto flush = [&]() { if (b.n) fwrite(b.d.data(), 1, b.n, fp); b.n = 0; };
+    // One section of the file = header line (already in `b`) + np formatted items.  Large snapshots are formatted by several host
+    // threads over contiguous particle ranges (multiples of 9, so every range starts at a line start for both the 3-per-line and
+    // the 9-per-line layouts) into private buffers that are written in order: the text of a 1 M-particle snapshot is ~150 MB and
+    // single-threaded formatting, not the GPU, bounds the drop-in path.
+    int nthreads = (np >= 200000) ? (int) std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+    if (const char *e = getenv("SSB_VTK_THREADS")) nthreads = std::max(1, std::min(64, atoi(e)));
+    auto section = [&](auto &&fmt_item) {
+        flush();
+        if (nthreads == 1) {
+            for (int i = 0; i < np; i++) { fmt_item(b, i); if (b.n > (1u << 22)) flush(); }
+            flush();
+            return;
+        }
+        const int per = ((np + nthreads - 1) / nthreads + 8) / 9 * 9;
+        std::vector<Buf> bufs((size_t) nthreads);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) {
+            th.emplace_back([&, t]() {
+                const int lo = std::min(np, t * per), hi = std::min(np, lo + per);
+                Buf &q = bufs[(size_t) t];
+                q.d.resize((size_t) (hi - lo) * 48 + 4096);
+                for (int i = lo; i < hi; i++) fmt_item(q, i);
+            });
+        }
+        for (auto &t : th) t.join();
+        for (auto &q : bufs) if (q.n) fwrite(q.d.data(), 1, q.n, fp);
+    };
     b.putf("# vtk DataFile Version 4.1\n");
     b.putf("Generated by SpatialPy\n");
     b.putf("ASCII\n");
     b.putf("DATASET POLYDATA\n");
     b.putf("POINTS %i float\n", np);
-    for (int i = 0; i < np; i++) {
-        b.reserve(128);
-        b.n += (size_t) snprintf(b.d.data() + b.n, 128, "%.10e %.10e %.10e ", J.x[i * 3], J.x[i * 3 + 1], J.x[i * 3 + 2]);
-        if ((i + 1) % 3 == 0) b.d[b.n++] = '\n';
-        if (b.n > (1u << 22)) flush();
-    }
+    section([&](Buf &q, int i) {
+        q.reserve(128);
+        q.n += (size_t) snprintf(q.d.data() + q.n, 128, "%.10e %.10e %.10e ", J.x[i * 3], J.x[i * 3 + 1], J.x[i * 3 + 2]);
+        if ((i + 1) % 3 == 0) q.d[q.n++] = '\n';
+    });
     b.putf("\n");
     b.putf("VERTICES %i %i\n", np, 2 * np);
-    for (int i = 0; i < np; i++) {
-        b.reserve(32);
-        b.d[b.n++] = '1'; b.d[b.n++] = ' ';
-        put_u(b, (unsigned) i);
-        b.d[b.n - 1] = '\n';
-        if (b.n > (1u << 22)) flush();
-    }
+    section([&](Buf &q, int i) {
+        q.reserve(32);
+        q.d[q.n++] = '1'; q.d[q.n++] = ' ';
+        put_u(q, (unsigned) i);
+        q.d[q.n - 1] = '\n';
+    });
     b.putf("\n");
     b.putf("POINT_DATA %i\n", np);
     int num_fields = 7;
@@ -618,35 +644,34 @@ static int write_vtk(ssb_handle *h, const OutputJob &J) {
     if (Sc > 0) num_fields += Sc;
     b.putf("FIELD FieldData %i\n", num_fields);
     b.putf("id 1 %i int\n", np);
-    for (int i = 0; i < np; i++) { put_u(b, (unsigned) i); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+    section([&](Buf &q, int i) { put_u(q, (unsigned) i); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
     b.putf("\n");
     b.putf("type 1 %i int\n", np);
-    for (int i = 0; i < np; i++) { put_u(b, (unsigned) J.type[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+    section([&](Buf &q, int i) { put_u(q, (unsigned) J.type[i]); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
     b.putf("\n");
     b.putf("v 3 %i double\n", np);
-    for (int i = 0; i < np; i++) {
-        put_lf(b, J.v[i * 3]); put_lf(b, J.v[i * 3 + 1]); put_lf(b, J.v[i * 3 + 2]);
-        if ((i + 1) % 3 == 0) { b.reserve(2); b.d[b.n++] = '\n'; }
-        if (b.n > (1u << 22)) flush();
-    }
+    section([&](Buf &q, int i) {
+        put_lf(q, J.v[i * 3]); put_lf(q, J.v[i * 3 + 1]); put_lf(q, J.v[i * 3 + 2]);
+        if ((i + 1) % 3 == 0) { q.reserve(2); q.d[q.n++] = '\n'; }
+    });
     b.putf("\n");
     const char *scal_names[4] = {"rho", "mass", "bvf_phi", "nu"};
     for (int f = 0; f < 4; f++) {
         b.putf("%s 1 %i double\n", scal_names[f], np);
         const double *a = J.scal + (size_t) f * np;
-        for (int i = 0; i < np; i++) { put_lf(b, a[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+        section([&](Buf &q, int i) { put_lf(q, a[i]); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
         b.putf("\n");
     }
     for (int s = 0; s < Sc; s++) {
         b.putf("C[%s] 1 %i double\n", h->species_names[s].c_str(), np);
         const double *a = J.C + (size_t) s * np;
-        for (int i = 0; i < np; i++) { put_lf(b, a[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+        section([&](Buf &q, int i) { put_lf(q, a[i]); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
         b.putf("\n");
     }
     for (int s = 0; s < Sd; s++) {
         b.putf("D[%s] 1 %i int\n", h->species_names[s].c_str(), np);
         const unsigned *a = J.xx + (size_t) s * np;
-        for (int i = 0; i < np; i++) { put_u(b, a[i]); if ((i + 1) % 9 == 0) { b.reserve(2); b.d[b.n++] = '\n'; } if (b.n > (1u << 22)) flush(); }
+        section([&](Buf &q, int i) { put_u(q, a[i]); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
         b.putf("\n");
     }
     flush();

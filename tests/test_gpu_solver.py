@@ -67,6 +67,18 @@ def test_vtk_bytes_match_reference_writer(diffusion_run):
     assert open(os.path.join(res.result_dir, "output0.vtk")).read() == _ref_file("output0.vtk")
 
 
+def test_vtk_bytes_identical_with_threaded_formatting(diffusion_run, monkeypatch):
+    """Large snapshots are formatted by several host threads; the bytes must not depend on the thread count."""
+    from spatialpy_b200 import Solver
+    _, res1 = diffusion_run
+    monkeypatch.setenv("SSB_VTK_THREADS", "5")
+    res5 = Solver(load_model("diffusion3d")).run(number_of_trajectories=1, seed=1000)
+    for k in (0, 1, 10):
+        a = open(os.path.join(res1.result_dir, f"output{k}.vtk"), "rb").read()
+        b = open(os.path.join(res5.result_dir, f"output{k}.vtk"), "rb").read()
+        assert a == b, f"output{k}.vtk differs between 1 and 5 formatting threads"
+
+
 def test_reader_roundtrip_and_step0_equals_u0(diffusion_run):
     sol, res = diffusion_run
     pts, data = res.read_step(0)
