@@ -273,6 +273,15 @@ __global__ void k_nbr_export(SsbView V, const long long *ptr, int *idx, double *
     }
 }
 
+// earliest pending sSSA event over all chunks (non-negative doubles order like their bit patterns)
+__global__ void k_min_time(int nchunks, const double *blk_tmin, unsigned long long *out_bits) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = (c < nchunks) ? blk_tmin[c] : INFINITY;
+    if (!(v >= 0.0)) v = 0.0;
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(out_bits, (unsigned long long) __double_as_longlong(v));
+}
+
 // ---- slab decomposition: halo pack / unpack (ids are particle ids of THIS rank's model; slot_of_id maps to storage) ----
 __global__ void k_slot_of_id(int N, const int *id, int *slot_of_id) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1194,6 +1203,35 @@ static int check_device_error(ssb_handle *h) {
     return SSB_OK;
 }
 
+// The reference's NSM loop tests `tt <= end_time` BEFORE it pops the next event (simulate_rdme.cpp:233-238), so every call executes
+// exactly one event that lies beyond the end of the step.  On static domains that event is merely executed early; on moving
+// domains the queue is rebuilt from scratch at the next step (simulate_rdme.cpp:54-65), so it is one EXTRA event per step —
+// dominant in small, quiet systems (the 512-particle tank fixture: 37 reference events in 25 steps).  Parity mode mirrors it:
+// after the windows of the step, the globally earliest pending event is executed (a window that ends exactly at its time).
+static int rdme_min_time(ssb_handle *h, double *tmin) {
+    const int nchunks = (h->N + h->unit->block - 1) / h->unit->block;
+    unsigned long long bits = 0x7ff0000000000000ull;      // +inf
+    CK(cudaMemcpyAsync(h->d_maxbits + 1, &bits, sizeof(bits), cudaMemcpyHostToDevice, h->stream));
+    k_min_time<<<gridN(nchunks), CORE_BLOCK, 0, h->stream>>>(nchunks, h->V.blk_tmin, h->d_maxbits + 1);
+    CK(cudaMemcpyAsync(&bits, h->d_maxbits + 1, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+    CK(ssb_sync(h));
+    memcpy(tmin, &bits, sizeof(bits));
+    h->launches += 1;
+    return SSB_OK;
+}
+static int rdme_extra_event(ssb_handle *h, double tmin) {
+    SsbView &V = h->V;
+    const SsbModelUnit *u = h->unit;
+    const double te = V.dt * (h->current_step + 1);
+    if (!(tmin < INFINITY) || !(tmin > te)) return SSB_OK;
+    if (u->rdme_window(&V, te, tmin, h->tau, h->seed, h->epoch++, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+    h->inbox_buf ^= 1;
+    if (u->rdme_window(&V, tmin, tmin, h->tau, h->seed, h->epoch++, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+    h->inbox_buf ^= 1;
+    h->launches += 2;
+    return SSB_OK;
+}
+
 static int rdme_step(ssb_handle *h) {
     SsbView &V = h->V;
     const SsbModelUnit *u = h->unit;
@@ -1244,6 +1282,12 @@ static int rdme_step(ssb_handle *h) {
     if (u->rdme_windows(&V, t0, V.dt, nwin, h->tau, h->seed, h->epoch, h->inbox_buf, &nl, st)) return fail(h, SSB_ERR_CUDA, "rdme_windows launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->epoch += (uint64_t) nwin + 1;
     h->inbox_buf ^= (int) ((nwin + 1) & 1);
+    if (!V.static_domain && !(V.flags & SSB_FLAG_CORRECTED_NSM_SELECT)) {
+        double tmin = INFINITY;
+        int rcx = rdme_min_time(h, &tmin);
+        if (!rcx) rcx = rdme_extra_event(h, tmin);
+        if (rcx) return rcx;
+    }
     prof_end(h, psw);
     h->launches += nl;
     if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
@@ -1671,7 +1715,8 @@ extern "C" int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total) {
 //     phase RDME_WINDOW / RDME_CLOSE one sSSA window each               -> inbox exchange (ssb_halo_inbox_*)
 //     phase END        step counter
 // ----------------------------------------------------------------------------------------------------
-enum { PH_PRE = 0, PH_CORRECTOR = 1, PH_FINISH = 2, PH_RDME_PREP = 3, PH_RDME_INIT = 4, PH_RDME_WINDOW = 5, PH_RDME_CLOSE = 6, PH_END = 7 };
+enum { PH_PRE = 0, PH_CORRECTOR = 1, PH_FINISH = 2, PH_RDME_PREP = 3, PH_RDME_INIT = 4, PH_RDME_WINDOW = 5, PH_RDME_CLOSE = 6, PH_END = 7,
+       PH_RDME_MIN = 8, PH_RDME_EXTRA = 9 };
 
 static int ensure_slot_map(ssb_handle *h) {
     if (!h->d_slot_of_id) CK(dalloc(h, &h->d_slot_of_id, (size_t) h->N));
@@ -1780,6 +1825,15 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
         h->launches++;
         break;
     }
+    case PH_RDME_MIN: {          // -> *out = this rank's earliest pending event (the caller all-reduces the minimum)
+        double tmin = INFINITY;
+        if ((rc = rdme_min_time(h, &tmin))) return rc;
+        if (out) *out = tmin;
+        break;
+    }
+    case PH_RDME_EXTRA:          // arg = GLOBAL earliest pending event: only its owner fires (see rdme_extra_event)
+        if (!(V.flags & SSB_FLAG_CORRECTED_NSM_SELECT)) { if ((rc = rdme_extra_event(h, arg))) return rc; }
+        break;
     case PH_END:
         h->current_step++;
         return check_device_error(h);

@@ -33,7 +33,7 @@ EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernel
            "ssb_nbr_stats", "ssb_step_phase", "ssb_halo_pack", "ssb_halo_unpack", "ssb_halo_inbox_pack", "ssb_halo_inbox_add",
            "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats"]
 
-PH_PRE, PH_CORRECTOR, PH_FINISH, PH_RDME_PREP, PH_RDME_INIT, PH_RDME_WINDOW, PH_RDME_CLOSE, PH_END = range(8)
+PH_PRE, PH_CORRECTOR, PH_FINISH, PH_RDME_PREP, PH_RDME_INIT, PH_RDME_WINDOW, PH_RDME_CLOSE, PH_END, PH_RDME_MIN, PH_RDME_EXTRA = range(10)
 
 PROFILE_CATEGORIES = ["cells", "predictor", "search", "force", "corrector", "finish", "diff_init", "rdme_init",
                       "rdme_window", "output"]

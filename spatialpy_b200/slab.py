@@ -23,7 +23,7 @@ if a particle has travelled further than the halo allows.  Re-partitioning at li
 import numpy as np
 
 from .engine import (Engine, FLAG_SKIP_STATIC_FORCES, PH_CORRECTOR, PH_END, PH_FINISH, PH_PRE, PH_RDME_CLOSE, PH_RDME_INIT,
-                     PH_RDME_PREP, PH_RDME_WINDOW)
+                     PH_RDME_PREP, PH_RDME_WINDOW, PH_RDME_MIN, PH_RDME_EXTRA)
 from .flatmodel import FlatModel
 
 
@@ -179,6 +179,15 @@ class SlabEngine:
                 for w in range(nwin):
                     e.phase(PH_RDME_WINDOW, w)
                     self._sync_inbox()
+                e.phase(PH_RDME_CLOSE)
+                # the reference's one event past the end of every step (simulate_rdme.cpp:233-238): globally earliest pending event
+                tmin = e.phase(PH_RDME_MIN)
+                if self.world > 1:
+                    t = self.torch.tensor([tmin], dtype=self.torch.float64, device=self.dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    tmin = float(t.item())
+                e.phase(PH_RDME_EXTRA, tmin)
+                self._sync_inbox()
                 e.phase(PH_RDME_CLOSE)
             e.phase(PH_END)
             # fixed ghost sets: a pair within h*(1+skin) must have both members present, so nobody may travel further than

@@ -48,8 +48,9 @@ TAPS = {
     "tank3d": [0, 1, 2, 21, 25],
     "cylinder": [0, 1],
     "cdc42": [0, 1, 2],
+    "cavity2d_rdme": [0, 1, 22, 45],
 }
-ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000, "cdc42": 600}
+ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000, "cdc42": 600, "cavity2d_rdme": 1000}
 XBINS = 8
 
 

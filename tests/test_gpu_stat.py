@@ -99,6 +99,12 @@ def test_cdc42_ensemble_matches_reference():
     check_against_reference("cdc42", 400)
 
 
+def test_moving_domain_rdme_matches_reference():
+    """Moving SDPD domain with an advected, decaying species: the reference rebuilds its NSM every step and executes one event
+    past each step's end (about 8 % of all events in this model); totals, spatial bins and per-voxel moments must agree."""
+    check_against_reference("cavity2d_rdme", 1000)
+
+
 def test_pure_diffusion_ensemble_matches_reference():
     check_against_reference("diffusion3d", 1000)
 
