@@ -176,7 +176,7 @@ def run_ours(args, rank, local_rank, world):
     if args.sps is None:
         args.sps = 50 if moving else 200
     N, SPS = fm.num_particles, args.sps
-    eng = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK)
+    eng = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK | args.extra_flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,7 +275,7 @@ def run_ours(args, rank, local_rank, world):
     fm_e2e.output_steps = __import__("numpy").array([0, SPS], dtype="uint32")
     eng.close()
     t_create0 = time.perf_counter()
-    eng2 = Engine(fm_e2e, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK)
+    eng2 = Engine(fm_e2e, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK | args.extra_flags)
     create_s = time.perf_counter() - t_create0
     eng2.run_no_files(2000 + rank, 1)           # warm-up trajectory
     barrier()
@@ -477,6 +477,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="ensemble workloads: concurrent engine handles per GPU (0 = auto)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
     ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
+    ap.add_argument("--extra-flags", type=int, default=0, help="extra SSB_FLAG_* bits for the engine (diagnostics)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--no-slab", action="store_true", help="skip the secondary slab-decomposed measurement")
     ap.add_argument("--decomp", default="ensemble", choices=["ensemble", "slab"],

@@ -44,6 +44,11 @@ extern "C" {
 #define SSB_FLAG_LEAP_DIFFUSION 32u        /* sSSA: advance the diffusion channel per window (binomial jump counts, multinomial destinations)
                                               instead of one event per jump; same law in the windowed scheme, O(1) per species and window */
 #define SSB_FLAG_SKIP_STATIC_FORCES 8u     /* static domains: skip F/Fbp/Frho (never consumed when static, simulate.cpp:68,137); default on via Python */
+#define SSB_FLAG_NO_STEP_OVERSHOOT 128u    /* moving domains: do not execute the reference's one event past each step's end
+                                             (`while(tt <= end_time)` tests the previous event's time, simulate_rdme.cpp:233-238) */
+#define SSB_FLAG_BINARY_STORE 64u         /* also write outputN.ssb next to (or, with SSB_FLAG_NO_VTK, instead of) outputN.vtk: the same snapshot as raw
+                                             little-endian arrays at full fp64 precision (layout in spatialpy_b200/vtk.py, read by Result.read_step;
+                                             SURVEY.md 8f item 1 - the reference's pure-Python ASCII parser, vtkreader.py:29-56, bounds large N*T) */
 
 /* Flat model description.  Replaces the generated-literal inputs of solver.py:100-419. */
 typedef struct ssb_model {

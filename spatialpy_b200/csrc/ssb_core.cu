@@ -192,6 +192,7 @@ __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (i < V.N) {
+        int any_solid = 0;
         const int N = V.N, dim = V.dim, cap = V.nbr_cap;
         const double h = V.h;
         const double h2 = __dmul_rn(h, h);             // ANNdist dist = system->h * system->h (particle.cpp:253)
@@ -212,11 +213,13 @@ __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_
                     if (take) {
                         if (cnt < cap) V.nbr[(size_t) cnt * N + i] = j;
                         cnt++;
+                        any_solid |= V.solid[j];
                     }
                 }
             }
         }
         V.nbr_count[i] = min(cnt, cap);
+        if (V.solid_nbr) V.solid_nbr[i] = any_solid != 0;      // lets the BVF sweep of bulk fluid stop early (k_finish)
     }
     int tot = cnt;
     for (int o = 16; o > 0; o >>= 1) { cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o)); tot += __shfl_xor_sync(0xffffffffu, tot, o); }
@@ -362,6 +365,7 @@ struct OutputJob {
     unsigned file_index = 0;
     int rdme_initialized = 0;
     int write_file = 1;
+    int write_bin = 0;
     std::string dir;
     cudaEvent_t ready = nullptr;
     // pinned staging (id order)
@@ -485,6 +489,14 @@ static cudaError_t ssb_sync(ssb_handle *h) {
     }
     cudaError_t e = cudaEventRecord(h->sync_ev, h->stream);
     if (e != cudaSuccess) return e;
+    // short waits (a scalar read-back behind a kernel that is about to finish) are polled: waking a sleeping thread costs far more
+    // than the wait itself (measured: ~70 us per blocking wait on a 1.6 ms moving-domain step)
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        e = cudaEventQuery(h->sync_ev);
+        if (e != cudaErrorNotReady) return e;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(40)) break;
+    }
     return cudaEventSynchronize(h->sync_ev);
 }
 
@@ -688,6 +700,36 @@ static int write_vtk(ssb_handle *h, const OutputJob &J) {
     return 0;
 }
 
+// Binary side-store (SSB_FLAG_BINARY_STORE): outputN.ssb = 8-byte magic, u64 length of an ASCII JSON header, the header padded with
+// blanks to a multiple of 64 bytes, then the raw little-endian arrays in id order:
+//   x f64[np*3]  v f64[np*3]  rho,mass,bvf_phi,nu f64[4*np]  C f64[Sc*np]  type i32[np]  D u32[Sd*np]
+static int write_bin(ssb_handle *h, const OutputJob &J) {
+    const size_t np = (size_t) h->N;
+    const int Sc = h->V.Sc, Sd = h->V.Sd;
+    char filename[4096];
+    snprintf(filename, sizeof(filename), "%s/output%u.ssb", J.dir.c_str(), J.file_index);
+    FILE *fp = fopen(filename, "wb");
+    if (!fp) return SSB_ERR_IO;
+    std::string hdr = "{\"np\": " + std::to_string(np) + ", \"Sc\": " + std::to_string(Sc) + ", \"Sd\": " + std::to_string(Sd) +
+                      ", \"step\": " + std::to_string(J.step) + ", \"rdme_initialized\": " + std::to_string(J.rdme_initialized) + ", \"species\": [";
+    const int ns = std::max(Sc, Sd);
+    for (int s = 0; s < ns; s++) hdr += std::string(s ? ", " : "") + "\"" + h->species_names[(size_t) s] + "\"";
+    hdr += "]}";
+    while ((16 + hdr.size()) % 64) hdr += ' ';
+    const unsigned long long hl = hdr.size();
+    size_t ok = fwrite("SSBOUT1\0", 1, 8, fp) == 8;
+    ok &= fwrite(&hl, 8, 1, fp) == 1;
+    ok &= fwrite(hdr.data(), 1, hdr.size(), fp) == hdr.size();
+    ok &= fwrite(J.x, sizeof(double), 3 * np, fp) == 3 * np;
+    ok &= fwrite(J.v, sizeof(double), 3 * np, fp) == 3 * np;
+    ok &= fwrite(J.scal, sizeof(double), 4 * np, fp) == 4 * np;
+    if (Sc > 0) ok &= fwrite(J.C, sizeof(double), (size_t) Sc * np, fp) == (size_t) Sc * np;
+    ok &= fwrite(J.type, sizeof(int), np, fp) == np;
+    if (Sd > 0) ok &= fwrite(J.xx, sizeof(unsigned), (size_t) Sd * np, fp) == (size_t) Sd * np;
+    ok &= fclose(fp) == 0;
+    return ok ? 0 : SSB_ERR_IO;
+}
+
 static void writer_main(ssb_handle *h) {
     cudaSetDevice(h->device);
     int next = 0;
@@ -700,6 +742,7 @@ static void writer_main(ssb_handle *h) {
         OutputJob &J = h->jobs[next];
         cudaEventSynchronize(J.ready);
         int rc = J.write_file ? write_vtk(h, J) : 0;
+        if (!rc && J.write_bin) rc = write_bin(h, J);
         {
             std::lock_guard<std::mutex> lk(h->mu);
             if (rc) h->writer_error = rc;
@@ -836,7 +879,7 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     if (V.static_domain) { for (int d = 0; d < 3; d++) V.x0[d] = nullptr; }   // aliased to x after allocation (below)
     else { for (int d = 0; d < 3; d++) CK(dalloc(h, &V.x0[d], (size_t) N)); }
     CK(dalloc(h, &V.rho_new, (size_t) N));
-    if (!V.static_domain) { CK(dalloc(h, &V.rec, (size_t) 16 * N)); CK(dalloc(h, &V.rec2, (size_t) 4 * N)); }
+    if (!V.static_domain) { CK(dalloc(h, &V.rec, (size_t) 16 * N)); CK(dalloc(h, &V.solid_nbr, (size_t) N)); }
     if (V.static_domain && Sc > 0) { CK(dalloc(h, &V.Cpre[0], (size_t) Sc * N)); CK(dalloc(h, &V.Cpre[1], (size_t) Sc * N)); }
     CK(dalloc(h, &V.nbr_count, (size_t) N));
     CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, h->stream));
@@ -1223,10 +1266,11 @@ static int rdme_extra_event(ssb_handle *h, double tmin) {
     SsbView &V = h->V;
     const SsbModelUnit *u = h->unit;
     const double te = V.dt * (h->current_step + 1);
+    h->epoch += 2;                 // the two window epochs are consumed whether or not an event is pending (same numbering on every path)
     if (!(tmin < INFINITY) || !(tmin > te)) return SSB_OK;
-    if (u->rdme_window(&V, te, tmin, h->tau, h->seed, h->epoch++, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+    if (u->rdme_window(&V, te, tmin, h->tau, h->seed, h->epoch - 2, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
     h->inbox_buf ^= 1;
-    if (u->rdme_window(&V, tmin, tmin, h->tau, h->seed, h->epoch++, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+    if (u->rdme_window(&V, tmin, tmin, h->tau, h->seed, h->epoch - 1, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
     h->inbox_buf ^= 1;
     h->launches += 2;
     return SSB_OK;
@@ -1279,14 +1323,20 @@ static int rdme_step(ssb_handle *h) {
     // all windows of the step plus the zero-length closing window (delivers in-flight molecules so that the state read at
     // the step boundary conserves molecules) — one cooperative launch when the device supports it
     int nl = 0;
-    if (u->rdme_windows(&V, t0, V.dt, nwin, h->tau, h->seed, h->epoch, h->inbox_buf, &nl, st)) return fail(h, SSB_ERR_CUDA, "rdme_windows launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const int rw = u->rdme_windows(&V, t0, V.dt, nwin, h->tau, h->seed, h->epoch, h->inbox_buf, &nl, st);
+    if (rw > 0) return fail(h, SSB_ERR_CUDA, "rdme_windows launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     h->epoch += (uint64_t) nwin + 1;
     h->inbox_buf ^= (int) ((nwin + 1) & 1);
-    if (!V.static_domain && !(V.flags & SSB_FLAG_CORRECTED_NSM_SELECT)) {
-        double tmin = INFINITY;
-        int rcx = rdme_min_time(h, &tmin);
-        if (!rcx) rcx = rdme_extra_event(h, tmin);
-        if (rcx) return rcx;
+    if (!V.static_domain && !(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT))) {
+        // the step-end overshoot event (simulate_rdme.cpp:233-238): done inside the cooperative launch (rw == 0), else from the host
+        if (rw < 0) {
+            double tmin = INFINITY;
+            int rcx = rdme_min_time(h, &tmin);
+            if (!rcx) rcx = rdme_extra_event(h, tmin);
+            if (rcx) return rcx;
+        } else {
+            h->epoch += 2;
+        }
     }
     prof_end(h, psw);
     h->launches += nl;
@@ -1473,7 +1523,8 @@ static int stage_output(ssb_handle *h, const char *dir, unsigned file_index) {
     J.step = h->current_step;
     J.file_index = file_index;
     J.rdme_initialized = h->rdme_initialized;
-    J.write_file = (h->m.flags & SSB_FLAG_NO_VTK) ? 0 : 1;
+    J.write_file = (dir && !(h->m.flags & SSB_FLAG_NO_VTK)) ? 1 : 0;
+    J.write_bin = (dir && (h->m.flags & SSB_FLAG_BINARY_STORE)) ? 1 : 0;
     J.dir = dir ? dir : "";
     {
         std::lock_guard<std::mutex> lk(h->mu);
@@ -1488,7 +1539,7 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
                        ssb_progress_cb cb, void *cb_user) {
     if (!h || ntraj < 0) return SSB_ERR_ARG;
     if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
-    const bool write_files = !(h->m.flags & SSB_FLAG_NO_VTK);
+    const bool write_files = !(h->m.flags & SSB_FLAG_NO_VTK) || (h->m.flags & SSB_FLAG_BINARY_STORE);
     if (write_files && !out_dirs) return SSB_ERR_ARG;
     const unsigned nt = h->m.nt;
     for (int k = 0; k < ntraj; k++) {
@@ -1832,7 +1883,7 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
         break;
     }
     case PH_RDME_EXTRA:          // arg = GLOBAL earliest pending event: only its owner fires (see rdme_extra_event)
-        if (!(V.flags & SSB_FLAG_CORRECTED_NSM_SELECT)) { if ((rc = rdme_extra_event(h, arg))) return rc; }
+        if (!(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT))) { if ((rc = rdme_extra_event(h, arg))) return rc; }
         break;
     case PH_END:
         h->current_step++;

@@ -50,10 +50,10 @@ struct SsbView {
     unsigned long long *disp_bits;
     double *Dij;        // [cap*N] cached D_i_j (static domains) or nullptr
     double *rho_search; // density at neighbour-search time (frozen into D_i_j, particle.cpp:187)
-    // moving-domain gather records (written by k_predictor, read by the neighbour sweeps): one 128-byte line per particle
+    // moving-domain gather record (written by k_predictor, read by the neighbour sweeps): one 128-byte line per particle
     //   rec[16*j + 0..2] x0   3..5 x   6..8 v   9..11 vt   12 rho   13 mass   14 nu   15 bits(id:32 | type:16 | solid:16)
-    //   rec2[4*j + 0] 1/rho   1 P/rho^2   2 mass/rho   3 (spare)
-    double *rec, *rec2;
+    double *rec;
+    int *solid_nbr;     // [N] moving domains: 1 if any CANDIDATE neighbour is a solid particle (written by k_search, read by k_finish)
     // static-domain fast path: cached chemistry pair coefficient dQc_base (model.cpp:155) and the double-buffered
     // half-stepped concentrations the next sweep reads (see k_static_step)
     double *coef;       // [cap*N] or nullptr

@@ -103,11 +103,6 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
         r2[5] = make_double2(V.vt[1][i], V.vt[2][i]);
         r2[6] = make_double2(p.rho, p.mass);
         r2[7] = make_double2(p.nu, __longlong_as_double(bits));
-        const double inv_rho = 1.0 / p.rho;
-        const double Pp = V.P0 * (p.rho / V.rho0 - 1.0);
-        double2 *q2 = reinterpret_cast<double2 *>(V.rec2 + (size_t) i * 4);
-        q2[0] = make_double2(inv_rho, Pp * inv_rho * inv_rho);
-        q2[1] = make_double2(p.mass * inv_rho, 0.0);
     }
 #pragma unroll
     for (int s = 0; s < SSB_SC; s++) {
@@ -278,12 +273,18 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
         const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
         const double *ri = V.rec + (size_t) i * 16;
         const ssb_d4 a0 = ssb_ld256(ri), a1 = ssb_ld256(ri + 4), a2 = ssb_ld256(ri + 8), a3 = ssb_ld256(ri + 12);
-        const ssb_d4 b0 = ssb_ld256(V.rec2 + (size_t) i * 4);
         const double xi0 = a0.d, xi1 = a1.a, xi2 = a1.b;
         const double vi0 = a1.c, vi1 = a1.d, vi2 = a2.a;
         const double wi0 = a2.b - vi0, wi1 = a2.c - vi1, wi2 = a2.d - vi2;
         const double rho_i = a3.a, m_i = a3.b, nu_i = a3.c;
-        const double inv_rho_i = b0.a, aP_i = b0.b, vol_i = b0.c;
+        // 1/rho, P/rho^2 and m/rho of both particles are recomputed from the record (two divisions per pair on an fp64 pipe that is
+        // ~30 % busy) rather than gathered from a second per-particle record: the sweep is bound by L1 tag lookups — each lane's
+        // gather touches its own 128-byte line — and a fifth sector per pair cost more (measured 0.77 -> 0.70 ms at 1 M particles).
+        const double rho0 = V.rho0, inv_rho0 = 1.0 / V.rho0;
+        const bool inv_exact = (__double_as_longlong(rho0) & 0x000fffffffffffffLL) == 0;    // power of two: rho * (1/rho0) == rho / rho0 bit for bit
+        const double inv_rho_i = 1.0 / rho_i;
+        const double aP_i = (P0 * (rho_i / rho0 - 1.0)) * inv_rho_i * inv_rho_i;
+        const double vol_i = m_i * inv_rho_i;
         const double volsq_i = vol_i * vol_i, inv_m_i = 1.0 / m_i;
         const double rv0 = rho_i * vi0, rv1 = rho_i * vi1, rv2 = rho_i * vi2;
         const int type_i = (int) ((__double_as_longlong(a3.d) >> 32) & 0xffff);
@@ -306,7 +307,10 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
             const int j = V.nbr[(size_t) k * N + i];
             const double *rj = V.rec + (size_t) j * 16;
             const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
-            const ssb_d4 e0 = ssb_ld256(V.rec2 + (size_t) j * 4);
+            ssb_d4 e0;
+            e0.a = 1.0 / c3.a;
+            e0.b = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * e0.a * e0.a;
+            e0.c = c3.b * e0.a;
             const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
             const double r = sqrt(d2);
             // candidate list -> ANN's exact set (the record loads above are issued before this test on purpose: a rejected
@@ -597,18 +601,24 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_finish(SsbView V, unsigned step) 
         double vos = 0.0, vtot = 0.0;
         const int cnt = V.nbr_count[i];
         const bool use_rec = (V.rec != nullptr) && !(V.flags & 16u /*SSB_FLAG_LITERAL_KERNELS*/);
+        // A fluid particle with no solid particle among its candidates has vos = 0 and a zero wall normal whatever the rest of the
+        // sum is: bvf_phi = |0 / vtot| only needs to know whether vtot > 0, i.e. the sweep may stop at the first neighbour that
+        // contributes.  The list build recorded that fact (V.solid_nbr, k_search); in a tank ~90 % of the fluid is bulk.
+        const bool bulk = V.solid_nbr != nullptr && V.solid_nbr[i] == 0;
         for (int k = 0; k < cnt; k++) {
+            if (bulk && vtot > 0.0) break;
             const int j = V.nbr[(size_t) k * N + i];
-            double x0j0, x0j1, x0j2, xj0, xj1, xj2, m_j, rho_pre_j;
+            double x0j0, x0j1, x0j2, xj0 = 0.0, xj1 = 0.0, xj2 = 0.0, m_j, rho_pre_j;
             int id_j, solid_j;
-            if (use_rec) {      // one 128-byte gather record per neighbour (3 of its 4 sectors are needed here)
+            if (use_rec) {      // one 128-byte gather record per neighbour: sectors 0 and 3, plus sector 1 (live x_j) for solid neighbours
                 const double *rj = V.rec + (size_t) j * 16;
-                const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c3 = ssb_ld256(rj + 12);
-                x0j0 = c0.a; x0j1 = c0.b; x0j2 = c0.c; xj0 = c0.d; xj1 = c1.a; xj2 = c1.b;
+                const ssb_d4 c0 = ssb_ld256(rj), c3 = ssb_ld256(rj + 12);
+                x0j0 = c0.a; x0j1 = c0.b; x0j2 = c0.c; xj0 = c0.d;
                 rho_pre_j = c3.a; m_j = c3.b;
                 const long long bits = __double_as_longlong(c3.d);
                 id_j = (int) (bits & 0xffffffffll);                       // global particle id
                 solid_j = (int) ((bits >> 48) & 0xffff);
+                if (solid_j) { const ssb_d4 c1 = ssb_ld256(rj + 4); xj1 = c1.a; xj2 = c1.b; }
             } else {
                 x0j0 = V.x0[0][j]; x0j1 = V.x0[1][j]; x0j2 = V.x0[2][j];
                 xj0 = V.x[0][j]; xj1 = V.x[1][j]; xj2 = V.x[2][j];
@@ -804,6 +814,7 @@ __device__ __forceinline__ int coop_pick_direction(const SsbView &V, int il, int
     const int N = V.N, lane = threadIdx.x & 31;
     const int cnt = V.nbr_count[il];
     const bool cached = V.Dij != nullptr;
+    const bool use_rec = !cached && V.rec != nullptr && !V.static_domain && !(V.flags & 16u /*SSB_FLAG_LITERAL_KERNELS*/);
     double xl0 = 0, xl1 = 0, xl2 = 0, m_l = 0, rho_l = 0;
     if (!cached) { xl0 = V.x[0][il]; xl1 = V.x[1][il]; xl2 = V.x[2][il]; m_l = V.mass[il]; rho_l = V.rho_search[il]; }
     double base = 0.0;
@@ -815,6 +826,20 @@ __device__ __forceinline__ int coop_pick_direction(const SsbView &V, int il, int
         bool ok = false;
         if (k < cnt) {
             j = V.nbr[(size_t) k * N + il];
+            if (use_rec) {
+                // moving domains: the search-time snapshot of j (x0, rho, mass, type) sits in two sectors of its gather record
+                // instead of seven separate arrays — the pick is bound by scattered sectors, not by arithmetic
+                const double *rj = V.rec + (size_t) j * 16;
+                const ssb_d4 c0 = ssb_ld256(rj), c3 = ssb_ld256(rj + 12);
+                const int tj = (int) ((__double_as_longlong(c3.d) >> 32) & 0xffff) - 1;
+                const double dc = V.dmat[spec * V.num_types + tj];
+                const double d2 = ssb_dist2(V.dim, xl0, xl1, xl2, c0.a, c0.b, c0.c);
+                const bool in = !V.filter || ssb_in_range(d2, V.h, __dmul_rn(V.h, V.h));
+                if (dc != 0.0 && in) {
+                    ok = true;
+                    w = ssb_Dij(d2, sqrt(d2), V.h, m_l, c3.b, rho_l, c3.a) * dc;
+                }
+            } else {
             const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
             bool in = true;
             if (V.filter) in = ssb_in_range(ssb_dist2(V.dim, xl0, xl1, xl2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h));
@@ -822,6 +847,7 @@ __device__ __forceinline__ int coop_pick_direction(const SsbView &V, int il, int
                 ok = true;
                 const double Dij = cached ? V.Dij[(size_t) k * N + il] : pair_Dij(V, il, j, xl0, xl1, xl2, m_l, rho_l);
                 w = Dij * dc;
+            }
             }
         }
         double incl = w;
@@ -845,10 +871,23 @@ __device__ __forceinline__ int serial_pick_direction(const SsbView &V, int il, i
     const bool cached = V.Dij != nullptr;
     double xl0 = 0, xl1 = 0, xl2 = 0, m_l = 0, rho_l = 0;
     if (!cached) { xl0 = V.x[0][il]; xl1 = V.x[1][il]; xl2 = V.x[2][il]; m_l = V.mass[il]; rho_l = V.rho_search[il]; }
+    const bool use_rec = !cached && V.rec != nullptr && !V.static_domain && !(V.flags & 16u);
     double cum = 0.0;
     int last_ok = -1;
     for (int k = 0; k < cnt; k++) {
         const int j = V.nbr[(size_t) k * N + il];
+        if (use_rec) {
+            const double *rj = V.rec + (size_t) j * 16;
+            const ssb_d4 c0 = ssb_ld256(rj), c3 = ssb_ld256(rj + 12);
+            const double dc = V.dmat[spec * V.num_types + ((int) ((__double_as_longlong(c3.d) >> 32) & 0xffff) - 1)];
+            if (dc == 0.0) continue;
+            const double d2 = ssb_dist2(V.dim, xl0, xl1, xl2, c0.a, c0.b, c0.c);
+            if (V.filter && !ssb_in_range(d2, V.h, __dmul_rn(V.h, V.h))) continue;
+            cum += ssb_Dij(d2, sqrt(d2), V.h, m_l, c3.b, rho_l, c3.a) * dc;
+            last_ok = j;
+            if (cum > target) return j;
+            continue;
+        }
         const double dc = V.dmat[spec * V.num_types + (V.type[j] - 1)];
         if (dc == 0.0) continue;
         if (V.filter && !ssb_in_range(ssb_dist2(V.dim, xl0, xl1, xl2, V.x0[0][j], V.x0[1][j], V.x0[2][j]), V.h, __dmul_rn(V.h, V.h))) continue;
@@ -869,28 +908,43 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
     // Inside a chunk the event loop is warp-synchronous: every lane runs the SSA of its own voxel, and the one long
     // operation of an event — the scan of the neighbour row for the jump direction — is done by the whole warp for one
     // lane at a time (coop_pick_direction), so an event costs a few memory round trips instead of one per neighbour.
+    // The active chunks are then cut into warp-sized slices that the CTA's warps take from a shared counter: a warp whose slice has
+    // no event moves on at once instead of waiting at a block barrier for the one warp of the chunk that is executing events, so
+    // the cost of a window is (events x event latency) / (resident warps), not the sum over chunks of their slowest warp.
     __shared__ int sh_act[SSB_BLOCK];
-    __shared__ int sh_nact;
+    __shared__ unsigned long long sh_tmin[SSB_BLOCK];    // earliest tnext per active chunk (bit pattern of a non-negative double)
+    __shared__ int sh_nact, sh_next;
+    constexpr int WPB = SSB_BLOCK / 32;
     const int N = V.N;
     const int nchunks = (N + SSB_BLOCK - 1) / SSB_BLOCK;
     const int lane = threadIdx.x & 31;
     for (int round0 = 0; blockIdx.x + (long long) round0 * gridDim.x < nchunks; round0 += SSB_BLOCK) {
     __syncthreads();
-    if (threadIdx.x == 0) sh_nact = 0;
+    if (threadIdx.x == 0) { sh_nact = 0; sh_next = 0; }
     __syncthreads();
     {
         const long long c = blockIdx.x + (long long) (round0 + threadIdx.x) * gridDim.x;
         if (c < nchunks) {
             const int mail = __ldcg(&V.blk_mail[buf ^ 1][c]);      // written by other CTAs: read through L2
             if (mail) V.blk_mail[buf ^ 1][c] = 0;
-            if (mail != 0 || V.blk_tmin[c] <= t_hi) sh_act[atomicAdd(&sh_nact, 1)] = (int) c;
+            if (mail != 0 || V.blk_tmin[c] <= t_hi) {
+                const int slot = atomicAdd(&sh_nact, 1);
+                sh_act[slot] = (int) c;
+                sh_tmin[slot] = 0x7ff0000000000000ull;             // +inf
+            }
         }
     }
     __syncthreads();
     const int nact = sh_nact;
-    for (int a = 0; a < nact; a++) {
+    const int nitems = nact * WPB;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&sh_next, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int a = item / WPB;
         const int chunk = sh_act[a];
-        const int i = chunk * SSB_BLOCK + threadIdx.x;
+        const int i = chunk * SSB_BLOCK + (item % WPB) * 32 + lane;
         const bool valid = i < N;
         const int ii = valid ? i : N - 1;                          // clamp so idle lanes can run the same code path
         const unsigned *in_prev = V.inbox[buf ^ 1];
@@ -1099,10 +1153,13 @@ __device__ __forceinline__ void rdme_window_body(const SsbView &V, double t_lo, 
             V.sdrate[i] = R.sd;
             V.tnext[i] = tnext;
         }
-        const double tn_final = block_min(valid ? tnext : INFINITY);
-        if (threadIdx.x == 0) V.blk_tmin[chunk] = tn_final;
-        __syncthreads();                 // block_min's shared scratch is reused by the next chunk
+        double tn_final = valid ? tnext : INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tn_final = fmin(tn_final, __shfl_xor_sync(0xffffffffu, tn_final, o));
+        if (lane == 0) atomicMin(&sh_tmin[a], (unsigned long long) __double_as_longlong(tn_final));
     }
+    __syncthreads();
+    if ((int) threadIdx.x < nact) V.blk_tmin[sh_act[threadIdx.x]] = __longlong_as_double((long long) sh_tmin[threadIdx.x]);
     }
 }
 
@@ -1422,18 +1479,43 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
 template <bool SINGLE, bool LEAP>
 __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_windows_coop(SsbView V, double t0, double dt, long long nwin, double tau,
                                                                 uint64_t seed, uint64_t epoch0, int buf0) {
+    // Moving domains, parity mode: the reference's `while(tt <= end_time)` tests the PREVIOUS event's time, so each take_step runs
+    // one event past the step's end (simulate_rdme.cpp:233-238) — and the NSM is rebuilt every step (:54-65), so that overshoot is a
+    // real extra event.  After the closing window every CTA reduces the chunk minima to the earliest pending clock t_min, window
+    // nwin+1 = [t_end, t_min] executes exactly that event and window nwin+2 = (t_min, t_min) delivers it.
+    // (Host-driven twin for slabs, where t_min is a minimum over ranks: rdme_min_time / rdme_extra_event in ssb_core.cu.)
+    __shared__ double sh_tmin_all;
+    const bool overshoot = !V.static_domain && !(V.flags & (1u | 128u));
+    const long long wlast = overshoot ? nwin + 2 : nwin;
+    const double te = t0 + dt;
     unsigned n_rx = 0, n_df = 0;
     int buf = buf0;
-    for (long long w = 0; w <= nwin; w++) {
+    double tmin = INFINITY;
+    for (long long w = 0; w <= wlast; w++) {
         double lo, hi;
         if (w < nwin) {
             lo = t0 + dt * ((double) w / (double) nwin);
-            hi = (w + 1 == nwin) ? t0 + dt : t0 + dt * ((double) (w + 1) / (double) nwin);
-        } else { lo = hi = t0 + dt; }
+            hi = (w + 1 == nwin) ? te : t0 + dt * ((double) (w + 1) / (double) nwin);
+        } else if (w == nwin) {
+            lo = hi = te;
+        } else if (w == nwin + 1) {
+            const int nchunks = (V.N + SSB_BLOCK - 1) / SSB_BLOCK;
+            double m = INFINITY;
+            for (int c = threadIdx.x; c < nchunks; c += SSB_BLOCK) m = fmin(m, __ldcg(&V.blk_tmin[c]));
+            m = block_min(m);
+            if (threadIdx.x == 0) sh_tmin_all = m;
+            __syncthreads();
+            tmin = sh_tmin_all;
+            if (!SINGLE) cooperative_groups::this_grid().sync();   // nobody may update a chunk minimum while another CTA is still reducing
+            if (!(tmin < INFINITY && tmin > te)) break;            // uniform over the grid
+            lo = te; hi = tmin;
+        } else {
+            lo = hi = tmin;
+        }
         if (LEAP) rdme_window_body_leap(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
         else rdme_window_body(V, lo, hi, tau, seed, epoch0 + (uint64_t) w, buf, n_rx, n_df);
         buf ^= 1;
-        if (w < nwin) {
+        if (w < wlast) {
             if (SINGLE) __syncthreads();       // one CTA: a block barrier orders the inbox traffic, and (unlike a device-scope fence) keeps L1 warm
             else cooperative_groups::this_grid().sync();
         }
@@ -1488,19 +1570,18 @@ static int l_rdme_init(const SsbView *V, double t0, double t_eval, double tau, u
 // all windows of a step; returns the number of kernel launches used through *launches
 static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin, double tau, uint64_t seed, uint64_t epoch0,
                           int buf0, int *launches, cudaStream_t st) {
-    static int coop_blocks = -1;       // co-resident CTAs of the cooperative kernel on this device (0 = unsupported)
-    if (coop_blocks < 0) {
+    static int coop_blocks_of[2] = {-1, -1};   // co-resident CTAs of the cooperative kernel on this device (0 = unsupported), [leap]
+    const bool leap = (V->flags & 32u) != 0;
+    if (coop_blocks_of[leap] < 0) {
         int dev = 0, coop = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int per_sm_leap = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop<false, false>, SSB_BLOCK, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_leap, k_rdme_windows_coop<false, true>, SSB_BLOCK, 0);
-        if (per_sm_leap < per_sm) per_sm = per_sm_leap;
-        coop_blocks = coop ? sms * per_sm : 0;
+        if (leap) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop<false, true>, SSB_BLOCK, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rdme_windows_coop<false, false>, SSB_BLOCK, 0);
+        coop_blocks_of[leap] = coop ? sms * per_sm : 0;
     }
-    const bool leap = (V->flags & 32u) != 0;
+    const int coop_blocks = coop_blocks_of[leap];
     const unsigned nchunks = grid_for(V->N);
     if (nchunks <= 8) {      // small model: one CTA walks all chunks; ordinary launch, block barrier between windows
         if (leap) k_rdme_windows_coop<true, true><<<1, SSB_BLOCK, 0, st>>>(*V, t0, dt, nwin, tau, seed, epoch0, buf0);
@@ -1528,7 +1609,9 @@ static int l_rdme_windows(const SsbView *V, double t0, double dt, long long nwin
         buf ^= 1;
     }
     if (launches) *launches = (int) (nwin + 1);
-    return (int) cudaGetLastError();
+    const int e = (int) cudaGetLastError();
+    if (e) return e;
+    return (!V->static_domain && !(V->flags & (1u | 128u))) ? -1 : 0;      // -1: fine, but the step-end overshoot event is left to the host
 }
 static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t st) {
     const unsigned nchunks = grid_for(V->N);

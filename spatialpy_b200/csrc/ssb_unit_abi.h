@@ -8,7 +8,7 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 9
+#define SSB_UNIT_ABI 10
 
 struct SsbModelUnit {
     int abi;

@@ -119,6 +119,7 @@ class SlabEngine:
         if part.local.static_domain:
             raise ValueError("slab decomposition is implemented for moving domains (static ensembles shard by trajectory)")
         self.dev = torch.device("cuda", device)
+        self.overshoot = not (flags & 129)     # FLAG_CORRECTED_NSM_SELECT | FLAG_NO_STEP_OVERSHOOT switch the extra event off
         self.eng = Engine(part.local, device=device, flags=flags, rdme_epsilon=rdme_epsilon, owned=part.owned,
                           rng_id=part.gids.astype(np.int32))
         self.Sd = part.local.num_stoch_species
@@ -181,14 +182,15 @@ class SlabEngine:
                     self._sync_inbox()
                 e.phase(PH_RDME_CLOSE)
                 # the reference's one event past the end of every step (simulate_rdme.cpp:233-238): globally earliest pending event
-                tmin = e.phase(PH_RDME_MIN)
-                if self.world > 1:
-                    t = self.torch.tensor([tmin], dtype=self.torch.float64, device=self.dev)
-                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
-                    tmin = float(t.item())
-                e.phase(PH_RDME_EXTRA, tmin)
-                self._sync_inbox()
-                e.phase(PH_RDME_CLOSE)
+                if self.overshoot:
+                    tmin = e.phase(PH_RDME_MIN)
+                    if self.world > 1:
+                        t = self.torch.tensor([tmin], dtype=self.torch.float64, device=self.dev)
+                        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                        tmin = float(t.item())
+                    e.phase(PH_RDME_EXTRA, tmin)
+                    self._sync_inbox()
+                    e.phase(PH_RDME_CLOSE)
             e.phase(PH_END)
             # fixed ghost sets: a pair within h*(1+skin) must have both members present, so nobody may travel further than
             # half of what the halo leaves beyond the candidate radius

@@ -7,8 +7,9 @@ propfilename, prop_file_name, executable_name, h` (solver.py:63-71), `compile(de
 with a `result_dir` of `output%u.vtk` files the reference's VTKReader parses (the file contract).
 What changed underneath: no generated C++ / SCons / subprocess — the model is flattened to arrays (flatmodel.py), the
 propensities / BCs are compiled into a CUDA model unit (codegen.py) and trajectories run in-process through the C-ABI
-(engine.py).  Additive keywords (not in the reference): `devices=[...]` to spread an ensemble over GPUs, `flags`,
-`rdme_epsilon`.
+(engine.py).  Additive keywords (not in the reference): `devices=[...]` to spread an ensemble over GPUs, `lanes`, `flags`,
+`rdme_epsilon`, `binary_store=True` (also write `output%u.ssb`, raw fp64 arrays that `Result.read_step` then loads
+instead of parsing the text) and `vtk=False` (binary files only).
 
 `install()` adds the `solver=` keyword that the reference's README promises but `Model.run` never implemented
 (model.py:1021-1056): `model.run(solver=spatialpy_b200.Solver, number_of_trajectories=..., seed=...)`.
@@ -51,17 +52,35 @@ class FlatResult:
         self.listOfResultObjects.append(item)
 
     def read_step(self, step_num, debug=False):
-        from .vtk import read_vtk
-        return read_vtk(os.path.join(self.result_dir, f"output{step_num}.vtk"))
+        from .vtk import read_output
+        return read_output(self.result_dir, step_num)
 
     def get_species(self, species, timepoints=None, concentration=False, deterministic=False):
         import numpy as np
         name = species if isinstance(species, str) else species.name
         key = f"C[{name}]" if (deterministic or concentration) else f"D[{name}]"
-        n_out = len([f for f in os.listdir(self.result_dir) if f.startswith("output") and "bounding" not in f])
+        n_out = len({os.path.splitext(f)[0] for f in os.listdir(self.result_dir) if f.startswith("output") and "bounding" not in f})
         steps = range(n_out) if timepoints is None else ([timepoints] if isinstance(timepoints, int) else timepoints)
         out = np.array([self.read_step(s)[1][key] for s in steps])
         return out[0] if isinstance(timepoints, int) else out
+
+
+def _result_class():
+    """The reference's Result with `read_step` served from the binary side-store when the run kept one (SURVEY.md §8f item 1);
+    everything else — get_species, plotting, __eq__, pickling of the result directory — is inherited unchanged."""
+    from spatialpy.core.result import Result
+
+    class B200Result(Result):
+        def read_step(self, step_num, debug=False):
+            path = os.path.join(self.result_dir, f"output{step_num}.ssb")
+            if os.path.exists(path):
+                from .vtk import read_ssb
+                points, arrays = read_ssb(path)
+                arrays.pop("__nfields_header__", None)
+                return points, arrays
+            return super().read_step(step_num, debug=debug)
+
+    return B200Result
 
 
 class Solver:
@@ -107,18 +126,21 @@ class Solver:
     def _new_result(self, outdir):
         if isinstance(self.model, FlatModel):
             return FlatResult(self.model, outdir)
-        from spatialpy.core.result import Result
-        return Result(self.model, outdir)
+        return _result_class()(self.model, outdir)
 
     def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False,
-            verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None):
-        from .engine import Engine, EngineError, FLAG_SKIP_STATIC_FORCES
+            verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None, binary_store=False, vtk=True):
+        from .engine import Engine, EngineError, FLAG_SKIP_STATIC_FORCES, FLAG_BINARY_STORE, FLAG_NO_VTK
         if not self.is_compiled:
             self.compile(debug=debug, profile=profile)
         if seed is None:                      # template:127 std::random_device
             seed = int.from_bytes(os.urandom(4), "little")
         devices = list(devices) if devices else [0]
         flags = FLAG_SKIP_STATIC_FORCES if flags is None else flags
+        if binary_store:                      # outputN.ssb next to outputN.vtk; vtk=False keeps only the binary files
+            flags |= FLAG_BINARY_STORE | (0 if vtk else FLAG_NO_VTK)
+        elif not vtk:
+            raise SimulationError("vtk=False needs binary_store=True (a run must leave some output behind).")
         results = []
         for _ in range(number_of_trajectories):
             outdir = tempfile.mkdtemp(prefix="spatialpy_result_", dir=os.environ.get("SPATIALPY_TMPDIR"))   # solver.py:548

@@ -127,3 +127,50 @@ def test_flattening_matches_reference_codegen_inputs():
     assert list(inspect.signature(Solver.run).parameters)[:len(ref_params)] == ref_params
     assert list(inspect.signature(Solver.__init__).parameters) == list(inspect.signature(RefSolver.__init__).parameters)
     assert list(inspect.signature(Solver.compile).parameters) == list(inspect.signature(RefSolver.compile).parameters)
+
+
+def test_binary_side_store_round_trip(tmp_path):
+    """outputN.ssb layout (written by ssb_core.cu write_bin on the GPU box): the Python twin round-trips, read_output prefers it."""
+    import numpy as np
+    from spatialpy_b200.solver import FlatResult
+    from spatialpy_b200.vtk import read_output, read_ssb, write_ssb
+    rng = np.random.default_rng(3)
+    n = 37
+    x, v, scal = rng.normal(size=(n, 3)), rng.normal(size=(n, 3)), rng.random((4, n))
+    C, D, typ = rng.random((2, n)), rng.integers(0, 1000, (2, n)), rng.integers(1, 4, n)
+    path = tmp_path / "output3.ssb"
+    write_ssb(path, x, v, scal, C, typ, D, ["A", "B_long_name"], step=30)
+    assert path.stat().st_size % 4 == 0 and (path.stat().st_size - n * (80 + 16 + 4 + 8)) % 64 == 0
+    pts, arr = read_ssb(path)
+    assert pts.dtype == np.float32 and np.array_equal(pts, x.astype(np.float32))
+    assert list(arr) == ["id", "type", "v", "rho", "mass", "bvf_phi", "nu", "C[A]", "C[B_long_name]", "D[A]", "D[B_long_name]",
+                         "__nfields_header__"]
+    assert np.array_equal(arr["v"], v) and np.array_equal(arr["nu"], scal[3]) and np.array_equal(arr["C[B_long_name]"], C[1])
+    assert arr["D[A]"].dtype == np.int64 and np.array_equal(arr["D[A]"], D[0]) and np.array_equal(arr["type"], typ)
+    assert arr["__nfields_header__"] == 11
+    p2, a2 = read_output(str(tmp_path), 3)
+    assert np.array_equal(p2, pts)
+    res = FlatResult(None, str(tmp_path))
+    assert np.array_equal(res.get_species("A", timepoints=3), D[0])
+    with open(path, "r+b") as f:
+        f.truncate(path.stat().st_size - 8)
+    with pytest.raises(ValueError):
+        read_ssb(path)
+
+
+def test_reference_result_subclass_reads_the_binary_store(tmp_path):
+    """With the spatialpy front-end importable the Solver returns the reference's own Result type; only read_step is overridden."""
+    pytest.importorskip("spatialpy")
+    import numpy as np
+    from spatialpy.core.result import Result
+    from spatialpy_b200.solver import _result_class
+    from spatialpy_b200.vtk import write_ssb
+    n = 5
+    write_ssb(tmp_path / "output0.ssb", np.zeros((n, 3)), np.ones((n, 3)), np.full((4, n), 2.0), None, np.ones(n, int),
+              np.arange(n)[None, :], ["A"], rdme_initialized=0)
+    cls = _result_class()
+    assert issubclass(cls, Result)
+    res = cls(None, str(tmp_path))
+    pts, arr = res.read_step(0)
+    assert pts.shape == (n, 3) and "__nfields_header__" not in arr and np.array_equal(arr["D[A]"], np.arange(n))
+    res.result_dir = None          # keep Result.__del__ away from pytest's tmp_path

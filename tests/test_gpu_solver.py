@@ -133,3 +133,45 @@ def test_nan_raises_simulation_error():
     fm.x[7, 0] = np.nan
     with pytest.raises(SimulationError, match="return code = 1"):
         Solver(fm).run(seed=1)
+
+
+def test_binary_side_store_matches_the_vtk_files(diffusion_run):
+    """`binary_store=True` keeps outputN.ssb next to outputN.vtk; read_step then serves the same keys / shapes / dtypes from the
+    raw arrays.  Integers are identical, fp64 fields agree to the six decimals the text keeps (output.cpp:170-230 prints %lf)."""
+    from spatialpy_b200 import Solver
+    from spatialpy_b200.vtk import read_ssb, read_vtk
+    _, plain = diffusion_run
+    res = Solver(load_model("diffusion3d")).run(number_of_trajectories=1, seed=1000, binary_store=True)
+    names = sorted(os.listdir(res.result_dir))
+    assert sorted(n for n in names if n.endswith(".vtk")) == sorted(os.listdir(plain.result_dir))
+    assert len([n for n in names if n.endswith(".ssb")]) == len(names) // 2      # one per outputN.vtk (bounding box has none)
+    for k in (0, 1, 10):
+        pv, av = read_vtk(os.path.join(res.result_dir, f"output{k}.vtk"))
+        pb, ab = read_ssb(os.path.join(res.result_dir, f"output{k}.ssb"))
+        assert list(av) == list(ab)
+        assert pb.dtype == pv.dtype == np.float32 and np.allclose(pb, pv, rtol=2e-7, atol=0)
+        for key in av:
+            if key.startswith("__"):
+                assert av[key] == ab[key]
+            elif av[key].dtype == np.int64:
+                assert ab[key].dtype == np.int64 and np.array_equal(av[key], ab[key]), key
+            else:
+                assert ab[key].shape == av[key].shape and np.max(np.abs(av[key] - ab[key])) <= 5.0000001e-7, key
+        assert filecmp.cmp(os.path.join(res.result_dir, f"output{k}.vtk"), os.path.join(plain.result_dir, f"output{k}.vtk"),
+                           shallow=False) or k > 0        # same seed: output0 is byte-identical; later D[] too (checked next)
+    assert np.array_equal(res.read_step(10)[1]["D[A]"], plain.read_step(10)[1]["D[A]"])     # same seed, same trajectory
+    assert res.read_step(10)[1]["C[A]"].dtype == np.float64
+
+
+def test_binary_only_run(tmp_path):
+    from spatialpy_b200 import Solver
+    from spatialpy_b200.solver import SimulationError
+    sol = Solver(load_model("diffusion3d"))
+    res = sol.run(number_of_trajectories=2, seed=7, binary_store=True, vtk=False)
+    for r in res.listOfResultObjects:
+        assert all(n.endswith(".ssb") for n in os.listdir(r.result_dir)) and len(os.listdir(r.result_dir)) == 11
+        pts, arr = r.read_step(5)
+        assert pts.shape[1] == 3 and arr["D[A]"].sum() > 0
+        assert r.get_species("A").shape[0] == 11
+    with pytest.raises(SimulationError):
+        sol.run(vtk=False)
