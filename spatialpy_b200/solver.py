@@ -55,14 +55,77 @@ class FlatResult:
         from .vtk import read_output
         return read_output(self.result_dir, step_num)
 
-    def get_species(self, species, timepoints=None, concentration=False, deterministic=False):
-        import numpy as np
+    def _num_outputs(self):
+        stems = {os.path.splitext(f)[0][6:] for f in os.listdir(self.result_dir) if f.startswith("output")}
+        return 1 + max((int(k) for k in stems if k.isdigit()), default=-1)
+
+    def get_species(self, species, timepoints=None, concentration=False, deterministic=False, debug=False):
+        """Same arguments, return shape and dtype as Result.get_species (result.py:334-402)."""
         name = species if isinstance(species, str) else species.name
-        key = f"C[{name}]" if (deterministic or concentration) else f"D[{name}]"
-        n_out = len({os.path.splitext(f)[0] for f in os.listdir(self.result_dir) if f.startswith("output") and "bounding" not in f})
-        steps = range(n_out) if timepoints is None else ([timepoints] if isinstance(timepoints, int) else timepoints)
-        out = np.array([self.read_step(s)[1][key] for s in steps])
-        return out[0] if isinstance(timepoints, int) else out
+        steps, scalar = _select_steps(self._num_outputs(), timepoints)
+        return _species_series(self, name, steps, concentration, deterministic)
+
+    def get_property(self, property_name, timepoints=None):
+        """Same arguments and return shape as Result.get_property (result.py:601-655), step-index quirk included."""
+        steps, scalar = _select_steps(self._num_outputs(), timepoints)
+        return _property_series(self, property_name, range(len(steps)))
+
+
+def _select_steps(n_out, timepoints):
+    """The output indices Result.get_species / get_property visit (result.py:378-392): all of them, or `timepoints` used as a
+    numpy index into them (an int, a slice or a list)."""
+    import numpy as np
+    idx = np.linspace(0, n_out - 1, num=n_out, dtype=int)
+    if timepoints is None:
+        return list(idx), False
+    if isinstance(timepoints, float):
+        raise _result_error()("timepoints argument must be an integer, the index of time timespan")
+    sel = idx[timepoints]
+    if np.ndim(sel) == 0:
+        return [int(sel)], True
+    return [int(t) for t in sel], False
+
+
+def _result_error():
+    try:
+        from spatialpy.core.spatialpyerror import ResultError
+        return ResultError
+    except Exception:  # pragma: no cover - GPU box: no spatialpy
+        return ValueError
+
+
+def _field(result, step, key):
+    """One array of one output step: by offset from outputN.ssb when the run kept the binary side-store, else through
+    read_step (the text parser)."""
+    path = os.path.join(result.result_dir, f"output{step}.ssb")
+    if os.path.exists(path):
+        from .vtk import read_ssb_field
+        return read_ssb_field(path, key)
+    return result.read_step(step)[1][key]
+
+
+def _species_series(result, name, steps, concentration, deterministic):
+    """(timepoints x voxels) float64 matrix of one species, 1-D for a single timepoint — result.py:390-402 without
+    materialising every other array of every step."""
+    import numpy as np
+    rows = []
+    for t in steps:
+        if deterministic:
+            rows.append(_field(result, t, f"C[{name}]"))
+        elif concentration:
+            rows.append(_field(result, t, f"D[{name}]") / (_field(result, t, "mass") / _field(result, t, "rho")))
+        else:
+            rows.append(_field(result, t, f"D[{name}]"))
+    ret = np.array(rows, dtype=np.float64)
+    return ret.flatten() if ret.shape[0] == 1 else ret
+
+
+def _property_series(result, property_name, steps):
+    """result.py:644-655.  The reference reads step `ndx` — the position in the selection, not the selected timepoint
+    (`read_step(ndx)`, result.py:648) — so `timepoints=k` returns step 0; callers pass the positions to keep that behaviour."""
+    import numpy as np
+    ret = np.array([_field(result, t, property_name) for t in steps], dtype=np.float64)
+    return ret.flatten() if ret.shape[0] == 1 else ret
 
 
 def _result_class():
@@ -79,6 +142,28 @@ def _result_class():
                 arrays.pop("__nfields_header__", None)
                 return points, arrays
             return super().read_step(step_num, debug=debug)
+
+        def _has_store(self, steps):
+            return all(os.path.exists(os.path.join(self.result_dir, f"output{t}.ssb")) for t in steps)
+
+        def get_species(self, species, timepoints=None, concentration=False, deterministic=False, debug=False):
+            """result.py:334-402 with every step's one field read by offset from the binary side-store (a 1 M-voxel,
+            100-output run: 100 x 8 MB instead of 100 full snapshots); without a store the inherited method runs."""
+            name = species if isinstance(species, str) else species.name
+            if name not in self.model.listOfSpecies.keys():
+                raise _result_error()(f"Species '{name}' not found")
+            steps, _ = _select_steps(len(self.get_timespan()), timepoints)
+            if not self._has_store(steps):
+                return super().get_species(species, timepoints=timepoints, concentration=concentration,
+                                           deterministic=deterministic, debug=debug)
+            return _species_series(self, name, steps, concentration, deterministic)
+
+        def get_property(self, property_name, timepoints=None):
+            steps, _ = _select_steps(len(self.get_timespan()), timepoints)
+            pos = range(len(steps))            # result.py:648 reads step `ndx`, not `t_index_arr[ndx]`; kept
+            if not self._has_store(pos):
+                return super().get_property(property_name, timepoints=timepoints)
+            return _property_series(self, property_name, pos)
 
     return B200Result
 

@@ -54,10 +54,7 @@ def read_ssb(path):
     but the fp64 fields carry full precision instead of the six decimals `%lf` leaves in the text file (output.cpp:170-230),
     and a 1 M-particle snapshot loads in milliseconds instead of the ~10 s the ASCII parser needs."""
     with open(path, "rb") as f:
-        if f.read(8) != SSB_MAGIC:
-            raise ValueError(f"{path} is not an SSB output file")
-        hl = int(np.frombuffer(f.read(8), dtype="<u8")[0])
-        hdr = json.loads(f.read(hl).decode("ascii"))
+        hdr, _ = _ssb_header(f, path)
         n, Sc, Sd = hdr["np"], hdr["Sc"], hdr["Sd"]
         raw = {}
         for name, dt, cnt in _ssb_layout(n, Sc, Sd):
@@ -74,6 +71,50 @@ def read_ssb(path):
     # output.cpp:151-154 undercounts FIELD in output0 (the RDME is not initialised yet); keep the reader-visible number
     arrays["__nfields_header__"] = 7 + Sc + (Sd if hdr["rdme_initialized"] else 0)
     return raw["x"].reshape(n, 3).astype(np.float32), arrays
+
+
+def _ssb_header(f, path):
+    if f.read(8) != SSB_MAGIC:
+        raise ValueError(f"{path} is not an SSB output file")
+    hl = int(np.frombuffer(f.read(8), dtype="<u8")[0])
+    return json.loads(f.read(hl).decode("ascii")), 16 + hl
+
+
+def read_ssb_field(path, key):
+    """One array of an outputN.ssb file, located by offset instead of loading the whole snapshot — what the all-timepoints
+    getters of Result (`get_species`, `get_property`; result.py:334-402,601-655) need: one field of every step.  Same keys,
+    shapes and dtypes as `read_ssb`; raises KeyError for a name the snapshot does not hold."""
+    with open(path, "rb") as f:
+        hdr, base = _ssb_header(f, path)
+        n, Sc, Sd = hdr["np"], hdr["Sc"], hdr["Sd"]
+        off = {}
+        for name, dt, cnt in _ssb_layout(n, Sc, Sd):
+            off[name] = base
+            base += cnt * np.dtype(dt).itemsize
+
+        def sect(name, dt, skip, cnt):
+            f.seek(off[name] + skip * np.dtype(dt).itemsize)
+            a = np.fromfile(f, dtype=dt, count=cnt)
+            if a.size != cnt:
+                raise ValueError(f"{path} is truncated in section {name}")
+            return a
+        if key == "id":
+            return np.arange(n, dtype=np.int64)
+        if key == "type":
+            return sect("type", "<i4", 0, n).astype(np.int64)
+        if key == "v":
+            return sect("v", "<f8", 0, 3 * n).reshape(n, 3)
+        if key == "points":
+            return sect("x", "<f8", 0, 3 * n).reshape(n, 3).astype(np.float32)
+        if key in ("rho", "mass", "bvf_phi", "nu"):
+            return sect("scal", "<f8", ("rho", "mass", "bvf_phi", "nu").index(key) * n, n)
+        if len(key) > 3 and key[1] == "[" and key[-1] == "]" and key[2:-1] in hdr["species"]:
+            s = hdr["species"].index(key[2:-1])
+            if key[0] == "C" and s < Sc:
+                return sect("C", "<f8", s * n, n)
+            if key[0] == "D" and s < Sd:
+                return sect("D", "<u4", s * n, n).astype(np.int64)
+        raise KeyError(key)
 
 
 def write_ssb(path, x, v, scal, C, type_, D, species, step=0, rdme_initialized=1):

@@ -174,3 +174,90 @@ def test_reference_result_subclass_reads_the_binary_store(tmp_path):
     pts, arr = res.read_step(0)
     assert pts.shape == (n, 3) and "__nfields_header__" not in arr and np.array_equal(arr["D[A]"], np.arange(n))
     res.result_dir = None          # keep Result.__del__ away from pytest's tmp_path
+
+
+def _write_series(tmp_path, n=23, T=6, seed=4):
+    import numpy as np
+    from spatialpy_b200.vtk import write_ssb
+    rng = np.random.default_rng(seed)
+    snaps = []
+    for t in range(T):
+        snap = dict(x=rng.normal(size=(n, 3)), v=rng.normal(size=(n, 3)), scal=rng.random((4, n)) + 0.5, C=rng.random((2, n)),
+                    typ=rng.integers(1, 4, n), D=rng.integers(0, 1000, (2, n)))
+        write_ssb(tmp_path / f"output{t}.ssb", snap["x"], snap["v"], snap["scal"], snap["C"], snap["typ"], snap["D"],
+                  ["A", "B"], step=10 * t)
+        snaps.append(snap)
+    return snaps
+
+
+def test_binary_store_field_reads_match_full_reads(tmp_path):
+    """read_ssb_field (one array by offset) == the same key of read_ssb, for every key and dtype."""
+    import numpy as np
+    from spatialpy_b200.vtk import read_ssb, read_ssb_field
+    _write_series(tmp_path, T=2)
+    path = tmp_path / "output1.ssb"
+    pts, arr = read_ssb(path)
+    for key, val in arr.items():
+        if key.startswith("__"):
+            continue
+        got = read_ssb_field(path, key)
+        assert got.dtype == val.dtype and got.shape == val.shape and np.array_equal(got, val), key
+    assert np.array_equal(read_ssb_field(path, "points"), pts)
+    for bad in ("C[Z]", "D[]", "nope", "E[A]"):
+        with pytest.raises(KeyError):
+            read_ssb_field(path, bad)
+
+
+def test_all_timepoint_getters_from_the_binary_store(tmp_path):
+    """FlatResult.get_species / get_property: the reference's argument handling and shapes (result.py:334-402,601-655)."""
+    import numpy as np
+    from spatialpy_b200.solver import FlatResult
+    snaps = _write_series(tmp_path)
+    res = FlatResult(None, str(tmp_path))
+    allA = res.get_species("A")
+    assert allA.dtype == np.float64 and allA.shape == (6, 23)
+    assert np.array_equal(allA, np.array([s["D"][0] for s in snaps], dtype=float))
+    assert np.array_equal(res.get_species("B", timepoints=4), snaps[4]["D"][1].astype(float))
+    assert np.array_equal(res.get_species("B", timepoints=[1, 5]), np.array([snaps[1]["D"][1], snaps[5]["D"][1]], dtype=float))
+    assert np.array_equal(res.get_species("A", timepoints=slice(2, 4)), allA[2:4])
+    assert np.array_equal(res.get_species("A", deterministic=True), np.array([s["C"][0] for s in snaps]))
+    conc = res.get_species("A", timepoints=2, concentration=True)
+    assert np.array_equal(conc, snaps[2]["D"][0] / (snaps[2]["scal"][1] / snaps[2]["scal"][0]))
+    with pytest.raises(Exception):
+        res.get_species("A", timepoints=1.0)
+    v = res.get_property("v")
+    assert v.shape == (6, 23, 3) and np.array_equal(v[3], snaps[3]["v"])
+    assert np.array_equal(res.get_property("rho"), np.array([s["scal"][0] for s in snaps]))
+    # result.py:648 reads step `ndx` (the position in the selection), so a single timepoint always returns step 0
+    assert np.array_equal(res.get_property("nu", timepoints=4), snaps[0]["scal"][3])
+
+
+def test_reference_result_getters_agree_with_the_inherited_ones(tmp_path):
+    """B200Result.get_species/get_property from the binary store == the reference's own methods run over read_step."""
+    pytest.importorskip("spatialpy")
+    import numpy as np
+    from spatialpy.core.result import Result
+    from spatialpy_b200.solver import _result_class
+
+    class _Dom:
+        def get_num_voxels(self):
+            return 23
+
+    class _Model:
+        tspan = np.arange(6.0)
+        domain = _Dom()
+        listOfSpecies = {"A": None, "B": None}
+
+    _write_series(tmp_path)
+    res = _result_class()(_Model(), str(tmp_path))
+    for kw in ({}, {"timepoints": 3}, {"timepoints": [0, 5]}, {"concentration": True}, {"deterministic": True, "timepoints": 1}):
+        fast = res.get_species("B", **kw)
+        slow = Result.get_species(res, "B", **kw)          # the inherited loop over read_step (binary-backed, full snapshots)
+        assert fast.shape == slow.shape and fast.dtype == slow.dtype and np.array_equal(fast, slow), kw
+    for name in ("v", "rho", "mass", "type", "bvf_phi", "nu"):
+        for kw in ({}, {"timepoints": 2}):
+            fast, slow = res.get_property(name, **kw), Result.get_property(res, name, **kw)
+            assert fast.shape == slow.shape and np.array_equal(fast, slow), (name, kw)
+    with pytest.raises(Exception, match="not found"):
+        res.get_species("Z")
+    res.result_dir = None          # keep Result.__del__ away from pytest's tmp_path
