@@ -1,0 +1,76 @@
+"""Array-at-a-time construction of the reference's `Domain` for GPU-sized inputs.
+
+`Domain.add_point` (spatialpy/core/domain.py:203-255) appends to eight numpy arrays per particle — every call copies all of
+them, so building N particles costs O(N²) (minutes at 10⁵, hopeless at 10⁶).  `domain_from_arrays` applies the same
+per-particle rules (volume sign, type-id characters, `type_` prefix, `rho = mass/vol` default) to whole arrays and fills a
+`Domain` in one pass; the result is attribute-for-attribute what the add_point loop produces (tests/test_cpu_abi.py), so
+`Model.add_domain`, `compile_prep` and both solvers accept it unchanged.
+"""
+import string
+
+import numpy as np
+
+_BAD_CHARS = set(string.punctuation.replace("_", "") + " ")
+
+
+def _per_particle(value, n, dtype, name):
+    a = np.asarray(value, dtype=dtype)
+    if a.ndim == 0:
+        return np.full(n, a, dtype=dtype)
+    if a.shape != (n,):
+        raise ValueError(f"{name} must be a scalar or have one entry per point ({n}), got shape {a.shape}")
+    return np.ascontiguousarray(a)
+
+
+def domain_from_arrays(points, type_id="UnAssigned", vol=1.0, mass=1.0, nu=0.0, fixed=False, rho=None, c=10.0,
+                       xlim=None, ylim=None, zlim=None, rho0=1.0, c0=10, P0=None, gravity=None):
+    """A `spatialpy.Domain` holding `points` ([N,3] or [N,2]; 2-D points get z = 0) with per-particle properties given as
+    scalars or length-N arrays — the vectorised equivalent of
+    `d = Domain(0, xlim, ylim, zlim, ...); for p in points: d.add_point(p, vol, mass, type_id, nu, fixed, rho, c)`.
+
+    `type_id` entries are ints (> 0) or strings without punctuation/space other than `_` (domain.py:236-242).  Limits default
+    to the bounding box of the points."""
+    from spatialpy.core.domain import Domain
+    from spatialpy.core.spatialpyerror import DomainError
+    pts = np.asarray(points, dtype=float)
+    if pts.ndim != 2 or pts.shape[1] not in (2, 3):
+        raise ValueError(f"points must be [N,2] or [N,3], got shape {pts.shape}")
+    n = pts.shape[0]
+    if pts.shape[1] == 2:
+        pts = np.concatenate([pts, np.zeros((n, 1))], axis=1)
+    vol = _per_particle(vol, n, float, "vol")
+    if (vol < 0).any():
+        raise DomainError("Volume must be a positive value.")                       # domain.py:232-233
+    mass = _per_particle(mass, n, float, "mass")
+    # type ids: validate each distinct value once, then prefix (domain.py:235-242)
+    tid = np.asarray(type_id, dtype=object)
+    tid = np.full(n, type_id, dtype=object) if tid.ndim == 0 else tid
+    if tid.shape != (n,):
+        raise ValueError(f"type_id must be a scalar or have one entry per point ({n})")
+    names = np.empty(n, dtype=object)
+    uniq = {}
+    for t in tid:                                # one dict lookup per particle; validation once per distinct id
+        if t not in uniq:
+            if isinstance(t, (int, np.integer)) and not isinstance(t, bool) and t <= 0:
+                raise DomainError("Type_id must be a non-zero positive integer or a string.")
+            if isinstance(t, str):
+                for ch in t:
+                    if ch in _BAD_CHARS:
+                        raise DomainError(f"Type_id cannot contain '{ch}'")
+            uniq[t] = f"type_{t}"
+    if len(uniq) == 1:
+        names[:] = next(iter(uniq.values()))
+    else:
+        names[:] = [uniq[t] for t in tid]
+    lim = [(float(pts[:, k].min()), float(pts[:, k].max())) if n else (0.0, 0.0) for k in range(3)]
+    dom = Domain(0, xlim if xlim is not None else lim[0], ylim if ylim is not None else lim[1],
+                 zlim if zlim is not None else lim[2], rho0=rho0, c0=c0, P0=P0, gravity=gravity)
+    dom.vertices = np.ascontiguousarray(pts)
+    dom.vol = vol
+    dom.mass = mass
+    dom.type_id = names
+    dom.nu = _per_particle(nu, n, float, "nu")
+    dom.c = _per_particle(c, n, float, "c")
+    dom.rho = mass / vol if rho is None else _per_particle(rho, n, float, "rho")  # domain.py:245-246
+    dom.fixed = _per_particle(fixed, n, bool, "fixed")
+    return dom

@@ -102,6 +102,15 @@ def test_ensemble_sharding_partitions_trajectories():
             assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
 
 
+def _need_spatialpy():
+    """The reference front-end, importable in the dev container only (plotly stubbed, oracle/build_ref.py)."""
+    if not has_reference():
+        pytest.skip("needs /root/reference")
+    import build_ref
+    build_ref.add_reference_to_path()
+    pytest.importorskip("spatialpy")
+
+
 @pytest.mark.reference
 @pytest.mark.skipif(not has_reference(), reason="needs /root/reference")
 def test_flattening_matches_reference_codegen_inputs():
@@ -160,7 +169,7 @@ def test_binary_side_store_round_trip(tmp_path):
 
 def test_reference_result_subclass_reads_the_binary_store(tmp_path):
     """With the spatialpy front-end importable the Solver returns the reference's own Result type; only read_step is overridden."""
-    pytest.importorskip("spatialpy")
+    _need_spatialpy()
     import numpy as np
     from spatialpy.core.result import Result
     from spatialpy_b200.solver import _result_class
@@ -234,7 +243,7 @@ def test_all_timepoint_getters_from_the_binary_store(tmp_path):
 
 def test_reference_result_getters_agree_with_the_inherited_ones(tmp_path):
     """B200Result.get_species/get_property from the binary store == the reference's own methods run over read_step."""
-    pytest.importorskip("spatialpy")
+    _need_spatialpy()
     import numpy as np
     from spatialpy.core.result import Result
     from spatialpy_b200.solver import _result_class
@@ -261,3 +270,54 @@ def test_reference_result_getters_agree_with_the_inherited_ones(tmp_path):
     with pytest.raises(Exception, match="not found"):
         res.get_species("Z")
     res.result_dir = None          # keep Result.__del__ away from pytest's tmp_path
+
+
+def test_domain_from_arrays_equals_the_add_point_loop():
+    """builders.domain_from_arrays == Domain.add_point per particle (domain.py:203-255), attribute for attribute, and the
+    flattened model the engine sees is the same."""
+    _need_spatialpy()
+    import numpy as np
+    import spatialpy
+    from spatialpy.core.spatialpyerror import DomainError
+    from spatialpy_b200 import FlatModel
+    from spatialpy_b200.builders import domain_from_arrays
+    rng = np.random.default_rng(7)
+    n = 200
+    pts = rng.random((n, 3))
+    vol = rng.random(n) + 0.5
+    mass = rng.random(n) + 0.5
+    tid = np.where(pts[:, 0] < 0.3, "Left", np.where(pts[:, 0] > 0.7, "Right_side", "Mid")).astype(object)
+    nu = rng.random(n)
+    fixed = pts[:, 2] < 0.2
+    lim = dict(xlim=(0, 1), ylim=(0, 1), zlim=(0, 1))
+    slow = spatialpy.Domain(0, **lim, rho0=2.0, c0=5, gravity=[0, 0, -1])
+    for i in range(n):
+        slow.add_point(pts[i], vol=vol[i], mass=mass[i], type_id=tid[i], nu=nu[i], fixed=fixed[i])
+    fast = domain_from_arrays(pts, type_id=tid, vol=vol, mass=mass, nu=nu, fixed=fixed, rho0=2.0, c0=5, gravity=[0, 0, -1], **lim)
+    for attr in ("vertices", "vol", "mass", "nu", "c", "rho", "fixed", "type_id"):
+        a, b = getattr(slow, attr), getattr(fast, attr)
+        assert a.shape == b.shape and a.dtype == b.dtype and (a == b).all(), attr
+    assert (slow.P0, slow.rho0, slow.c0, slow.gravity) == (fast.P0, fast.rho0, fast.c0, fast.gravity)
+    assert fast.get_num_voxels() == n and abs(fast.find_h() - slow.find_h()) == 0.0
+
+    def model(dom):
+        m = spatialpy.Model("m")
+        m.add_domain(dom)
+        a = spatialpy.Species("A", diffusion_coefficient=0.1, restrict_to=["Left", "Mid"])
+        m.add_species(a)
+        k = spatialpy.Parameter("k", expression=2.0)
+        m.add_parameter(k)
+        m.add_reaction(spatialpy.Reaction(name="r", reactants={}, products={"A": 1}, rate="k", restrict_to="Left"))
+        m.add_initial_condition(spatialpy.PlaceInitialCondition(a, 50, [0.5, 0.5, 0.5]))
+        m.timespan(spatialpy.TimeSpan.linspace(t=1, num_points=3, timestep_size=0.5))
+        return m
+    fa, fb = FlatModel.from_spatialpy(model(slow)), FlatModel.from_spatialpy(model(fast))
+    for name in FlatModel._ARRAYS:
+        assert np.array_equal(getattr(fa, name), getattr(fb, name)), name
+    assert fa.type_constants == fb.type_constants and fa.h == fb.h
+    # scalars broadcast, 2-D points get z = 0, the reference's validation errors are raised
+    d2 = domain_from_arrays(rng.random((10, 2)), type_id=3, mass=2.0, vol=4.0)
+    assert d2.vertices.shape == (10, 3) and not d2.vertices[:, 2].any() and (d2.rho == 0.5).all() and d2.type_id[0] == "type_3"
+    for bad in (dict(vol=-1.0), dict(type_id=0), dict(type_id="a b"), dict(type_id="a-b")):
+        with pytest.raises(DomainError):
+            domain_from_arrays(pts, **bad)
