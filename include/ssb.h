@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 2
+#define SSB_ABI_VERSION 3
 
 /* error codes */
 #define SSB_OK 0
@@ -135,6 +135,15 @@ int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t bytes);
  * Call with idx == NULL to obtain nnz in *nnz_out. */
 int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, double *dist, double *dWdr, double *Dij,
                       int64_t *nnz_out);
+
+/* State hand-over (slab re-partition: the particles a rank owns change, so the state of a trajectory moves between handles).
+ * ssb_set_field is the inverse of ssb_get_field for the fields that make up a particle's state between two engine steps —
+ * x v vt F Fbp (f64, N*3) | rho old_rho Frho bvf_phi nu (f64, N) | C Q (f64, N*S_c voxel-major) | xx (u32, N*S_d) — given in
+ * particle-id order; replacing x invalidates the neighbour lists (rebuilt at the next step).  ssb_get_step / ssb_set_step
+ * read and set the engine-step counter (system->current_step, E/include/particle_system.hpp:63) and the Philox window epoch. */
+int ssb_set_field(ssb_handle *h, const char *name, const void *src, int64_t bytes);
+int ssb_get_step(ssb_handle *h, uint32_t *step, uint64_t *epoch);
+int ssb_set_step(ssb_handle *h, uint32_t step, uint64_t epoch);
 
 int ssb_cancel(ssb_handle *h);                 /* async-signal-safe flag; the running ssb_run returns SSB_ERR_CANCELLED */
 const char *ssb_last_error(ssb_handle *h);     /* message for the last non-zero return (valid until next call) */

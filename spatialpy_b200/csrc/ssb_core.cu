@@ -238,6 +238,15 @@ __global__ void k_unperm32(int N, const int *id, const int *src, int *dst, int s
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N) dst[(size_t) id[i] * stride + offset] = src[i];
 }
+// scatter id order -> storage order (ssb_set_field: state handed over at a slab re-partition)
+__global__ void k_perm_in64(int N, const int *id, const double *src, double *dst, int stride, int offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[i] = src[(size_t) id[i] * stride + offset];
+}
+__global__ void k_perm_in32(int N, const int *id, const int *src, int *dst, int stride, int offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) dst[i] = src[(size_t) id[i] * stride + offset];
+}
 // neighbour list taps in id space
 __global__ void k_nbr_count_by_id(SsbView V, long long *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1657,6 +1666,75 @@ extern "C" int ssb_get_field(ssb_handle *h, const char *name, void *dst, int64_t
         return SSB_OK;
     }
     return fail(h, SSB_ERR_ARG, "unknown field '%s'", name);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// state hand-over (slab re-partition, spatialpy_b200/slab.py): the inverse of ssb_get_field for the fields that make up
+// a particle's state between two engine steps, and the step / Philox-epoch counters that go with them
+// ----------------------------------------------------------------------------------------------------
+extern "C" int ssb_set_field(ssb_handle *h, const char *name, const void *src, int64_t bytes) {
+    if (!h || !name || !src) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    SsbView &V = h->V;
+    const int N = h->N;
+    cudaStream_t st = h->stream;
+    std::string n(name);
+    if ((size_t) bytes > h->stage_bytes) return fail(h, SSB_ERR_ARG, "field %s: %lld bytes exceed the staging buffer", name, (long long) bytes);
+    double **v3 = nullptr;
+    if (n == "x") v3 = V.x; else if (n == "v") v3 = V.v; else if (n == "vt") v3 = V.vt; else if (n == "F") v3 = V.F; else if (n == "Fbp") v3 = V.Fbp;
+    if (v3) {
+        if (bytes != (int64_t) sizeof(double) * 3 * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * 3 * N);
+        if (n == "x" && V.static_domain) return fail(h, SSB_ERR_ARG, "positions of a static domain cannot be replaced (cached geometry)");
+        CK(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, st));
+        for (int d = 0; d < 3; d++) k_perm_in64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, h->d_stage, v3[d], 3, d);
+        if (n == "x") { h->lists_valid = 0; h->nbr_valid = 0; }       // candidate lists and storage order refer to the old positions
+        CK(ssb_sync(h));
+        return SSB_OK;
+    }
+    double *s1 = nullptr;
+    if (n == "rho") s1 = V.rho; else if (n == "old_rho") s1 = V.old_rho; else if (n == "Frho") s1 = V.Frho; else if (n == "bvf_phi") s1 = V.bvf;
+    else if (n == "nu") s1 = V.nu;
+    if (s1) {
+        if (bytes != (int64_t) sizeof(double) * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * N);
+        CK(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, st));
+        k_perm_in64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, h->d_stage, s1, 1, 0);
+        CK(ssb_sync(h));
+        return SSB_OK;
+    }
+    if (n == "C" || n == "Q") {            // host side voxel-major [N][S_c] -> species-major blocks
+        double *blk = (n == "C") ? V.C : V.Q;
+        const int K = V.Sc;
+        if (bytes != (int64_t) sizeof(double) * K * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * K * N);
+        if (K > 0) CK(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, st));
+        for (int s = 0; s < K; s++) k_perm_in64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, h->d_stage, blk + (size_t) s * N, K, s);
+        CK(ssb_sync(h));
+        return SSB_OK;
+    }
+    if (n == "xx") {
+        const int K = V.Sd;
+        if (bytes != (int64_t) sizeof(unsigned) * K * N) return fail(h, SSB_ERR_ARG, "field xx needs %lld bytes", (long long) sizeof(unsigned) * K * N);
+        if (K > 0) CK(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, st));
+        for (int s = 0; s < K; s++) k_perm_in32<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, (const int *) h->d_stage, (int *) V.xx + (size_t) s * N, K, s);
+        if (V.static_domain) h->rdme_initialized = 0;                  // propensities and clocks refer to the old populations
+        CK(ssb_sync(h));
+        return SSB_OK;
+    }
+    return fail(h, SSB_ERR_ARG, "field '%s' cannot be set", name);
+}
+
+extern "C" int ssb_get_step(ssb_handle *h, uint32_t *step, uint64_t *epoch) {
+    if (!h || !step || !epoch) return SSB_ERR_ARG;
+    *step = h->current_step;
+    *epoch = h->epoch;
+    return SSB_OK;
+}
+
+extern "C" int ssb_set_step(ssb_handle *h, uint32_t step, uint64_t epoch) {
+    if (!h) return SSB_ERR_ARG;
+    if (h->V.static_domain) return fail(h, SSB_ERR_ARG, "ssb_set_step is implemented for moving domains (a static domain keeps its step-0 geometry cache)");
+    h->current_step = step;
+    h->epoch = epoch;
+    return SSB_OK;
 }
 
 extern "C" int ssb_get_neighbors(ssb_handle *h, int64_t *ptr, int32_t *idx, double *dist, double *dWdr, double *Dij, int64_t *nnz_out) {

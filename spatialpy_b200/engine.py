@@ -15,7 +15,7 @@ import numpy as np
 from . import codegen
 from .flatmodel import FlatModel
 
-SSB_ABI_VERSION = 2
+SSB_ABI_VERSION = 3
 FLAG_CORRECTED_NSM_SELECT = 1
 FLAG_CORRECTED_STOICH = 2
 FLAG_NO_VTK = 4
@@ -33,7 +33,7 @@ EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernel
            "ssb_reset", "ssb_step", "ssb_counters", "ssb_get_field", "ssb_get_neighbors", "ssb_cancel",
            "ssb_last_error", "ssb_launch_count", "ssb_step_timed", "ssb_profile", "ssb_profile_read", "ssb_io_bytes",
            "ssb_nbr_stats", "ssb_step_phase", "ssb_halo_pack", "ssb_halo_unpack", "ssb_halo_inbox_pack", "ssb_halo_inbox_add",
-           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats"]
+           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats", "ssb_set_field", "ssb_get_step", "ssb_set_step"]
 
 PH_PRE, PH_CORRECTOR, PH_FINISH, PH_RDME_PREP, PH_RDME_INIT, PH_RDME_WINDOW, PH_RDME_CLOSE, PH_END, PH_RDME_MIN, PH_RDME_EXTRA = range(10)
 
@@ -112,6 +112,9 @@ def load_library(path=None):
     lib.ssb_halo_inbox_add.argtypes = [H, C.c_void_p, C.c_int32, C.c_void_p]
     lib.ssb_halo_width.argtypes = [H, C.c_int, C.POINTER(C.c_int32)]
     lib.ssb_skin_stats.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.ssb_set_field.argtypes = [H, C.c_char_p, C.c_void_p, C.c_int64]
+    lib.ssb_get_step.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    lib.ssb_set_step.argtypes = [H, C.c_uint32, C.c_uint64]
     lib.ssb_mark.argtypes = [H, C.c_int]
     lib.ssb_mark_elapsed_ms.argtypes = [H, C.POINTER(C.c_double)]
     for name in EXPORTS:
@@ -317,6 +320,28 @@ class Engine:
         out = np.empty((self.N, k) if (k != 1 or isinstance(cols, str)) else (self.N,), dtype=dtype)
         self._check(self.lib.ssb_get_field(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+    _SETTABLE = ("x", "v", "vt", "F", "Fbp", "rho", "old_rho", "Frho", "bvf_phi", "nu", "C", "Q", "xx")
+
+    def set(self, name, values):
+        """Replace a state field (particle-id order, same shapes as `get`) — the hand-over of a slab re-partition."""
+        if name not in self._SETTABLE:
+            raise KeyError(f"field '{name}' cannot be set")
+        dtype, cols = self._FIELDS[name]
+        k = self._sizes[cols] if isinstance(cols, str) else cols
+        a = np.ascontiguousarray(values, dtype=dtype)
+        if a.size != self.N * k:
+            raise ValueError(f"field '{name}' needs {self.N * k} values, got {a.size}")
+        self._check(self.lib.ssb_set_field(self._h, name.encode(), a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def get_step(self):
+        """(engine step counter, Philox window epoch) of the running trajectory."""
+        step, epoch = C.c_uint32(0), C.c_uint64(0)
+        self._check(self.lib.ssb_get_step(self._h, C.byref(step), C.byref(epoch)))
+        return step.value, epoch.value
+
+    def set_step(self, step, epoch):
+        self._check(self.lib.ssb_set_step(self._h, int(step), int(epoch)))
 
     def neighbors(self):
         """Neighbour lists in id space: (ptr[N+1], idx, dist, dWdr, Dij) — same shape as oracle dumps."""

@@ -46,6 +46,14 @@ def _worker(rank, world, port, q):
     recv = {nb: torch.empty(len(ids), dtype=torch.float64) for nb, ids in p.recv_ids.items()}
     exchange(send, recv, rank)
     ok = all(np.array_equal(recv[nb].numpy().astype(np.int64), p.gids[ids]) for nb, ids in p.recv_ids.items())
+    # the variable-length exchange and the scalar reductions the re-partition uses
+    from spatialpy_b200.slab import DistComm
+    comm = DistComm(rank, world)
+    rows = np.arange((3 + 2 * rank) * 4, dtype=np.float64).reshape(-1, 4) + 100 * rank
+    got = comm.exchange_rows({1 - rank: rows}, 4)
+    other = np.arange((3 + 2 * (1 - rank)) * 4, dtype=np.float64).reshape(-1, 4) + 100 * (1 - rank)
+    ok = ok and np.array_equal(got[1 - rank], other)
+    ok = ok and comm.allreduce(float(rank), "max") == 1.0 and comm.allreduce(float(rank) + 2.0, "min") == 2.0
     q.put((rank, ok, p.n_owned, len(p.gids)))
     dist.barrier()
     dist.destroy_process_group()
@@ -68,3 +76,97 @@ def test_two_rank_halo_exchange_gloo():
     assert all(o[1] for o in out)
     assert out[0][2] + out[1][2] == _model().num_particles
     assert all(o[3] > o[2] for o in out)          # both ranks carry ghosts
+
+
+def _moved_state(fm, seed=9):
+    """A global mid-trajectory state defined per global id: positions displaced by up to 0.3 h (some particles cross a
+    slab face), every other field an arbitrary function of the id."""
+    rng = np.random.default_rng(seed)
+    n = fm.num_particles
+    st = {"x": fm.x + rng.uniform(-0.3, 0.3, size=(n, 3)) * fm.h, "v": rng.normal(size=(n, 3)), "F": rng.normal(size=(n, 3)),
+          "Fbp": rng.normal(size=(n, 3)), "rho": 1.0 + 0.01 * rng.random(n), "Frho": rng.normal(size=n), "nu": fm.nu * 1.5,
+          "mass": fm.mass, "bvf_phi": rng.random(n), "type": fm.type,
+          "C": rng.random((n, fm.num_chem_species)), "Q": rng.normal(size=(n, fm.num_chem_species)),
+          "xx": rng.integers(0, 50, size=(n, fm.num_stoch_species)).astype(np.uint32)}
+    return st
+
+
+def test_repartition_equals_a_fresh_partition_of_the_moved_domain():
+    """pack_state -> rows_for_neighbour -> assemble_partition on every rank == partition() of the moved global model:
+    same owned / ghost sets in the same order, mirror-image exchange lists, and every field handed over intact."""
+    import copy
+    from spatialpy_b200.slab import StateLayout, assemble_partition, pack_state, partition, rows_for_neighbour, slab_bounds
+    fm = _model()
+    world = 3
+    edges = slab_bounds(fm.x[:, 0], world)
+    parts = [partition(fm, r, world, edges=edges) for r in range(world)]
+    st = _moved_state(fm)
+    lay = StateLayout.of(fm)
+    assert lay.width == 3 + 12 + 6 + 2 * fm.num_chem_species + fm.num_stoch_species + fm.num_data_fn
+    rows = [pack_state(lambda name, p=p: st[name][p.gids], p, lay) for p in parts]
+    assert sum(len(r) for r in rows) == fm.num_particles
+    moved = copy.copy(fm)
+    moved.x, moved.rho, moved.nu, moved.u0 = st["x"], st["rho"], st["nu"], st["xx"]
+    crossed = 0
+    for r in range(world):
+        nbs = [nb for nb in (r - 1, r + 1) if 0 <= nb < world]
+        got = [rows_for_neighbour(rows[nb], lay, edges, parts[r].halo, r) for nb in nbs]     # what the neighbours send to r
+        new, fields = assemble_partition(parts[r].local, lay, np.concatenate([rows[r]] + got), edges, parts[r].halo, r, world)
+        want = partition(moved, r, world, halo=parts[r].halo, edges=edges)
+        np.testing.assert_array_equal(new.gids, want.gids)
+        np.testing.assert_array_equal(new.owned, want.owned)
+        assert set(new.send_ids) == set(want.send_ids) and set(new.recv_ids) == set(want.recv_ids)
+        for nb in new.send_ids:
+            np.testing.assert_array_equal(new.send_ids[nb], want.send_ids[nb])
+            np.testing.assert_array_equal(new.recv_ids[nb], want.recv_ids[nb])
+        for name in ("x", "type", "nu", "mass", "c", "rho", "solid", "u0", "data_fn"):
+            np.testing.assert_array_equal(getattr(new.local, name), getattr(want.local, name), err_msg=name)
+        for name, val in fields.items():
+            np.testing.assert_array_equal(val, st[name][new.gids], err_msg=name)
+        assert new.local.reactions == fm.reactions and new.local.h == fm.h and new.edges is not None
+        crossed += int((~np.isin(new.gids[new.owned == 1], parts[r].gids[parts[r].owned == 1])).sum())
+    assert crossed > 0                                   # the test did move particles across slab faces
+
+
+def test_assemble_rejects_duplicate_ownership():
+    import pytest
+    from spatialpy_b200.slab import StateLayout, assemble_partition, pack_state, partition, slab_bounds
+    fm = _model()
+    edges = slab_bounds(fm.x[:, 0], 2)
+    p = partition(fm, 0, 2, edges=edges)
+    st = _moved_state(fm)
+    lay = StateLayout.of(fm)
+    rows = pack_state(lambda name: st[name][p.gids], p, lay)
+    with pytest.raises(RuntimeError, match="twice"):
+        assemble_partition(p.local, lay, np.concatenate([rows, rows[:3]]), edges, p.halo, 0, 2)
+
+
+def test_loopback_comm_matches_the_collective_semantics():
+    """LoopbackComm (ranks = threads of one process; the one-GPU test double of NCCL): neighbour exchange, scalar reductions
+    and the variable-length row exchange."""
+    import threading
+    from spatialpy_b200.slab import LoopbackComm, LoopbackHub
+    world = 3
+    hub = LoopbackHub(world, timeout=60.0)
+    out = {}
+
+    def body(rank):
+        comm = LoopbackComm(hub, rank)
+        nbs = [nb for nb in (rank - 1, rank + 1) if 0 <= nb < world]
+        res = []
+        for rep in range(3):                              # repeated rounds must not see stale posts
+            send = {nb: torch.full((4,), 10.0 * rank + nb + 100 * rep, dtype=torch.float64) for nb in nbs}
+            recv = {nb: torch.zeros(4, dtype=torch.float64) for nb in nbs}
+            comm.exchange(send, recv)
+            res.append(all(float(recv[nb][0]) == 10.0 * nb + rank + 100 * rep for nb in nbs))
+            res.append(comm.allreduce(rank + rep, "max") == world - 1 + rep and comm.allreduce(rank + rep, "min") == rep)
+            rows = comm.exchange_rows({nb: np.full((rank + 1 + rep, 2), float(rank)) for nb in nbs}, 2)
+            res.append(all(rows[nb].shape == (nb + 1 + rep, 2) and (rows[nb] == nb).all() for nb in nbs))
+        out[rank] = all(res)
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(120)
+    assert out == {0: True, 1: True, 2: True}

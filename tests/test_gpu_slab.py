@@ -82,3 +82,194 @@ def test_two_gpu_slab_matches_single_gpu():
     total = sum(int(outs[r]["xx"].sum()) for r in range(2))
     assert total == int(fm.u0.sum())                  # molecules that crossed the slab face were delivered, none lost
     assert sum(outs[r]["counters"]["diffusions"] for r in range(2)) > 0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# state hand-over and re-partition (ssb_set_field / ssb_set_step, SlabEngine.repartition)
+# ----------------------------------------------------------------------------------------------------------------------
+_FIELDS = ("x", "v", "rho", "F", "bvf_phi", "C")
+# written without a GPU at the end of round 1 (the GPU budget was spent): enabled once a GPU run has confirmed them
+handover = pytest.mark.skipif(os.environ.get("SSB_HANDOVER_TESTS") != "1",
+                              reason="state hand-over / re-partition tests await their first GPU run (set SSB_HANDOVER_TESTS=1)")
+
+
+def _assert_close(got, ref, tol=1e-9):
+    for f in _FIELDS:
+        scale = max(float(np.abs(ref[f]).max()), 1e-300)
+        err = float(np.abs(got[f] - ref[f]).max()) / scale
+        assert err <= tol, f"{f}: {err:.3e}"
+
+
+@handover
+def test_set_field_round_trip_and_step_counter():
+    """ssb_set_field is the inverse of ssb_get_field (particle-id order, whatever the storage order is)."""
+    from spatialpy_b200.engine import Engine, EngineError
+    fm = _model(False)
+    rng = np.random.default_rng(1)
+    with Engine(fm, device=0) as eng:
+        eng.reset(11)
+        eng.step(3)                                   # storage is cell-sorted by now
+        for name in ("v", "F", "Fbp", "vt", "rho", "old_rho", "Frho", "bvf_phi", "nu", "C", "Q"):
+            a = eng.get(name)
+            b = a + rng.normal(size=a.shape)
+            eng.set(name, b)
+            np.testing.assert_array_equal(eng.get(name), b)
+            eng.set(name, a)
+        xx = eng.get("xx")
+        eng.set("xx", xx[::-1].copy())
+        np.testing.assert_array_equal(eng.get("xx"), xx[::-1])
+        eng.set("xx", xx)
+        step, epoch = eng.get_step()
+        assert step == 3 and epoch > 0
+        eng.set_step(7, epoch + 5)
+        assert eng.get_step() == (7, epoch + 5)
+        with pytest.raises(EngineError):               # derived fields cannot be set
+            eng._check(eng.lib.ssb_set_field(eng._h, b"nbr_count", xx.ctypes.data, xx.nbytes))
+        with pytest.raises(ValueError):
+            eng.set("rho", np.zeros(3))
+
+
+@handover
+def test_trajectory_continues_in_a_fresh_handle():
+    """The hand-over a re-partition performs, on one rank: pack the state after k steps, build a new model + engine from the
+    rows, restore the fields and the step / epoch counters, continue — and land where the uninterrupted run lands (the
+    neighbour lists are rebuilt at the hand-over, so only the summation order inside a sweep differs)."""
+    from spatialpy_b200.engine import Engine
+    from spatialpy_b200.slab import StateLayout, assemble_partition, pack_state, partition
+    fm = _model(False)
+    k, steps = 21, 26                                # hand over right after the Shepard-filter step 20
+    with Engine(fm, device=0) as eng:
+        eng.reset(11)
+        eng.step(steps)
+        ref = {f: eng.get(f) for f in _FIELDS + ("xx",)}
+    part = partition(fm, 0, 1)
+    lay = StateLayout.of(fm)
+    with Engine(fm, device=0) as eng:
+        eng.reset(11)
+        eng.step(k)
+        rows = pack_state(eng.get, part, lay)
+        step, epoch = eng.get_step()
+    new, fields = assemble_partition(part.local, lay, rows, part.edges, part.halo, 0, 1)
+    np.testing.assert_array_equal(new.gids, np.arange(fm.num_particles))
+    with Engine(new.local, device=0, owned=new.owned, rng_id=new.gids.astype(np.int32)) as eng:
+        eng.reset(11)
+        for name, val in fields.items():
+            eng.set(name, val)
+        eng.set_step(step, epoch)
+        eng.step(steps - k)
+        got = {f: eng.get(f) for f in _FIELDS + ("xx",)}
+        assert eng.get_step()[0] == steps
+    _assert_close(got, ref)
+    assert int(got["xx"].sum()) == int(fm.u0.sum())
+
+
+def _loopback_run(world, steps, every):
+    """`world` slab ranks as threads of this process on cuda:0 (LoopbackComm), re-partitioning every `every` steps."""
+    import threading
+    import torch
+    from spatialpy_b200.slab import LoopbackComm, LoopbackHub, SlabEngine, partition
+    fm = _model(False)
+    hub = LoopbackHub(world, timeout=300.0)
+    outs, errs = {}, {}
+    from spatialpy_b200 import codegen
+    for r in range(world):                            # compile (or find) the model units before the threads race for them
+        codegen.build_model_unit(partition(fm, r, world).local)
+
+    def body(rank):
+        try:
+            torch.cuda.set_device(0)
+            part = partition(fm, rank, world)
+            se = SlabEngine(part, rank, world, device=0, comm=LoopbackComm(hub, rank, torch.device("cuda", 0)),
+                            auto_repartition=True, repartition_every=every)
+            se.reset(11)
+            se.step(steps)
+            out = {"gid": se.part.gids[se.part.owned == 1], "repartitions": se.repartitions, "counters": se.counters()}
+            for f in _FIELDS + ("xx",):
+                out[f] = se.owned_field(f)[1]
+            outs[rank] = out
+            se.close()
+        except BaseException as err:  # noqa: BLE001 - reported by the main thread
+            errs[rank] = err
+            hub.barrier.abort()
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(600)
+    if errs:          # the first real failure (the other ranks only see the barrier it broke)
+        real = [e for e in errs.values() if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or list(errs.values()))[0]
+    return fm, outs
+
+
+def _check_against_single(fm, outs, steps):
+    from spatialpy_b200.engine import Engine
+    with Engine(fm, device=0) as eng:
+        eng.reset(11)
+        eng.step(steps)
+        ref = {f: eng.get(f) for f in _FIELDS}
+    world = len(outs)
+    gid = np.concatenate([outs[r]["gid"] for r in range(world)])
+    assert sorted(gid.tolist()) == list(range(fm.num_particles))          # every particle owned exactly once
+    got = {}
+    for f in _FIELDS:
+        got[f] = np.empty_like(ref[f])
+        got[f][gid] = np.concatenate([outs[r][f] for r in range(world)])
+    _assert_close(got, ref)
+    assert sum(int(outs[r]["xx"].sum()) for r in range(world)) == int(fm.u0.sum())
+    assert sum(outs[r]["counters"]["diffusions"] for r in range(world)) > 0
+
+
+@handover
+@pytest.mark.parametrize("world,every", [(2, 0), (2, 5), (3, 4)])
+def test_loopback_slabs_with_repartition_match_single_gpu(world, every):
+    """The whole slab code path on ONE GPU: `world` ranks as threads, exchanges as device copies.  every = 0 is the fixed
+    partition (same as the 2-GPU NCCL test); every > 0 hands the trajectory over to fresh handles several times."""
+    steps = 22
+    fm, outs = _loopback_run(world, steps, every)
+    _check_against_single(fm, outs, steps)
+    want = 0 if every == 0 else (steps // every)
+    assert all(outs[r]["repartitions"] == want for r in range(world))
+
+
+def _worker_repart(rank, world, port, q, steps, every):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from spatialpy_b200.slab import SlabEngine, partition
+    fm = _model(False)
+    se = SlabEngine(partition(fm, rank, world), rank, world, device=rank, auto_repartition=True, repartition_every=every)
+    se.reset(11)
+    se.step(steps)
+    out = {"gid": se.part.gids[se.part.owned == 1], "repartitions": se.repartitions, "counters": se.counters()}
+    for f in _FIELDS + ("xx",):
+        out[f] = se.owned_field(f)[1]
+    q.put((rank, out))
+    dist.barrier()
+    se.close()
+    dist.destroy_process_group()
+
+
+@handover
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+def test_two_gpu_slab_with_repartition_matches_single_gpu():
+    import torch.multiprocessing as mp
+    steps, every = 22, 5
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_repart, args=(r, 2, port, q, steps, every)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    _check_against_single(_model(False), outs, steps)
+    assert all(outs[r]["repartitions"] == steps // every for r in range(2))
