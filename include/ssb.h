@@ -165,7 +165,8 @@ int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total);
  * ssb_step_phase runs one piece of an engine step (phases: 0 PRE = cell list + predictor + search + force sweep,
  * 1 CORRECTOR, 2 FINISH, 3 RDME_PREP -> *out = local max Ddiag, 4 RDME_INIT (arg = global max) -> *out = windows per step,
  * 5 RDME_WINDOW (arg = window index), 6 RDME_CLOSE, 7 END, 8 RDME_MIN -> *out = earliest pending event of this rank, 9 RDME_EXTRA
- * (arg = global earliest pending event: the reference's one event past the end of the step, simulate_rdme.cpp:233-238)).  ssb_halo_pack / ssb_halo_unpack move the field group that a
+ * (arg = global earliest pending event: the reference's one event past the end of the step, simulate_rdme.cpp:233-238; runs the
+ * event window only — follow it with the inbox exchange and RDME_CLOSE, which delivers the molecule if it jumped across a face)).  ssb_halo_pack / ssb_halo_unpack move the field group that a
  * phase produced between storage and a caller-owned DEVICE buffer for the particle ids listed in dev_ids (group 0: F[3]
  * Fbp[3] Frho Q[S_c]; 1: rho_new; 2: v[3] bvf_phi; 3: rho); ssb_halo_inbox_pack reads-and-clears the molecules that jumped
  * into ghost voxels in the last sSSA window, ssb_halo_inbox_add delivers them to the owner.  ssb_mark/ssb_mark_elapsed_ms

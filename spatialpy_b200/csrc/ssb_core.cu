@@ -1271,7 +1271,10 @@ static int rdme_min_time(ssb_handle *h, double *tmin) {
     h->launches += 1;
     return SSB_OK;
 }
-static int rdme_extra_event(ssb_handle *h, double tmin) {
+// deliver = false (slab decomposition): only the event window runs here; if the event is a jump into a ghost voxel the molecule
+// must first travel to its owner (ssb_halo_inbox_pack/add read the buffer the LAST window wrote), so the caller exchanges the
+// inboxes and then runs the delivering zero-length window itself (PH_RDME_CLOSE).
+static int rdme_extra_event(ssb_handle *h, double tmin, bool deliver = true) {
     SsbView &V = h->V;
     const SsbModelUnit *u = h->unit;
     const double te = V.dt * (h->current_step + 1);
@@ -1279,9 +1282,11 @@ static int rdme_extra_event(ssb_handle *h, double tmin) {
     if (!(tmin < INFINITY) || !(tmin > te)) return SSB_OK;
     if (u->rdme_window(&V, te, tmin, h->tau, h->seed, h->epoch - 2, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
     h->inbox_buf ^= 1;
+    h->launches += 1;
+    if (!deliver) return SSB_OK;
     if (u->rdme_window(&V, tmin, tmin, h->tau, h->seed, h->epoch - 1, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
     h->inbox_buf ^= 1;
-    h->launches += 2;
+    h->launches += 1;
     return SSB_OK;
 }
 
@@ -1960,8 +1965,8 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
         if (out) *out = tmin;
         break;
     }
-    case PH_RDME_EXTRA:          // arg = GLOBAL earliest pending event: only its owner fires (see rdme_extra_event)
-        if (!(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT))) { if ((rc = rdme_extra_event(h, arg))) return rc; }
+    case PH_RDME_EXTRA:          // arg = GLOBAL earliest pending event: only its owner fires; the caller syncs the inboxes and closes
+        if (!(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT))) { if ((rc = rdme_extra_event(h, arg, false))) return rc; }
         break;
     case PH_END:
         h->current_step++;

@@ -222,7 +222,7 @@ def _check_against_single(fm, outs, steps):
 
 
 @handover
-@pytest.mark.parametrize("world,every", [(2, 0), (2, 5), (3, 4)])
+@pytest.mark.parametrize("world,every", [(2, 0), (3, 0), (2, 5), (3, 4)])
 def test_loopback_slabs_with_repartition_match_single_gpu(world, every):
     """The whole slab code path on ONE GPU: `world` ranks as threads, exchanges as device copies.  every = 0 is the fixed
     partition (same as the 2-GPU NCCL test); every > 0 hands the trajectory over to fresh handles several times."""
