@@ -88,9 +88,6 @@ def test_two_gpu_slab_matches_single_gpu():
 # state hand-over and re-partition (ssb_set_field / ssb_set_step, SlabEngine.repartition)
 # ----------------------------------------------------------------------------------------------------------------------
 _FIELDS = ("x", "v", "rho", "F", "bvf_phi", "C")
-# written without a GPU at the end of round 1 (the GPU budget was spent): enabled once a GPU run has confirmed them
-handover = pytest.mark.skipif(os.environ.get("SSB_HANDOVER_TESTS") != "1",
-                              reason="state hand-over / re-partition tests await their first GPU run (set SSB_HANDOVER_TESTS=1)")
 
 
 def _assert_close(got, ref, tol=1e-9):
@@ -100,7 +97,6 @@ def _assert_close(got, ref, tol=1e-9):
         assert err <= tol, f"{f}: {err:.3e}"
 
 
-@handover
 def test_set_field_round_trip_and_step_counter():
     """ssb_set_field is the inverse of ssb_get_field (particle-id order, whatever the storage order is)."""
     from spatialpy_b200.engine import Engine, EngineError
@@ -129,7 +125,6 @@ def test_set_field_round_trip_and_step_counter():
             eng.set("rho", np.zeros(3))
 
 
-@handover
 def test_trajectory_continues_in_a_fresh_handle():
     """The hand-over a re-partition performs, on one rank: pack the state after k steps, build a new model + engine from the
     rows, restore the fields and the step / epoch counters, continue — and land where the uninterrupted run lands (the
@@ -221,7 +216,6 @@ def _check_against_single(fm, outs, steps):
     assert sum(outs[r]["counters"]["diffusions"] for r in range(world)) > 0
 
 
-@handover
 @pytest.mark.parametrize("world,every", [(2, 0), (3, 0), (2, 5), (3, 4)])
 def test_loopback_slabs_with_repartition_match_single_gpu(world, every):
     """The whole slab code path on ONE GPU: `world` ranks as threads, exchanges as device copies.  every = 0 is the fixed
@@ -253,7 +247,6 @@ def _worker_repart(rank, world, port, q, steps, every):
     dist.destroy_process_group()
 
 
-@handover
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
 def test_two_gpu_slab_with_repartition_matches_single_gpu():
     import torch.multiprocessing as mp
