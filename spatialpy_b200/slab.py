@@ -327,7 +327,7 @@ class SlabEngine:
     """One rank of a slab-decomposed run: an Engine on the local model + the halo exchanges between the step phases."""
 
     def __init__(self, part, rank, world, device=0, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, comm=None,
-                 auto_repartition=False, repartition_every=0):
+                 auto_repartition=True, repartition_every=0):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
