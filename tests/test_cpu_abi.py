@@ -321,3 +321,45 @@ def test_domain_from_arrays_equals_the_add_point_loop():
     for bad in (dict(vol=-1.0), dict(type_id=0), dict(type_id="a b"), dict(type_id="a-b")):
         with pytest.raises(DomainError):
             domain_from_arrays(pts, **bad)
+
+
+def test_install_adds_the_solver_keyword_to_model_run():
+    """spatialpy_b200.install(): `Model.run(solver=...)` (the keyword the reference's README promises, model.py:1021-1056) hands
+    the reference's own arguments to the given solver class or instance; without it the reference's path runs untouched."""
+    _need_spatialpy()
+    import spatialpy
+    from spatialpy.core.model import Model
+    import spatialpy_b200
+    orig = Model.run
+    try:
+        spatialpy_b200.install()
+        patched = Model.run
+        assert patched is not orig and getattr(patched, "_ssb_patched", False)
+        spatialpy_b200.install()                       # idempotent
+        assert Model.run is patched
+        assert spatialpy.B200Solver is spatialpy_b200.Solver
+        calls = []
+
+        class Dummy:
+            def __init__(self, model, debug_level=0):
+                calls.append(("init", model, debug_level))
+
+            def run(self, **kw):
+                calls.append(("run", kw))
+                return "result"
+
+        m = spatialpy.Model("m")
+        assert m.run(solver=Dummy, number_of_trajectories=3, seed=7, timeout=5, debug_level=2, devices=[0, 1]) == "result"
+        assert calls[0] == ("init", m, 2)
+        assert calls[1] == ("run", dict(number_of_trajectories=3, seed=7, timeout=5, number_of_threads=None, debug=False,
+                                        profile=False, devices=[0, 1]))
+        inst = Dummy(m)
+        calls.clear()
+        m.run(solver=inst, seed=1)
+        assert [c[0] for c in calls] == ["run"] and calls[0][1]["seed"] == 1
+        # no solver keyword: the reference's own Model.run runs (an empty model fails inside the reference's compile_prep)
+        with pytest.raises(Exception) as info:
+            m.run()
+        assert "reference/spatialpy" in str(info.traceback[-1].path) and not calls[1:]      # raised inside the reference
+    finally:
+        Model.run = orig
