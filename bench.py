@@ -288,6 +288,17 @@ def run_ours(args, rank, local_rank, world):
     e2e_value = world * N * SPS * args.steps / e2e_s
     eng2.close()
 
+    # fp64 companion of the HBM roofline: the moving-domain sweeps are gather / fp64-issue bound, so their flop
+    # rate is reported against the MEASURED fp64 FMA peak of this device (child process: it cannot take the line with it)
+    if rank == 0:
+        pk = fp64_peak_sample(local_rank)
+        roofline["fp64"] = pk
+        if "fp64_tflops" in pk and moving and dom_ms > 0:
+            sweep_ms = prof["force"]["ms"] / max(prof["force"]["launches"], 1)
+            if sweep_ms > 0:
+                tf = 230.0 * mean_nbr * N / (sweep_ms / 1e3) / 1e12
+                pk.update(force_sweep_tflops=tf, force_sweep_frac=tf / pk["fp64_tflops"],
+                          note="SURVEY 8(d) pair figure: 230 flop per stored neighbour-list entry of the force sweep")
     cpu = cpu_baseline_sample(args.workload) if (rank == 0 and world == 1 and not args.no_cpu) else None
     # the other sharding mode, measured in the same run: ONE 8 M-particle-per-GPU SDPD+sSSA box split into slabs with NCCL
     # halo exchange (BASELINE configs[4]); reported beside the headline so per-N lines carry both scaling modes
@@ -341,6 +352,22 @@ def run_slab(args, rank, local_rank, world):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def fp64_peak_sample(device):
+    """Measured fp64 FMA peak (TFLOP/s) from `python -m spatialpy_b200.peaks` (libssb_peaks.so, include/ssb_peaks.h)."""
+    import subprocess
+    try:
+        out = subprocess.run([sys.executable, "-m", "spatialpy_b200.peaks", str(device)], cwd=ROOT, capture_output=True,
+                             text=True, timeout=120)
+        if out.returncode != 0:
+            tail = (out.stderr.strip().splitlines() or ["?"])[-1]
+            return {"error": tail[:200]}
+        res = json.loads(out.stdout.strip().splitlines()[-1])
+        res["how"] = "issue-bound DFMA loop, 8 chains x 2048 threads per SM, best of 4 launches (CUDA events)"
+        return res
+    except Exception as err:   # noqa: BLE001 - a helper measurement must never cost the bench line
+        return {"error": f"{type(err).__name__}: {err}"[:200]}
 
 
 def slab_measure(args, rank, local_rank, world, steps, warmup, SPS):

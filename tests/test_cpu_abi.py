@@ -37,6 +37,25 @@ def test_only_sm100a_code_in_the_library():
     assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out)
 
 
+def test_peaks_library_exports_its_header_and_fails_loudly_without_a_gpu():
+    """include/ssb_peaks.h (the fp64 peak microbenchmark bench.py runs beside the roofline): symbol exported, sm_100a DFMA code,
+    and no silent number when there is no device."""
+    from spatialpy_b200 import codegen, peaks
+    path = codegen.build_peaks()
+    hdr = open(os.path.join(ROOT, "include", "ssb_peaks.h")).read()
+    declared = sorted(set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == ["ssb_fp64_peak"]
+    lib = ctypes.CDLL(path)
+    assert all(hasattr(lib, name) for name in declared)
+    elf = subprocess.run(["cuobjdump", "--list-elf", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf and not re.search(r"sm_(?!100a)\d+", elf)
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    assert sass.count("DFMA") >= 64
+    if not os.path.exists("/dev/nvidia0"):
+        with pytest.raises(RuntimeError, match="return code = 3"):
+            peaks.fp64_peak(0)
+
+
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
 def test_no_cpu_fallback_fails_loudly():
     from spatialpy_b200.engine import Engine, EngineError
