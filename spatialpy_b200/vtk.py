@@ -134,6 +134,70 @@ def write_ssb(path, x, v, scal, C, type_, D, species, step=0, rdme_initialized=1
             f.write(np.ascontiguousarray(a, dtype=dt).tobytes())
 
 
+def _section(f, fmt, values, per_line, chunk=90000):
+    """`values` formatted with `fmt` + one blank each, a newline after every `per_line`-th item — the layout of every
+    array of the reference's writer (output.cpp:133-229); written in chunks that end on a line boundary."""
+    values = np.asarray(values)
+    for lo in range(0, len(values), chunk):
+        part = values[lo:lo + chunk]
+        ends = np.full(len(part), " ", dtype="<U2")
+        ends[per_line - 1::per_line] = " \n"
+        f.write("".join(np.char.add(np.char.mod(fmt, part), ends).tolist()))
+
+
+def write_vtk(path, x, v, scal, C, type_, D, species, rdme_initialized=1):
+    """Python twin of the engine's VTK writer (ssb_core.cu write_vtk), i.e. of the reference's `output_vtk__async_step`
+    (E/src/output.cpp:130-229): ASCII VTK 4.1 POLYDATA, `POINTS n float` as `%.10e` three points per line, `VERTICES`,
+    `FIELD FieldData k` with k = 7 + S_c + (S_d once the RDME is initialised — the reference undercounts in output0,
+    output.cpp:151-154), arrays `id type` (`%u`), `v` (`%lf`, one particle's three components, three particles per line),
+    `rho mass bvf_phi nu C[name]` (`%lf`, nine per line), `D[name]` (`%u`).  Used where a snapshot is assembled on the host
+    (slab-decomposed runs gather the owned particles of every rank); pinned byte for byte against files written by the
+    reference itself (tests/golden/vtk_diffusion3d, tests/test_cpu_abi.py).  Arguments as `write_ssb`."""
+    n = len(type_)
+    x = np.asarray(x, dtype=np.float64).reshape(n, 3)
+    v = np.asarray(v, dtype=np.float64).reshape(n, 3)
+    scal = np.asarray(scal, dtype=np.float64).reshape(4, n)
+    C = np.zeros((0, n)) if C is None else np.asarray(C, dtype=np.float64).reshape(-1, n)
+    D = np.zeros((0, n), dtype=np.uint32) if D is None else np.asarray(D, dtype=np.uint32).reshape(-1, n)
+    Sc, Sd = C.shape[0], D.shape[0]
+    with open(path, "w", encoding="ascii", newline="") as f:
+        f.write("# vtk DataFile Version 4.1\nGenerated by SpatialPy\nASCII\nDATASET POLYDATA\n")
+        f.write(f"POINTS {n} float\n")
+        _section(f, "%.10e", x.reshape(-1), 9)
+        f.write(f"\nVERTICES {n} {2 * n}\n")
+        for lo in range(0, n, 90000):
+            f.write("".join(f"1 {i}\n" for i in range(lo, min(n, lo + 90000))))
+        f.write(f"\nPOINT_DATA {n}\n")
+        f.write(f"FIELD FieldData {7 + Sc + (Sd if rdme_initialized else 0)}\n")
+        f.write(f"id 1 {n} int\n")
+        _section(f, "%u", np.arange(n, dtype=np.int64), 9)
+        f.write(f"\ntype 1 {n} int\n")
+        _section(f, "%u", np.asarray(type_, dtype=np.int64), 9)
+        f.write(f"\nv 3 {n} double\n")
+        _section(f, "%f", v.reshape(-1), 9)
+        f.write("\n")
+        for k, name in enumerate(("rho", "mass", "bvf_phi", "nu")):
+            f.write(f"{name} 1 {n} double\n")
+            _section(f, "%f", scal[k], 9)
+            f.write("\n")
+        for s_ in range(Sc):
+            f.write(f"C[{species[s_]}] 1 {n} double\n")
+            _section(f, "%f", C[s_], 9)
+            f.write("\n")
+        for s_ in range(Sd):
+            f.write(f"D[{species[s_]}] 1 {n} int\n")
+            _section(f, "%u", D[s_].astype(np.int64), 9)
+            f.write("\n")
+
+
+def write_bounding_box(result_dir, xlim, ylim, zlim):
+    """output0_boundingBox.vtk (E/src/output.cpp:110-128)."""
+    with open(os.path.join(result_dir, "output0_boundingBox.vtk"), "w", encoding="ascii", newline="") as f:
+        f.write("# vtk DataFile Version 4.1\nGenerated by ssa_sdpd\nASCII\nDATASET RECTILINEAR_GRID\nDIMENSIONS 2 2 2\n")
+        for axis, (lo, hi) in zip("XYZ", (xlim, ylim, zlim)):
+            f.write(f"{axis}_COORDINATES 2 double\n%f %f\n" % (lo, hi))
+
+
 def read_output(result_dir, step_num):
     """outputN.ssb when the run kept a binary side-store, else outputN.vtk."""
     b = os.path.join(result_dir, f"output{step_num}.ssb")
