@@ -26,6 +26,7 @@ continues the trajectory in a fresh engine handle (`ssb_set_field` / `ssb_set_st
 Philox epoch.  Host-orchestrated and rare (hundreds of steps apart at SDPD time steps); the set logic is pure numpy and tested on
 the CPU (tests/test_cpu_slab.py), the hand-over on the GPU (tests/test_gpu_slab.py, loopback ranks on one GPU or NCCL on two).
 """
+import os
 import threading
 
 import numpy as np
@@ -481,3 +482,118 @@ class SlabEngine:
         a = self.eng.get(name)
         m = self.part.owned.astype(bool)
         return self.part.gids[m], a[m]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a whole trajectory with output files, slab-decomposed over the GPUs of one process (what Solver.run(decomposition="slab") calls)
+# ----------------------------------------------------------------------------------------------------------------------
+def output_schedule(nt, output_steps):
+    """[(file index, engine step)] of one trajectory: the output gate of run_simulation (E/src/simulate_threads.cpp:231-247,
+    283-288) exactly as ssb_run walks it — `next_output_step` starts at 0 and get_next_output() hands out the table from its
+    first entry (so step 0 is written twice when the table starts with 0: the reference's file->step off-by-one), and the
+    final state is written once more after the last step."""
+    out, nxt, k, f = [], 0, 0, 0
+    steps = [int(v) for v in output_steps]
+    for step in range(int(nt)):
+        if step >= nxt:
+            out.append((f, step))
+            f += 1
+            nxt = steps[k] if k < len(steps) else 0xFFFFFFFF
+            k += 1
+    out.append((f, int(nt)))
+    return out
+
+
+def _default_rank_engine(part, rank, world, device, hub, flags, rdme_epsilon):
+    import torch
+    return SlabEngine(part, rank, world, device=device, flags=flags, rdme_epsilon=rdme_epsilon,
+                      comm=LoopbackComm(hub, rank, torch.device("cuda", device)))
+
+
+def run_slab_trajectory(fm, devices, seed, out_dir, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, vtk=True, binary_store=False,
+                        halo=None, cancelled=None, rank_engine=_default_rank_engine):
+    """One trajectory of a moving-domain model split into len(devices) slabs, driven from ONE process: rank r is a thread
+    with its own engine handle on GPU devices[r]; the halo exchanges are device-to-device copies (`LoopbackComm`; peer copies
+    over NVLink between distinct GPUs, plain copies when a device is listed twice).  At the reference's output steps
+    (`output_schedule`) every rank drops its owned particles into one host snapshot in global-id order and rank 0 writes
+    `output%u.vtk` (+ `output0_boundingBox.vtk`) and/or `output%u.ssb` with the host-side twins of the engine's writers — the
+    same files, names and step map a single-GPU `ssb_run` leaves behind.  Returns the summed engine counters.
+    `cancelled`: optional callable polled once per step (Solver timeout)."""
+    from .vtk import write_bounding_box, write_ssb, write_vtk
+    fm = fm.finalize()
+    world = len(devices)
+    if fm.static_domain:
+        raise ValueError("slab decomposition is implemented for moving domains (static ensembles shard by trajectory)")
+    N, Sc, Sd = fm.num_particles, fm.num_chem_species, fm.num_stoch_species
+    edges = slab_bounds(fm.x[:, 0], world)
+    hub = LoopbackHub(world, timeout=3600.0)
+    snap = {"x": np.empty((N, 3)), "v": np.empty((N, 3)), "scal": np.empty((4, N)), "C": np.empty((Sc, N)),
+            "type": np.empty(N, np.int32), "D": np.empty((Sd, N), np.uint32)}
+    schedule = output_schedule(fm.nt, fm.output_steps)
+    errs, counters = {}, {}
+
+    def fill(se):
+        gid, x = se.owned_field("x")
+        snap["x"][gid] = x
+        snap["v"][gid] = se.owned_field("v")[1]
+        for k, name in enumerate(("rho", "mass", "bvf_phi", "nu")):
+            snap["scal"][k, gid] = se.owned_field(name)[1]
+        snap["type"][gid] = se.owned_field("type")[1]
+        if Sc:
+            snap["C"][:, gid] = se.owned_field("C")[1].T
+        if Sd:
+            snap["D"][:, gid] = se.owned_field("xx")[1].T
+
+    def write(file_index, step):
+        init = 1 if (Sd > 0 and step > 0) else 0          # output0 is staged before the first RDME step (output.cpp:151-154)
+        if file_index == 0 and vtk:
+            write_bounding_box(out_dir, fm.xlim, fm.ylim, fm.zlim)
+        args = (snap["x"], snap["v"], snap["scal"], snap["C"] if Sc else None, snap["type"], snap["D"] if Sd else None,
+                fm.species_names)
+        if vtk:
+            write_vtk(os.path.join(out_dir, f"output{file_index}.vtk"), *args, rdme_initialized=init)
+        if binary_store:
+            write_ssb(os.path.join(out_dir, f"output{file_index}.ssb"), *args, step=step, rdme_initialized=init)
+
+    def body(rank):
+        se = None
+        try:
+            part = partition(fm, rank, world, halo=halo, edges=edges)
+            se = rank_engine(part, rank, world, devices[rank], hub, flags, rdme_epsilon)
+            se.reset(seed)
+            done = 0
+            for file_index, step in schedule:
+                if step > done:
+                    for _ in range(step - done):
+                        if cancelled is not None and cancelled():
+                            raise InterruptedError("cancelled")
+                        se.step(1)
+                    done = step
+                fill(se)
+                hub.barrier.wait()                      # every rank has dropped its rows
+                if rank == 0:
+                    write(file_index, step)
+                hub.barrier.wait()                      # the snapshot may be overwritten again
+            counters[rank] = se.counters()
+        except BaseException as err:  # noqa: BLE001 - re-raised by the caller's thread
+            errs[rank] = err
+            hub.barrier.abort()
+        finally:
+            if se is not None:
+                se.close()
+
+    threads = [threading.Thread(target=body, args=(r,), name=f"slab-rank-{r}") for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:          # the first real failure (the other ranks only see the barrier it broke)
+        real = [e for e in errs.values() if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or list(errs.values()))[0]
+    total = {"reactions": 0, "diffusions": 0, "seconds": 0.0, "windows": 0}
+    for c in counters.values():
+        total["reactions"] += c["reactions"]
+        total["diffusions"] += c["diffusions"]
+        total["seconds"] = max(total["seconds"], c["seconds"])
+        total["windows"] = max(total["windows"], c["windows"])
+    return total

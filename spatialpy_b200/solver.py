@@ -9,7 +9,8 @@ What changed underneath: no generated C++ / SCons / subprocess — the model is 
 propensities / BCs are compiled into a CUDA model unit (codegen.py) and trajectories run in-process through the C-ABI
 (engine.py).  Additive keywords (not in the reference): `devices=[...]` to spread an ensemble over GPUs, `lanes`, `flags`,
 `rdme_epsilon`, `binary_store=True` (also write `output%u.ssb`, raw fp64 arrays that `Result.read_step` then loads
-instead of parsing the text) and `vtk=False` (binary files only).
+instead of parsing the text), `vtk=False` (binary files only) and `decomposition="slab"` (ONE moving domain split into
+len(devices) slabs with halo exchange, spatialpy_b200/slab.py, instead of one trajectory per device).
 
 `install()` adds the `solver=` keyword that the reference's README promises but `Model.run` never implemented
 (model.py:1021-1056): `model.run(solver=spatialpy_b200.Solver, number_of_trajectories=..., seed=...)`.
@@ -214,13 +215,16 @@ class Solver:
         return _result_class()(self.model, outdir)
 
     def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False,
-            verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None, binary_store=False, vtk=True):
+            verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None, binary_store=False, vtk=True,
+            decomposition=None):
         from .engine import Engine, EngineError, FLAG_SKIP_STATIC_FORCES, FLAG_BINARY_STORE, FLAG_NO_VTK
         if not self.is_compiled:
             self.compile(debug=debug, profile=profile)
         if seed is None:                      # template:127 std::random_device
             seed = int.from_bytes(os.urandom(4), "little")
         devices = list(devices) if devices else [0]
+        if decomposition not in (None, "ensemble", "slab"):
+            raise SimulationError(f"unknown decomposition '{decomposition}' (None/'ensemble': trajectories over devices; 'slab': one domain over devices)")
         flags = FLAG_SKIP_STATIC_FORCES if flags is None else flags
         if binary_store:                      # outputN.ssb next to outputN.vtk; vtk=False keeps only the binary files
             flags |= FLAG_BINARY_STORE | (0 if vtk else FLAG_NO_VTK)
@@ -236,6 +240,21 @@ class Solver:
         state = {"error": None, "done": False}
         out_dirs = [r.result_dir for r in results]
 
+        def body_slab():
+            # one domain split into len(devices) slabs (moving domains); trajectories run one after the other on all devices
+            from .slab import run_slab_trajectory
+            try:
+                for k in range(number_of_trajectories):
+                    run_slab_trajectory(self.flat, devices, seed + k, out_dirs[k], flags=flags & ~(FLAG_BINARY_STORE | FLAG_NO_VTK),
+                                        rdme_epsilon=rdme_epsilon, vtk=vtk, binary_store=binary_store,
+                                        cancelled=lambda: state.get("cancel", False))
+                    results[k].success = True
+            except InterruptedError:
+                pass
+            except (EngineError, ValueError) as err:
+                state["error"] = err
+            state["done"] = True
+
         def body():
             try:
                 done = run_ensemble(self.flat, number_of_trajectories, seed, devices=devices, lanes=lanes, out_dirs=out_dirs,
@@ -247,12 +266,13 @@ class Solver:
                 state["error"] = err
             state["done"] = True
 
-        t = threading.Thread(target=body)
+        t = threading.Thread(target=body_slab if decomposition == "slab" else body)
         t.start()
         timed_out = False
         t.join(timeout)
         if t.is_alive():                       # solver.py:583-586: SIGINT on timeout, result.timeout = True
             timed_out = True
+            state["cancel"] = True
             while t.is_alive():
                 with lock:
                     for e in engines:
@@ -266,7 +286,8 @@ class Solver:
                     r.timeout = True
         elif state["error"] is not None:
             err = state["error"]
-            raise SimulationError(f"Solver execution failed, return code = {err.code}") from err   # solver.py:595-597
+            code = getattr(err, "code", 4)       # SSB_ERR_ARG for a model the chosen decomposition cannot run
+            raise SimulationError(f"Solver execution failed, return code = {code}") from err   # solver.py:595-597
         first = results[0]
         for r in results[1:]:
             first.append(r)

@@ -170,3 +170,91 @@ def test_loopback_comm_matches_the_collective_semantics():
     for t in ts:
         t.join(120)
     assert out == {0: True, 1: True, 2: True}
+
+
+class _FakeRank:
+    """Stands in for SlabEngine in run_slab_trajectory: every field is a known function of (global id, engine step)."""
+
+    def __init__(self, part, rank, world, device, hub, flags, rdme_epsilon, fail_at=None):
+        self.part, self.rank, self.t, self.fail_at = part, rank, 0, fail_at
+        self.m = part.owned.astype(bool)
+
+    def reset(self, seed):
+        self.t = 0
+
+    def step(self, n=1):
+        self.t += n
+        if self.fail_at is not None and self.rank == 1 and self.t == self.fail_at:
+            raise RuntimeError("boom")
+
+    @staticmethod
+    def field(fm, name, gid, t):
+        g = gid.astype(np.float64)
+        if name == "x":
+            return fm.x[gid] + 1e-3 * t
+        if name == "v":
+            return np.stack([g, -g, g * 0 + t], axis=1) * 1e-2
+        if name in ("rho", "mass", "bvf_phi", "nu"):
+            return {"rho": 1.0, "mass": 2.0, "bvf_phi": 0.0, "nu": 3.0}[name] + 1e-4 * g + t
+        if name == "type":
+            return fm.type[gid]
+        if name == "C":
+            return np.stack([g + 0.5 * t + s for s in range(fm.num_chem_species)], axis=1)
+        if name == "xx":
+            return np.stack([(gid + 3 * t + s) % 17 for s in range(fm.num_stoch_species)], axis=1).astype(np.uint32)
+        raise KeyError(name)
+
+    def owned_field(self, name):
+        gid = self.part.gids[self.m]
+        return gid, self.field(self._fm, name, gid, self.t)
+
+    def counters(self):
+        return {"reactions": 1, "diffusions": 2 + self.rank, "seconds": 0.5 * self.rank, "windows": 7}
+
+    def close(self):
+        pass
+
+
+def test_slab_trajectory_driver_writes_the_reference_file_set(tmp_path):
+    """run_slab_trajectory with fake rank engines (3 ranks as threads): the file -> step map of the reference's output gate,
+    host-assembled snapshots in global-id order, both writers, FIELD undercount in output0, counters summed."""
+    from spatialpy_b200.slab import output_schedule, run_slab_trajectory
+    from spatialpy_b200.vtk import read_ssb, read_vtk
+    fm = _model()
+    fm.nt, fm.output_steps = 12, np.array([0, 5, 10], dtype=np.uint32)
+    _FakeRank._fm = fm
+    assert output_schedule(12, [0, 5, 10]) == [(0, 0), (1, 1), (2, 5), (3, 10), (4, 12)]     # simulate_threads.cpp:231-247,283-288
+    total = run_slab_trajectory(fm, [0, 0, 0], 3, str(tmp_path), vtk=True, binary_store=True, rank_engine=_FakeRank)
+    assert total == {"reactions": 3, "diffusions": 9, "seconds": 1.0, "windows": 7}
+    names = sorted(os.listdir(tmp_path))
+    assert names == sorted(["output0_boundingBox.vtk"] + [f"output{k}.{e}" for k in range(5) for e in ("vtk", "ssb")])
+    gid = np.arange(fm.num_particles)
+    for k, step in output_schedule(12, [0, 5, 10]):
+        pts, arr = read_ssb(str(tmp_path / f"output{k}.ssb"))
+        np.testing.assert_array_equal(pts, _FakeRank.field(fm, "x", gid, step).astype(np.float32))
+        np.testing.assert_array_equal(arr["v"], _FakeRank.field(fm, "v", gid, step))
+        for name in ("rho", "mass", "bvf_phi", "nu"):
+            np.testing.assert_array_equal(arr[name], _FakeRank.field(fm, name, gid, step))
+        np.testing.assert_array_equal(arr["type"], fm.type)
+        for s, sp in enumerate(fm.species_names):
+            np.testing.assert_array_equal(arr[f"C[{sp}]"], _FakeRank.field(fm, "C", gid, step)[:, s])
+            np.testing.assert_array_equal(arr[f"D[{sp}]"], _FakeRank.field(fm, "xx", gid, step)[:, s])
+        pv, av = read_vtk(str(tmp_path / f"output{k}.vtk"))
+        assert av["__nfields_header__"] == arr["__nfields_header__"] == 7 + fm.num_chem_species + (fm.num_stoch_species if step else 0)
+        np.testing.assert_allclose(av["rho"], arr["rho"], atol=5e-7)
+        np.testing.assert_array_equal(av[f"D[{fm.species_names[0]}]"], arr[f"D[{fm.species_names[0]}]"])
+        np.testing.assert_allclose(pv, pts, rtol=1e-6)
+
+
+def test_slab_trajectory_driver_propagates_a_rank_failure(tmp_path):
+    import functools
+    import pytest
+    from spatialpy_b200.slab import run_slab_trajectory
+    fm = _model()
+    fm.nt, fm.output_steps = 6, np.array([0, 3, 6], dtype=np.uint32)
+    _FakeRank._fm = fm
+    with pytest.raises(RuntimeError, match="boom"):
+        run_slab_trajectory(fm, [0, 0], 3, str(tmp_path), rank_engine=functools.partial(_FakeRank, fail_at=2))
+    polled = []
+    with pytest.raises(InterruptedError):
+        run_slab_trajectory(fm, [0, 0], 3, str(tmp_path), rank_engine=_FakeRank, cancelled=lambda: polled.append(1) or len(polled) > 3)
