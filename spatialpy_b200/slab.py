@@ -506,6 +506,7 @@ def output_schedule(nt, output_steps):
 
 def _default_rank_engine(part, rank, world, device, hub, flags, rdme_epsilon):
     import torch
+    torch.cuda.set_device(device)             # thread-local: this rank's copies and synchronisations go to its own GPU
     return SlabEngine(part, rank, world, device=device, flags=flags, rdme_epsilon=rdme_epsilon,
                       comm=LoopbackComm(hub, rank, torch.device("cuda", device)))
 
