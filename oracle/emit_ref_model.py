@@ -11,10 +11,6 @@ with the same substitutions solver.py makes, field for field:
   __DEFINE_CHEM_FUNS__    solver.py:160-190     __INIT_PARTICLES__   solver.py:312-331
   __DEFINE_GET_NEXT_OUTPUT__ solver.py:290-299  __BOUNDARY_CONDITIONS__ solver.py:131-133
 """
-import os
-
-import numpy as np
-
 
 def _body(expr, restrict_to):
     if not restrict_to:

@@ -217,7 +217,7 @@ class Solver:
     def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False,
             verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None, binary_store=False, vtk=True,
             decomposition=None):
-        from .engine import Engine, EngineError, FLAG_SKIP_STATIC_FORCES, FLAG_BINARY_STORE, FLAG_NO_VTK
+        from .engine import EngineError, FLAG_SKIP_STATIC_FORCES, FLAG_BINARY_STORE, FLAG_NO_VTK
         if not self.is_compiled:
             self.compile(debug=debug, profile=profile)
         if seed is None:                      # template:127 std::random_device

@@ -2,7 +2,6 @@
 import os
 import socket
 
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
