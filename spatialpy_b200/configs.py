@@ -199,4 +199,7 @@ def box_slab(rank, world, nx_per_rank=200, ny=200, nz=200, ghost_cols=5, nt=100,
         send_ids[rank + 1] = loc[(owned == 1) & (col_of >= i1 - ghost_cols)].astype(np.int32)
         recv_ids[rank + 1] = loc[(owned == 0) & (col_of >= i1)].astype(np.int32)
     assert n_own == nx_per_rank * ny * nz
-    return SlabPartition(fm, gid, owned, send_ids, recv_ids, (i0 * delta, i1 * delta), ghost_cols * delta)
+    # slab faces half a lattice spacing before each rank's first column (jitter is 0.05 delta): the same owner / ghost rule as
+    # slab.partition(), so a re-partition of this domain re-derives consistent sets
+    edges = np.array([-np.inf] + [(k * nx_per_rank - 0.5) * delta for k in range(1, world)] + [np.inf])
+    return SlabPartition(fm, gid, owned, send_ids, recv_ids, (i0 * delta, i1 * delta), ghost_cols * delta, edges=edges)

@@ -433,7 +433,7 @@ class SlabEngine:
             # half of what the halo leaves beyond the candidate radius
             disp = e.skin_stats()["step_disp_max"]
             limit = 0.5 * (self.part.halo - 1.1 * self.part.local.h)
-            if not self.auto_repartition and self.repartition_every <= 0:
+            if (not self.auto_repartition and self.repartition_every <= 0) or self.part.edges is None:
                 self.travel_bound += disp
                 if self.travel_bound > limit:
                     raise RuntimeError(f"slab partition is stale: particles may have travelled {self.travel_bound:g} since the "

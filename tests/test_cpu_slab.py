@@ -258,3 +258,37 @@ def test_slab_trajectory_driver_propagates_a_rank_failure(tmp_path):
     polled = []
     with pytest.raises(InterruptedError):
         run_slab_trajectory(fm, [0, 0], 3, str(tmp_path), rank_engine=_FakeRank, cancelled=lambda: polled.append(1) or len(polled) > 3)
+
+
+def test_box_slab_builder_follows_the_partition_rule_and_survives_a_repartition():
+    """configs.box_slab (rank-local builder of the 64 M-particle workload) = the owner/ghost rule of partition() for its slab
+    faces, and a re-partition of the unmoved domain gives the same sets and exchange lists back."""
+    from spatialpy_b200 import configs
+    from spatialpy_b200.slab import StateLayout, assemble_partition, pack_state, rows_for_neighbour
+    world = 3
+    parts = [configs.box_slab(r, world, nx_per_rank=12, ny=6, nz=8) for r in range(world)]
+    lay = StateLayout.of(parts[0].local)
+
+    def getter(p):
+        fm = p.local
+        n = fm.num_particles
+        zero3, zero = np.zeros((n, 3)), np.zeros(n)
+        fields = {"x": fm.x, "v": zero3, "F": zero3, "Fbp": zero3, "rho": fm.rho, "Frho": zero, "nu": fm.nu, "mass": fm.mass,
+                  "bvf_phi": zero, "type": fm.type, "C": fm.u0.astype(float), "Q": np.zeros((n, lay.Sc)), "xx": fm.u0}
+        return lambda name: fields[name]
+
+    rows = [pack_state(getter(p), p, lay) for p in parts]
+    for r, p in enumerate(parts):
+        x = p.local.x[:, 0]
+        owner = np.clip(np.searchsorted(p.edges, x, side="right") - 1, 0, world - 1)
+        assert ((owner == r) == (p.owned == 1)).all()
+        nbs = [nb for nb in (r - 1, r + 1) if 0 <= nb < world]
+        got = [rows_for_neighbour(rows[nb], lay, p.edges, p.halo, r) for nb in nbs]
+        new, _ = assemble_partition(p.local, lay, np.concatenate([rows[r]] + got), p.edges, p.halo, r, world)
+        np.testing.assert_array_equal(new.gids, p.gids)
+        np.testing.assert_array_equal(new.owned, p.owned)
+        for nb in nbs:
+            np.testing.assert_array_equal(new.send_ids[nb], p.send_ids[nb])
+            np.testing.assert_array_equal(new.recv_ids[nb], p.recv_ids[nb])
+        np.testing.assert_array_equal(new.local.x, p.local.x)
+        np.testing.assert_array_equal(new.local.u0, p.local.u0)
