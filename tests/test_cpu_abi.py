@@ -441,3 +441,25 @@ def test_python_vtk_writer_line_layout_for_every_remainder(tmp_path):
         assert np.allclose(arr["v"], v, atol=5e-7) and np.allclose(arr["C[S]"], C[0], atol=5e-7) and arr["__nfields_header__"] == 9
         i = body.index(f"id 1 {n} int")
         assert len(body[i + 1].split()) == min(9, n) and all(len(l.split()) <= 9 for l in body[i + 1:i + 1 + (n + 8) // 9])
+
+
+@pytest.mark.parametrize("mesh,sub", [("cylinder.xml", None), ("GRN_Spatial.mesh.xml", "GRN_Spatial.subdomains.txt")])
+def test_fast_xml_mesh_reader_equals_the_reference_reader(mesh, sub):
+    """builders.read_xml_mesh == Domain.read_xml_mesh (domain.py:1148-1180) on the meshes the reference ships: every Domain
+    attribute identical, volumes to one ulp (the reference's 3-vector dot goes through BLAS)."""
+    _need_spatialpy()
+    import spatialpy
+    from spatialpy_b200.builders import read_xml_mesh
+    base = os.path.join(os.environ.get("SSB_REFERENCE_ROOT", "/root/reference"), "examples", "Domain_Files")
+    kw = {} if sub is None else {"subdomain_file": os.path.join(base, sub)}
+    ref = spatialpy.Domain.read_xml_mesh(os.path.join(base, mesh), **kw)
+    fast = read_xml_mesh(os.path.join(base, mesh), **kw)
+    for key, val in vars(ref).items():
+        got = getattr(fast, key)
+        if key in ("vol", "mass", "tetrahedron_vol"):
+            np.testing.assert_allclose(got, val, rtol=4e-16 * 8, atol=0)
+        elif isinstance(val, np.ndarray):
+            assert got.dtype == val.dtype and got.shape == val.shape and (got == val).all(), key
+        elif key != "actions":
+            assert got == val, key
+    assert abs(fast.find_h() - ref.find_h()) == 0.0
