@@ -328,14 +328,17 @@ class SlabEngine:
     """One rank of a slab-decomposed run: an Engine on the local model + the halo exchanges between the step phases."""
 
     def __init__(self, part, rank, world, device=0, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, comm=None,
-                 auto_repartition=True, repartition_every=0):
+                 auto_repartition=True, repartition_every=0, engine_factory=None, torch_device=None):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
         if part.local.static_domain:
             raise ValueError("slab decomposition is implemented for moving domains (static ensembles shard by trajectory)")
         self.device_index = device
-        self.dev = torch.device("cuda", device)
+        # engine_factory / torch_device exist for the CPU tier only (tests/test_cpu_slab.py drives this class over gloo with a
+        # numpy stand-in for the engine handle to exercise the exchange protocol); the product path is Engine on a CUDA device
+        self.engine_factory = engine_factory or Engine
+        self.dev = torch_device if torch_device is not None else torch.device("cuda", device)
         self.comm = comm if comm is not None else DistComm(rank, world, self.dev)
         self.flags, self.rdme_epsilon = flags, rdme_epsilon
         self.overshoot = not (flags & 129)     # FLAG_CORRECTED_NSM_SELECT | FLAG_NO_STEP_OVERSHOOT switch the extra event off
@@ -354,8 +357,8 @@ class SlabEngine:
         """Engine handle + exchange buffers for a partition (the first one, and every re-partition)."""
         torch = self.torch
         self.part = part
-        self.eng = Engine(part.local, device=self.device_index, flags=self.flags, rdme_epsilon=self.rdme_epsilon, owned=part.owned,
-                          rng_id=part.gids.astype(np.int32))
+        self.eng = self.engine_factory(part.local, device=self.device_index, flags=self.flags, rdme_epsilon=self.rdme_epsilon,
+                                       owned=part.owned, rng_id=part.gids.astype(np.int32))
         self.Sd = part.local.num_stoch_species
         self.send_ids = {nb: torch.as_tensor(v, device=self.dev) for nb, v in part.send_ids.items()}
         self.recv_ids = {nb: torch.as_tensor(v, device=self.dev) for nb, v in part.recv_ids.items()}

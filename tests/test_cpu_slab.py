@@ -292,3 +292,90 @@ def test_box_slab_builder_follows_the_partition_rule_and_survives_a_repartition(
             np.testing.assert_array_equal(new.recv_ids[nb], p.recv_ids[nb])
         np.testing.assert_array_equal(new.local.x, p.local.x)
         np.testing.assert_array_equal(new.local.u0, p.local.u0)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the stepping protocol itself over gloo: SlabEngine drives a numpy stand-in for the engine handle (tests/fake_engine.py)
+# ----------------------------------------------------------------------------------------------------------------------
+_PROTO_FIELDS = ("x", "v", "F", "rho", "bvf_phi", "C", "xx")
+
+
+def _proto_model():
+    from spatialpy_b200 import configs
+    return configs.tank_sdpd(n=12, nt=10, output_every=10, dt=2e-5)
+
+
+def _proto_engine_factory(fm, **kw):
+    """FakeEngine whose particles start with a per-id velocity of 0.05 h per step along +-x, so that they cross slab faces."""
+    from fake_engine import FakeEngine
+
+    class Drifting(FakeEngine):
+        def reset(self, seed):
+            super().reset(seed)
+            sign = np.where(self.gid % 2 == 0, 1.0, -1.0)
+            self.v[:, 0] = sign * 0.05 * self.fm.h / self.fm.dt * (self.fm.solid == 0)
+    return Drifting(fm, **kw)
+
+
+def _proto_run(rank, world, steps, every):
+    from spatialpy_b200.slab import SlabEngine, partition
+    fm = _proto_model()
+    se = SlabEngine(partition(fm, rank, world), rank, world, flags=128 | 8, engine_factory=_proto_engine_factory,
+                    torch_device=torch.device("cpu"), auto_repartition=True, repartition_every=every)
+    se.reset(1)
+    se.step(steps)
+    out = {"gid": se.part.gids[se.part.owned == 1], "repartitions": se.repartitions, "jumps": se.counters()["diffusions"]}
+    for f in _PROTO_FIELDS:
+        out[f] = se.owned_field(f)[1]
+    se.close()
+    return out
+
+
+def _proto_worker(rank, world, port, q, steps, every):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank, _proto_run(rank, world, steps, every)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_stepping_protocol_over_gloo_reproduces_the_single_rank_run():
+    """SlabEngine.step + repartition over gloo (2 ranks) with the numpy stand-in engine: ghost synchronisation after every
+    sweep, inbox traffic across the face, and the re-partition hand-over must give the single-rank result BIT FOR BIT (the
+    stand-in sums neighbours in global-id order), with particles migrating between the slabs on the way."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    steps, every = 8, 2
+    ref = _proto_run(0, 1, steps, 0)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_proto_worker, args=(r, 2, port, q, steps, every)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    fm = _proto_model()
+    gid = np.concatenate([outs[r]["gid"] for r in range(2)])
+    assert sorted(gid.tolist()) == list(range(fm.num_particles))
+    order = np.argsort(ref["gid"])
+    for f in _PROTO_FIELDS:
+        got = np.empty_like(ref[f])
+        got[gid] = np.concatenate([outs[r][f] for r in range(2)])
+        np.testing.assert_array_equal(got, ref[f][order], err_msg=f)
+    assert all(outs[r]["repartitions"] == steps // every for r in range(2))
+    assert int(sum(outs[r]["xx"].sum() for r in range(2))) == int(fm.u0.sum())
+    assert sum(outs[r]["jumps"] for r in range(2)) == ref["jumps"] > 0
+    # particles did change owner on the way
+    from spatialpy_b200.slab import partition
+    first = partition(fm, 0, 2)
+    assert set(outs[0]["gid"].tolist()) != set(first.gids[first.owned == 1].tolist())
