@@ -455,7 +455,9 @@ def run_ensemble_bench(args, rank, local_rank, world):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    name = {"ens_birth_death": "birth_death", "ens_cdc42": "cdc42"}[args.workload]
+    # ens_cdc42_full = BASELINE configs[3] at its named size (create_cdc42_model(DX=50): 2 500 particles) on a bounded horizon
+    # (t = 0.001, ~6e6 events per trajectory; the notebook's t = 100 is ~6e11 events per trajectory for any engine)
+    name = {"ens_birth_death": "birth_death", "ens_cdc42": "cdc42", "ens_cdc42_full": "cdc42_full"}[args.workload]
     fm = FlatModel.load(os.path.join(ROOT, "tests", "golden", f"{name}.model.npz"))
     lanes = args.lanes or default_lanes(fm.num_particles)
     per_gpu = args.trajectories
@@ -499,7 +501,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box", "ens_birth_death", "ens_cdc42"])
+    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box", "ens_birth_death", "ens_cdc42", "ens_cdc42_full"])
     ap.add_argument("--trajectories", type=int, default=128, help="ensemble workloads: trajectories per GPU")
     ap.add_argument("--lanes", type=int, default=0, help="ensemble workloads: concurrent engine handles per GPU (0 = auto)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")

@@ -49,6 +49,7 @@ TAPS = {
     "cylinder": [0, 1],
     "cdc42": [0, 1, 2],
     "cavity2d_rdme": [0, 1, 22, 45],
+    "cdc42_full": [0, 1, 2],
 }
 ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000, "cdc42": 600, "cavity2d_rdme": 1000}
 XBINS = 8

@@ -241,5 +241,12 @@ def cdc42(DX=12, end_time=0.02, steps=2):
     return model
 
 
+def cdc42_full():
+    """BASELINE config 4 at its NAMED size — create_cdc42_model(DX=50): 2 500 particles — on a horizon the reference finishes in
+    seconds (the notebook's end_time=100 is ~7e10 events per trajectory): full-size parity taps for the deterministic parts
+    (neighbour lists, D_i_j, Ddiag, propensities) and the model the `ens_cdc42_full` bench workload runs."""
+    return cdc42(DX=50, end_time=0.001, steps=2)
+
+
 BUILDERS = {"birth_death": birth_death, "diffusion3d": diffusion3d, "cavity2d": cavity2d, "tank3d": tank3d,
-            "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme}
+            "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme, "cdc42_full": cdc42_full}

@@ -8,7 +8,7 @@ from util import RTOL_STEP, RTOL_TRAJ, csr_sorted, load_model, load_ref, rel_err
 import sdpd_oracle
 
 
-@pytest.mark.parametrize("name", ["birth_death", "diffusion3d", "cavity2d", "tank3d", "cylinder", "cdc42"])
+@pytest.mark.parametrize("name", ["birth_death", "diffusion3d", "cavity2d", "tank3d", "cylinder", "cdc42", "cdc42_full"])
 def test_oracle_neighbours_match_reference(name):
     fm, ref = load_model(name), load_ref(name)
     o = sdpd_oracle.SdpdOracle(fm)
@@ -39,7 +39,7 @@ def test_oracle_trajectory_matches_reference(name):
             np.testing.assert_array_equal(o.nbr["ptr"], ref[f"s{s}_nbr_ptr"])
 
 
-@pytest.mark.parametrize("name", ["birth_death", "diffusion3d", "cylinder", "cdc42"])
+@pytest.mark.parametrize("name", ["birth_death", "diffusion3d", "cylinder", "cdc42", "cdc42_full"])
 def test_oracle_ddiag_matches_reference(name):
     fm, ref = load_model(name), load_ref(name)
     o = sdpd_oracle.SdpdOracle(fm)

@@ -271,8 +271,8 @@ def test_two_gpu_slab_with_repartition_matches_single_gpu():
 # written after the round-1 GPU budget was spent: the driver logic is CPU-tested with fake rank engines (tests/test_cpu_slab.py)
 # and its building blocks (loopback ranks, SlabEngine, both host writers) are GPU- / byte-tested; the end-to-end call awaits
 # its first GPU run
-slab_solver = pytest.mark.skipif(os.environ.get("SSB_SLAB_SOLVER_TESTS") != "1",
-                                 reason="Solver.run(decomposition='slab') awaits its first GPU run (set SSB_SLAB_SOLVER_TESTS=1)")
+slab_solver = pytest.mark.skipif(os.environ.get("SSB_PENDING_GPU_TESTS") != "1",
+                                 reason="Solver.run(decomposition='slab') awaits its first GPU run (set SSB_PENDING_GPU_TESTS=1)")
 
 
 @slab_solver
