@@ -535,6 +535,10 @@ def run_slab_trajectory(fm, devices, seed, out_dir, flags=FLAG_SKIP_STATIC_FORCE
             "type": np.empty(N, np.int32), "D": np.empty((Sd, N), np.uint32)}
     schedule = output_schedule(fm.nt, fm.output_steps)
     errs, counters = {}, {}
+    if rank_engine is _default_rank_engine:
+        from . import codegen
+        codegen.build_core()
+        codegen.build_model_unit(fm)          # model units are particle independent: compile once, before the ranks race for it
 
     def fill(se):
         gid, x = se.owned_field("x")
