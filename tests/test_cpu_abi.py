@@ -463,3 +463,24 @@ def test_fast_xml_mesh_reader_equals_the_reference_reader(mesh, sub):
         elif key != "actions":
             assert got == val, key
     assert abs(fast.find_h() - ref.find_h()) == 0.0
+
+
+def test_header_is_valid_c_and_matches_the_ctypes_binding(tmp_path):
+    """include/ssb.h + include/ssb_peaks.h compile as pedantic C11 and link from a plain-C program (tests/c/abi_smoke.c); the C
+    struct the header declares has the size of the ctypes mirror in spatialpy_b200/engine.py; argument errors are return codes."""
+    from spatialpy_b200 import codegen, engine
+    _lib()
+    codegen.build_peaks()
+    exe = tmp_path / "abi_smoke"
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L", codegen.LIB_DIR, "-lssb_core", "-lssb_peaks",
+           f"-Wl,-rpath,{codegen.LIB_DIR}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    m = re.search(r"abi (\d+), sizeof\(ssb_model\) (\d+), device_count rc (\d+)", run.stdout)
+    assert m and int(m.group(1)) == engine.SSB_ABI_VERSION
+    assert int(m.group(2)) == ctypes.sizeof(engine.SsbModel)
+    if not os.path.exists("/dev/nvidia0"):
+        assert int(m.group(3)) == 3                      # SSB_ERR_CUDA: no device, reported as a code, not a crash
