@@ -1,6 +1,7 @@
 /* Plain-C consumer of the C-ABI: proves include/ssb.h and include/ssb_peaks.h compile as C (not only as C++) and that the
  * libraries link from C.  Without a GPU it exercises the no-compute entry points and the loud failure of ssb_create;
  * with `run` as argv[1] it also creates an engine for a 2-particle model (GPU box only). */
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 #include "ssb.h"
@@ -20,6 +21,10 @@ int main(int argc, char **argv) {
     int count = -1;
     int rc = ssb_device_count(&count);
     printf("abi %d, sizeof(ssb_model) %zu, device_count rc %d count %d\n", ssb_abi_version(), sizeof(ssb_model), rc, count);
+    printf("offsets output_steps %zu h %zu gravity %zu x %zu u0 %zu species_names %zu rdme_epsilon %zu device %zu owned %zu rng_id %zu\n",
+           offsetof(ssb_model, output_steps), offsetof(ssb_model, h), offsetof(ssb_model, gravity), offsetof(ssb_model, x),
+           offsetof(ssb_model, u0), offsetof(ssb_model, species_names), offsetof(ssb_model, rdme_epsilon), offsetof(ssb_model, device),
+           offsetof(ssb_model, owned), offsetof(ssb_model, rng_id));
     if (argc > 1 && strcmp(argv[1], "peak") == 0) {
         double tf = 0.0, ms = 0.0;
         rc = ssb_fp64_peak(0, &tf, &ms);

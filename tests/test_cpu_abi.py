@@ -482,5 +482,8 @@ def test_header_is_valid_c_and_matches_the_ctypes_binding(tmp_path):
     m = re.search(r"abi (\d+), sizeof\(ssb_model\) (\d+), device_count rc (\d+)", run.stdout)
     assert m and int(m.group(1)) == engine.SSB_ABI_VERSION
     assert int(m.group(2)) == ctypes.sizeof(engine.SsbModel)
+    offs = re.search(r"offsets (.*)", run.stdout).group(1).split()
+    for name, off in zip(offs[0::2], offs[1::2]):
+        assert getattr(engine.SsbModel, name).offset == int(off), name
     if not os.path.exists("/dev/nvidia0"):
         assert int(m.group(3)) == 3                      # SSB_ERR_CUDA: no device, reported as a code, not a crash
