@@ -379,3 +379,34 @@ def test_slab_stepping_protocol_over_gloo_reproduces_the_single_rank_run():
     from spatialpy_b200.slab import partition
     first = partition(fm, 0, 2)
     assert set(outs[0]["gid"].tolist()) != set(first.gids[first.owned == 1].tolist())
+
+
+def test_solver_slab_keyword_plumbing(monkeypatch):
+    """Solver.run(decomposition="slab"): one driver call per trajectory with seed+k (solver.py:558-559), the output flags turned
+    into the driver's vtk / binary_store arguments, success flags set, a model the decomposition cannot run reported as the
+    reference reports engine failures (SimulationError with a return code, solver.py:595-597)."""
+    import pytest
+    import spatialpy_b200.slab as slab
+    from spatialpy_b200 import SimulationError, Solver, configs
+    from spatialpy_b200.engine import FLAG_BINARY_STORE, FLAG_NO_VTK
+    calls = []
+
+    def stub(fm, devices, seed, out_dir, flags=0, rdme_epsilon=0.0, vtk=True, binary_store=False, cancelled=None, **kw):
+        assert os.path.isdir(out_dir) and not (flags & (FLAG_BINARY_STORE | FLAG_NO_VTK)) and not cancelled()
+        calls.append((list(devices), seed, vtk, binary_store, rdme_epsilon))
+        if fm.static_domain:
+            raise ValueError("slab decomposition is implemented for moving domains")
+        return {}
+
+    monkeypatch.setattr(slab, "run_slab_trajectory", stub)
+    sol = Solver(_model())
+    res = sol.run(number_of_trajectories=3, seed=40, decomposition="slab", devices=[0, 1], binary_store=True, vtk=False,
+                  rdme_epsilon=0.1)
+    assert calls == [([0, 1], 40 + k, False, True, 0.1) for k in range(3)]
+    assert len(res) == 3 and all(r.success and not r.timeout for r in res)
+    assert len({r.result_dir for r in res}) == 3
+    with pytest.raises(SimulationError, match="unknown decomposition"):
+        sol.run(decomposition="pencil")
+    static = Solver(configs.cylinder_rdme(delta=0.25, nt=10, output_every=10))
+    with pytest.raises(SimulationError, match="return code = 4"):
+        static.run(seed=1, decomposition="slab", devices=[0, 1])
