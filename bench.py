@@ -142,8 +142,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def _time_reference(exe, threads, seed=1000):
+    d = tempfile.mkdtemp(prefix="ssb_ref_")
+    t0 = time.perf_counter()
+    subprocess.run([exe, "-t", str(threads), "-s", str(seed)], cwd=d, stdout=subprocess.DEVNULL, check=True)
+    dt = time.perf_counter() - t0
+    subprocess.run(["rm", "-rf", d])
+    return dt
+
+
 def cpu_baseline_sample(workload):
-    """Bounded sample of the reference on the host cores (rank 0, N=1 only)."""
+    """Bounded sample of the reference on the host cores (rank 0, N=1 only).  `value` is the strongest CPU arm (g++ -O3, all
+    cores); `variants` adds what SURVEY.md 8(d) asks to see beside it: one thread, the reference's own default thread cap
+    (min(8, cores), E/propensity_file_template.cpp:129-132) and the build the reference actually ships (no -O, E/build/SConstruct:23)."""
     name = {"cylinder": "bench_cylinder", "tank": "bench_tank", "box": "bench_tank"}[workload]
     base = os.path.join(ROOT, "oracle", "_ref", name)
     exe = os.path.join(base, "fast", "ssa_sdpd.exe")
@@ -151,13 +162,21 @@ def cpu_baseline_sample(workload):
         return None
     meta = json.load(open(os.path.join(base, "meta.json")))
     cores = os.cpu_count() or 1
-    d = tempfile.mkdtemp(prefix="ssb_ref_")
-    t0 = time.perf_counter()
-    subprocess.run([exe, "-t", str(cores), "-s", "1000"], cwd=d, stdout=subprocess.DEVNULL, check=True)
-    dt = time.perf_counter() - t0
-    subprocess.run(["rm", "-rf", d])
-    return {"value": meta["N"] * meta["nt"] / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"unmodified reference engine (g++ -O3) on {meta['builder']}{meta['kwargs']}: N={meta['N']} x {meta['nt']} steps, -t {cores}, {dt:.2f} s wall"}
+    work = meta["N"] * meta["nt"]
+    dt = _time_reference(exe, cores)
+    variants = {f"O3_t{cores}": work / dt}
+    try:
+        variants["O3_t1"] = work / _time_reference(exe, 1)
+        if cores > 8:
+            variants["O3_t8"] = work / _time_reference(exe, 8)
+        shipped = os.path.join(base, "shipped", "ssa_sdpd.exe")
+        if os.path.exists(shipped):
+            variants[f"shipped_noopt_t{cores}"] = work / _time_reference(shipped, cores)
+    except Exception:   # noqa: BLE001 - the extra arms are informative only
+        pass
+    return {"value": work / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"unmodified reference engine (g++ -O3) on {meta['builder']}{meta['kwargs']}: N={meta['N']} x {meta['nt']} steps, -t {cores}, {dt:.2f} s wall",
+            "variants": {k: round(v, 1) for k, v in variants.items()}}
 
 
 # ---------------------------------------------------------------------------------------------------------
