@@ -50,7 +50,9 @@ TAPS = {
     "cdc42": [0, 1, 2],
     "cavity2d_rdme": [0, 1, 22, 45],
     "cdc42_full": [0, 1, 2],
+    "line1d": [0, 1, 2, 3, 4],
 }
+EXPECTED_ABORT = {"line1d_isolated": "ERROR: nan/inf detected!!!"}
 ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000, "cdc42": 600, "cavity2d_rdme": 1000}
 XBINS = 8
 
@@ -78,11 +80,29 @@ def make(name):
     model = models.BUILDERS[name]()
     # compile_prep() re-applies the (random) scatter initial conditions every time it is called
     # (model.py:178-185), and both flattenings call it: re-seed so the two engines get the same u0.
-    np.random.seed(12345)
-    fm = FlatModel.from_spatialpy(model)
-    fm.save(os.path.join(HERE, f"{name}.model.npz"))
-    np.random.seed(12345)
-    exe = build_ref.build_model(model, name, variant="parity", dump=True, h=fm.h)
+    if isinstance(model, FlatModel):          # synthetic edge-case models: the reference's own template filled from the arrays
+        fm = model
+        fm.save(os.path.join(HERE, f"{name}.model.npz"))
+        exe = build_ref.build_flat(fm, name, variant="parity", dump=True)
+    else:
+        np.random.seed(12345)
+        fm = FlatModel.from_spatialpy(model)
+        fm.save(os.path.join(HERE, f"{name}.model.npz"))
+        np.random.seed(12345)
+        exe = build_ref.build_model(model, name, variant="parity", dump=True, h=fm.h)
+    if name in EXPECTED_ABORT:                # error-behaviour fixture: the reference must exit(1) with this message
+        try:
+            run_one(exe, SEED)
+        except RuntimeError as err:
+            text = str(err)
+            assert EXPECTED_ABORT[name] in text, text[:400]
+            ident = int(text.split("\nid=")[1].split("\n")[0])
+            step = int(text.split("sys->current_step=")[1].split("\n")[0])
+            np.savez_compressed(os.path.join(HERE, f"{name}.ref.npz"), exit_code=np.array(1), message=np.array(EXPECTED_ABORT[name]),
+                                particle=np.array(ident), step=np.array(step))
+            print(f"{name}: reference aborted as expected: '{EXPECTED_ABORT[name]}' particle {ident} at step {step}")
+            return
+        raise SystemExit(f"{name}: the reference was expected to abort but ran through")
     dumps = run_one(exe, SEED)
     out = {"steps": np.array(TAPS[name]), "seed": np.array(SEED)}
     for s in TAPS[name]:

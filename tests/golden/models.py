@@ -241,6 +241,37 @@ def cdc42(DX=12, end_time=0.02, steps=2):
     return model
 
 
+def line1d(steps=4, isolated=False):
+    """Edge cases in one model, fed to the reference through its own template (oracle/emit_ref_model.py): a 1-D MOVING domain
+    (all y = z = 0 => dimension 1, solver.py:407-413; kernel normalisation alpha = h, particle.cpp:174), ragged neighbour lists
+    (end particles), fixed end walls, one diffusing species with populations from 0 upwards.  isolated=True moves the last
+    particle out of everybody's reach: its Shepard-filtered density is 0/0 at step 0 (model.cpp:194-233 runs for every
+    particle of a moving domain when step % 20 == 0), so the REFERENCE aborts at step 1 with "nan/inf detected"
+    (particle.cpp:88-126) — the error-behaviour fixture."""
+    from spatialpy_b200 import FlatModel, ReactionSource
+    n = 14
+    x = numpy.zeros((n, 3))
+    x[:, 0] = numpy.arange(n) * 0.1 + 0.003 * numpy.sin(numpy.arange(n) * 1.7)
+    if isolated:
+        x[-1, 0] = 5.0
+    solid = numpy.zeros(n, numpy.int32)
+    solid[[0, 1, n - 2, n - 1]] = 1
+    u0 = (numpy.arange(n) % 5 * 3).astype(numpy.uint32).reshape(n, 1)
+    dt = 1e-3
+    return FlatModel(
+        name="line1d_isolated" if isolated else "line1d", x=x, type=numpy.where(solid == 1, 1, 2).astype(numpy.int32), nu=numpy.full(n, 0.05), mass=numpy.full(n, 0.1),
+        c=numpy.zeros(n), rho=numpy.full(n, 1.0), solid=solid, species_names=["A"],
+        reactions=[ReactionSource(name="decay", propensity="P0*x[0]", ode_propensity="P0*x[0]", restrict_to=None)],
+        parameters={"P0": 0.0}, type_constants={"type_Walls": 1, "type_Fluid": 2}, u0=u0,
+        N_dense=numpy.array([[-1]], numpy.int32), diffusion_matrix=numpy.array([[0.02, 0.02]]), enable_pde=True, enable_rdme=True,
+        static_domain=False, dt=dt, nt=steps, output_steps=numpy.arange(steps + 1, dtype=numpy.uint32), h=0.25, rho0=1.0, c0=10.0,
+        P0=100.0, xlim=(0.0, 5.0), ylim=(0.0, 0.0), zlim=(0.0, 0.0), dimension=1, gravity=(0.3, 0.0, 0.0)).finalize()
+
+
+def line1d_isolated():
+    return line1d(isolated=True)
+
+
 def cdc42_full():
     """BASELINE config 4 at its NAMED size — create_cdc42_model(DX=50): 2 500 particles — on a horizon the reference finishes in
     seconds (the notebook's end_time=100 is ~7e10 events per trajectory): full-size parity taps for the deterministic parts
@@ -249,4 +280,4 @@ def cdc42_full():
 
 
 BUILDERS = {"birth_death": birth_death, "diffusion3d": diffusion3d, "cavity2d": cavity2d, "tank3d": tank3d,
-            "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme, "cdc42_full": cdc42_full}
+            "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme, "cdc42_full": cdc42_full, "line1d": line1d, "line1d_isolated": line1d_isolated}

@@ -8,7 +8,7 @@ from util import RTOL_STEP, RTOL_TRAJ, csr_sorted, load_model, load_ref, rel_err
 import sdpd_oracle
 
 
-@pytest.mark.parametrize("name", ["birth_death", "diffusion3d", "cavity2d", "tank3d", "cylinder", "cdc42", "cdc42_full"])
+@pytest.mark.parametrize("name", ["birth_death", "diffusion3d", "cavity2d", "tank3d", "cylinder", "cdc42", "cdc42_full", "line1d"])
 def test_oracle_neighbours_match_reference(name):
     fm, ref = load_model(name), load_ref(name)
     o = sdpd_oracle.SdpdOracle(fm)
@@ -23,7 +23,7 @@ def test_oracle_neighbours_match_reference(name):
     assert rel_err(gd, rd) <= RTOL_STEP and rel_err(gw, rw) <= RTOL_STEP and rel_err(gD, rD) <= RTOL_STEP
 
 
-@pytest.mark.parametrize("name", ["cavity2d", "tank3d", "diffusion3d", "cavity2d_rdme"])
+@pytest.mark.parametrize("name", ["cavity2d", "tank3d", "diffusion3d", "cavity2d_rdme", "line1d"])
 def test_oracle_trajectory_matches_reference(name):
     fm, ref = load_model(name), load_ref(name)
     o = sdpd_oracle.SdpdOracle(fm)
@@ -45,6 +45,21 @@ def test_oracle_ddiag_matches_reference(name):
     o = sdpd_oracle.SdpdOracle(fm)
     o.find_neighbors(o.x, o.x)
     assert rel_err(o.ddiag(), ref["s1_Ddiag"]) <= RTOL_STEP
+
+
+def test_oracle_reproduces_the_reference_abort_on_an_isolated_particle():
+    """Error behaviour: a particle with no neighbour on a MOVING domain gets a Shepard-filtered density of 0/0 at step 0
+    (model.cpp:194-233), and the reference exits at the NaN check of step 1 (particle.cpp:88-126) — recorded from the
+    reference itself in line1d_isolated.ref.npz.  The restatement must produce the same NaN on the same particle at the same
+    step (the CUDA engine reports it as SSB_ERR_NAN, tests/test_gpu_oracle.py)."""
+    fm, ref = load_model("line1d_isolated"), load_ref("line1d_isolated")
+    assert int(ref["exit_code"]) == 1 and str(ref["message"]) == "ERROR: nan/inf detected!!!"
+    o = sdpd_oracle.SdpdOracle(fm)
+    assert np.isfinite(o.rho).all()
+    o.step()                                              # step 0 runs through: the check sits at the top of a step
+    bad = np.nonzero(~np.isfinite(o.rho))[0]
+    assert bad.tolist() == [int(ref["particle"])] and o.step_no == int(ref["step"])
+    assert np.isfinite(o.x).all() and np.isfinite(o.v).all()
 
 
 # ---------------------------------------------------------------------------------------------------------------
