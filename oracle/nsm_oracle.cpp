@@ -142,3 +142,11 @@ extern "C" int nsm_oracle_run(int N, const int64_t *nbr_ptr, const int32_t *nbr_
     if (n_df) *n_df = ndf;
     return 0;
 }
+
+/* Tap for tests/test_cpu_abi.py: the generated propensity functions evaluated on the host — the same text nvcc compiles into
+ * the CUDA model unit — so the reference's expression-conversion test (test/integration_tests/test_solver.py:202-256) can be
+ * replayed on this code generator. */
+extern "C" void nsm_oracle_eval_propensities(const int *x, double t, double vol, const double *data_fn, int sd, double *out) {
+    ssb_gen::eval_propensities(x, t, vol, data_fn, sd, out);
+}
+

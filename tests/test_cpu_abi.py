@@ -487,3 +487,57 @@ def test_header_is_valid_c_and_matches_the_ctypes_binding(tmp_path):
         assert getattr(engine.SsbModel, name).offset == int(off), name
     if not os.path.exists("/dev/nvidia0"):
         assert int(m.group(3)) == 3                      # SSB_ERR_CUDA: no device, reported as a code, not a crash
+
+
+def test_converted_expressions_evaluate_like_python():
+    """The reference's own expression test (test/integration_tests/test_solver.py:76-121,202-256: BuildExpression's C text must
+    evaluate like Python to 3 places) replayed on THIS code generator: every converted expression becomes a reaction propensity,
+    the generated `ssb_gen` functions are compiled for the host (the same text nvcc compiles for sm_100a — also checked) and
+    evaluated at the reference's value sets."""
+    _need_spatialpy()
+    import ctypes as C
+    import nsm_oracle
+    from spatialpy.core.model import Model  # noqa: F401  (front-end importable)
+    from spatialpy.solvers.build_expression import BuildExpression, ExpressionConverter
+    from spatialpy_b200 import FlatModel, ReactionSource, codegen
+    numeric = [({"x": 0}, "x*2", [[0.0], [1.0], [-1.0], [9.999], [-9.999]]),
+               ({"x": 0}, "x*2 + x/2 - (x*3)^2 + x/3^2", [[0.0], [1.0], [-1.0], [3.333], [-3.333], [9.8765], [-9.8765]]),
+               ({"x": 0, "y": 1}, "(x-1)*y^2+x", [[1.0, 2.4], [5.1, 0.0], [5.1, 1.0], [5.1, -1.0], [9.8765, -1.0], [-1.0, 9.8765]]),
+               ({"x": 0, "y": 1, "z": 2}, "(x^2/y^2/z^2)/x^2/y^2/z^2**1/x**1/y**1/z",
+                [[5.1, 0.1, 2.0], [0.1, 5.1, 2.0], [2.0, 0.1, 5.1], [2.0, 5.1, 0.1]])]
+    boolean = [({"x": 0}, "x > 0", [[100], [0], [0.001], [-1]]),
+               ({"x": 0, "y": 1}, "x > y", [[100, 99], [99, 100], [-10, 10], [10, -10], [0.001, 0.0], [0.0, 0.001], [-99.999, -99.998]]),
+               ({"x": 0, "y": 1}, "x > 0 and y < x", [[100, 99], [99, 100], [0, -100], [-0.001, -99.0], [0, 0.001], [-0.001, 0]]),
+               ({"x": 0, "y": 1}, "x > 0 and y < 10 and x > y",
+                [[100, 9], [0.01, 0.00], [100, 200], [0.01, 0.02], [0, 0], [-0.01, -0.02], [-0.01, 0]]),
+               ({"x": 0, "y": 1}, "x > 0 and y < 10 or y > 100", [[10, 9], [0.01, 9.99], [0, 10], [-1.0, -1.0]]),
+               ({"x": 0, "y": 1, "z": 2}, "x^2>x and y<y^2 or z^2!=z^3 and y!=z",
+                [[1.0, 1.0, 1.0], [99.9, 99.9, 100.0], [0.0, -1.0, 99.9], [-1.0, -1.0, 0.00]])]
+    cases = [(a, e, v, False) for a, e, v in numeric] + [(a, e, v, True) for a, e, v in boolean]
+    reactions, pyfuncs = [], []
+    for k, (args, expr, _, _) in enumerate(cases):
+        converted = ExpressionConverter.convert_str(expr)
+        text = BuildExpression(namespace={name: f"data_fn[{slot}]" for name, slot in args.items()}, sanitize=True).getexpr_cpp(converted)
+        reactions.append(ReactionSource(name=f"e{k}", propensity=text, ode_propensity=text, restrict_to=None))
+        pyfuncs.append(eval(f"lambda {','.join(args)}: {converted}"))
+    n = 2
+    fm = FlatModel(name="expr", x=np.array([[0.0, 0, 0], [0.1, 0, 0]]), type=np.ones(n, np.int32), nu=np.ones(n), mass=np.ones(n),
+                   c=np.zeros(n), rho=np.ones(n), solid=np.ones(n, np.int32), species_names=["A"], reactions=reactions,
+                   u0=np.ones((n, 1), np.uint32), N_dense=np.zeros((1, len(reactions)), np.int32),
+                   diffusion_matrix=np.zeros((1, 1)), data_fn=np.zeros((3, n)), static_domain=True, dt=1.0, nt=1,
+                   output_steps=np.array([0, 1], np.uint32), h=0.25, dimension=1).finalize()
+    assert os.path.exists(codegen.build_model_unit(fm))          # the same text compiles as sm_100a device code
+    lib = nsm_oracle.build(fm)
+    out = np.zeros(len(reactions))
+    x = np.ones(1, np.int32)
+    for k, (args, expr, values, is_bool) in enumerate(cases):
+        for vals in values:
+            df = np.zeros(3)
+            df[:len(vals)] = vals
+            lib.nsm_oracle_eval_propensities(x.ctypes.data_as(C.c_void_p), C.c_double(0.0), C.c_double(1.0),
+                                             df.ctypes.data_as(C.c_void_p), C.c_int(1), out.ctypes.data_as(C.c_void_p))
+            want = pyfuncs[k](*vals)
+            if is_bool:
+                assert bool(out[k]) == bool(want), (expr, vals, out[k])
+            else:
+                assert abs(out[k] - want) < 5e-4 * max(1.0, abs(want)) or round(out[k] - want, 3) == 0, (expr, vals, out[k], want)
