@@ -51,6 +51,8 @@ TAPS = {
     "cavity2d_rdme": [0, 1, 22, 45],
     "cdc42_full": [0, 1, 2],
     "line1d": [0, 1, 2, 3, 4],
+    "letters": [0, 1],
+    "datafn": [0, 1],
 }
 EXPECTED_ABORT = {"line1d_isolated": "ERROR: nan/inf detected!!!"}
 ENSEMBLES = {"birth_death": 1500, "cylinder": 1000, "diffusion3d": 1000, "cdc42": 600, "cavity2d_rdme": 1000}

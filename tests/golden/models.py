@@ -272,6 +272,35 @@ def line1d_isolated():
     return line1d(isolated=True)
 
 
+def letters():
+    """test/integration_tests/test_model.py:60-78: every single-letter species name that is not reserved (51 species) must
+    survive the compilation namespace — here: the generated device code (x, t, vol ... are identifiers of the propensity ABI)."""
+    import string
+    import spatialpy
+    model = spatialpy.Model("letters")
+    for ch in string.ascii_letters:
+        if ch not in spatialpy.Model.reserved_names:
+            model.add_species(spatialpy.Species(ch, 0))
+    model.set_timesteps(output_interval=1, num_steps=1, timestep_size=1)
+    model.add_domain(spatialpy.Domain.create_2D_domain([0, 1], [0, 1], 2, 2))
+    return model
+
+
+def datafn():
+    """test/integration_tests/test_model.py:81-104: a data function (10000 * x) used as a propensity must reach the engine:
+    no births where x = 0, births where x = 1."""
+    import spatialpy
+    model = spatialpy.Model("datafn")
+    df = spatialpy.DataFunction(name="df")
+    df.map = lambda x: x[0] * 10000
+    model.add_data_function(df)
+    model.set_timesteps(output_interval=1, num_steps=1, timestep_size=1)
+    model.add_domain(spatialpy.Domain.create_2D_domain([0, 1], [0, 1], 2, 2))
+    model.add_species(spatialpy.Species('A', 0))
+    model.add_reaction(spatialpy.Reaction(products={'A': 1}, propensity_function="df"))
+    return model
+
+
 def cdc42_full():
     """BASELINE config 4 at its NAMED size — create_cdc42_model(DX=50): 2 500 particles — on a horizon the reference finishes in
     seconds (the notebook's end_time=100 is ~7e10 events per trajectory): full-size parity taps for the deterministic parts
@@ -280,4 +309,5 @@ def cdc42_full():
 
 
 BUILDERS = {"birth_death": birth_death, "diffusion3d": diffusion3d, "cavity2d": cavity2d, "tank3d": tank3d,
-            "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme, "cdc42_full": cdc42_full, "line1d": line1d, "line1d_isolated": line1d_isolated}
+            "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme, "cdc42_full": cdc42_full, "line1d": line1d, "line1d_isolated": line1d_isolated,
+            "letters": letters, "datafn": datafn}

@@ -95,3 +95,30 @@ def test_nsm_oracle_matches_reference_ensemble(name):
     ok = se > 0
     z = np.abs(mean_g - ens["t1_vox_mean"])[ok] / se[ok]
     assert (z > 3).mean() <= 0.01 and z.max() < 4.5, (z.max(), (z > 3).mean())
+
+
+def test_data_function_reaches_the_propensities():
+    """test/integration_tests/test_model.py:81-104 (propensity = data function 10000*x): no births where x = 0, Poisson(10^4)
+    births per unit time where x = 1 — the reference's own run is in datafn.ref.npz; the NSM restatement agrees."""
+    import nsm_oracle
+    fm, ref = load_model("datafn"), load_ref("datafn")
+    rx = ref["s1_xx"].ravel().astype(np.int64)
+    assert rx[0] == 0 and rx[1] == 0 and rx[2] > 0 and rx[3] > 0          # the reference test's own assertions
+    o = sdpd_oracle.SdpdOracle(fm)
+    nb = o.find_neighbors(o.x, o.x)
+    xx, n_rx, n_df = nsm_oracle.run(nsm_oracle.build(fm), fm, nb, 5, fm.nt * fm.dt)
+    xx = xx.ravel().astype(np.int64)
+    assert xx[0] == 0 and xx[1] == 0 and n_df == 0 and n_rx == xx.sum()
+    assert abs(xx[2] - 10000) < 500 and abs(xx[3] - 10000) < 500 and abs(rx[2] - 10000) < 500     # 5 sigma of Poisson(10^4)
+
+
+def test_single_letter_species_names_compile_for_the_device():
+    """test/integration_tests/test_model.py:60-78: all 51 non-reserved single-letter species names.  The propensity ABI's own
+    identifiers (x, t, vol, sd ...) must not collide with species named like them: the model unit builds for sm_100a and the
+    fixture's step-0 state is what the reference produced."""
+    from spatialpy_b200 import codegen
+    fm, ref = load_model("letters"), load_ref("letters")
+    assert fm.num_species == 51 and {"x", "e", "s", "d", "N", "S"} <= set(fm.species_names) and "t" not in fm.species_names
+    assert ref["s1_xx"].shape == (fm.num_particles, 51) and not ref["s1_xx"].any()
+    import os
+    assert os.path.exists(codegen.build_model_unit(fm))
