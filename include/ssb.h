@@ -46,6 +46,9 @@ extern "C" {
 #define SSB_FLAG_SKIP_STATIC_FORCES 8u     /* static domains: skip F/Fbp/Frho (never consumed when static, simulate.cpp:68,137); default on via Python */
 #define SSB_FLAG_NO_STEP_OVERSHOOT 128u    /* moving domains: do not execute the reference's one event past each step's end
                                              (`while(tt <= end_time)` tests the previous event's time, simulate_rdme.cpp:233-238) */
+#define SSB_FLAG_TILE_SWEEP 256u           /* moving domains, opt-in: force sweep that stages the neighbour records of each 128-particle CTA in shared
+                                             memory (k_force_mv_tile, ssb_model_unit.cuh) instead of one 128-byte gather per pair; same lists, same
+                                             pair arithmetic in the same order => bit-identical forces.  Awaits its first GPU measurement. */
 #define SSB_FLAG_BINARY_STORE 64u         /* also write outputN.ssb next to (or, with SSB_FLAG_NO_VTK, instead of) outputN.vtk: the same snapshot as raw
                                              little-endian arrays at full fp64 precision (layout in spatialpy_b200/vtk.py, read by Result.read_step;
                                              SURVEY.md 8f item 1 - the reference's pure-Python ASCII parser, vtkreader.py:29-56, bounds large N*T) */

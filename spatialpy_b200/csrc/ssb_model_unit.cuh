@@ -406,6 +406,252 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3 (tile form, opt-in: SSB_FLAG_TILE_SWEEP)  same sweep as k_force_mv — same candidate lists, same pair arithmetic in the same
+// (ascending slot) order, so the results are bit-identical — but the neighbour records come from SHARED MEMORY instead of one
+// 4-sector gather per pair.  k_force_mv is bound by the L1TEX pipe (87 %): 128 particles x 36 candidates = 4 600 record fetches
+// per CTA, although the cell-sorted CTA only touches ~1 400 DISTINCT records (the nine cell-row runs around its cells).  Here the
+// CTA (1) marks the 64-slot blocks its candidates fall into in a shared bitmap, (2) turns the set blocks into ascending chunks of
+// <= SSB_TILE_REC consecutive records, (3) stages one chunk at a time with coalesced 16-byte loads and lets every thread consume
+// the part of its (ascending) candidate list that falls into the chunk — a cursor per thread, no index remapping.  A CTA whose
+// candidates span more than the bitmap covers falls back to the gather loop.  DESIGN.md section 9 item 1 has the budget.
+// The pair body below is a verbatim copy of k_force_mv's (kept separate so that the validated kernel's code is untouched).
+// ---------------------------------------------------------------------------------------------
+#define SSB_TILE_REC 256          // records per staged chunk (32 KB)
+#define SSB_TILE_GRAN 64          // slots per bitmap bit
+#define SSB_TILE_WORDS 512        // 16 384 bits: candidates of one CTA may span up to 2^20 slots
+#define SSB_TILE_MAXCH 96         // chunks per CTA
+
+__device__ __forceinline__ ssb_d4 ssb_lds256(const double *p) {
+    const double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + 2);
+    ssb_d4 r;
+    r.a = lo.x; r.b = lo.y; r.c = hi.x; r.d = hi.y;
+    return r;
+}
+
+__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv_tile(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
+    __shared__ __align__(32) double s_rec[SSB_TILE_REC * 16];
+    __shared__ unsigned s_bits[SSB_TILE_WORDS];
+    __shared__ int s_lo[SSB_TILE_MAXCH], s_hi[SSB_TILE_MAXCH];
+    __shared__ int s_nch, s_min, s_max, s_fallback;
+    const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i_raw < V.N;
+    const int i = live ? i_raw : V.N - 1;          // idle lanes of the last CTA run the same straight-line code on a valid slot
+    double mx = 0.0;
+    const int N = V.N, dim = V.dim;
+    const double h = V.h, P0 = V.P0;
+    const double inv_h = 1.0 / h;
+    const double c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
+    const double eps_r = 0.001 * h, eps2 = 0.01 * h * h;
+    const double h2x = __dmul_rn(h, h);
+    const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
+    const double *ri = V.rec + (size_t) i * 16;
+    const ssb_d4 a0 = ssb_ld256(ri), a1 = ssb_ld256(ri + 4), a2 = ssb_ld256(ri + 8), a3 = ssb_ld256(ri + 12);
+    const double xi0 = a0.d, xi1 = a1.a, xi2 = a1.b;
+    const double vi0 = a1.c, vi1 = a1.d, vi2 = a2.a;
+    const double wi0 = a2.b - vi0, wi1 = a2.c - vi1, wi2 = a2.d - vi2;
+    const double rho_i = a3.a, m_i = a3.b, nu_i = a3.c;
+    // 1/rho, P/rho^2 and m/rho of both particles are recomputed from the record (two divisions per pair on an fp64 pipe that is
+    // ~30 % busy) rather than gathered from a second per-particle record: the sweep is bound by L1 tag lookups — each lane's
+    // gather touches its own 128-byte line — and a fifth sector per pair cost more (measured 0.77 -> 0.70 ms at 1 M particles).
+    const double rho0 = V.rho0, inv_rho0 = 1.0 / V.rho0;
+    const bool inv_exact = (__double_as_longlong(rho0) & 0x000fffffffffffffLL) == 0;    // power of two: rho * (1/rho0) == rho / rho0 bit for bit
+    const double inv_rho_i = 1.0 / rho_i;
+    const double aP_i = (P0 * (rho_i / rho0 - 1.0)) * inv_rho_i * inv_rho_i;
+    const double vol_i = m_i * inv_rho_i;
+    const double volsq_i = vol_i * vol_i, inv_m_i = 1.0 / m_i;
+    const double rv0 = rho_i * vi0, rv1 = rho_i * vi1, rv2 = rho_i * vi2;
+    const int type_i = (int) ((__double_as_longlong(a3.d) >> 32) & 0xffff);
+    double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1], Dd[SSB_SD > 0 ? SSB_SD : 1];
+#pragma unroll
+    for (int s = 0; s < SSB_SC; s++) {
+        Ci[s] = V.C[(size_t) s * N + i];
+        Qi[s] = V.Q[(size_t) s * N + i];
+        int k = SSB_SC * (type_i - 1) + s;
+        Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < SSB_SD; s++) Dd[s] = 0.0;
+    double F0 = V.F[0][i], F1 = V.F[1][i], F2 = V.F[2][i];
+    double B0 = V.Fbp[0][i], B1 = V.Fbp[1][i], B2 = V.Fbp[2][i];
+    double Frho = V.Frho[i];
+    const int cnt = (live && V.owned[i]) ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
+    // one accepted-or-rejected candidate j with its record in c0..c3 — verbatim pair body of k_force_mv
+    auto pair = [&](const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const int j) {
+        ssb_d4 e0;
+        e0.a = 1.0 / c3.a;
+        e0.b = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * e0.a * e0.a;
+        e0.c = c3.b * e0.a;
+        const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
+        const double r = sqrt(d2);
+        // candidate list -> ANN's exact set (the record loads above are issued before this test on purpose: a rejected
+        // candidate wastes 4 sectors, a dependent second round trip per accepted neighbour would cost far more)
+        if (V.filter && !((d2 <= h2x) && (d2 != 0.0) && !(r > h))) return;
+        double dx0 = xi0 - c0.d, dx1 = 0.0, dx2 = 0.0;
+        if (dim > 1) dx1 = xi1 - c1.a;
+        if (dim > 2) dx2 = xi2 - c1.b;
+        const double vj0 = c1.c, vj1 = c1.d, vj2 = c2.a;
+        const double wj0 = c2.b - vj0, wj1 = c2.c - vj1, wj2 = c2.d - vj2;
+        const double rho_j = c3.a, m_j = c3.b, nu_j = c3.c;
+        const double inv_rho_j = e0.a, aP_j = e0.b, vol_j = e0.c;
+        // one division for three reciprocals
+        const double reg = r + eps_r, nusum = nu_i + nu_j, r2 = r * r;
+        const double md = (m_i + m_j) * (r2 + eps2);
+        const double rn = reg * nusum;
+        const double q = 1.0 / (rn * md);
+        const double inv_reg = q * (nusum * md), inv_nusum = q * (reg * md), inv_md = q * rn;
+        const double R = r * inv_h, omR = 1.0 - R;
+        const double dWdr = c12 * r * (omR * omR);                           // particle.cpp:178
+        const double wr = dWdr * inv_reg;                                    // dWdr / (r + 0.001 h)
+        double dv0 = vi0 - vj0, dv1 = 0.0, dv2 = 0.0;
+        if (dim > 1) dv1 = vi1 - vj1;
+        if (dim > 2) dv2 = vi2 - vj2;
+        const double dv_dx = dv0 * dx0 + dv1 * dx1 + dv2 * dx2;
+        double pg = aP_i + aP_j;                                             // model.cpp:111
+        if (pg < 0) pg = -aP_i + aP_j;                                       // model.cpp:112
+        const double fp = -m_j * pg * wr;                                    // model.cpp:115
+        const double fv = m_j * (2.0 * (nu_i * nu_j) * inv_nusum) * wr * (inv_rho_i * inv_rho_j);   // model.cpp:118
+        const double vv = volsq_i + vol_j * vol_j;
+        const double fbp = -10.0 * P0 * inv_m_i * vv * wr;                   // model.cpp:121
+        const double widx = wi0 * dx0 + wi1 * dx1 + wi2 * dx2;
+        const double wjdx = wj0 * dx0 + wj1 * dx1 + wj2 * dx2;
+        const double ftc = 0.5 * inv_m_i * vv * wr;                          // model.cpp:124-132
+        const double rj_w = rho_j * wjdx;
+        const double ft0 = ftc * (rv0 * widx + vj0 * rj_w);
+        const double ft1 = ftc * (rv1 * widx + vj1 * rj_w);
+        const double ft2 = ftc * (rv2 * widx + vj2 * rj_w);
+        F0 += fp * dx0 + fv * dv0 + ft0;                                     // model.cpp:135-138
+        B0 += fbp * dx0;
+        if (dim > 1) { F1 += fp * dx1 + fv * dv1 + ft1; B1 += fbp * dx1; }
+        if (dim > 2) { F2 += fp * dx2 + fv * dv2 + ft2; B2 += fbp * dx2; }
+        Frho += wr * vol_j * (rho_i * dv_dx + rho_i * widx + rj_w);          // model.cpp:143-146
+        if (SSB_SC > 0 || SSB_SD > 0) {
+            const double G = 2.0 * (m_i * m_j) * (inv_rho_i + inv_rho_j) * r2 * inv_md;   // shared by model.cpp:155 and particle.cpp:187
+            if (SSB_SC > 0) {
+                const double base = G * wr;
+#pragma unroll
+                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - V.C[(size_t) s * N + j]) * base;
+            }
+            if (SSB_SD > 0) {
+                const double hr = h - r;
+                const double Dij = G * (ih7c * hr * hr);                     // particle.cpp:182-187 (sign folded)
+                const int tj = (int) ((__double_as_longlong(c3.d) >> 32) & 0xffff) - 1;
+#pragma unroll
+                for (int s = 0; s < SSB_SD; s++) Dd[s] += V.dmat[s * V.num_types + tj] * Dij;
+            }
+        }
+    };
+    // ---- (1) which 64-slot blocks do this CTA's candidates fall into?  Lists are ascending (k_search walks the cell rows in
+    // storage order), so a thread's first / last entry bound its range.
+    if (threadIdx.x == 0) { s_min = 0x7fffffff; s_max = -1; s_nch = 0; s_fallback = 0; }
+    for (int w = threadIdx.x; w < SSB_TILE_WORDS; w += blockDim.x) s_bits[w] = 0u;
+    __syncthreads();
+    if (cnt > 0) {
+        atomicMin(&s_min, V.nbr[i]);
+        atomicMax(&s_max, V.nbr[(size_t) (cnt - 1) * N + i]);
+    }
+    __syncthreads();
+    const int base = (s_max >= 0) ? (s_min & ~(SSB_TILE_GRAN - 1)) : 0;
+    const int nblk = (s_max >= 0) ? (s_max - base) / SSB_TILE_GRAN + 1 : 0;
+    const bool too_wide = nblk > SSB_TILE_WORDS * 32;
+    if (!too_wide) {
+        for (int k = 0; k < cnt; k++) {
+            const int b = (V.nbr[(size_t) k * N + i] - base) / SSB_TILE_GRAN;
+            atomicOr(&s_bits[b >> 5], 1u << (b & 31));
+        }
+    }
+    __syncthreads();
+    // ---- (2) set blocks -> ascending chunks of at most SSB_TILE_REC consecutive records
+    if (threadIdx.x == 0) {
+        int n = 0, run_lo = -1, run_hi = -1, overflow = too_wide ? 1 : 0;
+        const int nwords = too_wide ? 0 : (nblk + 31) / 32;
+        for (int w = 0; w < nwords && !overflow; w++) {
+            unsigned bits = s_bits[w];
+            while (bits) {
+                const int b = w * 32 + __ffs((int) bits) - 1;
+                bits &= bits - 1u;
+                if (run_lo >= 0 && b == run_hi && (run_hi - run_lo) < SSB_TILE_REC / SSB_TILE_GRAN) { run_hi = b + 1; continue; }
+                if (run_lo >= 0) {
+                    if (n == SSB_TILE_MAXCH) { overflow = 1; break; }
+                    s_lo[n] = base + run_lo * SSB_TILE_GRAN; s_hi[n] = min(base + run_hi * SSB_TILE_GRAN, N); n++;
+                }
+                run_lo = b; run_hi = b + 1;
+            }
+        }
+        if (run_lo >= 0 && !overflow) {
+            if (n == SSB_TILE_MAXCH) overflow = 1;
+            else { s_lo[n] = base + run_lo * SSB_TILE_GRAN; s_hi[n] = min(base + run_hi * SSB_TILE_GRAN, N); n++; }
+        }
+        s_nch = overflow ? 0 : n;
+        s_fallback = overflow;
+    }
+    __syncthreads();
+    if (s_fallback) {
+        // candidates too scattered for the bitmap / chunk table: the gather loop of k_force_mv
+        for (int k = 0; k < cnt; k++) {
+            const int j = V.nbr[(size_t) k * N + i];
+            const double *rj = V.rec + (size_t) j * 16;
+            const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
+            pair(c0, c1, c2, c3, j);
+        }
+    } else {
+        // ---- (3) stage chunk by chunk; every thread consumes the candidates that fall into the staged chunk
+        const int nch = s_nch;
+        int k = 0;
+        int jn = (cnt > 0) ? V.nbr[i] : 0x7fffffff;                 // next candidate of this thread
+        double2 *s2 = reinterpret_cast<double2 *>(s_rec);
+        for (int c = 0; c < nch; c++) {
+            const int lo = s_lo[c], hi = s_hi[c];
+            if (c > 0) __syncthreads();                              // the previous chunk has been consumed by everybody
+            const double2 *g2 = reinterpret_cast<const double2 *>(V.rec + (size_t) lo * 16);
+            const int n2 = (hi - lo) * 8;                            // 16 doubles per record = 8 double2
+            for (int t = threadIdx.x; t < n2; t += blockDim.x) s2[t] = g2[t];
+            __syncthreads();
+            while (jn < hi) {                                        // jn >= lo: chunks and lists are both ascending
+                const double *rj = s_rec + (size_t) (jn - lo) * 16;
+                const ssb_d4 c0 = ssb_lds256(rj), c1 = ssb_lds256(rj + 4), c2 = ssb_lds256(rj + 8), c3 = ssb_lds256(rj + 12);
+                pair(c0, c1, c2, c3, jn);
+                k++;
+                jn = (k < cnt) ? V.nbr[(size_t) k * N + i] : 0x7fffffff;
+            }
+        }
+    }
+    if (live) {
+        V.F[0][i] = F0; V.F[1][i] = F1; V.F[2][i] = F2;
+        V.Fbp[0][i] = B0; V.Fbp[1][i] = B1; V.Fbp[2][i] = B2;
+        V.Frho[i] = Frho;
+        if (SSB_SC > 0) {
+            if (SSB_RC > 0) {                                                    // model.cpp:181-189
+                const double vol = m_i / rho_i;
+                const double cur_time = step * V.dt;
+                double df[SSB_NDF > 0 ? SSB_NDF : 1];
+#pragma unroll
+                for (int qd = 0; qd < SSB_NDF; qd++) df[qd] = V.data_fn[(size_t) qd * N + i];
+                double flux[SSB_RC > 0 ? SSB_RC : 1];
+                ssb_gen::eval_det(Ci, cur_time, vol, df, type_i, flux);
+#pragma unroll
+                for (int rxn = 0; rxn < SSB_RC; rxn++) {
+#pragma unroll
+                    for (int s = 0; s < SSB_SC; s++) {
+                        int nval;
+                        if (V.flags & 2u) nval = ssb_gen::N_dense(s * SSB_R + rxn);
+                        else { int kk = SSB_RC * rxn + s; nval = (kk < SSB_S * SSB_R) ? ssb_gen::N_dense(kk) : 0; }
+                        Qi[s] += nval * flux[rxn];
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SSB_SC; s++) V.Q[(size_t) s * N + i] = Qi[s];
+        }
+#pragma unroll
+        for (int s = 0; s < SSB_SD; s++) { V.Ddiag[(size_t) s * N + i] = Dd[s]; mx = fmax(mx, Dd[s]); }
+    }
+    if (SSB_SD > 0) {
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Static-domain fast path (positions, masses and densities never change: simulate.cpp:68,137 skip the integrator).
 //   k_static_coef  once: the chemistry pair coefficient dQc_base of model.cpp:155 per ELL entry.
 //   k_static_step  one launch per engine step, fusing  [compute_forces: Q = sweep(C)]  [take_step2: C += dt/2 Q; BC]
@@ -1538,7 +1784,8 @@ static int l_force(const SsbView *V, unsigned step, int full, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 static int l_force_mv(const SsbView *V, unsigned step, unsigned long long *max_bits, cudaStream_t st) {
-    k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
+    if (V->flags & 256u) k_force_mv_tile<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);      // SSB_FLAG_TILE_SWEEP (opt-in)
+    else k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
     return (int) cudaGetLastError();
 }
 static int l_corrector(const SsbView *V, unsigned step, cudaStream_t st) {

@@ -541,3 +541,76 @@ def test_converted_expressions_evaluate_like_python():
                 assert bool(out[k]) == bool(want), (expr, vals, out[k])
             else:
                 assert abs(out[k] - want) < 5e-4 * max(1.0, abs(want)) or round(out[k] - want, 3) == 0, (expr, vals, out[k], want)
+
+
+def _tile_chunks(lists, n_slots, gran=64, rec=256, words=512, maxch=96):
+    """Python restatement of steps (1)-(2) of k_force_mv_tile (ssb_model_unit.cuh) for one CTA: ascending candidate lists ->
+    ascending chunks [lo, hi) of at most `rec` consecutive slots, or None for the gather fallback."""
+    firsts = [l[0] for l in lists if len(l)]
+    if not firsts:
+        return []
+    smin, smax = min(firsts), max(l[-1] for l in lists if len(l))
+    base = smin & ~(gran - 1)
+    nblk = (smax - base) // gran + 1
+    if nblk > words * 32:
+        return None
+    bits = np.zeros(nblk, bool)
+    for l in lists:
+        bits[(np.asarray(l, dtype=np.int64) - base) // gran] = True
+    chunks, run_lo, run_hi = [], -1, -1
+    for b in np.nonzero(bits)[0]:
+        if run_lo >= 0 and b == run_hi and (run_hi - run_lo) < rec // gran:
+            run_hi = b + 1
+            continue
+        if run_lo >= 0:
+            if len(chunks) == maxch:
+                return None
+            chunks.append((base + run_lo * gran, min(base + run_hi * gran, n_slots)))
+        run_lo, run_hi = b, b + 1
+    if run_lo >= 0:
+        if len(chunks) == maxch:
+            return None
+        chunks.append((base + run_lo * gran, min(base + run_hi * gran, n_slots)))
+    return chunks
+
+
+def test_tile_sweep_chunking_consumes_every_candidate_once_in_order():
+    """The algorithm of the opt-in shared-memory force sweep (k_force_mv_tile): on cell-sorted candidate lists of a jittered
+    tank, every CTA's chunks are ascending, disjoint, at most 256 records long and inside the array, and the per-thread cursor
+    consumes each candidate exactly once, in list order, while its record is staged — which is why the tile form can be
+    bit-identical to the gather form.  Also the fallback conditions."""
+    from scipy.spatial import cKDTree
+    from spatialpy_b200 import configs
+    fm = configs.tank_sdpd(n=16, nt=10, output_every=10)
+    rng = np.random.default_rng(1)
+    x = fm.x + rng.uniform(-0.002, 0.002, fm.x.shape)
+    rad = fm.h * 1.1
+    cell = np.floor((x - x.min(axis=0)) / rad).astype(np.int64)
+    ncell = cell.max(axis=0) + 1
+    key = (cell[:, 2] * ncell[1] + cell[:, 1]) * ncell[0] + cell[:, 0]          # storage order of the engine's cell list
+    order = np.argsort(key, kind="stable")
+    xs = x[order]
+    n = len(xs)
+    lists = [sorted(l) for l in cKDTree(xs).query_ball_point(xs, rad)]           # self included, like the candidate lists
+    staged_total, pairs_total = 0, 0
+    for b0 in range(0, n, 128):
+        cta = lists[b0:b0 + 128]
+        chunks = _tile_chunks(cta, n)
+        assert chunks is not None and 0 < len(chunks) <= 96
+        assert all(lo < hi <= n and hi - lo <= 256 for lo, hi in chunks)
+        assert all(chunks[c][1] <= chunks[c + 1][0] for c in range(len(chunks) - 1))
+        staged_total += sum(hi - lo for lo, hi in chunks)
+        for l in cta:                                                          # the cursor of one thread
+            k, seen = 0, []
+            for lo, hi in chunks:
+                while k < len(l) and l[k] < hi:
+                    assert l[k] >= lo                                          # its record is in the staged chunk
+                    seen.append(l[k])
+                    k += 1
+            assert seen == l
+            pairs_total += len(l)
+    assert staged_total < 0.6 * pairs_total            # the point of staging: far fewer record fetches than pairs
+    # fallbacks: candidates spread over more slots than the bitmap covers, or over more chunks than the table holds
+    assert _tile_chunks([[0, 64 * 512 * 32 + 5]], 10 ** 8) is None
+    assert _tile_chunks([[k * 128 for k in range(200)]], 10 ** 6) is None
+    assert _tile_chunks([[], []], 100) == []
