@@ -614,3 +614,42 @@ def test_tile_sweep_chunking_consumes_every_candidate_once_in_order():
     assert _tile_chunks([[0, 64 * 512 * 32 + 5]], 10 ** 8) is None
     assert _tile_chunks([[k * 128 for k in range(200)]], 10 ** 6) is None
     assert _tile_chunks([[], []], 100) == []
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the contract's keys, timed on the
+    unmodified reference executable built from /root/reference (oracle/_ref); skipped where that binary does not exist."""
+    import json
+    import sys
+    exe = os.path.join(ROOT, "oracle", "_ref", "bench_cylinder", "fast", "ssa_sdpd.exe")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref is not built here")
+    run = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [l for l in run.stdout.strip().split("\n") if l.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "particle-steps/s" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+
+
+def test_bench_helper_measurements_degrade_to_an_error_field():
+    """The fp64 peak helper runs in a child process and reports failure as data (it must never cost the bench line)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    res = bench.fp64_peak_sample(0)
+    if os.path.exists("/dev/nvidia0"):
+        assert res.get("fp64_tflops", 0) > 1.0
+    else:
+        assert set(res) == {"error"} and "return code = 3" in res["error"]
+    from spatialpy_b200 import configs
+    fm = configs.tank_sdpd(n=12, nt=10, output_every=10)
+    assert bench.algorithmic_bytes(fm, True) == 698 + 64 * fm.num_chem_species + (68 + 12 * fm.num_stoch_species + 8 * fm.num_stoch_rxns)
