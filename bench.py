@@ -487,13 +487,26 @@ def run_ensemble_bench(args, rank, local_rank, world):
         if use_dist:
             dist.barrier()
 
-    run_ensemble(fm, lanes * world, 1, devices=[local_rank], lanes=lanes, rank=rank, world_size=world)      # warm-up (JIT, contexts)
-    barrier()
-    t0 = time.perf_counter()
-    res = run_ensemble(fm, total, 1000, devices=[local_rank], lanes=lanes, rank=rank, world_size=world)
-    barrier()
-    dt = time.perf_counter() - t0
-    ev = float(sum(c["reactions"] + c["diffusions"] for c in res.values()))
+    if args.batch:
+        # opt-in: `--batch n` trajectories per engine handle as disjoint copies of the model (ensemble.replicate_model); rank r runs
+        # its per_gpu trajectories with seeds 1000 + r * per_gpu ...
+        from spatialpy_b200.ensemble import run_ensemble_batched
+        run_ensemble_batched(fm, min(args.batch, per_gpu), 1, device=local_rank, batch=args.batch)              # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        resb = run_ensemble_batched(fm, per_gpu, 1000 + rank * per_gpu, device=local_rank, batch=args.batch)
+        barrier()
+        dt = time.perf_counter() - t0
+        ev = float(resb["counters"]["reactions"] + resb["counters"]["diffusions"])
+        lanes = f"1 handle x {min(args.batch, per_gpu)} copies"
+    else:
+        run_ensemble(fm, lanes * world, 1, devices=[local_rank], lanes=lanes, rank=rank, world_size=world)      # warm-up (JIT, contexts)
+        barrier()
+        t0 = time.perf_counter()
+        res = run_ensemble(fm, total, 1000, devices=[local_rank], lanes=lanes, rank=rank, world_size=world)
+        barrier()
+        dt = time.perf_counter() - t0
+        ev = float(sum(c["reactions"] + c["diffusions"] for c in res.values()))
     if use_dist:
         t = torch.tensor([dt, ev], dtype=torch.float64, device="cuda")
         tm = t.clone()
@@ -523,6 +536,7 @@ def main():
     ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box", "ens_birth_death", "ens_cdc42", "ens_cdc42_full"])
     ap.add_argument("--trajectories", type=int, default=128, help="ensemble workloads: trajectories per GPU")
     ap.add_argument("--lanes", type=int, default=0, help="ensemble workloads: concurrent engine handles per GPU (0 = auto)")
+    ap.add_argument("--batch", type=int, default=0, help="ensemble workloads: trajectories per engine handle as disjoint copies of the model (0 = off)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
     ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
     ap.add_argument("--extra-flags", type=int, default=0, help="extra SSB_FLAG_* bits for the engine (diagnostics)")

@@ -104,3 +104,116 @@ def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out
     if errors:
         raise errors[0]
     return results
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Batched ensembles (opt-in): many trajectories of a small STATIC model in ONE engine handle
+# ----------------------------------------------------------------------------------------------------------------------
+def replicate_model(fm, copies, gap=None):
+    """`copies` disjoint copies of a static-domain model laid out along x as ONE FlatModel (pitch = extent + gap, gap >= 2 h
+    so no neighbour list crosses copies).  Copy r owns particle ids r*N .. (r+1)*N-1.
+
+    Why: a 121-voxel model occupies one CTA; even with 24 engine handles side by side (run_ensemble) a B200 runs ~50 of its
+    ~600 resident CTAs.  The copies share nothing — the reference runs trajectories as separate processes
+    (spatialpy/solvers/solver.py:547-605) — and nothing in a static-domain step couples them: events are per voxel, jumps go
+    to neighbours within h (E/src/simulate_rdme.cpp:359-366), the sSSA window length comes from max Ddiag, which every copy
+    shares, and the Philox counters are keyed by particle id, which differs between copies.  So every copy is a statistically
+    independent trajectory of the original model (moving domains are excluded: their step-end overshoot event is one per
+    SYSTEM, simulate_rdme.cpp:233-238)."""
+    import numpy as np
+    from .flatmodel import FlatModel
+    fm = fm.finalize()
+    if not fm.static_domain:
+        raise ValueError("replicate_model is for static domains (a moving domain's step-end event couples the copies)")
+    copies = int(copies)
+    if copies < 1:
+        raise ValueError("copies must be >= 1")
+    gap = 2.0 * fm.h if gap is None else float(gap)
+    if gap < 1.5 * fm.h:
+        raise ValueError("gap must be at least 1.5 h so that no neighbour list crosses copies")
+    pitch = float(fm.x[:, 0].max() - fm.x[:, 0].min()) + gap
+    x = np.tile(fm.x, (copies, 1))
+    x[:, 0] += np.repeat(np.arange(copies) * pitch, fm.num_particles)
+    t1 = lambda a: np.tile(a, copies)                       # noqa: E731  per-particle vectors
+    return FlatModel(
+        name=f"{fm.name}_x{copies}", x=x, type=t1(fm.type), nu=t1(fm.nu), mass=t1(fm.mass), c=t1(fm.c), rho=t1(fm.rho),
+        solid=t1(fm.solid), species_names=list(fm.species_names), reactions=list(fm.reactions), parameters=dict(fm.parameters),
+        type_constants=dict(fm.type_constants), u0=np.tile(fm.u0, (copies, 1)), N_dense=fm.N_dense, irN=fm.irN, jcN=fm.jcN,
+        prN=fm.prN, irG=fm.irG, jcG=fm.jcG, diffusion_matrix=fm.diffusion_matrix, data_fn=np.tile(fm.data_fn, (1, copies)),
+        bc_source=fm.bc_source, enable_pde=fm.enable_pde, enable_rdme=fm.enable_rdme, static_domain=True, dt=fm.dt, nt=fm.nt,
+        output_steps=fm.output_steps, h=fm.h, rho0=fm.rho0, c0=fm.c0, P0=fm.P0,
+        xlim=(fm.xlim[0], fm.xlim[1] + (copies - 1) * pitch), ylim=fm.ylim, zlim=fm.zlim, dimension=fm.dimension,
+        gravity=fm.gravity).finalize()
+
+
+def default_batch(num_particles, number_of_trajectories):
+    """Copies per engine handle: enough voxels (~2^18) to give every SM several chunks of the sSSA window kernel."""
+    return max(1, min(int(number_of_trajectories), 262144 // max(int(num_particles), 1)))
+
+
+def run_ensemble_batched(fm, number_of_trajectories, seed, device=0, out_dirs=None, batch=None, flags=None, rdme_epsilon=0.0,
+                         vtk=True, binary_store=False, engine_factory=None, on_engine=None):
+    """The ensemble as batches of `batch` trajectories per engine handle (`replicate_model`).  Trajectory k is copy k mod batch
+    of batch k // batch; batch b is seeded with seed + b * batch, so a run is reproducible for a given (seed, batch) — the
+    reference's "trajectory k uses seed + k" mapping (solver.py:558-559) holds for the ENSEMBLE LAW, not trajectory by trajectory.
+    With `out_dirs`, every trajectory gets the reference's own file set (output%u.vtk / .ssb, output0_boundingBox.vtk, same
+    file -> step map), written by the host-side twins of the engine's writers from the copies' slices of the state.
+    Returns {k: {"xx_final": [N, S_d] populations}} plus the summed counters under key "counters"."""
+    import os
+    import numpy as np
+    from .engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+    from .slab import output_schedule
+    from .vtk import write_bounding_box, write_ssb, write_vtk
+    fm = fm.finalize()
+    ntraj = int(number_of_trajectories)
+    B = int(batch) if batch else default_batch(fm.num_particles, ntraj)
+    N, Sc, Sd = fm.num_particles, fm.num_chem_species, fm.num_stoch_species
+    flags = (FLAG_SKIP_STATIC_FORCES if flags is None else flags) | FLAG_NO_VTK
+    factory = engine_factory or Engine
+    schedule = output_schedule(fm.nt, fm.output_steps)
+    results, totals = {}, {"reactions": 0, "diffusions": 0, "seconds": 0.0, "windows": 0}
+    eng, eng_copies = None, 0
+    try:
+        for b0 in range(0, ntraj, B):
+            nb = min(B, ntraj - b0)
+            if eng is None or eng_copies != nb:           # the last batch may be smaller
+                if eng is not None:
+                    eng.close()
+                eng = factory(replicate_model(fm, nb), device=device, flags=flags, rdme_epsilon=rdme_epsilon)
+                eng_copies = nb
+                if on_engine:
+                    on_engine(eng)
+            eng.reset(seed + b0)
+            done = 0
+            for file_index, step in schedule:
+                if step > done:
+                    eng.step(step - done)
+                    done = step
+                if out_dirs is None:
+                    continue
+                v = eng.get("v").reshape(nb, N, 3)
+                scal = np.stack([eng.get(name).reshape(nb, N) for name in ("rho", "mass", "bvf_phi", "nu")], axis=1)    # [nb, 4, N]
+                C = eng.get("C").reshape(nb, N, Sc) if Sc else None
+                D = eng.get("xx").reshape(nb, N, Sd) if Sd else None
+                init = 1 if (Sd > 0 and step > 0) else 0          # output.cpp:151-154: output0 undercounts FIELD
+                for r in range(nb):
+                    d = out_dirs[b0 + r]
+                    args = (fm.x, v[r], scal[r], C[r].T if Sc else None, fm.type, D[r].T if Sd else None, fm.species_names)
+                    if file_index == 0 and vtk:
+                        write_bounding_box(d, fm.xlim, fm.ylim, fm.zlim)
+                    if vtk:
+                        write_vtk(os.path.join(d, f"output{file_index}.vtk"), *args, rdme_initialized=init)
+                    if binary_store:
+                        write_ssb(os.path.join(d, f"output{file_index}.ssb"), *args, step=step, rdme_initialized=init)
+            xx = eng.get("xx").reshape(nb, N, Sd) if Sd else np.zeros((nb, N, 0), np.uint32)
+            for r in range(nb):
+                results[b0 + r] = {"xx_final": xx[r].copy()}
+            c = eng.counters()
+            for key in ("reactions", "diffusions", "windows"):
+                totals[key] += c[key]
+            totals["seconds"] += c["seconds"]
+    finally:
+        if eng is not None:
+            eng.close()
+    results["counters"] = totals
+    return results

@@ -10,7 +10,9 @@ propensities / BCs are compiled into a CUDA model unit (codegen.py) and trajecto
 (engine.py).  Additive keywords (not in the reference): `devices=[...]` to spread an ensemble over GPUs, `lanes`, `flags`,
 `rdme_epsilon`, `binary_store=True` (also write `output%u.ssb`, raw fp64 arrays that `Result.read_step` then loads
 instead of parsing the text), `vtk=False` (binary files only) and `decomposition="slab"` (ONE moving domain split into
-len(devices) slabs with halo exchange, spatialpy_b200/slab.py, instead of one trajectory per device).
+len(devices) slabs with halo exchange, spatialpy_b200/slab.py, instead of one trajectory per device) and `batch=True|n`
+(small STATIC models: n trajectories run as disjoint copies of the model in one engine handle, ensemble.replicate_model —
+the ensemble law is the reference's, the per-trajectory seed mapping is per batch).
 
 `install()` adds the `solver=` keyword that the reference's README promises but `Model.run` never implemented
 (model.py:1021-1056): `model.run(solver=spatialpy_b200.Solver, number_of_trajectories=..., seed=...)`.
@@ -216,7 +218,7 @@ class Solver:
 
     def run(self, number_of_trajectories=1, seed=None, timeout=None, number_of_threads=None, debug=False, profile=False,
             verbose=True, devices=None, flags=None, rdme_epsilon=0.0, lanes=None, binary_store=False, vtk=True,
-            decomposition=None):
+            decomposition=None, batch=None):
         from .engine import EngineError, FLAG_SKIP_STATIC_FORCES, FLAG_BINARY_STORE, FLAG_NO_VTK
         if not self.is_compiled:
             self.compile(debug=debug, profile=profile)
@@ -255,6 +257,22 @@ class Solver:
                 state["error"] = err
             state["done"] = True
 
+        def body_batched():
+            # small static models: `batch` trajectories as disjoint copies in one engine handle (ensemble.replicate_model)
+            from .ensemble import run_ensemble_batched
+            try:
+                res = run_ensemble_batched(self.flat, number_of_trajectories, seed, device=devices[0], out_dirs=out_dirs,
+                                           batch=None if batch is True else int(batch),
+                                           flags=flags & ~(FLAG_BINARY_STORE | FLAG_NO_VTK), rdme_epsilon=rdme_epsilon, vtk=vtk,
+                                           binary_store=binary_store,
+                                           on_engine=lambda e: (lock.acquire(), engines.append(e), lock.release()))
+                for k in res:
+                    if k != "counters":
+                        results[k].success = True
+            except (EngineError, ValueError) as err:
+                state["error"] = err
+            state["done"] = True
+
         def body():
             try:
                 done = run_ensemble(self.flat, number_of_trajectories, seed, devices=devices, lanes=lanes, out_dirs=out_dirs,
@@ -266,7 +284,7 @@ class Solver:
                 state["error"] = err
             state["done"] = True
 
-        t = threading.Thread(target=body_slab if decomposition == "slab" else body)
+        t = threading.Thread(target=body_slab if decomposition == "slab" else (body_batched if batch else body))
         t.start()
         timed_out = False
         t.join(timeout)

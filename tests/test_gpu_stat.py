@@ -133,3 +133,32 @@ def test_leap_form_diffusion_parity_and_conservation():
     g = gpu_ensemble("diffusion3d", 3, [10], flags=flags)
     fm = load_model("diffusion3d")
     np.testing.assert_array_equal(g[10].sum(axis=1), np.tile(fm.u0.sum(axis=0), (3, 1)))
+
+
+# written after the round-1 GPU budget was spent; the construction is pinned on the CPU (tests/test_cpu_gloo.py: the copies of a
+# replicated model pass the same KS test through the serial NSM restatement); the GPU run of it is pending
+@pytest.mark.skipif(__import__("os").environ.get("SSB_PENDING_GPU_TESTS") != "1", reason="awaits its first GPU run (set SSB_PENDING_GPU_TESTS=1)")
+@pytest.mark.parametrize("name", ["birth_death", "cdc42"])
+def test_batched_ensemble_has_the_reference_law(name):
+    """run_ensemble_batched: 256 trajectories per engine handle as disjoint copies of the model.  Totals of every species at
+    the last output step vs the reference ensemble (KS p > 0.01), and the copies of one batch are uncorrelated."""
+    from spatialpy_b200.ensemble import run_ensemble_batched
+    fm = load_model(name)
+    ens = load_ens(name)
+    ntraj = 1024
+    res = run_ensemble_batched(fm, ntraj, 70_000, batch=256)
+    xx = np.array([res[k]["xx_final"] for k in range(ntraj)]).astype(np.int64)        # [ntraj, N, S]
+    # the fixture's last ensemble tap is the end of the run only if nt matches; both fixtures are generated that way
+    assert int(ens["steps"][1]) == fm.nt
+    tot = xx.sum(axis=1)
+    for j in range(tot.shape[1]):
+        ref = ens["t1_totals"][:, j]
+        if ref.std() == 0 and tot[:, j].std() == 0:
+            assert ref[0] == tot[0, j]
+            continue
+        p = stats.ks_2samp(tot[:, j], ref).pvalue
+        assert p > 0.01, f"{name} species {j}: KS p={p:.4f}"
+    j = int(np.argmax(tot.std(axis=0)))
+    a = tot[:, j].reshape(4, 256)
+    r_adj = np.corrcoef(a[:, :-1].ravel(), a[:, 1:].ravel())[0, 1]
+    assert abs(r_adj) < 4.0 / np.sqrt(a[:, 1:].size), r_adj
