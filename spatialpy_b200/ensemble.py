@@ -110,8 +110,8 @@ def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out
 # Batched ensembles (opt-in): many trajectories of a small STATIC model in ONE engine handle
 # ----------------------------------------------------------------------------------------------------------------------
 def replicate_model(fm, copies, gap=None):
-    """`copies` disjoint copies of a static-domain model laid out along x as ONE FlatModel (pitch = extent + gap, gap >= 2 h
-    so no neighbour list crosses copies).  Copy r owns particle ids r*N .. (r+1)*N-1.
+    """`copies` disjoint copies of a static-domain model laid out on a grid of tiles as ONE FlatModel (pitch = extent + gap,
+    gap >= 2 h so no neighbour list crosses copies).  Copy r owns particle ids r*N .. (r+1)*N-1.
 
     Why: a 121-voxel model occupies one CTA; even with 24 engine handles side by side (run_ensemble) a B200 runs ~50 of its
     ~600 resident CTAs.  The copies share nothing — the reference runs trajectories as separate processes
@@ -131,9 +131,15 @@ def replicate_model(fm, copies, gap=None):
     gap = 2.0 * fm.h if gap is None else float(gap)
     if gap < 1.5 * fm.h:
         raise ValueError("gap must be at least 1.5 h so that no neighbour list crosses copies")
-    pitch = float(fm.x[:, 0].max() - fm.x[:, 0].min()) + gap
+    # copies sit on a near-square grid of tiles in x (and y for 2-D / 3-D models): the engine's cell list has at most 4096 cells
+    # per axis (ssb_core.cu setup_grid), so a single row of a thousand copies would coarsen the cells
+    nx = copies if fm.dimension < 2 else int(np.ceil(np.sqrt(copies)))
+    ny = -(-copies // nx)
+    pitch = [float(fm.x[:, d].max() - fm.x[:, d].min()) + gap for d in range(2)]
     x = np.tile(fm.x, (copies, 1))
-    x[:, 0] += np.repeat(np.arange(copies) * pitch, fm.num_particles)
+    r = np.repeat(np.arange(copies), fm.num_particles)
+    x[:, 0] += (r % nx) * pitch[0]
+    x[:, 1] += (r // nx) * pitch[1]
     t1 = lambda a: np.tile(a, copies)                       # noqa: E731  per-particle vectors
     return FlatModel(
         name=f"{fm.name}_x{copies}", x=x, type=t1(fm.type), nu=t1(fm.nu), mass=t1(fm.mass), c=t1(fm.c), rho=t1(fm.rho),
@@ -142,7 +148,8 @@ def replicate_model(fm, copies, gap=None):
         prN=fm.prN, irG=fm.irG, jcG=fm.jcG, diffusion_matrix=fm.diffusion_matrix, data_fn=np.tile(fm.data_fn, (1, copies)),
         bc_source=fm.bc_source, enable_pde=fm.enable_pde, enable_rdme=fm.enable_rdme, static_domain=True, dt=fm.dt, nt=fm.nt,
         output_steps=fm.output_steps, h=fm.h, rho0=fm.rho0, c0=fm.c0, P0=fm.P0,
-        xlim=(fm.xlim[0], fm.xlim[1] + (copies - 1) * pitch), ylim=fm.ylim, zlim=fm.zlim, dimension=fm.dimension,
+        xlim=(fm.xlim[0], fm.xlim[1] + (nx - 1) * pitch[0]), ylim=(fm.ylim[0], fm.ylim[1] + (ny - 1) * pitch[1]), zlim=fm.zlim,
+        dimension=fm.dimension,
         gravity=fm.gravity).finalize()
 
 
