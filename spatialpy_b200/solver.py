@@ -258,19 +258,36 @@ class Solver:
             state["done"] = True
 
         def body_batched():
-            # small static models: `batch` trajectories as disjoint copies in one engine handle (ensemble.replicate_model)
+            # small static models: `batch` trajectories as disjoint copies in one engine handle (ensemble.replicate_model);
+            # with several devices the ensemble is cut into contiguous shards, one host thread per device; a batch is seeded
+            # with seed + (global index of its first trajectory), so the seeds of different shards never coincide
             from .ensemble import run_ensemble_batched
-            try:
-                res = run_ensemble_batched(self.flat, number_of_trajectories, seed, device=devices[0], out_dirs=out_dirs,
-                                           batch=None if batch is True else int(batch),
-                                           flags=flags & ~(FLAG_BINARY_STORE | FLAG_NO_VTK), rdme_epsilon=rdme_epsilon, vtk=vtk,
-                                           binary_store=binary_store,
-                                           on_engine=lambda e: (lock.acquire(), engines.append(e), lock.release()))
-                for k in res:
-                    if k != "counters":
-                        results[k].success = True
-            except (EngineError, ValueError) as err:
-                state["error"] = err
+            per_dev = -(-number_of_trajectories // len(devices))
+            shard_errors = []
+
+            def shard(d):
+                k0, k1 = d * per_dev, min((d + 1) * per_dev, number_of_trajectories)
+                if k0 >= k1:
+                    return
+                try:
+                    res = run_ensemble_batched(self.flat, k1 - k0, seed + k0, device=devices[d], out_dirs=out_dirs[k0:k1],
+                                               batch=None if batch is True else int(batch),
+                                               flags=flags & ~(FLAG_BINARY_STORE | FLAG_NO_VTK), rdme_epsilon=rdme_epsilon,
+                                               vtk=vtk, binary_store=binary_store,
+                                               on_engine=lambda e: (lock.acquire(), engines.append(e), lock.release()))
+                    for k in res:
+                        if k != "counters":
+                            results[k0 + k].success = True
+                except (EngineError, ValueError) as err:
+                    shard_errors.append(err)
+
+            workers = [threading.Thread(target=shard, args=(d,)) for d in range(len(devices))]
+            for w in workers:
+                w.start()
+            for w in workers:
+                w.join()
+            if shard_errors:
+                state["error"] = shard_errors[0]
             state["done"] = True
 
         def body():

@@ -192,5 +192,10 @@ def test_solver_batch_keyword_plumbing(monkeypatch):
     assert calls == [(5, 9, 2, 5, None, True, True)] and len(res) == 5 and all(r.success for r in res)
     Solver(fm).run(number_of_trajectories=5, seed=9, batch=2)
     assert calls[-1][4] == 2
+    # several devices: contiguous shards, each seeded with seed + its first trajectory index
+    calls.clear()
+    res = Solver(fm).run(number_of_trajectories=7, seed=100, batch=True, devices=[0, 1, 3])
+    assert sorted(calls) == [(1, 106, 3, 1, None, True, False), (3, 100, 0, 3, None, True, False), (3, 103, 1, 3, None, True, False)]
+    assert len(res) == 7 and all(r.success for r in res)
     with pytest.raises(SimulationError, match="return code = 4"):
         Solver(load_model("tank3d")).run(seed=1, batch=True)
