@@ -148,6 +148,14 @@ int ssb_set_field(ssb_handle *h, const char *name, const void *src, int64_t byte
 int ssb_get_step(ssb_handle *h, uint32_t *step, uint64_t *epoch);
 int ssb_set_step(ssb_handle *h, uint32_t step, uint64_t epoch);
 
+/* The engine's own file writers (E/src/output.cpp:104-229 byte format; the outputN.ssb side-store) applied to a snapshot in CALLER
+ * memory, id order: x v [np*3] | scal = rho,mass,bvf_phi,nu [4*np] | C [Sc*np] species-major | type [np] | xx [Sd*np] species-major;
+ * lims6 = xlo xhi ylo yhi zlo zhi (output0_boundingBox.vtk is written with file_index 0 / step 0); what = 1 VTK, 2 binary, 3 both.
+ * Used for snapshots assembled on the host (slab-decomposed runs, batched ensembles).  No handle, no device work. */
+int ssb_write_snapshot(const char *dir, uint32_t file_index, uint32_t step, int32_t rdme_initialized, int64_t np, int32_t Sc, int32_t Sd,
+                       const char *const *species_names, const double *lims6, const double *x, const double *v, const double *scal,
+                       const double *C, const int32_t *type, const uint32_t *xx, uint32_t what);
+
 int ssb_cancel(ssb_handle *h);                 /* async-signal-safe flag; the running ssb_run returns SSB_ERR_CANCELLED */
 const char *ssb_last_error(ssb_handle *h);     /* message for the last non-zero return (valid until next call) */
 

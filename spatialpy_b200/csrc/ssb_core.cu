@@ -595,9 +595,17 @@ static inline void put_u(Buf &b, unsigned v) {
     b.n = (size_t) (p - b.d.data());
 }
 
-static int write_vtk(ssb_handle *h, const OutputJob &J) {
-    const int np = h->N;
-    const int Sc = h->V.Sc, Sd = h->V.Sd;
+// what the two file writers need besides the staged arrays: sizes, bounding box, species names (a handle's, or a caller's for
+// snapshots assembled on the host: ssb_write_snapshot)
+struct SnapMeta {
+    int np, Sc, Sd;
+    double xlo, xhi, ylo, yhi, zlo, zhi;
+    const std::vector<std::string> *names;
+};
+
+static int write_vtk_impl(const SnapMeta &M, const OutputJob &J) {
+    const int np = M.np;
+    const int Sc = M.Sc, Sd = M.Sd;
     char filename[4096];
     if (J.step == 0 && J.file_index == 0) {
         snprintf(filename, sizeof(filename), "%s/output0_boundingBox.vtk", J.dir.c_str());
@@ -609,11 +617,11 @@ static int write_vtk(ssb_handle *h, const OutputJob &J) {
         fprintf(fp, "DATASET RECTILINEAR_GRID\n");
         fprintf(fp, "DIMENSIONS 2 2 2\n");
         fprintf(fp, "X_COORDINATES 2 double\n");
-        fprintf(fp, "%lf %lf\n", h->m.xlo, h->m.xhi);
+        fprintf(fp, "%lf %lf\n", M.xlo, M.xhi);
         fprintf(fp, "Y_COORDINATES 2 double\n");
-        fprintf(fp, "%lf %lf\n", h->m.ylo, h->m.yhi);
+        fprintf(fp, "%lf %lf\n", M.ylo, M.yhi);
         fprintf(fp, "Z_COORDINATES 2 double\n");
-        fprintf(fp, "%lf %lf\n", h->m.zlo, h->m.zhi);
+        fprintf(fp, "%lf %lf\n", M.zlo, M.zhi);
         fclose(fp);
     }
     snprintf(filename, sizeof(filename), "%s/output%u.vtk", J.dir.c_str(), J.file_index);
@@ -693,13 +701,13 @@ static int write_vtk(ssb_handle *h, const OutputJob &J) {
         b.putf("\n");
     }
     for (int s = 0; s < Sc; s++) {
-        b.putf("C[%s] 1 %i double\n", h->species_names[s].c_str(), np);
+        b.putf("C[%s] 1 %i double\n", (*M.names)[(size_t) s].c_str(), np);
         const double *a = J.C + (size_t) s * np;
         section([&](Buf &q, int i) { put_lf(q, a[i]); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
         b.putf("\n");
     }
     for (int s = 0; s < Sd; s++) {
-        b.putf("D[%s] 1 %i int\n", h->species_names[s].c_str(), np);
+        b.putf("D[%s] 1 %i int\n", (*M.names)[(size_t) s].c_str(), np);
         const unsigned *a = J.xx + (size_t) s * np;
         section([&](Buf &q, int i) { put_u(q, a[i]); if ((i + 1) % 9 == 0) { q.reserve(2); q.d[q.n++] = '\n'; } });
         b.putf("\n");
@@ -712,9 +720,9 @@ static int write_vtk(ssb_handle *h, const OutputJob &J) {
 // Binary side-store (SSB_FLAG_BINARY_STORE): outputN.ssb = 8-byte magic, u64 length of an ASCII JSON header, the header padded with
 // blanks to a multiple of 64 bytes, then the raw little-endian arrays in id order:
 //   x f64[np*3]  v f64[np*3]  rho,mass,bvf_phi,nu f64[4*np]  C f64[Sc*np]  type i32[np]  D u32[Sd*np]
-static int write_bin(ssb_handle *h, const OutputJob &J) {
-    const size_t np = (size_t) h->N;
-    const int Sc = h->V.Sc, Sd = h->V.Sd;
+static int write_bin_impl(const SnapMeta &M, const OutputJob &J) {
+    const size_t np = (size_t) M.np;
+    const int Sc = M.Sc, Sd = M.Sd;
     char filename[4096];
     snprintf(filename, sizeof(filename), "%s/output%u.ssb", J.dir.c_str(), J.file_index);
     FILE *fp = fopen(filename, "wb");
@@ -722,7 +730,7 @@ static int write_bin(ssb_handle *h, const OutputJob &J) {
     std::string hdr = "{\"np\": " + std::to_string(np) + ", \"Sc\": " + std::to_string(Sc) + ", \"Sd\": " + std::to_string(Sd) +
                       ", \"step\": " + std::to_string(J.step) + ", \"rdme_initialized\": " + std::to_string(J.rdme_initialized) + ", \"species\": [";
     const int ns = std::max(Sc, Sd);
-    for (int s = 0; s < ns; s++) hdr += std::string(s ? ", " : "") + "\"" + h->species_names[(size_t) s] + "\"";
+    for (int s = 0; s < ns; s++) hdr += std::string(s ? ", " : "") + "\"" + (*M.names)[(size_t) s] + "\"";
     hdr += "]}";
     while ((16 + hdr.size()) % 64) hdr += ' ';
     const unsigned long long hl = hdr.size();
@@ -738,6 +746,12 @@ static int write_bin(ssb_handle *h, const OutputJob &J) {
     ok &= fclose(fp) == 0;
     return ok ? 0 : SSB_ERR_IO;
 }
+
+static SnapMeta meta_of(const ssb_handle *h) {
+    return SnapMeta{h->N, h->V.Sc, h->V.Sd, h->m.xlo, h->m.xhi, h->m.ylo, h->m.yhi, h->m.zlo, h->m.zhi, &h->species_names};
+}
+static int write_vtk(ssb_handle *h, const OutputJob &J) { return write_vtk_impl(meta_of(h), J); }
+static int write_bin(ssb_handle *h, const OutputJob &J) { return write_bin_impl(meta_of(h), J); }
 
 static void writer_main(ssb_handle *h) {
     cudaSetDevice(h->device);
@@ -1602,6 +1616,26 @@ extern "C" int ssb_counters(ssb_handle *h, int64_t *reactions, int64_t *diffusio
     if (seconds) *seconds = h->step_seconds;
     if (windows) *windows = h->windows;
     return SSB_OK;
+}
+
+// Host-assembled snapshots (slab runs gather the owned particles of every rank; batched ensembles cut one state into its copies):
+// the SAME writers as the engine's own output thread, fed from caller memory.  No device work, no handle.
+extern "C" int ssb_write_snapshot(const char *dir, uint32_t file_index, uint32_t step, int32_t rdme_initialized, int64_t np, int32_t Sc,
+                                  int32_t Sd, const char *const *species_names, const double *lims6, const double *x, const double *v,
+                                  const double *scal, const double *C, const int32_t *type, const uint32_t *xx, uint32_t what) {
+    if (!dir || !lims6 || !x || !v || !scal || !type || np < 0 || np > 0x7fffffff || Sc < 0 || Sd < 0) return SSB_ERR_ARG;
+    if ((Sc > 0 && !C) || (Sd > 0 && !xx) || ((Sc > 0 || Sd > 0) && !species_names)) return SSB_ERR_ARG;
+    std::vector<std::string> names;
+    for (int s = 0; s < std::max(Sc, Sd); s++) names.emplace_back(species_names[s] ? species_names[s] : "");
+    SnapMeta M{(int) np, Sc, Sd, lims6[0], lims6[1], lims6[2], lims6[3], lims6[4], lims6[5], &names};
+    OutputJob J;
+    J.step = step; J.file_index = file_index; J.rdme_initialized = rdme_initialized; J.dir = dir;
+    J.x = const_cast<double *>(x); J.v = const_cast<double *>(v); J.scal = const_cast<double *>(scal);
+    J.C = const_cast<double *>(C); J.type = const_cast<int *>(type); J.xx = const_cast<unsigned *>(xx);
+    int rc = 0;
+    if (what & 1u) rc = write_vtk_impl(M, J);
+    if (!rc && (what & 2u)) rc = write_bin_impl(M, J);
+    return rc;
 }
 
 extern "C" int ssb_launch_count(ssb_handle *h, int64_t *launches) {

@@ -34,7 +34,7 @@ EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernel
            "ssb_reset", "ssb_step", "ssb_counters", "ssb_get_field", "ssb_get_neighbors", "ssb_cancel",
            "ssb_last_error", "ssb_launch_count", "ssb_step_timed", "ssb_profile", "ssb_profile_read", "ssb_io_bytes",
            "ssb_nbr_stats", "ssb_step_phase", "ssb_halo_pack", "ssb_halo_unpack", "ssb_halo_inbox_pack", "ssb_halo_inbox_add",
-           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats", "ssb_set_field", "ssb_get_step", "ssb_set_step"]
+           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats", "ssb_set_field", "ssb_get_step", "ssb_set_step", "ssb_write_snapshot"]
 
 PH_PRE, PH_CORRECTOR, PH_FINISH, PH_RDME_PREP, PH_RDME_INIT, PH_RDME_WINDOW, PH_RDME_CLOSE, PH_END, PH_RDME_MIN, PH_RDME_EXTRA = range(10)
 
@@ -116,6 +116,9 @@ def load_library(path=None):
     lib.ssb_set_field.argtypes = [H, C.c_char_p, C.c_void_p, C.c_int64]
     lib.ssb_get_step.argtypes = [H, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     lib.ssb_set_step.argtypes = [H, C.c_uint32, C.c_uint64]
+    lib.ssb_write_snapshot.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                       C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_uint32]
     lib.ssb_mark.argtypes = [H, C.c_int]
     lib.ssb_mark_elapsed_ms.argtypes = [H, C.POINTER(C.c_double)]
     for name in EXPORTS:

@@ -159,18 +159,19 @@ def default_batch(num_particles, number_of_trajectories):
 
 
 def run_ensemble_batched(fm, number_of_trajectories, seed, device=0, out_dirs=None, batch=None, flags=None, rdme_epsilon=0.0,
-                         vtk=True, binary_store=False, engine_factory=None, on_engine=None):
+                         vtk=True, binary_store=False, engine_factory=None, on_engine=None, writer=None):
     """The ensemble as batches of `batch` trajectories per engine handle (`replicate_model`).  Trajectory k is copy k mod batch
     of batch k // batch; batch b is seeded with seed + b * batch, so a run is reproducible for a given (seed, batch) — the
     reference's "trajectory k uses seed + k" mapping (solver.py:558-559) holds for the ENSEMBLE LAW, not trajectory by trajectory.
     With `out_dirs`, every trajectory gets the reference's own file set (output%u.vtk / .ssb, output0_boundingBox.vtk, same
-    file -> step map), written by the host-side twins of the engine's writers from the copies' slices of the state.
+    file -> step map), written by the engine's own writers (`ssb_write_snapshot`) from the copies' slices of the state.
     Returns {k: {"xx_final": [N, S_d] populations}} plus the summed counters under key "counters"."""
-    import os
     import numpy as np
     from .engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
     from .slab import output_schedule
-    from .vtk import write_bounding_box, write_ssb, write_vtk
+    from .vtk import write_snapshot, write_snapshot_py
+    if writer is None:      # the engine's C++ writers; the Python twins when a fake engine stands in (CPU tier)
+        writer = write_snapshot if engine_factory is None else write_snapshot_py
     fm = fm.finalize()
     ntraj = int(number_of_trajectories)
     B = int(batch) if batch else default_batch(fm.num_particles, ntraj)
@@ -204,14 +205,8 @@ def run_ensemble_batched(fm, number_of_trajectories, seed, device=0, out_dirs=No
                 D = eng.get("xx").reshape(nb, N, Sd) if Sd else None
                 init = 1 if (Sd > 0 and step > 0) else 0          # output.cpp:151-154: output0 undercounts FIELD
                 for r in range(nb):
-                    d = out_dirs[b0 + r]
-                    args = (fm.x, v[r], scal[r], C[r].T if Sc else None, fm.type, D[r].T if Sd else None, fm.species_names)
-                    if file_index == 0 and vtk:
-                        write_bounding_box(d, fm.xlim, fm.ylim, fm.zlim)
-                    if vtk:
-                        write_vtk(os.path.join(d, f"output{file_index}.vtk"), *args, rdme_initialized=init)
-                    if binary_store:
-                        write_ssb(os.path.join(d, f"output{file_index}.ssb"), *args, step=step, rdme_initialized=init)
+                    writer(out_dirs[b0 + r], file_index, fm.x, v[r], scal[r], C[r].T if Sc else None, fm.type, D[r].T if Sd else None,
+                           fm.species_names, (fm.xlim, fm.ylim, fm.zlim), step=step, rdme_initialized=init, vtk=vtk, binary=binary_store)
             xx = eng.get("xx").reshape(nb, N, Sd) if Sd else np.zeros((nb, N, 0), np.uint32)
             for r in range(nb):
                 results[b0 + r] = {"xx_final": xx[r].copy()}

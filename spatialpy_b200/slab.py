@@ -515,15 +515,18 @@ def _default_rank_engine(part, rank, world, device, hub, flags, rdme_epsilon):
 
 
 def run_slab_trajectory(fm, devices, seed, out_dir, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, vtk=True, binary_store=False,
-                        halo=None, cancelled=None, rank_engine=_default_rank_engine):
+                        halo=None, cancelled=None, rank_engine=_default_rank_engine, writer=None):
     """One trajectory of a moving-domain model split into len(devices) slabs, driven from ONE process: rank r is a thread
     with its own engine handle on GPU devices[r]; the halo exchanges are device-to-device copies (`LoopbackComm`; peer copies
     over NVLink between distinct GPUs, plain copies when a device is listed twice).  At the reference's output steps
     (`output_schedule`) every rank drops its owned particles into one host snapshot in global-id order and rank 0 writes
-    `output%u.vtk` (+ `output0_boundingBox.vtk`) and/or `output%u.ssb` with the host-side twins of the engine's writers — the
-    same files, names and step map a single-GPU `ssb_run` leaves behind.  Returns the summed engine counters.
+    `output%u.vtk` (+ `output0_boundingBox.vtk`) and/or `output%u.ssb` through the engine's own writers applied to host memory
+    (`ssb_write_snapshot`) — the same files, names and step map a single-GPU `ssb_run` leaves behind.  Returns the summed engine counters.
     `cancelled`: optional callable polled once per step (Solver timeout)."""
-    from .vtk import write_bounding_box, write_ssb, write_vtk
+    from .vtk import write_snapshot, write_snapshot_py
+    # the engine's own C++ writers on the host snapshot; the CPU tier (fake rank engines, maybe no libssb_core.so) uses the Python twins
+    if writer is None:
+        writer = write_snapshot if rank_engine is _default_rank_engine else write_snapshot_py
     fm = fm.finalize()
     world = len(devices)
     if fm.static_domain:
@@ -554,14 +557,9 @@ def run_slab_trajectory(fm, devices, seed, out_dir, flags=FLAG_SKIP_STATIC_FORCE
 
     def write(file_index, step):
         init = 1 if (Sd > 0 and step > 0) else 0          # output0 is staged before the first RDME step (output.cpp:151-154)
-        if file_index == 0 and vtk:
-            write_bounding_box(out_dir, fm.xlim, fm.ylim, fm.zlim)
-        args = (snap["x"], snap["v"], snap["scal"], snap["C"] if Sc else None, snap["type"], snap["D"] if Sd else None,
-                fm.species_names)
-        if vtk:
-            write_vtk(os.path.join(out_dir, f"output{file_index}.vtk"), *args, rdme_initialized=init)
-        if binary_store:
-            write_ssb(os.path.join(out_dir, f"output{file_index}.ssb"), *args, step=step, rdme_initialized=init)
+        writer(out_dir, file_index, snap["x"], snap["v"], snap["scal"], snap["C"] if Sc else None, snap["type"],
+               snap["D"] if Sd else None, fm.species_names, (fm.xlim, fm.ylim, fm.zlim), step=step, rdme_initialized=init,
+               vtk=vtk, binary=binary_store)
 
     def body(rank):
         se = None

@@ -198,6 +198,46 @@ def write_bounding_box(result_dir, xlim, ylim, zlim):
             f.write(f"{axis}_COORDINATES 2 double\n%f %f\n" % (lo, hi))
 
 
+def write_snapshot(result_dir, file_index, x, v, scal, C, type_, D, species, lims, step=0, rdme_initialized=1, vtk=True,
+                   binary=False):
+    """One output of a run from HOST arrays through the engine's own C++ writers (`ssb_write_snapshot`, include/ssb.h): the
+    byte format of E/src/output.cpp:104-229 (and/or the outputN.ssb side-store), multi-threaded for large snapshots — what
+    slab-decomposed runs and batched ensembles call once they have assembled a snapshot.  Arguments as `write_vtk`;
+    lims = (xlim, ylim, zlim); file 0 also gets output0_boundingBox.vtk."""
+    import ctypes as C_
+    from .engine import load_library
+    n = len(type_)
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(n, 3)
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, 3)
+    scal = np.ascontiguousarray(scal, dtype=np.float64).reshape(4, n)
+    Cc = None if C is None else np.ascontiguousarray(C, dtype=np.float64).reshape(-1, n)
+    Dd = None if D is None else np.ascontiguousarray(D, dtype=np.uint32).reshape(-1, n)
+    Sc = 0 if Cc is None else Cc.shape[0]
+    Sd = 0 if Dd is None else Dd.shape[0]
+    typ = np.ascontiguousarray(type_, dtype=np.int32)
+    names = (C_.c_char_p * max(1, len(species)))(*[str(s_).encode() for s_ in species])
+    lim = np.array([lims[0][0], lims[0][1], lims[1][0], lims[1][1], lims[2][0], lims[2][1]], dtype=np.float64)
+    ptr = lambda a: None if a is None or a.size == 0 else a.ctypes.data_as(C_.c_void_p)      # noqa: E731
+    rc = load_library().ssb_write_snapshot(os.fsencode(result_dir), int(file_index), int(step), int(rdme_initialized), n, Sc, Sd,
+                                           C_.cast(names, C_.POINTER(C_.c_char_p)), ptr(lim), ptr(x), ptr(v), ptr(scal),
+                                           ptr(Cc) if Sc else None, ptr(typ), ptr(Dd) if Sd else None,
+                                           (1 if vtk else 0) | (2 if binary else 0))
+    if rc != 0:
+        raise OSError(f"ssb_write_snapshot failed, return code = {rc} (directory {result_dir})")
+
+
+def write_snapshot_py(result_dir, file_index, x, v, scal, C, type_, D, species, lims, step=0, rdme_initialized=1, vtk=True,
+                      binary=False):
+    """`write_snapshot` with the pure-Python twins of the writers (same files, no libssb_core.so needed; slow for large N)."""
+    if file_index == 0 and vtk:
+        write_bounding_box(result_dir, *lims)
+    if vtk:
+        write_vtk(os.path.join(result_dir, f"output{file_index}.vtk"), x, v, scal, C, type_, D, species, rdme_initialized=rdme_initialized)
+    if binary:
+        write_ssb(os.path.join(result_dir, f"output{file_index}.ssb"), x, v, scal, C, type_, D, species, step=step,
+                  rdme_initialized=rdme_initialized)
+
+
 def read_output(result_dir, step_num):
     """outputN.ssb when the run kept a binary side-store, else outputN.vtk."""
     b = os.path.join(result_dir, f"output{step_num}.ssb")

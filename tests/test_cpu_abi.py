@@ -653,3 +653,63 @@ def test_bench_helper_measurements_degrade_to_an_error_field():
     from spatialpy_b200 import configs
     fm = configs.tank_sdpd(n=12, nt=10, output_every=10)
     assert bench.algorithmic_bytes(fm, True) == 698 + 64 * fm.num_chem_species + (68 + 12 * fm.num_stoch_species + 8 * fm.num_stoch_rxns)
+
+
+@pytest.mark.parametrize("name", ["output0.vtk", "output1.vtk", "output10.vtk"])
+def test_engine_writers_on_host_snapshots_reproduce_the_reference_files(tmp_path, name):
+    """ssb_write_snapshot = the engine's own C++ writers fed from caller memory (no device): byte for byte the files the
+    REFERENCE wrote (tests/golden/vtk_diffusion3d), bounding box included; the binary side-store equals the Python twin's."""
+    import gzip
+    from spatialpy_b200.vtk import read_vtk, write_snapshot, write_ssb
+    gold = os.path.join(ROOT, "tests", "golden", "vtk_diffusion3d")
+    text = gzip.open(os.path.join(gold, name + ".gz"), "rt", encoding="ascii").read()
+    raw = tmp_path / "ref.vtk"
+    raw.write_text(text)
+    x = _parse_reference_vtk(text)
+    _, arr = read_vtk(str(raw))
+    species = ["A", "B"]
+    scal = np.stack([arr[k] for k in ("rho", "mass", "bvf_phi", "nu")])
+    C = np.stack([arr[f"C[{s}]"] for s in species])
+    D = np.stack([arr[f"D[{s}]"] for s in species])
+    k = int(name[6:-4])
+    init = int(arr["__nfields_header__"] == 11)
+    bb = gzip.open(os.path.join(gold, "output0_boundingBox.vtk.gz"), "rt").read()
+    lims = [tuple(float(t) for t in bb.split("\n")[q].split()) for q in (6, 8, 10)]
+    out = tmp_path / "run"
+    out.mkdir()
+    write_snapshot(str(out), k, x, arr["v"], scal, C, arr["type"], D, species, lims, step=k, rdme_initialized=init, vtk=True, binary=True)
+    assert (out / name).read_bytes() == text.encode("ascii")
+    if k == 0:
+        assert (out / "output0_boundingBox.vtk").read_text() == bb
+    else:
+        assert not (out / "output0_boundingBox.vtk").exists()
+    twin = tmp_path / "twin.ssb"
+    write_ssb(str(twin), x, arr["v"], scal, C, arr["type"], D, species, step=k, rdme_initialized=init)
+    assert (out / f"output{k}.ssb").read_bytes() == twin.read_bytes()
+    with pytest.raises(OSError):
+        write_snapshot(str(tmp_path / "missing_dir"), 1, x, arr["v"], scal, C, arr["type"], D, species, lims)
+
+
+def test_engine_writers_large_snapshot_threads_and_python_twin_agree(tmp_path, monkeypatch):
+    """>= 200 k particles are formatted by several host threads over line-aligned ranges: the bytes must not depend on the thread
+    count and must equal the independent Python twin (vtk.write_vtk)."""
+    from spatialpy_b200.vtk import write_snapshot, write_vtk
+    rng = np.random.default_rng(5)
+    n = 200_003
+    x, v = rng.normal(size=(n, 3)), rng.normal(size=(n, 3)) * 1e-3
+    scal, C = rng.random((4, n)), -rng.random((1, n))
+    D, typ = rng.integers(0, 100000, (1, n)), rng.integers(1, 4, n)
+    lims = [(-1.0, 1.0), (0.0, 2.0), (0.0, 0.0)]
+    outs = []
+    for threads in ("1", "7", None):
+        d = tmp_path / f"t{threads}"
+        d.mkdir()
+        if threads is None:
+            monkeypatch.delenv("SSB_VTK_THREADS", raising=False)
+        else:
+            monkeypatch.setenv("SSB_VTK_THREADS", threads)
+        write_snapshot(str(d), 3, x, v, scal, C, typ, D, ["S"], lims, step=30)
+        outs.append((d / "output3.vtk").read_bytes())
+    assert outs[0] == outs[1] == outs[2]
+    write_vtk(str(tmp_path / "twin.vtk"), x, v, scal, C, typ, D, ["S"])
+    assert (tmp_path / "twin.vtk").read_bytes() == outs[0]

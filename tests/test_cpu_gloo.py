@@ -165,6 +165,18 @@ def test_batched_ensemble_driver_splits_batches_seeds_and_files(tmp_path):
             assert av["__nfields_header__"] == arr["__nfields_header__"] == 7 + fm.num_chem_species + (fm.num_stoch_species if step else 0)
         np.testing.assert_array_equal(res[k]["xx_final"][:, 0], (pid + 3 * fm.nt + 100 + b0) % 19)
     assert default_batch(121, 1024) == 1024 and default_batch(2500, 1024) == 104 and default_batch(10 ** 6, 8) == 1
+    # the product path writes through the engine's C++ writers (ssb_write_snapshot): same bytes as the Python twins used above
+    import filecmp
+    from spatialpy_b200.vtk import write_snapshot
+    dirs2 = [str(tmp_path / f"cxx{k}") for k in range(10)]
+    for d in dirs2:
+        os.makedirs(d)
+    run_ensemble_batched(fm, 10, 100, out_dirs=dirs2, batch=4, binary_store=True, engine_factory=_FakeBatchEngine, writer=write_snapshot)
+    for a, b in zip(dirs, dirs2):
+        cmp = filecmp.dircmp(a, b)
+        assert not cmp.left_only and not cmp.right_only
+        match, mismatch, errors = filecmp.cmpfiles(a, b, cmp.common_files, shallow=False)
+        assert not mismatch and not errors and len(match) == len(cmp.common_files)
 
 
 def test_solver_batch_keyword_plumbing(monkeypatch):
