@@ -25,6 +25,14 @@ int main(int argc, char **argv) {
            offsetof(ssb_model, output_steps), offsetof(ssb_model, h), offsetof(ssb_model, gravity), offsetof(ssb_model, x),
            offsetof(ssb_model, u0), offsetof(ssb_model, species_names), offsetof(ssb_model, rdme_epsilon), offsetof(ssb_model, device),
            offsetof(ssb_model, owned), offsetof(ssb_model, rng_id));
+    if (argc > 2 && strcmp(argv[1], "snapshot") == 0) {   /* the engine's writers from C: a 3-particle snapshot into argv[2] */
+        const double x[9] = {0.0, 0.0, 0.0, 0.5, 0.25, 0.0, 1.0, 0.5, 0.0}, v[9] = {0}, lims[6] = {0.0, 1.0, 0.0, 0.5, 0.0, 0.0};
+        const double scal[12] = {1.0, 1.0, 1.0, 0.1, 0.1, 0.1, 0.0, 0.0, 0.0, 2.0, 2.0, 2.0}, conc[3] = {0.5, 1.5, 2.5};
+        const int32_t type[3] = {1, 2, 1};
+        const uint32_t pop[3] = {7, 0, 42};
+        const char *names[1] = {"A"};
+        return ssb_write_snapshot(argv[2], 1, 10, 1, 3, 1, 1, names, lims, x, v, scal, conc, type, pop, 3u);
+    }
     if (argc > 1 && strcmp(argv[1], "peak") == 0) {
         double tf = 0.0, ms = 0.0;
         rc = ssb_fp64_peak(0, &tf, &ms);

@@ -487,6 +487,15 @@ def test_header_is_valid_c_and_matches_the_ctypes_binding(tmp_path):
         assert getattr(engine.SsbModel, name).offset == int(off), name
     if not os.path.exists("/dev/nvidia0"):
         assert int(m.group(3)) == 3                      # SSB_ERR_CUDA: no device, reported as a code, not a crash
+    # the engine's file writers driven from C (ssb_write_snapshot): the Python readers see what the C program wrote
+    from spatialpy_b200.vtk import read_ssb, read_vtk
+    out = tmp_path / "snap"
+    out.mkdir()
+    assert subprocess.run([str(exe), "snapshot", str(out)]).returncode == 0
+    pts, arr = read_vtk(str(out / "output1.vtk"))
+    assert pts.shape == (3, 3) and arr["D[A]"].tolist() == [7, 0, 42] and arr["type"].tolist() == [1, 2, 1] and arr["nu"].tolist() == [2.0] * 3
+    _, arb = read_ssb(str(out / "output1.ssb"))
+    assert arb["C[A]"].tolist() == [0.5, 1.5, 2.5] and arb["mass"].tolist() == [0.1] * 3
 
 
 def test_converted_expressions_evaluate_like_python():
