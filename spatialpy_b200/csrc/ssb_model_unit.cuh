@@ -416,10 +416,12 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
 // candidates span more than the bitmap covers falls back to the gather loop.  DESIGN.md section 9 item 1 has the budget.
 // The pair body below is a verbatim copy of k_force_mv's (kept separate so that the validated kernel's code is untouched).
 // ---------------------------------------------------------------------------------------------
+#ifndef SSB_TILE_REC              // (overridable: the host emulation in tests/cuda_emu shrinks them to force the fallback paths)
 #define SSB_TILE_REC 256          // records per staged chunk (32 KB)
 #define SSB_TILE_GRAN 64          // slots per bitmap bit
 #define SSB_TILE_WORDS 512        // 16 384 bits: candidates of one CTA may span up to 2^20 slots
 #define SSB_TILE_MAXCH 96         // chunks per CTA
+#endif
 
 __device__ __forceinline__ ssb_d4 ssb_lds256(const double *p) {
     const double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + 2);

@@ -722,3 +722,117 @@ def test_engine_writers_large_snapshot_threads_and_python_twin_agree(tmp_path, m
     assert outs[0] == outs[1] == outs[2]
     write_vtk(str(tmp_path / "twin.vtk"), x, v, scal, C, typ, D, ["S"])
     assert (tmp_path / "twin.vtk").read_bytes() == outs[0]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the opt-in tile force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu), against the
+# default gather sweep's source executed the same way
+# ----------------------------------------------------------------------------------------------------------------------
+def _build_force_emulator(fm, tmp_path, defines=()):
+    from spatialpy_b200 import codegen
+    src = open(os.path.join(codegen.CSRC, "ssb_model_unit.cuh")).read()
+    a = src.index("__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V")
+    b = src.index("// ---------------------------------------------------------------------------------------------\n// Static-domain fast path")
+    kern = tmp_path / "kernels.inc"
+    kern.write_text(src[a:b])
+    hdr = tmp_path / "model.h"
+    hdr.write_text(codegen.generate_model_header(fm))
+    so = tmp_path / ("force_emu" + "".join(d.replace("=", "_") for d in defines) + ".so")
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(codegen.nvcc_path())), "include")
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", "-I", cuda_inc, "-I", codegen.CSRC,
+           "-I", os.path.join(ROOT, "tests", "cuda_emu"), f"-DSSB_MODEL_HEADER=\"{hdr}\"", f"-DEMU_KERNELS=\"{kern}\""]
+    cmd += [f"-D{d}" for d in defines] + [os.path.join(ROOT, "tests", "cuda_emu", "force_emu.cpp"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return ctypes.CDLL(str(so))
+
+
+class _EmuArgs(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("dim", ctypes.c_int), ("num_types", ctypes.c_int), ("filter", ctypes.c_int),
+                ("flags", ctypes.c_uint), ("dt", ctypes.c_double), ("h", ctypes.c_double), ("rho0", ctypes.c_double),
+                ("P0", ctypes.c_double), ("rec", ctypes.c_void_p), ("nbr", ctypes.c_void_p), ("nbr_count", ctypes.c_void_p),
+                ("nbr_cap", ctypes.c_int), ("owned", ctypes.c_void_p), ("F", ctypes.c_void_p * 3), ("Fbp", ctypes.c_void_p * 3),
+                ("Frho", ctypes.c_void_p), ("C", ctypes.c_void_p), ("Q", ctypes.c_void_p), ("Ddiag", ctypes.c_void_p),
+                ("data_fn", ctypes.c_void_p), ("dmat", ctypes.c_void_p), ("max_bits", ctypes.c_void_p)]
+
+
+def _force_sweep_inputs(fm, seed=2):
+    """A mid-trajectory state in the engine's layout: cell-sorted storage order, ascending candidate lists of radius 1.1 h
+    (ELL, transposed), 128-byte gather records, a few ghost particles."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    n = fm.num_particles
+    rad = fm.h * 1.1
+    x0 = fm.x + rng.uniform(-0.004, 0.004, fm.x.shape)
+    cell = np.floor((x0 - x0.min(axis=0)) / rad).astype(np.int64)
+    nc = cell.max(axis=0) + 1
+    order = np.argsort((cell[:, 2] * nc[1] + cell[:, 1]) * nc[0] + cell[:, 0], kind="stable")
+    x0 = x0[order]
+    typ, solid, mass, nu = fm.type[order], fm.solid[order], fm.mass[order], fm.nu[order]
+    xl = x0 + rng.uniform(-1e-4, 1e-4, x0.shape) * (solid == 0)[:, None]       # live positions after the predictor
+    v = rng.normal(size=(n, 3)) * 0.1 * (solid == 0)[:, None]
+    vt = v + rng.normal(size=(n, 3)) * 0.01
+    rho = 1.0 + 0.02 * rng.random(n)
+    bits = (order.astype(np.int64) & 0xffffffff) | (typ.astype(np.int64) << 32) | (solid.astype(np.int64) << 48)
+    rec = np.zeros((n, 16))
+    rec[:, 0:3], rec[:, 3:6], rec[:, 6:9], rec[:, 9:12] = x0, xl, v, vt
+    rec[:, 12], rec[:, 13], rec[:, 14] = rho, mass, nu
+    rec[:, 15] = bits.view(np.float64)
+    lists = [sorted(l) for l in cKDTree(x0).query_ball_point(x0, rad)]
+    cnt = np.array([len(l) for l in lists], np.int32)
+    cap = int(cnt.max())
+    nbr = np.zeros((cap, n), np.int32)
+    for i, l in enumerate(lists):
+        nbr[:len(l), i] = l
+    owned = np.ones(n, np.int32)
+    owned[rng.choice(n, 9, replace=False)] = 0
+    Sc, Sd = fm.num_chem_species, fm.num_stoch_species
+    st = dict(rec=rec, nbr=nbr, cnt=cnt, cap=cap, owned=owned, F=rng.normal(size=(3, n)), Fbp=rng.normal(size=(3, n)),
+              Frho=rng.normal(size=n), C=rng.random((max(Sc, 1), n)), Q=rng.normal(size=(max(Sc, 1), n)),
+              dmat=np.ascontiguousarray(fm.diffusion_matrix, dtype=np.float64), Sd=Sd, n=n)
+    return st
+
+
+def _run_force_emulator(lib, fm, st, tile):
+    n = st["n"]
+    out = {k: np.ascontiguousarray(st[k]).copy() for k in ("F", "Fbp", "Frho", "Q")}
+    out["Ddiag"] = np.full((max(st["Sd"], 1), n), -1.0)
+    mb = np.zeros(1, np.uint64)
+    keep = [np.ascontiguousarray(st[k]) for k in ("rec", "nbr", "cnt", "owned", "C", "dmat")]
+    a = _EmuArgs()
+    a.N, a.dim, a.num_types, a.filter, a.flags = n, fm.dimension, fm.num_types, 1, 8
+    a.dt, a.h, a.rho0, a.P0 = fm.dt, fm.h, fm.rho0, fm.P0
+    a.rec, a.nbr, a.nbr_count, a.nbr_cap, a.owned = keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, st["cap"], keep[3].ctypes.data
+    for d in range(3):
+        a.F[d] = out["F"][d].ctypes.data
+        a.Fbp[d] = out["Fbp"][d].ctypes.data
+    a.Frho, a.C, a.Q, a.Ddiag = out["Frho"].ctypes.data, keep[4].ctypes.data, out["Q"].ctypes.data, out["Ddiag"].ctypes.data
+    a.data_fn, a.dmat, a.max_bits = None, keep[5].ctypes.data, mb.ctypes.data
+    assert lib.emu_force(ctypes.byref(a), int(tile), 3) == 0
+    out["max_bits"] = mb
+    return out
+
+
+def test_tile_force_sweep_source_equals_the_gather_sweep_on_the_host(tmp_path):
+    """k_force_mv_tile vs k_force_mv, both as CUDA SOURCE run by the block emulator (one host thread per CUDA thread, real
+    barriers, shared arrays, atomics): every output of the sweep is bit-identical — with the tile path taken, and with the
+    tile constants shrunk so that the bitmap-too-small and too-many-chunks fallbacks are taken."""
+    from spatialpy_b200 import configs
+    fm = configs.tank_sdpd(n=14, nt=10, output_every=10)     # ~2 000 particles: 16 CTAs whose candidates sit in several separate runs
+    st = _force_sweep_inputs(fm)
+    chunks = [_tile_chunks([sorted(st["nbr"][:st["cnt"][i], i].tolist()) for i in range(b0, min(b0 + 128, st["n"]))], st["n"])
+              for b0 in range(0, st["n"], 128)]
+    assert all(c is not None for c in chunks) and max(len(c) for c in chunks) >= 3          # the tile path, with gaps between chunks
+    lib = _build_force_emulator(fm, tmp_path)
+    ref = _run_force_emulator(lib, fm, st, tile=0)
+    assert np.abs(ref["F"] - st["F"]).max() > 0 and (ref["Ddiag"][:, st["owned"] == 1] >= 0).all()   # the sweep did something
+    got = _run_force_emulator(lib, fm, st, tile=1)
+    for k in ref:
+        assert np.array_equal(ref[k], got[k]), k
+    for defines in (("SSB_TILE_REC=16", "SSB_TILE_GRAN=4", "SSB_TILE_WORDS=1", "SSB_TILE_MAXCH=96"),        # span > bitmap
+                    ("SSB_TILE_REC=64", "SSB_TILE_GRAN=64", "SSB_TILE_WORDS=512", "SSB_TILE_MAXCH=2"),     # chunk table overflow
+                    ("SSB_TILE_REC=128", "SSB_TILE_GRAN=32", "SSB_TILE_WORDS=512", "SSB_TILE_MAXCH=96")):  # other geometry
+        lib2 = _build_force_emulator(fm, tmp_path, defines)
+        got2 = _run_force_emulator(lib2, fm, st, tile=1)
+        for k in ref:
+            assert np.array_equal(ref[k], got2[k]), (defines, k)
