@@ -836,3 +836,16 @@ def test_tile_force_sweep_source_equals_the_gather_sweep_on_the_host(tmp_path):
         got2 = _run_force_emulator(lib2, fm, st, tile=1)
         for k in ref:
             assert np.array_equal(ref[k], got2[k]), (defines, k)
+
+
+def test_tile_force_sweep_source_on_a_2d_model(tmp_path):
+    """Same comparison on a 2-D moving model (cavity2d_rdme fixture: other species / reaction counts => another instantiation
+    of the generated code)."""
+    fm = load_model("cavity2d_rdme")
+    st = _force_sweep_inputs(fm, seed=7)
+    lib = _build_force_emulator(fm, tmp_path)
+    ref = _run_force_emulator(lib, fm, st, tile=0)
+    got = _run_force_emulator(lib, fm, st, tile=1)
+    assert np.abs(ref["F"] - st["F"]).max() > 0
+    for k in ref:
+        assert np.array_equal(ref[k], got[k]), k
