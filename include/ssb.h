@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SSB_ABI_VERSION 3
+#define SSB_ABI_VERSION 4
 
 /* error codes */
 #define SSB_OK 0
@@ -32,6 +32,7 @@ extern "C" {
 #define SSB_ERR_IO 5
 #define SSB_ERR_CANCELLED 6    /* ssb_cancel() — reference: SIGINT to the process group on timeout, solver.py:579-586 */
 #define SSB_ERR_MODEL_UNIT 7   /* model unit missing / compiled for different sizes */
+#define SSB_ERR_HALO 8         /* slab decomposition: a neighbouring rank's halo message did not arrive within the device-side timeout */
 
 /* flags (ssb_model.flags) */
 #define SSB_FLAG_CORRECTED_NSM_SELECT 1u   /* draw the reaction/diffusion channel with the textbook NSM rule instead of the reference's
@@ -46,9 +47,6 @@ extern "C" {
 #define SSB_FLAG_SKIP_STATIC_FORCES 8u     /* static domains: skip F/Fbp/Frho (never consumed when static, simulate.cpp:68,137); default on via Python */
 #define SSB_FLAG_NO_STEP_OVERSHOOT 128u    /* moving domains: do not execute the reference's one event past each step's end
                                              (`while(tt <= end_time)` tests the previous event's time, simulate_rdme.cpp:233-238) */
-#define SSB_FLAG_TILE_SWEEP 256u           /* moving domains, opt-in: force sweep that stages the neighbour records of each 128-particle CTA in shared
-                                             memory (k_force_mv_tile, ssb_model_unit.cuh) instead of one 128-byte gather per pair; same lists, same
-                                             pair arithmetic in the same order => bit-identical forces.  Awaits its first GPU measurement. */
 #define SSB_FLAG_BINARY_STORE 64u         /* also write outputN.ssb next to (or, with SSB_FLAG_NO_VTK, instead of) outputN.vtk: the same snapshot as raw
                                              little-endian arrays at full fp64 precision (layout in spatialpy_b200/vtk.py, read by Result.read_step;
                                              SURVEY.md 8f item 1 - the reference's pure-Python ASCII parser, vtkreader.py:29-56, bounds large N*T) */
@@ -177,7 +175,8 @@ int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total);
  * 1 CORRECTOR, 2 FINISH, 3 RDME_PREP -> *out = local max Ddiag, 4 RDME_INIT (arg = global max) -> *out = windows per step,
  * 5 RDME_WINDOW (arg = window index), 6 RDME_CLOSE, 7 END, 8 RDME_MIN -> *out = earliest pending event of this rank, 9 RDME_EXTRA
  * (arg = global earliest pending event: the reference's one event past the end of the step, simulate_rdme.cpp:233-238; runs the
- * event window only — follow it with the inbox exchange and RDME_CLOSE, which delivers the molecule if it jumped across a face)).  ssb_halo_pack / ssb_halo_unpack move the field group that a
+ * event window only — follow it with the inbox exchange and RDME_CLOSE with arg < 0, which delivers the molecule if it jumped across
+ * a face under the Philox epoch the overshoot reserved for it)).  ssb_halo_pack / ssb_halo_unpack move the field group that a
  * phase produced between storage and a caller-owned DEVICE buffer for the particle ids listed in dev_ids (group 0: F[3]
  * Fbp[3] Frho Q[S_c]; 1: rho_new; 2: v[3] bvf_phi; 3: rho); ssb_halo_inbox_pack reads-and-clears the molecules that jumped
  * into ghost voxels in the last sSSA window, ssb_halo_inbox_add delivers them to the owner.  ssb_mark/ssb_mark_elapsed_ms
@@ -188,6 +187,27 @@ int ssb_halo_unpack(ssb_handle *h, int group, const int32_t *dev_ids, int32_t n,
 int ssb_halo_inbox_pack(ssb_handle *h, const int32_t *dev_ids, int32_t n, uint32_t *dev_out);
 int ssb_halo_inbox_add(ssb_handle *h, const int32_t *dev_ids, int32_t n, const uint32_t *dev_in);
 int ssb_halo_width(ssb_handle *h, int group, int32_t *width);
+/* Native slab transport — the product path of spatial decomposition (one process, or one thread, per GPU; all GPUs of a B200 box are
+ * NVLink peers).  The reference has no decomposition (one shared-memory process, E/src/simulate_threads.cpp:171-312); the phase
+ * boundaries respected here are its substeps (:232-281).  ssb_slab_setup allocates this rank's RECEIVE WINDOWS (one per slab face;
+ * host arrays of local particle ids: send_* = my owned particles that are ghosts on that neighbour, recv_* = my ghosts owned by it,
+ * both in the order the neighbour lists them, i.e. by global id) and its scalar board.  ssb_slab_export fills a blob of
+ * ssb_slab_blob_bytes() bytes (CUDA IPC handles + raw pointers + process id); the caller gathers the blobs of all ranks in rank
+ * order (torch.distributed, MPI, a thread hub — control plane only) and hands them to ssb_slab_connect, which maps the neighbours'
+ * windows and every board (cudaIpcOpenMemHandle, or the pointer itself when the rank lives in this process).  ssb_slab_step then runs
+ * engine steps whose halo traffic never touches the host: pack kernels store straight into the neighbour's window over NVLink and
+ * raise a sequence flag, a one-warp kernel waits for the incoming flag, unpack reads the local window; the three scalar reductions
+ * of a step (max Ddiag -> windows per step, earliest pending event -> the step-end overshoot event, step displacement -> travel
+ * bound) go through the boards the same way.  It stops early, on all ranks after the same step, once particles may have travelled
+ * `travel_limit` (> 0) since ssb_slab_setup / ssb_reset; *done = steps executed, *travel = the bound so far.
+ * ssb_slab_disconnect unmaps the neighbours' memory: every rank calls it, all ranks meet, then handles may be destroyed. */
+int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const int32_t *send_lo, int32_t n_send_lo, const int32_t *recv_lo, int32_t n_recv_lo,
+                   const int32_t *send_hi, int32_t n_send_hi, const int32_t *recv_hi, int32_t n_recv_hi);
+int ssb_slab_blob_bytes(void);
+int ssb_slab_export(ssb_handle *h, void *blob, int64_t bytes);
+int ssb_slab_connect(ssb_handle *h, const void *blobs, int64_t bytes);
+int ssb_slab_disconnect(ssb_handle *h);
+int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit, uint32_t *done, double *travel);
 /* Verlet-skin bookkeeping of moving domains: chosen skin (fraction of h), largest single-step displacement seen, list rebuilds */
 int ssb_skin_stats(ssb_handle *h, double *skin, double *step_disp_max, int64_t *rebuilds);
 int ssb_mark(ssb_handle *h, int which);

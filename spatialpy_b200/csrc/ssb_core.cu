@@ -14,6 +14,7 @@
 // fails with SSB_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -169,8 +170,12 @@ __global__ void k_sort_cells(int ncells, const int *cell_start, int N, int *perm
     if (moved) *nonidentity = 1;
 }
 
-#define PERM_MAX64 96
-#define PERM_MAX32 40
+// Permutation into cell-sorted storage order.  The fixed per-particle fields travel in one kernel whose pointer table is a kernel
+// ARGUMENT (no device-side table, no host synchronisation for its lifetime); the species-indexed blocks (C, Q, data_fn, xx — any
+// number of rows: the reference has no species limit, test/integration_tests/test_model.py:61-79 runs 51) are permuted row by row
+// by a 2-D launch and swapped with their alternates.
+#define PERM_MAX64 32
+#define PERM_MAX32 8
 struct PermTable {
     int n64, n32;
     const double *src64[PERM_MAX64];
@@ -178,12 +183,59 @@ struct PermTable {
     const int *src32[PERM_MAX32];
     int *dst32[PERM_MAX32];
 };
-__global__ void k_permute(int N, const int *perm, const PermTable *T) {
+__global__ void k_permute(int N, const int *perm, const PermTable T) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
-    int src = perm[p];
-    for (int f = 0; f < T->n64; f++) T->dst64[f][p] = T->src64[f][src];
-    for (int f = 0; f < T->n32; f++) T->dst32[f][p] = T->src32[f][src];
+    const int src = perm[p];
+#pragma unroll
+    for (int f = 0; f < PERM_MAX64; f++) if (f < T.n64) T.dst64[f][p] = T.src64[f][src];
+#pragma unroll
+    for (int f = 0; f < PERM_MAX32; f++) if (f < T.n32) T.dst32[f][p] = T.src32[f][src];
+}
+// rows of a species-major block: dst[r*N + p] = src[r*N + perm[p]], blockIdx.y = row
+__global__ void k_permute_rows64(int N, const int *perm, const double *src, double *dst) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) dst[(size_t) blockIdx.y * N + p] = src[(size_t) blockIdx.y * N + perm[p]];
+}
+__global__ void k_permute_rows32(int N, const int *perm, const int *src, int *dst) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) dst[(size_t) blockIdx.y * N + p] = src[(size_t) blockIdx.y * N + perm[p]];
+}
+
+// Look-ahead displacement (moving domains with a Verlet skin).  After a step is complete, everything the NEXT predictor will do to
+// the positions is known: x' = x + dt*((v + dt/2 F) + dt/2 Fbp) for non-solid particles (take_step1, simulate.cpp:68-79; v is only
+// reassigned by the boundary conditions AFTER the position update).  out[0] = max |x' - xref|^2, out[1] = max |x' - x|^2,
+// out[2] = max |x - xref|^2 (bit patterns of non-negative doubles, atomicMax).  The host reads them while the sSSA of the same step
+// is still queued, and decides whether the next step keeps its candidate lists — no blocking read-back after the predictor and no
+// "skin exceeded" failure mode: a step whose displacement would not fit simply rebuilds.
+__global__ void k_lookahead(SsbView V, unsigned long long *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double a = 0.0, b = 0.0, c = 0.0;
+    if (i < V.N) {
+        const bool moves = V.solid[i] == 0;
+        const double dt = V.dt;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double x = V.x[d][i], xr = V.xref[d][i];
+            double xn = x;
+            if (moves) {
+                const double v = V.v[d][i] + 0.5 * dt * V.F[d][i];
+                const double vt = v + 0.5 * dt * V.Fbp[d][i];
+                xn = x + dt * vt;
+            }
+            a += (xn - xr) * (xn - xr); b += (xn - x) * (xn - x); c += (x - xr) * (x - xr);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+        c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a > 0.0) atomicMax(&out[0], (unsigned long long) __double_as_longlong(a));
+        if (b > 0.0) atomicMax(&out[1], (unsigned long long) __double_as_longlong(b));
+        if (c > 0.0) atomicMax(&out[2], (unsigned long long) __double_as_longlong(c));
+    }
 }
 
 // neighbour search: query = live x_i, data = snapshot x0 (cell-sorted).  One thread per particle; the three
@@ -191,7 +243,10 @@ __global__ void k_permute(int N, const int *perm, const PermTable *T) {
 __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_count, unsigned long long *total_count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
-    if (i < V.N) {
+    if (i < V.N && !V.owned[i]) {                       // ghost copies of a neighbouring slab's particles: no sweep reads their lists
+        V.nbr_count[i] = 0;
+        if (V.solid_nbr) V.solid_nbr[i] = 0;
+    } else if (i < V.N) {
         int any_solid = 0;
         const int N = V.N, dim = V.dim, cap = V.nbr_cap;
         const double h = V.h;
@@ -365,6 +420,169 @@ __global__ void k_inbox_add(SsbView V, int buf, const int *ids, int n, const int
     if (any) V.blk_mail[buf][p / block] = 1;
 }
 
+// ---- slab decomposition, native transport: pack kernels that WRITE INTO THE NEIGHBOUR'S RECEIVE WINDOW over NVLink (peer-mapped
+// memory), a sequence flag per channel raised by the last CTA of the pack kernel, a one-warp wait kernel, unpack from the local
+// window.  Everything is ordered by the engine stream; the host never waits for a message.  Messages are column-major
+// (buf[f*n + t]) so that a warp stores / loads whole 256-byte runs.
+#define HALO_NCH 4                   // channels 0..2 = field groups 0..2, 3 = sSSA inbox (compacted entries)
+#define HALO_CH_INBOX 3
+#define HALO_HDR_BYTES 1024          // window header: flag[ch] at 64*ch, inbox entry count of parity q at 512 + 64*q
+#define HALO_TIMEOUT_NS 20000000000ull
+#define SSB_BOARD_NCH 3              // scalar all-reduce boards: 0 max Ddiag (max), 1 earliest pending event (min), 2 step displacement (max)
+#define SSB_BOARD_MAXW 16
+struct HaloPackSide { const int *ids; int n; char *peer_buf; unsigned long long *peer_flag; unsigned long long *peer_count; };
+struct HaloPackArgs { HaloPackSide side[2]; unsigned long long seq; unsigned *done; unsigned *icount; };
+struct HaloUnpackSide { const int *ids; int n; const char *buf; const unsigned long long *count; };
+struct HaloUnpackArgs { HaloUnpackSide side[2]; };
+
+__device__ __forceinline__ unsigned long long ssb_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned long long ssb_ld_flag(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+// last CTA of a pack kernel: everything every CTA wrote to the peer is fenced, raise the flags (and the inbox entry counts)
+__device__ __forceinline__ void halo_publish(const HaloPackArgs &A, bool with_counts) {
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(A.done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && threadIdx.x < 2) {
+        const HaloPackSide &S = A.side[threadIdx.x];
+        if (S.peer_flag) {
+            if (with_counts) { *(volatile unsigned long long *) S.peer_count = (unsigned long long) atomicExch(&A.icount[threadIdx.x], 0u); }
+            __threadfence_system();
+            *(volatile unsigned long long *) S.peer_flag = A.seq;
+        }
+        if (threadIdx.x == 0) *A.done = 0u;
+    }
+}
+__global__ void k_halo_send(SsbView V, int group, HaloPackArgs A, const int *slot_of_id) {
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sd = (t0 < A.side[0].n) ? 0 : 1;
+    const int t = sd ? t0 - A.side[0].n : t0;
+    const HaloPackSide &S = A.side[sd];
+    if (t < S.n) {
+        const int p = slot_of_id[S.ids[t]];
+        double *o = (double *) S.peer_buf;
+        const size_t n = (size_t) S.n;
+        if (group == 0) {
+            for (int d = 0; d < 3; d++) { o[d * n + t] = V.F[d][p]; o[(3 + d) * n + t] = V.Fbp[d][p]; }
+            o[6 * n + t] = V.Frho[p];
+            for (int sp = 0; sp < V.Sc; sp++) o[(7 + sp) * n + t] = V.Q[(size_t) sp * V.N + p];
+        } else if (group == 1) {
+            o[t] = V.rho_new[p];
+        } else {
+            for (int d = 0; d < 3; d++) o[d * n + t] = V.v[d][p];
+            o[3 * n + t] = V.bvf[p];
+        }
+    }
+    halo_publish(A, false);
+}
+__global__ void k_halo_recv(SsbView V, int group, HaloUnpackArgs A, const int *slot_of_id) {
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sd = (t0 < A.side[0].n) ? 0 : 1;
+    const int t = sd ? t0 - A.side[0].n : t0;
+    const HaloUnpackSide &S = A.side[sd];
+    if (t >= S.n) return;
+    const int p = slot_of_id[S.ids[t]];
+    const double *o = (const double *) S.buf;
+    const size_t n = (size_t) S.n;
+    if (group == 0) {
+        for (int d = 0; d < 3; d++) { V.F[d][p] = o[d * n + t]; V.Fbp[d][p] = o[(3 + d) * n + t]; }
+        V.Frho[p] = o[6 * n + t];
+        for (int sp = 0; sp < V.Sc; sp++) V.Q[(size_t) sp * V.N + p] = o[(7 + sp) * n + t];
+    } else if (group == 1) {
+        V.rho_new[p] = o[t];
+    } else {
+        for (int d = 0; d < 3; d++) V.v[d][p] = o[d * n + t];
+        V.bvf[p] = o[3 * n + t];
+    }
+}
+// one warp: lane s < 2 waits for the flag of side s.  A peer that never arrives raises SSB_ERR_HALO instead of hanging the GPU.
+__global__ void k_halo_wait(const unsigned long long *flag0, const unsigned long long *flag1, unsigned long long seq, int *err_flag) {
+    const unsigned long long *f = threadIdx.x == 0 ? flag0 : (threadIdx.x == 1 ? flag1 : nullptr);
+    if (f) {
+        const unsigned long long t0 = ssb_globaltimer();
+        while (ssb_ld_flag(f) < seq) {
+            __nanosleep(100);
+            if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) { atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/); break; }
+        }
+    }
+    __threadfence_system();
+}
+// molecules that jumped into ghost voxels in the last sSSA window travel as (row in the exchange list, species, count) entries: the
+// pack kernel reads-and-clears the ghosts' inboxes and appends only what is non-zero — a handful of entries instead of a dense
+// [ghosts x S_d] array per window
+__global__ void k_inbox_send(SsbView V, int buf, HaloPackArgs A, const int *slot_of_id) {
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sd = (t0 < A.side[0].n) ? 0 : 1;
+    const int t = sd ? t0 - A.side[0].n : t0;
+    const HaloPackSide &S = A.side[sd];
+    if (t < S.n) {
+        const int p = slot_of_id[S.ids[t]];
+        for (int sp = 0; sp < V.Sd; sp++) {
+            unsigned *q = &V.inbox[buf][(size_t) sp * V.N + p];
+            const unsigned c = *q;
+            if (c) {
+                *q = 0u;
+                const unsigned e = atomicAdd(&A.icount[sd], 1u);
+                ((uint4 *) S.peer_buf)[e] = make_uint4((unsigned) t, (unsigned) sp, c, 0u);
+            }
+        }
+        V.inbox_src[buf][p] = 0;
+    }
+    halo_publish(A, true);
+}
+__global__ void k_inbox_recv(SsbView V, int buf, HaloUnpackArgs A, const int *slot_of_id, int block) {
+    for (int sd = 0; sd < 2; sd++) {
+        const HaloUnpackSide &S = A.side[sd];
+        if (!S.count) continue;
+        const unsigned n = (unsigned) ssb_ld_flag(S.count);
+        for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+            const uint4 m = ((const uint4 *) S.buf)[e];
+            const int p = slot_of_id[S.ids[m.x]];
+            atomicAdd(&V.inbox[buf][(size_t) m.y * V.N + p], m.z);
+            V.blk_mail[buf][p / block] = 1;
+        }
+    }
+}
+// scalar all-reduce over peer-mapped boards: every rank writes its value into slot `me` of EVERY rank's board, then each rank
+// reduces its own board once all slots carry the sequence number.  Values are bit patterns of non-negative doubles (they order
+// like unsigned integers).  Board entry of (channel, parity, rank) = {value, flag}.
+__device__ __forceinline__ size_t board_slot(int ch, int parity, int r) { return ((size_t) (ch * 2 + parity) * SSB_BOARD_MAXW + r) * 2; }
+struct BoardPeers { unsigned long long *b[SSB_BOARD_MAXW]; };
+__global__ void k_board_post(BoardPeers P, int world, int me, int ch, unsigned long long seq, const unsigned long long *src) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const unsigned long long v = *src;
+    unsigned long long *slot = P.b[r] + board_slot(ch, (int) (seq & 1ull), me);
+    *(volatile unsigned long long *) slot = v;
+    __threadfence_system();
+    *(volatile unsigned long long *) (slot + 1) = seq;
+}
+__global__ void k_board_reduce(const unsigned long long *board, int world, int ch, unsigned long long seq, int take_min,
+                               unsigned long long *out_dev, int *err_flag) {
+    const int r = threadIdx.x;
+    unsigned long long v = take_min ? ~0ull : 0ull;
+    if (r < world) {
+        const unsigned long long *slot = board + board_slot(ch, (int) (seq & 1ull), r);
+        const unsigned long long t0 = ssb_globaltimer();
+        while (ssb_ld_flag(slot + 1) < seq) {
+            __nanosleep(100);
+            if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) { atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/); break; }
+        }
+        __threadfence_system();
+        v = ssb_ld_flag(slot);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = take_min ? (w < v ? w : v) : (w > v ? w : v);
+    }
+    if (r == 0) *out_dev = v;
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -386,6 +604,7 @@ struct OutputJob {
     unsigned *xx = nullptr;  // Sd*N (species-major)
 };
 
+struct SlabComm;
 struct ssb_handle {
     ssb_model m;       // scalars (pointers inside are NOT retained)
     int N = 0, S = 0, R = 0;
@@ -404,7 +623,14 @@ struct ssb_handle {
     std::vector<double *> f64_alt;
     std::vector<int **> i32_slots;
     std::vector<int *> i32_alt;
-    PermTable *d_permtable = nullptr;
+    double *C_alt = nullptr, *Q_alt = nullptr, *df_alt = nullptr;   // alternates of the species-major blocks (swapped by a permutation)
+    unsigned *xx_alt = nullptr;
+    // pinned scalars the device reports through (async copies + events instead of blocking read-backs):
+    //   [0..2] look-ahead displacement (k_lookahead)  [3] max Ddiag of this step's force sweep  [4..7] slab scalar reductions
+    unsigned long long *pin = nullptr;
+    unsigned long long *d_look = nullptr;     // device side of pin[0..2]
+    cudaEvent_t ev_look = nullptr, ev_maxd = nullptr;
+    int look_valid = 0;           // pin[0..2] describe the step that is about to run
     // cell list
     CellGrid grid;
     int *d_key = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr, *d_perm = nullptr;
@@ -437,6 +663,7 @@ struct ssb_handle {
     // slab decomposition support
     int *d_slot_of_id = nullptr;  // particle id -> storage slot (rebuilt lazily after a permutation)
     int slot_dirty = 1;
+    struct SlabComm *slab = nullptr;   // native transport (ssb_slab_*): receive windows, peer mappings, boards
     cudaEvent_t mark_a = nullptr, mark_b = nullptr, sync_ev = nullptr;
     int static_cached = 0;        // static domain: storage order, neighbour lists, coefficients and Ddiag survive ssb_reset
     int *d_static_perm = nullptr; // slot -> particle id of the cached storage order
@@ -889,15 +1116,14 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     for (int d = 0; d < 3; d++) { register_f64(h, &V.x[d]); register_f64(h, &V.v[d]); register_f64(h, &V.vt[d]); register_f64(h, &V.F[d]); register_f64(h, &V.Fbp[d]); }
     register_f64(h, &V.rho); register_f64(h, &V.old_rho); register_f64(h, &V.Frho); register_f64(h, &V.bvf);
     register_f64(h, &V.mass); register_f64(h, &V.nu);
-    if (h->f64_slots.size() + 2 > PERM_MAX64) return fail(h, SSB_ERR_ARG, "too many fields");
+    if (h->f64_slots.size() > PERM_MAX64) return fail(h, SSB_ERR_ARG, "too many fields");
     for (auto slot : h->f64_slots) { CK(dalloc(h, slot, (size_t) N)); double *alt; CK(dalloc(h, &alt, (size_t) N)); h->f64_alt.push_back(alt); }
     // species-major blocks are permuted row by row; allocate as blocks and register rows through shadow pointers
     CK(dalloc(h, &V.C, (size_t) Sc * N)); CK(dalloc(h, &V.Q, (size_t) Sc * N));
     CK(dalloc(h, &V.xx, (size_t) Sd * N)); CK(dalloc(h, &V.data_fn, (size_t) ndf * N));
     register_i32(h, &V.type); register_i32(h, &V.solid); register_i32(h, &V.id); register_i32(h, &V.owned); register_i32(h, &V.gid);
     for (auto slot : h->i32_slots) { CK(dalloc(h, slot, (size_t) N)); int *alt; CK(dalloc(h, &alt, (size_t) N)); h->i32_alt.push_back(alt); }
-    if ((size_t) (2 * Sc + ndf) + h->f64_slots.size() > PERM_MAX64 || (size_t) Sd + h->i32_slots.size() > PERM_MAX32)
-        return fail(h, SSB_ERR_ARG, "too many species for the permutation table");
+    if (h->i32_slots.size() > PERM_MAX32) return fail(h, SSB_ERR_ARG, "too many fields");
     // non-permuted scratch
     if (V.static_domain) { for (int d = 0; d < 3; d++) V.x0[d] = nullptr; }   // aliased to x after allocation (below)
     else { for (int d = 0; d < 3; d++) CK(dalloc(h, &V.x0[d], (size_t) N)); }
@@ -921,11 +1147,15 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     // alternates for the species blocks
     {
         double *alt;
-        CK(dalloc(h, &alt, (size_t) (2 * Sc + ndf) * N)); h->f64_alt.push_back(alt);   // one block: [C | Q | data_fn]
-        int *ialt;
-        CK(dalloc(h, &ialt, (size_t) Sd * N)); h->i32_alt.push_back(ialt);
+        CK(dalloc(h, &alt, (size_t) (2 * Sc + ndf) * N));   // one block: [C | Q | data_fn]
+        h->C_alt = alt; h->Q_alt = alt + (size_t) Sc * N; h->df_alt = alt + (size_t) 2 * Sc * N;
+        CK(dalloc(h, &h->xx_alt, (size_t) Sd * N));
     }
-    CK(dalloc(h, &h->d_permtable, 1));
+    CK(cudaHostAlloc((void **) &h->pin, sizeof(unsigned long long) * 16, cudaHostAllocDefault));
+    memset(h->pin, 0, sizeof(unsigned long long) * 16);
+    CK(dalloc(h, &h->d_look, 4));
+    CK(cudaEventCreateWithFlags(&h->ev_look, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_maxd, cudaEventDisableTiming));
     // Verlet skin: moving domains keep candidate lists across steps unless the literal kernels are requested
     h->skin = (!V.static_domain && !(m->flags & SSB_FLAG_LITERAL_KERNELS)) ? 0.1 : 0.0;
     if (const char *e = getenv("SSB_SKIN")) { if (!V.static_domain && !(m->flags & SSB_FLAG_LITERAL_KERNELS)) { h->skin = atof(e); h->skin_chosen = 1; } }
@@ -995,6 +1225,9 @@ extern "C" int ssb_load_kernels(ssb_handle *h, const char *path) {
     return SSB_OK;
 }
 
+static void slab_free(ssb_handle *h);
+static void slab_reset(ssb_handle *h);
+
 static int drain_writer(ssb_handle *h) {
     std::unique_lock<std::mutex> lk(h->mu);
     h->cv.wait(lk, [&] { return !h->writer_pending[0] && !h->writer_pending[1]; });
@@ -1012,6 +1245,7 @@ extern "C" int ssb_destroy(ssb_handle *h) {
     }
     cudaSetDevice(h->device);
     if (h->stream) ssb_sync(h);
+    slab_free(h);
     for (void *p : h->allocs) cudaFree(p);
     for (int b = 0; b < 2; b++) {
         OutputJob &J = h->jobs[b];
@@ -1020,6 +1254,9 @@ extern "C" int ssb_destroy(ssb_handle *h) {
     }
     if (h->mark_a) { cudaEventDestroy(h->mark_a); cudaEventDestroy(h->mark_b); }
     if (h->sync_ev) cudaEventDestroy(h->sync_ev);
+    if (h->ev_look) cudaEventDestroy(h->ev_look);
+    if (h->ev_maxd) cudaEventDestroy(h->ev_maxd);
+    if (h->pin) cudaFreeHost(h->pin);
     for (auto e : h->ev_a) cudaEventDestroy(e);
     for (auto e : h->ev_b) cudaEventDestroy(e);
     if (h->init_f64) cudaFreeHost(h->init_f64);
@@ -1100,6 +1337,7 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     h->inbox_buf = 0;
     h->nbr_valid = 0;
     h->lists_valid = 0;
+    h->look_valid = 0;
     h->disp_prev = 0.0;
     h->step_disp_max = 0.0;
     h->ddiag_fresh = 0;
@@ -1111,6 +1349,7 @@ extern "C" int ssb_reset(ssb_handle *h, uint64_t seed) {
     h->total_reactions = h->total_diffusion = 0;
     h->step_seconds = 0.0;
     h->cancel.store(0);
+    slab_reset(h);
     return SSB_OK;
 }
 
@@ -1132,45 +1371,35 @@ static int build_cells(ssb_handle *h) {
     k_scatter<<<gridN(N), CORE_BLOCK, 0, st>>>(N, h->d_key, h->d_cell_start, h->d_cursor, h->d_perm);
     k_sort_cells<<<gridN(nc), CORE_BLOCK, 0, st>>>(nc, h->d_cell_start, N, h->d_perm, h->d_flags);
     h->launches += 6;
-    int nonid = 0;
-    CK(cudaMemcpyAsync(&nonid, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(ssb_sync(h));
-    if (!nonid) return SSB_OK;
+    // always permute (an identity permutation costs one pass over the state at a list build; testing for it would cost a
+    // host round trip on every build)
     return apply_permutation(h, h->d_perm);
 }
 
-// dst[p] = src[perm[p]] for every per-particle field (alternate buffers, then swap)
+// dst[p] = src[perm[p]] for every per-particle field (alternate buffers, then swap); stream-ordered, no host synchronisation
 static int apply_permutation(ssb_handle *h, const int *d_perm) {
     SsbView &V = h->V;
     const int N = h->N;
     cudaStream_t st = h->stream;
     PermTable T;
     memset(&T, 0, sizeof(T));
-    size_t nf = h->f64_slots.size();
+    const size_t nf = h->f64_slots.size(), ni = h->i32_slots.size();
     for (size_t f = 0; f < nf; f++) { T.src64[T.n64] = *h->f64_slots[f]; T.dst64[T.n64] = h->f64_alt[f]; T.n64++; }
-    double *blk_alt = h->f64_alt[nf];
-    const int Sc = V.Sc, Sd = V.Sd, ndf = V.ndf;
-    for (int s = 0; s < Sc; s++) { T.src64[T.n64] = V.C + (size_t) s * N; T.dst64[T.n64] = blk_alt + (size_t) s * N; T.n64++; }
-    for (int s = 0; s < Sc; s++) { T.src64[T.n64] = V.Q + (size_t) s * N; T.dst64[T.n64] = blk_alt + (size_t) (Sc + s) * N; T.n64++; }
-    for (int q = 0; q < ndf; q++) { T.src64[T.n64] = V.data_fn + (size_t) q * N; T.dst64[T.n64] = blk_alt + (size_t) (2 * Sc + q) * N; T.n64++; }
-    size_t ni = h->i32_slots.size();
     for (size_t f = 0; f < ni; f++) { T.src32[T.n32] = *h->i32_slots[f]; T.dst32[T.n32] = h->i32_alt[f]; T.n32++; }
-    int *xx_alt = h->i32_alt[ni];
-    for (int s = 0; s < Sd; s++) { T.src32[T.n32] = (int *) V.xx + (size_t) s * N; T.dst32[T.n32] = xx_alt + (size_t) s * N; T.n32++; }
-    CK(cudaMemcpyAsync(h->d_permtable, &T, sizeof(T), cudaMemcpyHostToDevice, st));
-    k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, d_perm, h->d_permtable);
+    k_permute<<<gridN(N), CORE_BLOCK, 0, st>>>(N, d_perm, T);
+    const int Sc = V.Sc, Sd = V.Sd, ndf = V.ndf;
+    if (Sc > 0) {
+        k_permute_rows64<<<dim3(gridN(N), (unsigned) Sc), CORE_BLOCK, 0, st>>>(N, d_perm, V.C, h->C_alt);
+        k_permute_rows64<<<dim3(gridN(N), (unsigned) Sc), CORE_BLOCK, 0, st>>>(N, d_perm, V.Q, h->Q_alt);
+        std::swap(V.C, h->C_alt); std::swap(V.Q, h->Q_alt);
+    }
+    if (ndf > 0) { k_permute_rows64<<<dim3(gridN(N), (unsigned) ndf), CORE_BLOCK, 0, st>>>(N, d_perm, V.data_fn, h->df_alt); std::swap(V.data_fn, h->df_alt); }
+    if (Sd > 0) { k_permute_rows32<<<dim3(gridN(N), (unsigned) Sd), CORE_BLOCK, 0, st>>>(N, d_perm, (const int *) V.xx, (int *) h->xx_alt); std::swap(V.xx, h->xx_alt); }
+    CK(cudaGetLastError());
     h->slot_dirty = 1;
-    h->launches += 1;
-    CK(ssb_sync(h));   // T lives on this stack frame
+    h->launches += 1 + (Sc > 0 ? 2 : 0) + (ndf > 0) + (Sd > 0);
     for (size_t f = 0; f < nf; f++) { double *cur = *h->f64_slots[f]; *h->f64_slots[f] = h->f64_alt[f]; h->f64_alt[f] = cur; }
     for (size_t f = 0; f < ni; f++) { int *cur = *h->i32_slots[f]; *h->i32_slots[f] = h->i32_alt[f]; h->i32_alt[f] = cur; }
-    // species blocks: copy back (blocks keep their identity so C/Q/data_fn/xx stay contiguous)
-    if (2 * Sc + ndf > 0) {
-        if (Sc > 0) { CK(cudaMemcpyAsync(V.C, blk_alt, sizeof(double) * Sc * N, cudaMemcpyDeviceToDevice, st));
-                      CK(cudaMemcpyAsync(V.Q, blk_alt + (size_t) Sc * N, sizeof(double) * Sc * N, cudaMemcpyDeviceToDevice, st)); }
-        if (ndf > 0) CK(cudaMemcpyAsync(V.data_fn, blk_alt + (size_t) 2 * Sc * N, sizeof(double) * ndf * N, cudaMemcpyDeviceToDevice, st));
-    }
-    if (Sd > 0) CK(cudaMemcpyAsync(V.xx, xx_alt, sizeof(unsigned) * Sd * N, cudaMemcpyDeviceToDevice, st));
     if (V.static_domain) for (int d = 0; d < 3; d++) V.x0[d] = V.x[d];
     V.rho_search = V.rho;
     return SSB_OK;
@@ -1203,7 +1432,8 @@ static int choose_skin(ssb_handle *h) {
     if ((rc = count_candidates(h, &exact))) return rc;
     V.filter = 1;
     double pick = 0.0;
-    for (double sk = skin_max; sk >= 0.004; sk *= 0.5) {
+    // (skins below 2 % of h are not worth their bookkeeping: such clouds rebuild exact lists every step)
+    for (double sk = skin_max; sk >= 0.02; sk *= 0.5) {
         V.search_h2 = (V.h * (1.0 + sk)) * (V.h * (1.0 + sk));
         double cand = 0.0;
         if ((rc = count_candidates(h, &cand))) return rc;
@@ -1266,6 +1496,7 @@ static int check_device_error(ssb_handle *h) {
     CK(ssb_sync(h));
     if (flag == SSB_ERR_NAN) return fail(h, SSB_ERR_NAN, "ERROR: nan/inf detected!!! (step %u)", h->current_step);
     if (flag == SSB_ERR_RDME) return fail(h, SSB_ERR_RDME, "RDME state error (negative population or propensity overflow) at step %u", h->current_step);
+    if (flag == SSB_ERR_HALO) return fail(h, SSB_ERR_HALO, "halo exchange timed out: a neighbouring slab rank did not deliver its message (step %u)", h->current_step);
     return SSB_OK;
 }
 
@@ -1304,6 +1535,58 @@ static int rdme_extra_event(ssb_handle *h, double tmin, bool deliver = true) {
     return SSB_OK;
 }
 
+// Host wait for ONE event recorded earlier on the engine stream (a scalar the device reports through pinned memory) while later
+// kernels are already queued behind it: the GPU never idles for the wait.  Short waits are polled, long ones sleep (see ssb_sync).
+static cudaError_t wait_event(cudaEvent_t ev) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        cudaError_t e = cudaEventQuery(ev);
+        if (e != cudaErrorNotReady) return e;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+    }
+    return cudaEventSynchronize(ev);
+}
+
+// window controller: tau * (largest per-molecule jump rate) <= rdme_epsilon, and an integer number of windows per step
+static int set_windows(ssb_handle *h, double max_ddiag) {
+    const SsbView &V = h->V;
+    const double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
+    const double tau = (max_ddiag > 0.0) ? eps / max_ddiag : V.dt;
+    double nwin_d = ceil(V.dt / tau);
+    if (!(nwin_d >= 1.0)) nwin_d = 1.0;
+    if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
+    h->nwin = (long long) nwin_d;
+    h->tau = V.dt / (double) h->nwin;
+    return SSB_OK;
+}
+
+// largest Ddiag of this step -> *mx.  Moving domains: the force sweep assembled Ddiag and its maximum, and its copy into pinned memory
+// was queued right behind the sweep (ev_maxd) — by now the corrector and the BVF sweep are queued behind that, so the wait is free.
+static int step_max_ddiag(ssb_handle *h, double *mx) {
+    SsbView &V = h->V;
+    cudaStream_t st = h->stream;
+    unsigned long long bits = 0;
+    if (h->static_cached && V.static_domain) h->ddiag_fresh = 2;   // Ddiag, D_ij, tau from the first trajectory are still valid
+    if (h->ddiag_fresh == 2) {
+        memcpy(&bits, &h->max_ddiag_cached, sizeof(bits));
+    } else if (h->ddiag_fresh == 1) {
+        CK(wait_event(h->ev_maxd));
+        bits = h->pin[3];
+    } else {
+        CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+        int ps0 = prof_begin(h, CAT_DIFF_INIT, 1);
+        if (h->unit->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
+        prof_end(h, ps0);
+        h->launches += 1;
+        CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        CK(ssb_sync(h));
+    }
+    h->ddiag_fresh = 0;
+    memcpy(mx, &bits, sizeof(*mx));
+    h->max_ddiag_cached = *mx;
+    return SSB_OK;
+}
+
 static int rdme_step(ssb_handle *h) {
     SsbView &V = h->V;
     const SsbModelUnit *u = h->unit;
@@ -1311,33 +1594,10 @@ static int rdme_step(ssb_handle *h) {
     if (V.Sd == 0) return SSB_OK;
     const double t0 = V.dt * h->current_step;
     if (!V.static_domain || !h->rdme_initialized) {      // simulate_rdme.cpp:54-65
-        if (h->static_cached && V.static_domain) h->ddiag_fresh = 2;   // Ddiag, D_ij, tau from the first trajectory are still valid
-        if (!h->ddiag_fresh) {     // the optimised moving-domain force sweep already assembled Ddiag and its maximum
-            CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
-            int ps0 = prof_begin(h, CAT_DIFF_INIT, 1);
-            if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
-            prof_end(h, ps0);
-            h->launches += 1;
-        }
-        unsigned long long bits = 0;
-        if (h->ddiag_fresh == 2) {
-            memcpy(&bits, &h->max_ddiag_cached, sizeof(bits));
-        } else {
-            CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-            CK(ssb_sync(h));
-        }
-        h->ddiag_fresh = 0;
-        double mx;
-        memcpy(&mx, &bits, sizeof(mx));
-        h->max_ddiag_cached = mx;
-        // window controller: tau * (largest per-molecule jump rate) <= rdme_epsilon, and an integer number of windows per step
-        double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
-        double tau = (mx > 0.0) ? eps / mx : V.dt;
-        double nwin_d = ceil(V.dt / tau);
-        if (!(nwin_d >= 1.0)) nwin_d = 1.0;
-        if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
-        h->nwin = (long long) nwin_d;
-        h->tau = V.dt / (double) h->nwin;
+        double mx = 0.0;
+        int rc = step_max_ddiag(h, &mx);
+        if (!rc) rc = set_windows(h, mx);
+        if (rc) return rc;
         // propensities are (re)initialised at t = 0.0 in the reference (simulate_rdme.cpp:124)
         int ps1 = prof_begin(h, CAT_RDME_INIT, 1);
         if (u->rdme_init(&V, t0, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
@@ -1373,6 +1633,113 @@ static int rdme_step(ssb_handle *h) {
     return SSB_OK;
 }
 
+// ---- the pieces of a MOVING-domain step (shared by engine_step, the phase API and the native slab step) -----------------------
+// Verlet skin: the candidate lists of radius h*(1+skin) and the storage order survive while no pair that is within h NOW can lie
+// outside the candidate radius at the positions the lists were built from: |xref_i - xref_j| <= h + D(x_i) + D(x0_j) with
+// D = displacement from xref, x0 = the previous step's x.  Both displacements of the step that is about to run are known in
+// advance (k_lookahead), so the decision is exact and taken before anything of the step is queued.
+static int mv_decide_keep(ssb_handle *h, bool *keep) {
+    SsbView &V = h->V;
+    *keep = false;
+    if (!V.filter || !h->lists_valid || !h->look_valid) return SSB_OK;
+    CK(wait_event(h->ev_look));
+    double d2next, s2next, d2cur;
+    memcpy(&d2next, &h->pin[0], 8); memcpy(&s2next, &h->pin[1], 8); memcpy(&d2cur, &h->pin[2], 8);
+    const double Dnext = sqrt(d2next), Dcur = sqrt(d2cur), budget = h->skin * V.h * (1.0 - 1e-9);
+    if (sqrt(s2next) > h->step_disp_max) h->step_disp_max = sqrt(s2next);
+    h->disp_prev = Dcur;
+    *keep = (Dnext + Dcur <= budget);
+    return SSB_OK;
+}
+
+// cell list (if due) + predictor + neighbour search (if due) + force sweep; queues the copy of max Ddiag behind the sweep
+static int mv_pre(ssb_handle *h) {
+    SsbView &V = h->V;
+    const SsbModelUnit *u = h->unit;
+    cudaStream_t st = h->stream;
+    const unsigned step = h->current_step;
+    int rc, ps;
+    bool keep_lists = false;
+    if ((rc = mv_decide_keep(h, &keep_lists))) return rc;
+    if (!keep_lists) {                                                       // buildKDTree (simulate_threads.cpp:80-108)
+        ps = prof_begin(h, CAT_CELLS, 7);
+        rc = build_cells(h);
+        if (!rc && V.filter) {
+            for (int d = 0; d < 3; d++) CK(cudaMemcpyAsync(V.xref[d], V.x[d], sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
+            h->disp_prev = 0.0;
+        }
+        h->rebuilds++;
+        prof_end(h, ps);
+        if (rc) return rc;
+    }
+    ps = prof_begin(h, CAT_PREDICTOR, 1);
+    if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
+    prof_end(h, ps);
+    h->launches++;
+    V.rho_search = V.rho;
+    if (!keep_lists) {                                                       // find_neighbors (simulate.cpp:61-63,121-123)
+        ps = prof_begin(h, CAT_SEARCH, 1);
+        rc = neighbour_search(h);
+        prof_end(h, ps);
+        if (rc) return rc;
+        h->lists_valid = 1;
+    }
+    if (!(V.flags & SSB_FLAG_LITERAL_KERNELS)) {
+        // optimised moving-domain sweep; also produces Ddiag + its maximum for the sSSA window controller
+        if (V.Sd > 0) CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+        ps = prof_begin(h, CAT_FORCE, 1);
+        if (u->force_mv(&V, step, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
+        prof_end(h, ps);
+        h->launches++;
+        if (V.Sd > 0) {
+            CK(cudaMemcpyAsync(&h->pin[3], h->d_maxbits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->ev_maxd, st));
+            h->ddiag_fresh = 1;
+        }
+    } else {
+        ps = prof_begin(h, CAT_FORCE, 1);
+        if (u->force(&V, step, 1, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
+        prof_end(h, ps);
+        h->launches++;
+    }
+    return SSB_OK;
+}
+static int mv_corrector(ssb_handle *h) {
+    int ps = prof_begin(h, CAT_CORRECTOR, 1);
+    if (h->unit->corrector(&h->V, h->current_step, h->stream)) return fail(h, SSB_ERR_CUDA, "corrector launch failed");
+    prof_end(h, ps);
+    h->launches++;
+    return SSB_OK;
+}
+static int mv_finish(ssb_handle *h) {
+    SsbView &V = h->V;
+    int ps = prof_begin(h, CAT_FINISH, 1);
+    if (h->unit->finish(&V, h->current_step, 1, h->stream)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
+    prof_end(h, ps);
+    h->launches++;
+    // rho <- post-corrector density; the old buffer keeps the search-time density frozen into D_i_j
+    double *pre = V.rho;
+    V.rho = V.rho_new;
+    V.rho_new = pre;
+    V.rho_search = pre;
+    return SSB_OK;
+}
+// displacement bookkeeping of the NEXT step (after the last kernel that changes v, F or Fbp of any particle, ghost copies included)
+static int mv_lookahead(ssb_handle *h) {
+    SsbView &V = h->V;
+    if (!V.filter) return SSB_OK;
+    cudaStream_t st = h->stream;
+    int ps = prof_begin(h, CAT_FINISH, 1);
+    CK(cudaMemsetAsync(h->d_look, 0, sizeof(unsigned long long) * 3, st));
+    k_lookahead<<<gridN(V.N), CORE_BLOCK, 0, st>>>(V, h->d_look);
+    CK(cudaMemcpyAsync(h->pin, h->d_look, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev_look, st));
+    prof_end(h, ps);
+    h->look_valid = 1;
+    h->launches++;
+    return SSB_OK;
+}
+
 static int engine_step(ssb_handle *h) {
     SsbView &V = h->V;
     const SsbModelUnit *u = h->unit;
@@ -1381,9 +1748,20 @@ static int engine_step(ssb_handle *h) {
     const bool moving = !V.static_domain;
     int rc;
     int ps;
+    if (moving) {
+        // simulate_threads.cpp:232-281: substeps 0-2, then the RDME.  Steady state: no blocking synchronisation — two event waits
+        // (look-ahead displacement at the start, max Ddiag before the sSSA), both behind kernels that are already queued.
+        if ((rc = mv_pre(h))) return rc;
+        if ((rc = mv_corrector(h))) return rc;
+        if ((rc = mv_finish(h))) return rc;
+        if ((rc = mv_lookahead(h))) return rc;
+        if ((rc = rdme_step(h))) return rc;
+        h->current_step++;
+        return SSB_OK;
+    }
     // static-domain fast path: one fused chemistry kernel per step (k_static_step); with no continuous species a static
     // step has no SDPD work at all after step 0 (boundary conditions are idempotent assignments)
-    const bool fast_static = !moving && (V.flags & SSB_FLAG_SKIP_STATIC_FORCES) && !u->bc_touches_rho;
+    const bool fast_static = (V.flags & SSB_FLAG_SKIP_STATIC_FORCES) && !u->bc_touches_rho;
     if (fast_static && step > 0) {
         if (V.Sc > 0) {
             ps = prof_begin(h, CAT_FORCE, 1);
@@ -1395,18 +1773,10 @@ static int engine_step(ssb_handle *h) {
         h->current_step++;
         return SSB_OK;
     }
-    const bool reuse = !moving && h->static_cached;                          // geometry work of step 0 already done by an earlier trajectory
-    // moving domains with a Verlet skin: storage order + candidate lists survive until particles have moved skin*h/2
-    const bool keep_lists = moving && V.filter && h->lists_valid;
-    if (moving && V.filter) CK(cudaMemsetAsync(V.disp_bits, 0, sizeof(unsigned long long), st));   // [0] recomputed each step, [1] running max
-    if ((step == 0 && !reuse) || (moving && !keep_lists)) {                  // buildKDTree (simulate_threads.cpp:80-108)
+    const bool reuse = h->static_cached;                                     // geometry work of step 0 already done by an earlier trajectory
+    if (step == 0 && !reuse) {                                               // buildKDTree (simulate_threads.cpp:80-108)
         ps = prof_begin(h, CAT_CELLS, 7);
         rc = build_cells(h);
-        if (!rc && moving && V.filter) {
-            for (int d = 0; d < 3; d++) CK(cudaMemcpyAsync(V.xref[d], V.x[d], sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
-            h->disp_prev = 0.0;
-            h->rebuilds++;
-        }
         prof_end(h, ps);
         if (rc) return rc;
     }
@@ -1414,30 +1784,12 @@ static int engine_step(ssb_handle *h) {
     if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
     prof_end(h, ps);
     h->launches++;
-    if (moving) V.rho_search = V.rho;
-    if ((step == 0 && !reuse) || (moving && !keep_lists)) {                  // find_neighbors (simulate.cpp:61-63,121-123)
+    if (step == 0 && !reuse) {                                               // find_neighbors (simulate.cpp:61-63,121-123)
         V.rho_search = V.rho;
         ps = prof_begin(h, CAT_SEARCH, 1);
         rc = neighbour_search(h);
         prof_end(h, ps);
         if (rc) return rc;
-    }
-    if (moving && V.filter) {
-        // displacement bookkeeping of the skin: D = max |x - xref| after this predictor, s = largest single-step move so far.
-        // A pair within h now has |xref_i - xref_j| <= h + D_now + D_prev, so the lists are complete iff D_now + D_prev <= skin*h.
-        unsigned long long bits[2] = {0, 0};
-        CK(cudaMemcpyAsync(bits, V.disp_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-        CK(ssb_sync(h));
-        double d2now, s2;
-        memcpy(&d2now, &bits[0], 8); memcpy(&s2, &bits[1], 8);
-        const double Dnow = sqrt(d2now), budget = h->skin * V.h;
-        h->step_disp_max = sqrt(s2);
-        if (Dnow + h->disp_prev > budget)
-            return fail(h, SSB_ERR_ARG, "Verlet skin exceeded within one step (displacement %g + %g > %g): particles move more than skin*h per step; "
-                        "set SSB_SKIN=0 or reduce the time step", Dnow, h->disp_prev, budget);
-        // keep the lists for the next step only if even two more worst-case steps stay inside the budget
-        h->lists_valid = (2.0 * (Dnow + 2.0 * h->step_disp_max) <= budget) ? 1 : 0;
-        h->disp_prev = Dnow;
     }
     if (fast_static) {
         // step 0 of the fast path: cache the pair coefficients, then run the fused kernel from a copy of C
@@ -1457,39 +1809,17 @@ static int engine_step(ssb_handle *h) {
         h->current_step++;
         return SSB_OK;
     }
-    const bool full = moving || !(V.flags & SSB_FLAG_SKIP_STATIC_FORCES);
-    if (moving && !(V.flags & SSB_FLAG_LITERAL_KERNELS)) {
-        // optimised moving-domain sweep; also produces Ddiag + its maximum for the sSSA window controller
-        if (V.Sd > 0) CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
-        ps = prof_begin(h, CAT_FORCE, 1);
-        if (u->force_mv(&V, step, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
-        prof_end(h, ps);
-        h->launches++;
-        h->ddiag_fresh = 1;
-    } else if (full || V.Sc > 0) {
+    const bool full = !(V.flags & SSB_FLAG_SKIP_STATIC_FORCES);
+    if (full || V.Sc > 0) {
         ps = prof_begin(h, CAT_FORCE, 1);
         if (u->force(&V, step, full ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
         prof_end(h, ps);
         h->launches++;
     }
-    if (moving) {
-        ps = prof_begin(h, CAT_CORRECTOR, 1);
-        if (u->corrector(&V, step, st)) return fail(h, SSB_ERR_CUDA, "corrector launch failed");
-        prof_end(h, ps);
-        h->launches++;
-    }
     ps = prof_begin(h, CAT_FINISH, 1);
-    if (u->finish(&V, step, moving ? 1 : 0, st)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
+    if (u->finish(&V, step, 0, st)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
     prof_end(h, ps);
     h->launches++;
-    if (moving) {
-        // rho <- post-corrector density; the old buffer keeps the search-time density frozen into D_i_j
-        double *pre = V.rho;
-        V.rho = V.rho_new;
-        V.rho_new = pre;
-        V.rho_search = pre;
-        // keep the permutation table consistent: V.rho is a registered slot (swapped in place above)
-    }
     if ((rc = rdme_step(h))) return rc;
     h->current_step++;
     return SSB_OK;
@@ -1722,11 +2052,12 @@ extern "C" int ssb_set_field(ssb_handle *h, const char *name, const void *src, i
     double **v3 = nullptr;
     if (n == "x") v3 = V.x; else if (n == "v") v3 = V.v; else if (n == "vt") v3 = V.vt; else if (n == "F") v3 = V.F; else if (n == "Fbp") v3 = V.Fbp;
     if (v3) {
+        h->look_valid = 0;       // (the look-ahead displacement was computed from the old x, v, F, Fbp)
         if (bytes != (int64_t) sizeof(double) * 3 * N) return fail(h, SSB_ERR_ARG, "field %s needs %lld bytes", name, (long long) sizeof(double) * 3 * N);
         if (n == "x" && V.static_domain) return fail(h, SSB_ERR_ARG, "positions of a static domain cannot be replaced (cached geometry)");
         CK(cudaMemcpyAsync(h->d_stage, src, bytes, cudaMemcpyHostToDevice, st));
         for (int d = 0; d < 3; d++) k_perm_in64<<<gridN(N), CORE_BLOCK, 0, st>>>(N, V.id, h->d_stage, v3[d], 3, d);
-        if (n == "x") { h->lists_valid = 0; h->nbr_valid = 0; }       // candidate lists and storage order refer to the old positions
+        if (n == "x") { h->lists_valid = 0; h->nbr_valid = 0; h->look_valid = 0; }       // candidate lists and storage order refer to the old positions
         CK(ssb_sync(h));
         return SSB_OK;
     }
@@ -1872,16 +2203,15 @@ extern "C" int ssb_nbr_stats(ssb_handle *h, int32_t *capacity, int64_t *total) {
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Slab decomposition support (spatialpy_b200/slab.py drives these; NCCL send/recv happens between the phases).
-// A rank's model = its owned particles + ghost copies (ssb_model.owned).  Ghosts run the same per-particle kernels as
-// everyone else (predictor / corrector updates are deterministic functions of synced inputs), but their neighbour sweeps
-// are skipped; after each sweep the owner's results overwrite the ghost copies:
-//     phase PRE        cell list (if due) + predictor + neighbour search (if due) + force sweep   -> exchange group 0
-//     phase CORRECTOR  corrector (+ Shepard filter)                                               -> exchange group 1
-//     phase FINISH     BVF sweep, bounce-back, chemistry half step, BCs                           -> exchange group 2
-//     phase RDME_PREP  -> local max Ddiag (all-reduced by the caller)   phase RDME_INIT (global max) -> number of windows
-//     phase RDME_WINDOW / RDME_CLOSE one sSSA window each               -> inbox exchange (ssb_halo_inbox_*)
-//     phase END        step counter
+// Slab decomposition support.  A rank's model = its owned particles + ghost copies (ssb_model.owned).  Ghosts run the same
+// per-particle kernels as everyone else (predictor / corrector updates are deterministic functions of synced inputs), but their
+// neighbour sweeps are skipped; after each sweep the owner's results overwrite the ghost copies:
+//     PRE        cell list (if due) + predictor + neighbour search (if due) + force sweep   -> exchange group 0
+//     CORRECTOR  corrector (+ Shepard filter)                                               -> exchange group 1
+//     FINISH     BVF sweep, bounce-back, chemistry half step, BCs                           -> exchange group 2
+//     RDME       global max Ddiag -> windows; one inbox exchange after every sSSA window; the step-end overshoot event
+// Two drivers share these pieces: ssb_slab_step (native transport below: the product path) and ssb_step_phase + ssb_halo_*
+// (caller-orchestrated, any transport — the CPU-tier protocol tests and the cross-check of the native path).
 // ----------------------------------------------------------------------------------------------------
 enum { PH_PRE = 0, PH_CORRECTOR = 1, PH_FINISH = 2, PH_RDME_PREP = 3, PH_RDME_INIT = 4, PH_RDME_WINDOW = 5, PH_RDME_CLOSE = 6, PH_END = 7,
        PH_RDME_MIN = 8, PH_RDME_EXTRA = 9 };
@@ -1892,6 +2222,25 @@ static int ensure_slot_map(ssb_handle *h) {
         k_slot_of_id<<<gridN(h->N), CORE_BLOCK, 0, h->stream>>>(h->N, h->V.id, h->d_slot_of_id);
         h->slot_dirty = 0;
     }
+    return SSB_OK;
+}
+
+static int rdme_window_phase(ssb_handle *h, bool closing, long long w) {
+    SsbView &V = h->V;
+    const double t0 = V.dt * h->current_step;
+    const long long nwin = h->nwin;
+    double lo, hi;
+    if (!closing) {
+        lo = t0 + V.dt * ((double) w / (double) nwin);
+        hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
+        h->windows++;
+    } else { lo = hi = t0 + V.dt; }
+    // closing window with w < 0: the delivery of the step-end overshoot event, which runs under the epoch rdme_extra_event reserved
+    // for it (the numbering of the Philox epochs is the same on every path: +2 per step for the overshoot)
+    const uint64_t epoch = (closing && w < 0) ? h->epoch - 1 : h->epoch++;
+    if (h->unit->rdme_window(&V, lo, hi, h->tau, h->seed, epoch, h->inbox_buf, h->stream)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+    h->inbox_buf ^= 1;
+    h->launches++;
     return SSB_OK;
 }
 
@@ -1906,71 +2255,23 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
     if (V.static_domain) return fail(h, SSB_ERR_ARG, "phase stepping (slab decomposition) is implemented for moving domains");
     int rc;
     switch (phase) {
-    case PH_PRE: {
-        const bool keep_lists = V.filter && h->lists_valid;
-        if (V.filter) CK(cudaMemsetAsync(V.disp_bits, 0, sizeof(unsigned long long), st));
-        if (!keep_lists) {
-            if ((rc = build_cells(h))) return rc;
-            if (V.filter) {
-                for (int d = 0; d < 3; d++) CK(cudaMemcpyAsync(V.xref[d], V.x[d], sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
-                h->disp_prev = 0.0;
-                h->rebuilds++;
-            }
-        }
-        if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
-        h->launches++;
-        V.rho_search = V.rho;
-        if (!keep_lists) { if ((rc = neighbour_search(h))) return rc; }
-        if (V.filter) {
-            unsigned long long bits[2] = {0, 0};
-            CK(cudaMemcpyAsync(bits, V.disp_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-            CK(ssb_sync(h));
-            double d2now, s2;
-            memcpy(&d2now, &bits[0], 8); memcpy(&s2, &bits[1], 8);
-            const double Dnow = sqrt(d2now), budget = h->skin * V.h;
-            h->step_disp_max = sqrt(s2);
-            if (Dnow + h->disp_prev > budget) return fail(h, SSB_ERR_ARG, "Verlet skin exceeded within one step");
-            h->lists_valid = (2.0 * (Dnow + 2.0 * h->step_disp_max) <= budget) ? 1 : 0;
-            h->disp_prev = Dnow;
-        }
-        if (V.Sd > 0) CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
-        if (u->force_mv(&V, step, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
-        h->launches++;
-        h->ddiag_fresh = 1;
+    case PH_PRE:
+        if ((rc = mv_pre(h))) return rc;
         break;
-    }
     case PH_CORRECTOR:
-        if (u->corrector(&V, step, st)) return fail(h, SSB_ERR_CUDA, "corrector launch failed");
-        h->launches++;
+        if ((rc = mv_corrector(h))) return rc;
         break;
-    case PH_FINISH: {
-        if (u->finish(&V, step, 1, st)) return fail(h, SSB_ERR_CUDA, "finish launch failed");
-        h->launches++;
-        double *pre = V.rho;
-        V.rho = V.rho_new;
-        V.rho_new = pre;
-        V.rho_search = pre;
+    case PH_FINISH:
+        if ((rc = mv_finish(h))) return rc;
         break;
-    }
     case PH_RDME_PREP: {
-        unsigned long long bits = 0;
-        CK(cudaMemcpyAsync(&bits, h->d_maxbits, sizeof(bits), cudaMemcpyDeviceToHost, st));
-        CK(ssb_sync(h));
-        double mx;
-        memcpy(&mx, &bits, sizeof(mx));
+        double mx = 0.0;
+        if ((rc = step_max_ddiag(h, &mx))) return rc;
         if (out) *out = mx;
         break;
     }
     case PH_RDME_INIT: {
-        const double mx = arg;       // GLOBAL max Ddiag: every rank must use the same windows
-        const double eps = (h->m.rdme_epsilon > 0.0) ? h->m.rdme_epsilon : 0.05;
-        const double tau = (mx > 0.0) ? eps / mx : V.dt;
-        double nwin_d = ceil(V.dt / tau);
-        if (!(nwin_d >= 1.0)) nwin_d = 1.0;
-        if (nwin_d > 5.0e7) return fail(h, SSB_ERR_ARG, "sSSA window count per step (%g) too large; raise rdme_epsilon", nwin_d);
-        h->nwin = (long long) nwin_d;
-        h->tau = V.dt / (double) h->nwin;
-        h->ddiag_fresh = 0;
+        if ((rc = set_windows(h, arg))) return rc;       // arg = GLOBAL max Ddiag: every rank must use the same windows
         if (u->rdme_init(&V, V.dt * step, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
         h->launches++;
         h->rdme_initialized = 1;
@@ -1979,30 +2280,21 @@ extern "C" int ssb_step_phase(ssb_handle *h, int phase, double arg, double *out)
         break;
     }
     case PH_RDME_WINDOW:
-    case PH_RDME_CLOSE: {
-        const double t0 = V.dt * step;
-        const long long nwin = h->nwin, w = (long long) arg;
-        double lo, hi;
-        if (phase == PH_RDME_WINDOW) {
-            lo = t0 + V.dt * ((double) w / (double) nwin);
-            hi = (w + 1 == nwin) ? t0 + V.dt : t0 + V.dt * ((double) (w + 1) / (double) nwin);
-            h->windows++;
-        } else { lo = hi = t0 + V.dt; }
-        if (u->rdme_window(&V, lo, hi, h->tau, h->seed, h->epoch++, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
-        h->inbox_buf ^= 1;
-        h->launches++;
+    case PH_RDME_CLOSE:
+        if ((rc = rdme_window_phase(h, phase == PH_RDME_CLOSE, (long long) arg))) return rc;
         break;
-    }
     case PH_RDME_MIN: {          // -> *out = this rank's earliest pending event (the caller all-reduces the minimum)
         double tmin = INFINITY;
         if ((rc = rdme_min_time(h, &tmin))) return rc;
         if (out) *out = tmin;
         break;
     }
-    case PH_RDME_EXTRA:          // arg = GLOBAL earliest pending event: only its owner fires; the caller syncs the inboxes and closes
+    case PH_RDME_EXTRA:          // arg = GLOBAL earliest pending event: only its owner fires; the caller syncs the inboxes and then
+                                 // delivers (PH_RDME_CLOSE with arg < 0 reuses the epoch rdme_extra_event reserved for the delivery)
         if (!(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT))) { if ((rc = rdme_extra_event(h, arg, false))) return rc; }
         break;
     case PH_END:
+        if ((rc = mv_lookahead(h))) return rc;            // (after the caller's last halo unpack: ghost v, F, Fbp are final)
         h->current_step++;
         return check_device_error(h);
     default:
@@ -2057,6 +2349,366 @@ extern "C" int ssb_halo_inbox_add(ssb_handle *h, const int32_t *dev_ids, int32_t
 extern "C" int ssb_halo_width(ssb_handle *h, int group, int32_t *width) {
     if (!h || !width) return SSB_ERR_ARG;
     *width = group == 0 ? 7 + h->V.Sc : (group == 2 ? 4 : 1);
+    return SSB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Native slab transport (include/ssb.h: ssb_slab_*).  Every rank owns one RECEIVE WINDOW per slab face (device memory, exported
+// through CUDA IPC, or by raw pointer when the neighbour rank lives in the same process) and one scalar BOARD (mapped by all ranks).
+// A message is written by the SENDER's pack kernel straight into the receiver's window over NVLink; buffers are double-buffered by
+// the parity of the channel's sequence number (a sender can be at most one message ahead of the receiver's consumption: it only
+// sends message k+2 after it has received the neighbour's message k+1, which the neighbour sent after consuming message k).
+// ----------------------------------------------------------------------------------------------------
+struct HaloSide {
+    int active = 0;
+    int n_send = 0, n_recv = 0;
+    int *d_send_ids = nullptr, *d_recv_ids = nullptr;
+    char *win = nullptr;          // my window facing this neighbour
+    size_t win_bytes = 0;
+    char *peer = nullptr;         // the neighbour's window facing me
+    int peer_ipc = 0;
+    size_t off[HALO_NCH][2];      // buffer offsets in MY window   (group rows = n_recv, inbox entries <= n_send * Sd)
+    size_t poff[HALO_NCH][2];     // buffer offsets in the PEER's  (group rows = n_send, inbox entries <= n_recv * Sd)
+};
+struct SlabComm {
+    int rank = 0, world = 1, connected = 0;
+    HaloSide side[2];             // 0 = rank-1, 1 = rank+1
+    unsigned long long seq[HALO_NCH] = {0, 0, 0, 0};
+    char *board = nullptr;
+    unsigned long long *peer_board[SSB_BOARD_MAXW] = {nullptr};
+    int peer_board_ipc[SSB_BOARD_MAXW] = {0};
+    unsigned long long bseq[SSB_BOARD_NCH] = {0, 0, 0};
+    unsigned *d_done = nullptr, *d_icount = nullptr;
+    unsigned long long *d_red = nullptr;      // [SSB_BOARD_NCH] reduced scalars (device)
+    unsigned long long *d_inf = nullptr;      // bit pattern of +inf
+    cudaEvent_t ev_post[SSB_BOARD_NCH] = {nullptr}, ev_red[SSB_BOARD_NCH] = {nullptr}, ev_disp[2] = {nullptr, nullptr};
+    double travel = 0.0, gdisp_max = 0.0;
+    uint32_t steps = 0;           // steps run since the windows were set up
+};
+struct SlabBlob {                 // what a rank publishes about itself (exchanged by the caller: torch.distributed / a thread hub)
+    int64_t pid;
+    int32_t device, rank;
+    int32_t n_send[2], n_recv[2];
+    uint64_t ptr[3];              // window 0, window 1, board
+    cudaIpcMemHandle_t ipc[3];
+};
+
+static size_t halo_layout(int rows, int inbox_entries, int Sc, size_t off[HALO_NCH][2]) {
+    size_t o = HALO_HDR_BYTES;
+    const int width[3] = {7 + Sc, 1, 4};
+    for (int ch = 0; ch < 3; ch++)
+        for (int q = 0; q < 2; q++) { off[ch][q] = o; o += (((size_t) rows * width[ch] * sizeof(double)) + 255) & ~(size_t) 255; }
+    for (int q = 0; q < 2; q++) { off[HALO_CH_INBOX][q] = o; o += (((size_t) inbox_entries * sizeof(uint4)) + 255) & ~(size_t) 255; }
+    return o;
+}
+
+extern "C" int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const int32_t *send_lo, int32_t n_send_lo, const int32_t *recv_lo,
+                              int32_t n_recv_lo, const int32_t *send_hi, int32_t n_send_hi, const int32_t *recv_hi, int32_t n_recv_hi) {
+    if (!h || rank < 0 || rank >= world || world > SSB_BOARD_MAXW) return SSB_ERR_ARG;
+    if (h->V.static_domain) return fail(h, SSB_ERR_ARG, "slab decomposition is implemented for moving domains");
+    if (h->slab) return fail(h, SSB_ERR_ARG, "ssb_slab_setup: already set up");
+    CK(cudaSetDevice(h->device));
+    SlabComm *c = h->slab = new SlabComm();
+    c->rank = rank; c->world = world;
+    const int32_t *ids[2][2] = {{send_lo, recv_lo}, {send_hi, recv_hi}};
+    const int cnt[2][2] = {{n_send_lo, n_recv_lo}, {n_send_hi, n_recv_hi}};
+    for (int sd = 0; sd < 2; sd++) {
+        HaloSide &S = c->side[sd];
+        const int nb = sd ? rank + 1 : rank - 1;
+        S.active = (nb >= 0 && nb < world) ? 1 : 0;
+        if (!S.active) continue;
+        S.n_send = cnt[sd][0]; S.n_recv = cnt[sd][1];
+        if (S.n_send < 0 || S.n_recv < 0 || (S.n_send && !ids[sd][0]) || (S.n_recv && !ids[sd][1])) return SSB_ERR_ARG;
+        CK(dalloc(h, &S.d_send_ids, (size_t) S.n_send)); CK(dalloc(h, &S.d_recv_ids, (size_t) S.n_recv));
+        if (S.n_send) CK(cudaMemcpyAsync(S.d_send_ids, ids[sd][0], sizeof(int) * S.n_send, cudaMemcpyHostToDevice, h->stream));
+        if (S.n_recv) CK(cudaMemcpyAsync(S.d_recv_ids, ids[sd][1], sizeof(int) * S.n_recv, cudaMemcpyHostToDevice, h->stream));
+        S.win_bytes = halo_layout(S.n_recv, S.n_send * std::max(h->V.Sd, 1), h->V.Sc, S.off);
+        halo_layout(S.n_send, S.n_recv * std::max(h->V.Sd, 1), h->V.Sc, S.poff);
+        CK(cudaMalloc((void **) &S.win, S.win_bytes));          // (own allocation: exported whole through CUDA IPC)
+        h->allocs.push_back(S.win);
+        CK(cudaMemsetAsync(S.win, 0, HALO_HDR_BYTES, h->stream));
+    }
+    const size_t board_bytes = sizeof(unsigned long long) * 2 * SSB_BOARD_NCH * 2 * SSB_BOARD_MAXW;
+    CK(cudaMalloc((void **) &c->board, board_bytes));
+    h->allocs.push_back(c->board);
+    CK(cudaMemsetAsync(c->board, 0, board_bytes, h->stream));
+    CK(dalloc(h, &c->d_done, 4)); CK(dalloc(h, &c->d_icount, 4)); CK(dalloc(h, &c->d_red, SSB_BOARD_NCH + 1)); CK(dalloc(h, &c->d_inf, 1));
+    CK(cudaMemsetAsync(c->d_done, 0, 16, h->stream)); CK(cudaMemsetAsync(c->d_icount, 0, 16, h->stream));
+    const unsigned long long inf_bits = 0x7ff0000000000000ull;
+    CK(cudaMemcpyAsync(c->d_inf, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, h->stream));
+    for (int k = 0; k < SSB_BOARD_NCH; k++) {
+        CK(cudaEventCreateWithFlags(&c->ev_post[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_red[k], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c->ev_disp[k], cudaEventDisableTiming));
+    CK(ssb_sync(h));
+    return SSB_OK;
+}
+
+extern "C" int ssb_slab_blob_bytes(void) { return (int) sizeof(SlabBlob); }
+
+extern "C" int ssb_slab_export(ssb_handle *h, void *blob, int64_t bytes) {
+    if (!h || !h->slab || !blob || bytes < (int64_t) sizeof(SlabBlob)) return SSB_ERR_ARG;
+    CK(cudaSetDevice(h->device));
+    SlabComm *c = h->slab;
+    SlabBlob B;
+    memset(&B, 0, sizeof(B));
+    B.pid = (int64_t) getpid(); B.device = h->device; B.rank = c->rank;
+    char *ptr[3] = {c->side[0].win, c->side[1].win, c->board};
+    for (int k = 0; k < 3; k++) {
+        B.ptr[k] = (uint64_t) (uintptr_t) ptr[k];
+        if (ptr[k]) CK(cudaIpcGetMemHandle(&B.ipc[k], ptr[k]));
+    }
+    for (int sd = 0; sd < 2; sd++) { B.n_send[sd] = c->side[sd].n_send; B.n_recv[sd] = c->side[sd].n_recv; }
+    memcpy(blob, &B, sizeof(B));
+    return SSB_OK;
+}
+
+static int slab_map(ssb_handle *h, const SlabBlob &B, int k, char **out, int *is_ipc) {
+    *out = nullptr; *is_ipc = 0;
+    if (!B.ptr[k]) return fail(h, SSB_ERR_ARG, "rank %d exported no window %d", B.rank, k);
+    if (B.pid == (int64_t) getpid()) {                   // same process (ranks as threads): the pointer itself, peer access if another GPU
+        if (B.device != h->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(B.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, SSB_ERR_CUDA, "no peer access from GPU %d to GPU %d: %s", h->device, B.device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        *out = (char *) (uintptr_t) B.ptr[k];
+        return SSB_OK;
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&q, B.ipc[k], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(h, SSB_ERR_CUDA, "cudaIpcOpenMemHandle (rank %d, window %d): %s", B.rank, k, cudaGetErrorString(e));
+    *out = (char *) q; *is_ipc = 1;
+    return SSB_OK;
+}
+
+// blobs = the SlabBlob of every rank, in rank order
+extern "C" int ssb_slab_connect(ssb_handle *h, const void *blobs, int64_t bytes) {
+    if (!h || !h->slab || !blobs) return SSB_ERR_ARG;
+    SlabComm *c = h->slab;
+    if (bytes != (int64_t) sizeof(SlabBlob) * c->world) return fail(h, SSB_ERR_ARG, "ssb_slab_connect: expected %d blobs of %d bytes", c->world, (int) sizeof(SlabBlob));
+    CK(cudaSetDevice(h->device));
+    const SlabBlob *B = (const SlabBlob *) blobs;
+    int rc;
+    for (int sd = 0; sd < 2; sd++) {
+        HaloSide &S = c->side[sd];
+        if (!S.active) continue;
+        const SlabBlob &P = B[sd ? c->rank + 1 : c->rank - 1];
+        const int theirs = sd ? 0 : 1;                   // my upper face is the neighbour's lower face
+        if (P.n_recv[theirs] != S.n_send || P.n_send[theirs] != S.n_recv)
+            return fail(h, SSB_ERR_ARG, "slab faces disagree: rank %d sends %d / expects %d, rank %d expects %d / sends %d", c->rank, S.n_send, S.n_recv,
+                        P.rank, P.n_recv[theirs], P.n_send[theirs]);
+        if ((rc = slab_map(h, P, theirs, &S.peer, &S.peer_ipc))) return rc;
+    }
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank) { c->peer_board[r] = (unsigned long long *) c->board; continue; }
+        char *q; int ipc;
+        if ((rc = slab_map(h, B[r], 2, &q, &ipc))) return rc;
+        c->peer_board[r] = (unsigned long long *) q; c->peer_board_ipc[r] = ipc;
+    }
+    c->connected = 1;
+    return SSB_OK;
+}
+
+// unmap the neighbours' memory (every rank calls this, then all ranks meet, then the handles may be destroyed)
+extern "C" int ssb_slab_disconnect(ssb_handle *h) {
+    if (!h || !h->slab) return SSB_OK;
+    SlabComm *c = h->slab;
+    cudaSetDevice(h->device);
+    if (h->stream) ssb_sync(h);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    for (int sd = 0; sd < 2; sd++) { if (c->side[sd].peer && c->side[sd].peer_ipc) cudaIpcCloseMemHandle(c->side[sd].peer); c->side[sd].peer = nullptr; }
+    for (int r = 0; r < c->world; r++) { if (c->peer_board[r] && c->peer_board_ipc[r]) cudaIpcCloseMemHandle(c->peer_board[r]); c->peer_board[r] = nullptr; }
+    c->connected = 0;
+    return SSB_OK;
+}
+
+static void slab_reset(ssb_handle *h) {        // ssb_reset: the particles are back where the partition was made
+    if (!h->slab) return;
+    h->slab->travel = 0.0; h->slab->gdisp_max = 0.0; h->slab->steps = 0;
+}
+static void slab_free(ssb_handle *h) {
+    if (!h->slab) return;
+    ssb_slab_disconnect(h);
+    SlabComm *c = h->slab;
+    for (int k = 0; k < SSB_BOARD_NCH; k++) { if (c->ev_post[k]) cudaEventDestroy(c->ev_post[k]); if (c->ev_red[k]) cudaEventDestroy(c->ev_red[k]); }
+    for (int k = 0; k < 2; k++) if (c->ev_disp[k]) cudaEventDestroy(c->ev_disp[k]);
+    delete c;
+    h->slab = nullptr;
+}
+
+// one field group to both neighbours and back: pack+send (peer writes, flags raised by the last CTA), wait, unpack
+static int slab_exchange(ssb_handle *h, int group) {
+    SlabComm *c = h->slab;
+    cudaStream_t st = h->stream;
+    int rc = ensure_slot_map(h);
+    if (rc) return rc;
+    const unsigned long long seq = ++c->seq[group];
+    const int q = (int) (seq & 1ull);
+    HaloPackArgs P;
+    HaloUnpackArgs U;
+    memset(&P, 0, sizeof(P)); memset(&U, 0, sizeof(U));
+    P.seq = seq; P.done = c->d_done; P.icount = c->d_icount;
+    const unsigned long long *flag[2] = {nullptr, nullptr};
+    for (int sd = 0; sd < 2; sd++) {
+        HaloSide &S = c->side[sd];
+        if (!S.active) continue;
+        P.side[sd].ids = S.d_send_ids; P.side[sd].n = S.n_send;
+        P.side[sd].peer_buf = S.peer + S.poff[group][q];
+        P.side[sd].peer_flag = (unsigned long long *) (S.peer + 64 * group);
+        U.side[sd].ids = S.d_recv_ids; U.side[sd].n = S.n_recv; U.side[sd].buf = S.win + S.off[group][q];
+        flag[sd] = (const unsigned long long *) (S.win + 64 * group);
+    }
+    const int ns = P.side[0].n + P.side[1].n, nr = U.side[0].n + U.side[1].n;
+    k_halo_send<<<std::max(gridN(ns), 1u), CORE_BLOCK, 0, st>>>(h->V, group, P, h->d_slot_of_id);
+    k_halo_wait<<<1, 32, 0, st>>>(flag[0], flag[1], seq, h->V.err_flag);
+    if (nr > 0) k_halo_recv<<<gridN(nr), CORE_BLOCK, 0, st>>>(h->V, group, U, h->d_slot_of_id);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    return SSB_OK;
+}
+// mail of the sSSA window that just ran: my ghosts' inboxes -> their owners (the neighbour's inbox of the same buffer)
+static int slab_exchange_inbox(ssb_handle *h) {
+    SlabComm *c = h->slab;
+    cudaStream_t st = h->stream;
+    if (h->V.Sd == 0) return SSB_OK;
+    int rc = ensure_slot_map(h);
+    if (rc) return rc;
+    const unsigned long long seq = ++c->seq[HALO_CH_INBOX];
+    const int q = (int) (seq & 1ull), buf = h->inbox_buf ^ 1;
+    HaloPackArgs P;
+    HaloUnpackArgs U;
+    memset(&P, 0, sizeof(P)); memset(&U, 0, sizeof(U));
+    P.seq = seq; P.done = c->d_done; P.icount = c->d_icount;
+    const unsigned long long *flag[2] = {nullptr, nullptr};
+    for (int sd = 0; sd < 2; sd++) {
+        HaloSide &S = c->side[sd];
+        if (!S.active) continue;
+        P.side[sd].ids = S.d_recv_ids; P.side[sd].n = S.n_recv;              // my ghosts
+        P.side[sd].peer_buf = S.peer + S.poff[HALO_CH_INBOX][q];
+        P.side[sd].peer_flag = (unsigned long long *) (S.peer + 64 * HALO_CH_INBOX);
+        P.side[sd].peer_count = (unsigned long long *) (S.peer + 512 + 64 * q);
+        U.side[sd].ids = S.d_send_ids; U.side[sd].n = S.n_send; U.side[sd].buf = S.win + S.off[HALO_CH_INBOX][q];
+        U.side[sd].count = (const unsigned long long *) (S.win + 512 + 64 * q);
+        flag[sd] = (const unsigned long long *) (S.win + 64 * HALO_CH_INBOX);
+    }
+    const int ns = P.side[0].n + P.side[1].n;
+    k_inbox_send<<<std::max(gridN(ns), 1u), CORE_BLOCK, 0, st>>>(h->V, buf, P, h->d_slot_of_id);
+    k_halo_wait<<<1, 32, 0, st>>>(flag[0], flag[1], seq, h->V.err_flag);
+    k_inbox_recv<<<64, CORE_BLOCK, 0, st>>>(h->V, buf, U, h->d_slot_of_id, h->unit->block);
+    CK(cudaGetLastError());
+    h->launches += 3;
+    return SSB_OK;
+}
+// scalar all-reduce, device to device: post my value to every board (engine stream), reduce my own board on `on` (the engine
+// stream, or the side stream when the host wants the result without stalling the engine stream) -> c->d_red[ch]
+static int slab_allreduce(ssb_handle *h, int ch, const unsigned long long *src, bool take_min, cudaStream_t on) {
+    SlabComm *c = h->slab;
+    cudaStream_t st = h->stream;
+    const unsigned long long seq = ++c->bseq[ch];
+    BoardPeers P;
+    memset(&P, 0, sizeof(P));
+    for (int r = 0; r < c->world; r++) P.b[r] = c->peer_board[r];
+    if (seq > 1) CK(cudaStreamWaitEvent(st, c->ev_red[ch], 0));          // my previous reduction of this channel has read its slots
+    k_board_post<<<1, 32, 0, st>>>(P, c->world, c->rank, ch, seq, src);
+    if (on != st) { CK(cudaEventRecord(c->ev_post[ch], st)); CK(cudaStreamWaitEvent(on, c->ev_post[ch], 0)); }
+    k_board_reduce<<<1, 32, 0, on>>>((const unsigned long long *) c->board, c->world, ch, seq, take_min ? 1 : 0, c->d_red + ch, h->V.err_flag);
+    CK(cudaEventRecord(c->ev_red[ch], on));
+    CK(cudaGetLastError());
+    h->launches += 2;
+    return SSB_OK;
+}
+
+// n engine steps of one slab rank, everything stream-ordered; per step the host waits for two scalars only (its own look-ahead
+// displacement, the global max Ddiag), both behind queued work.  Stops early — on every rank after the same step — when particles
+// may have travelled `travel_limit` since the windows were set up (the caller re-partitions); *done = steps executed.
+extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit, uint32_t *done, double *travel) {
+    if (!h || !h->slab) return SSB_ERR_ARG;
+    if (!h->unit) return fail(h, SSB_ERR_MODEL_UNIT, "no model unit loaded (ssb_load_kernels)");
+    SlabComm *c = h->slab;
+    if (!c->connected && c->world > 1) return fail(h, SSB_ERR_ARG, "ssb_slab_step before ssb_slab_connect");
+    CK(cudaSetDevice(h->device));
+    SsbView &V = h->V;
+    const SsbModelUnit *u = h->unit;
+    cudaStream_t st = h->stream, aux = h->copy_stream;
+    const bool overshoot = !(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT));
+    auto t0w = std::chrono::steady_clock::now();
+    int rc;
+    uint32_t s = 0;
+    for (; s < nsteps; s++) {
+        // global step displacement of the step before the previous one (two steps of lag keep the read free of any wait)
+        if (c->steps >= 2) {
+            CK(wait_event(c->ev_disp[c->steps & 1]));
+            double g2;
+            memcpy(&g2, &h->pin[8 + (c->steps & 1)], 8);
+            const double g = sqrt(g2);
+            c->travel += g;
+            if (g > c->gdisp_max) c->gdisp_max = g;
+            if (travel_limit > 0.0 && c->travel + 3.0 * c->gdisp_max > travel_limit) break;
+        }
+        const unsigned step = h->current_step;
+        if ((rc = mv_pre(h))) return rc;
+        if (V.Sd > 0) {
+            if ((rc = slab_allreduce(h, 0, h->d_maxbits, false, aux))) return rc;
+            CK(cudaMemcpyAsync(&h->pin[4], c->d_red + 0, sizeof(unsigned long long), cudaMemcpyDeviceToHost, aux));
+            CK(cudaEventRecord(h->ev_maxd, aux));
+        }
+        if ((rc = slab_exchange(h, 0))) return rc;
+        if ((rc = mv_corrector(h))) return rc;
+        if ((rc = slab_exchange(h, 1))) return rc;
+        if ((rc = mv_finish(h))) return rc;
+        if ((rc = slab_exchange(h, 2))) return rc;
+        if ((rc = mv_lookahead(h))) return rc;
+        if (V.filter) {
+            if ((rc = slab_allreduce(h, 2, h->d_look + 1, false, aux))) return rc;
+            CK(cudaMemcpyAsync(&h->pin[8 + (c->steps & 1)], c->d_red + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, aux));
+            CK(cudaEventRecord(c->ev_disp[c->steps & 1], aux));
+        } else {
+            h->pin[8 + (c->steps & 1)] = 0;
+            CK(cudaEventRecord(c->ev_disp[c->steps & 1], aux));
+        }
+        if (V.Sd > 0) {
+            CK(wait_event(h->ev_maxd));                      // every rank's force sweep is done; corrector .. look-ahead are still queued
+            double mx;
+            memcpy(&mx, &h->pin[4], 8);
+            h->ddiag_fresh = 0;
+            if ((rc = set_windows(h, mx))) return rc;        // GLOBAL max Ddiag: every rank uses the same windows
+            if (u->rdme_init(&V, V.dt * step, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
+            h->launches++;
+            h->rdme_initialized = 1;
+            h->inbox_buf = 0;
+            for (long long w = 0; w < h->nwin; w++) {
+                if ((rc = rdme_window_phase(h, false, w))) return rc;
+                if ((rc = slab_exchange_inbox(h))) return rc;
+            }
+            if ((rc = rdme_window_phase(h, true, 0))) return rc;
+            if (overshoot) {
+                // the reference's one event past the end of the step (simulate_rdme.cpp:233-238): the globally earliest pending clock
+                // is reduced on the device and read by the two windows from device memory
+                const int nchunks = (h->N + u->block - 1) / u->block;
+                CK(cudaMemcpyAsync(h->d_maxbits + 1, c->d_inf, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+                k_min_time<<<gridN(nchunks), CORE_BLOCK, 0, st>>>(nchunks, V.blk_tmin, h->d_maxbits + 1);
+                if ((rc = slab_allreduce(h, 1, h->d_maxbits + 1, true, st))) return rc;
+                const double te = V.dt * (step + 1);
+                h->epoch += 2;
+                if (u->rdme_window_dev(&V, c->d_red + 1, te, 0, h->tau, h->seed, h->epoch - 2, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+                h->inbox_buf ^= 1;
+                if ((rc = slab_exchange_inbox(h))) return rc;
+                if (u->rdme_window_dev(&V, c->d_red + 1, te, 1, h->tau, h->seed, h->epoch - 1, h->inbox_buf, st)) return fail(h, SSB_ERR_CUDA, "rdme_window launch failed");
+                h->inbox_buf ^= 1;
+                h->launches += 3;
+            }
+        }
+        h->current_step++;
+        c->steps++;
+        if ((c->steps & 15) == 0) { if ((rc = check_device_error(h))) return rc; }
+        if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
+    }
+    if ((rc = check_device_error(h))) return rc;
+    h->step_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0w).count();
+    if (done) *done = s;
+    if (travel) *travel = c->travel;
     return SSB_OK;
 }
 

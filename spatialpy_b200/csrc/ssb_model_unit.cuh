@@ -49,7 +49,6 @@ __device__ __forceinline__ System make_system(const SsbView &V, unsigned step) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned step) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double step2 = 0.0, ref2 = 0.0;        // Verlet-skin bookkeeping: squared displacement this step / since the list build
     if (i < V.N) {
     Particle p;
     bc_load(V, i, p);
@@ -69,10 +68,8 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
             p.v[d] = p.v[d] + 0.5 * dt * V.F[d][i];
             double vt = p.v[d] + 0.5 * dt * V.Fbp[d][i];
             V.vt[d][i] = vt;
-            const double xo = p.x[d];
-            p.x[d] = p.x[d] + dt * vt;
+            p.x[d] = p.x[d] + dt * vt;      // (the Verlet-skin displacement bookkeeping of this update ran ahead of it: k_lookahead, ssb_core.cu)
             V.x[d][i] = p.x[d];
-            if (V.filter) { const double a = p.x[d] - xo, b = p.x[d] - V.xref[d][i]; step2 += a * a; ref2 += b * b; }
         }
         p.rho = p.rho + 0.5 * dt * V.Frho[i];
     }
@@ -109,16 +106,6 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
         V.C[(size_t) s * V.N + i] = p.C[s];
         V.Q[(size_t) s * V.N + i] = 0.0;                // simulate.cpp:101-103
     }
-    }
-    if (V.filter) {     // one atomic pair per warp
-        for (int o = 16; o > 0; o >>= 1) {
-            ref2 = fmax(ref2, __shfl_xor_sync(0xffffffffu, ref2, o));
-            step2 = fmax(step2, __shfl_xor_sync(0xffffffffu, step2, o));
-        }
-        if ((threadIdx.x & 31) == 0 && step2 > 0.0) {
-            atomicMax(&V.disp_bits[0], (unsigned long long) __double_as_longlong(ref2));
-            atomicMax(&V.disp_bits[1], (unsigned long long) __double_as_longlong(step2));
-        }
     }
 }
 
@@ -251,44 +238,63 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
 
 // ---------------------------------------------------------------------------------------------
 // K3 (moving domains, optimised form of k_force<true>): same physics as model.cpp:39-191, restructured for B200:
-//   * neighbour data comes from ONE 128-byte record + one 32-byte record per neighbour (5 sectors instead of 17 scattered
-//     8-byte gathers);
-//   * per-particle quantities (1/rho, P/rho^2, m/rho) are precomputed once in k_predictor instead of once per pair;
+//   * neighbour data comes from ONE 128-byte gather record per neighbour (4 sectors instead of 17 scattered 8-byte gathers);
 //   * the three per-pair reciprocals 1/(r+0.001h), 1/(nu_i+nu_j), 1/((m_i+m_j)(r^2+0.01h^2)) share ONE division;
 //   * the 3x3 transport tensor contraction T.dx is factorised as 0.5*(rho_i v_i (w_i.dx) + rho_j v_j (w_j.dx)), w = vt - v;
 //   * K6 (D_i_j, Ddiag, max for the window controller; simulate_rdme.cpp:131-152) is fused in — it shares r and the
 //     (m, rho, r^2) factor with the chemistry flux.
 // Results differ from the literal evaluation order by a few ulp per pair (parity gate: 1e-12 of the field scale).
+//
+// COOP = 4 (default, "quad gather"): the sweep is bound by L1 tag lookups, not by bytes — with one record per lane every LDG.E.256
+// of a warp touches 32 distinct 128-byte lines (32 wavefronts for 32 sectors).  Here the four lanes of a quad fetch the records of
+// their four candidates TOGETHER: lane q of the quad loads sector q of each of the four records (one line per quad and instruction:
+// 8 wavefronts, each delivering a whole line), and a 4x4 transpose over two shuffle rounds hands every lane the full record of its
+// own candidate.  Same records, same pair arithmetic in the same order => bit-identical to COOP = 1 (one gather per lane), which
+// stays as the cross-check (`-DSSB_FORCE_COOP=1`).  The round-1 shared-memory tile form measured 2x SLOWER than the plain gather
+// (1.42 vs 0.70 ms at 1 M particles, profiles/r2a_bench_tank_tile.json: 128-byte record stride = 32-way bank conflicts, a serial
+// chunk table per CTA, two barriers per chunk) and was deleted.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double mx = 0.0;
-    if (i < V.N) {
-        const int N = V.N, dim = V.dim;
-        const double h = V.h, P0 = V.P0;
-        const double inv_h = 1.0 / h;
-        const double c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
-        const double eps_r = 0.001 * h, eps2 = 0.01 * h * h;
-        const double h2x = __dmul_rn(h, h);
-        const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
+#ifndef SSB_FORCE_COOP
+#define SSB_FORCE_COOP 4
+#endif
+
+// per-particle state of the sweep + the pair body (ONE copy, whatever feeds it the records)
+struct ForceSweep {
+    int N, dim, filter, num_types;
+    double h, P0, inv_h, c12, eps_r, eps2, h2x, ih7c, rho0, inv_rho0;
+    bool inv_exact;
+    double xi0, xi1, xi2, vi0, vi1, vi2, wi0, wi1, wi2, rho_i, m_i, nu_i;
+    double inv_rho_i, aP_i, volsq_i, inv_m_i, rv0, rv1, rv2;
+    int type_i;
+    double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1], Dd[SSB_SD > 0 ? SSB_SD : 1];
+    double F0, F1, F2, B0, B1, B2, Frho;
+    const double *Cg, *dmat;
+
+    __device__ __forceinline__ void init(const SsbView &V, int i) {
+        N = V.N; dim = V.dim; filter = V.filter; num_types = V.num_types;
+        h = V.h; P0 = V.P0;
+        inv_h = 1.0 / h;
+        c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
+        eps_r = 0.001 * h; eps2 = 0.01 * h * h;
+        h2x = __dmul_rn(h, h);
+        ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
         const double *ri = V.rec + (size_t) i * 16;
         const ssb_d4 a0 = ssb_ld256(ri), a1 = ssb_ld256(ri + 4), a2 = ssb_ld256(ri + 8), a3 = ssb_ld256(ri + 12);
-        const double xi0 = a0.d, xi1 = a1.a, xi2 = a1.b;
-        const double vi0 = a1.c, vi1 = a1.d, vi2 = a2.a;
-        const double wi0 = a2.b - vi0, wi1 = a2.c - vi1, wi2 = a2.d - vi2;
-        const double rho_i = a3.a, m_i = a3.b, nu_i = a3.c;
-        // 1/rho, P/rho^2 and m/rho of both particles are recomputed from the record (two divisions per pair on an fp64 pipe that is
-        // ~30 % busy) rather than gathered from a second per-particle record: the sweep is bound by L1 tag lookups — each lane's
-        // gather touches its own 128-byte line — and a fifth sector per pair cost more (measured 0.77 -> 0.70 ms at 1 M particles).
-        const double rho0 = V.rho0, inv_rho0 = 1.0 / V.rho0;
-        const bool inv_exact = (__double_as_longlong(rho0) & 0x000fffffffffffffLL) == 0;    // power of two: rho * (1/rho0) == rho / rho0 bit for bit
-        const double inv_rho_i = 1.0 / rho_i;
-        const double aP_i = (P0 * (rho_i / rho0 - 1.0)) * inv_rho_i * inv_rho_i;
+        xi0 = a0.d; xi1 = a1.a; xi2 = a1.b;
+        vi0 = a1.c; vi1 = a1.d; vi2 = a2.a;
+        wi0 = a2.b - vi0; wi1 = a2.c - vi1; wi2 = a2.d - vi2;
+        rho_i = a3.a; m_i = a3.b; nu_i = a3.c;
+        // 1/rho, P/rho^2 and m/rho of the neighbour are recomputed from its record (two divisions per pair) rather than gathered
+        // from a second per-particle record: a fifth sector per pair cost more than the divisions (measured 0.77 -> 0.70 ms at 1 M).
+        rho0 = V.rho0; inv_rho0 = 1.0 / V.rho0;
+        inv_exact = (__double_as_longlong(rho0) & 0x000fffffffffffffLL) == 0;    // power of two: rho * (1/rho0) == rho / rho0 bit for bit
+        inv_rho_i = 1.0 / rho_i;
+        aP_i = (P0 * (rho_i / rho0 - 1.0)) * inv_rho_i * inv_rho_i;
         const double vol_i = m_i * inv_rho_i;
-        const double volsq_i = vol_i * vol_i, inv_m_i = 1.0 / m_i;
-        const double rv0 = rho_i * vi0, rv1 = rho_i * vi1, rv2 = rho_i * vi2;
-        const int type_i = (int) ((__double_as_longlong(a3.d) >> 32) & 0xffff);
-        double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1], Dd[SSB_SD > 0 ? SSB_SD : 1];
+        volsq_i = vol_i * vol_i; inv_m_i = 1.0 / m_i;
+        rv0 = rho_i * vi0; rv1 = rho_i * vi1; rv2 = rho_i * vi2;
+        type_i = (int) ((__double_as_longlong(a3.d) >> 32) & 0xffff);
+        Cg = V.C; dmat = V.dmat;
 #pragma unroll
         for (int s = 0; s < SSB_SC; s++) {
             Ci[s] = V.C[(size_t) s * N + i];
@@ -298,203 +304,27 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
         }
 #pragma unroll
         for (int s = 0; s < SSB_SD; s++) Dd[s] = 0.0;
-        double F0 = V.F[0][i], F1 = V.F[1][i], F2 = V.F[2][i];
-        double B0 = V.Fbp[0][i], B1 = V.Fbp[1][i], B2 = V.Fbp[2][i];
-        double Frho = V.Frho[i];
-        const int cnt = V.owned[i] ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
-#pragma unroll 2
-        for (int k = 0; k < cnt; k++) {
-            const int j = V.nbr[(size_t) k * N + i];
-            const double *rj = V.rec + (size_t) j * 16;
-            const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
-            ssb_d4 e0;
-            e0.a = 1.0 / c3.a;
-            e0.b = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * e0.a * e0.a;
-            e0.c = c3.b * e0.a;
-            const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
-            const double r = sqrt(d2);
-            // candidate list -> ANN's exact set (the record loads above are issued before this test on purpose: a rejected
-            // candidate wastes 4 sectors, a dependent second round trip per accepted neighbour would cost far more)
-            if (V.filter && !((d2 <= h2x) && (d2 != 0.0) && !(r > h))) continue;
-            double dx0 = xi0 - c0.d, dx1 = 0.0, dx2 = 0.0;
-            if (dim > 1) dx1 = xi1 - c1.a;
-            if (dim > 2) dx2 = xi2 - c1.b;
-            const double vj0 = c1.c, vj1 = c1.d, vj2 = c2.a;
-            const double wj0 = c2.b - vj0, wj1 = c2.c - vj1, wj2 = c2.d - vj2;
-            const double rho_j = c3.a, m_j = c3.b, nu_j = c3.c;
-            const double inv_rho_j = e0.a, aP_j = e0.b, vol_j = e0.c;
-            // one division for three reciprocals
-            const double reg = r + eps_r, nusum = nu_i + nu_j, r2 = r * r;
-            const double md = (m_i + m_j) * (r2 + eps2);
-            const double rn = reg * nusum;
-            const double q = 1.0 / (rn * md);
-            const double inv_reg = q * (nusum * md), inv_nusum = q * (reg * md), inv_md = q * rn;
-            const double R = r * inv_h, omR = 1.0 - R;
-            const double dWdr = c12 * r * (omR * omR);                           // particle.cpp:178
-            const double wr = dWdr * inv_reg;                                    // dWdr / (r + 0.001 h)
-            double dv0 = vi0 - vj0, dv1 = 0.0, dv2 = 0.0;
-            if (dim > 1) dv1 = vi1 - vj1;
-            if (dim > 2) dv2 = vi2 - vj2;
-            const double dv_dx = dv0 * dx0 + dv1 * dx1 + dv2 * dx2;
-            double pg = aP_i + aP_j;                                             // model.cpp:111
-            if (pg < 0) pg = -aP_i + aP_j;                                       // model.cpp:112
-            const double fp = -m_j * pg * wr;                                    // model.cpp:115
-            const double fv = m_j * (2.0 * (nu_i * nu_j) * inv_nusum) * wr * (inv_rho_i * inv_rho_j);   // model.cpp:118
-            const double vv = volsq_i + vol_j * vol_j;
-            const double fbp = -10.0 * P0 * inv_m_i * vv * wr;                   // model.cpp:121
-            const double widx = wi0 * dx0 + wi1 * dx1 + wi2 * dx2;
-            const double wjdx = wj0 * dx0 + wj1 * dx1 + wj2 * dx2;
-            const double ftc = 0.5 * inv_m_i * vv * wr;                          // model.cpp:124-132
-            const double rj_w = rho_j * wjdx;
-            const double ft0 = ftc * (rv0 * widx + vj0 * rj_w);
-            const double ft1 = ftc * (rv1 * widx + vj1 * rj_w);
-            const double ft2 = ftc * (rv2 * widx + vj2 * rj_w);
-            F0 += fp * dx0 + fv * dv0 + ft0;                                     // model.cpp:135-138
-            B0 += fbp * dx0;
-            if (dim > 1) { F1 += fp * dx1 + fv * dv1 + ft1; B1 += fbp * dx1; }
-            if (dim > 2) { F2 += fp * dx2 + fv * dv2 + ft2; B2 += fbp * dx2; }
-            Frho += wr * vol_j * (rho_i * dv_dx + rho_i * widx + rj_w);          // model.cpp:143-146
-            if (SSB_SC > 0 || SSB_SD > 0) {
-                const double G = 2.0 * (m_i * m_j) * (inv_rho_i + inv_rho_j) * r2 * inv_md;   // shared by model.cpp:155 and particle.cpp:187
-                if (SSB_SC > 0) {
-                    const double base = G * wr;
-#pragma unroll
-                    for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - V.C[(size_t) s * N + j]) * base;
-                }
-                if (SSB_SD > 0) {
-                    const double hr = h - r;
-                    const double Dij = G * (ih7c * hr * hr);                     // particle.cpp:182-187 (sign folded)
-                    const int tj = (int) ((__double_as_longlong(c3.d) >> 32) & 0xffff) - 1;
-#pragma unroll
-                    for (int s = 0; s < SSB_SD; s++) Dd[s] += V.dmat[s * V.num_types + tj] * Dij;
-                }
-            }
-        }
-        V.F[0][i] = F0; V.F[1][i] = F1; V.F[2][i] = F2;
-        V.Fbp[0][i] = B0; V.Fbp[1][i] = B1; V.Fbp[2][i] = B2;
-        V.Frho[i] = Frho;
-        if (SSB_SC > 0) {
-            if (SSB_RC > 0) {                                                    // model.cpp:181-189
-                const double vol = m_i / rho_i;
-                const double cur_time = step * V.dt;
-                double df[SSB_NDF > 0 ? SSB_NDF : 1];
-#pragma unroll
-                for (int qd = 0; qd < SSB_NDF; qd++) df[qd] = V.data_fn[(size_t) qd * N + i];
-                double flux[SSB_RC > 0 ? SSB_RC : 1];
-                ssb_gen::eval_det(Ci, cur_time, vol, df, type_i, flux);
-#pragma unroll
-                for (int rxn = 0; rxn < SSB_RC; rxn++) {
-#pragma unroll
-                    for (int s = 0; s < SSB_SC; s++) {
-                        int nval;
-                        if (V.flags & 2u) nval = ssb_gen::N_dense(s * SSB_R + rxn);
-                        else { int kk = SSB_RC * rxn + s; nval = (kk < SSB_S * SSB_R) ? ssb_gen::N_dense(kk) : 0; }
-                        Qi[s] += nval * flux[rxn];
-                    }
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < SSB_SC; s++) V.Q[(size_t) s * N + i] = Qi[s];
-        }
-#pragma unroll
-        for (int s = 0; s < SSB_SD; s++) { V.Ddiag[(size_t) s * N + i] = Dd[s]; mx = fmax(mx, Dd[s]); }
+        F0 = V.F[0][i]; F1 = V.F[1][i]; F2 = V.F[2][i];
+        B0 = V.Fbp[0][i]; B1 = V.Fbp[1][i]; B2 = V.Fbp[2][i];
+        Frho = V.Frho[i];
     }
-    if (SSB_SD > 0) {
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
-    }
-}
 
-// ---------------------------------------------------------------------------------------------
-// K3 (tile form, opt-in: SSB_FLAG_TILE_SWEEP)  same sweep as k_force_mv — same candidate lists, same pair arithmetic in the same
-// (ascending slot) order, so the results are bit-identical — but the neighbour records come from SHARED MEMORY instead of one
-// 4-sector gather per pair.  k_force_mv is bound by the L1TEX pipe (87 %): 128 particles x 36 candidates = 4 600 record fetches
-// per CTA, although the cell-sorted CTA only touches ~1 400 DISTINCT records (the nine cell-row runs around its cells).  Here the
-// CTA (1) marks the 64-slot blocks its candidates fall into in a shared bitmap, (2) turns the set blocks into ascending chunks of
-// <= SSB_TILE_REC consecutive records, (3) stages one chunk at a time with coalesced 16-byte loads and lets every thread consume
-// the part of its (ascending) candidate list that falls into the chunk — a cursor per thread, no index remapping.  A CTA whose
-// candidates span more than the bitmap covers falls back to the gather loop.  DESIGN.md section 9 item 1 has the budget.
-// The pair body below is a verbatim copy of k_force_mv's (kept separate so that the validated kernel's code is untouched).
-// ---------------------------------------------------------------------------------------------
-#ifndef SSB_TILE_REC              // (overridable: the host emulation in tests/cuda_emu shrinks them to force the fallback paths)
-#define SSB_TILE_REC 256          // records per staged chunk (32 KB)
-#define SSB_TILE_GRAN 64          // slots per bitmap bit
-#define SSB_TILE_WORDS 512        // 16 384 bits: candidates of one CTA may span up to 2^20 slots
-#define SSB_TILE_MAXCH 96         // chunks per CTA
-#endif
-
-__device__ __forceinline__ ssb_d4 ssb_lds256(const double *p) {
-    const double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + 2);
-    ssb_d4 r;
-    r.a = lo.x; r.b = lo.y; r.c = hi.x; r.d = hi.y;
-    return r;
-}
-
-__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv_tile(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
-    __shared__ __align__(32) double s_rec[SSB_TILE_REC * 16];
-    __shared__ unsigned s_bits[SSB_TILE_WORDS];
-    __shared__ int s_lo[SSB_TILE_MAXCH], s_hi[SSB_TILE_MAXCH];
-    __shared__ int s_nch, s_min, s_max, s_fallback;
-    const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i_raw < V.N;
-    const int i = live ? i_raw : V.N - 1;          // idle lanes of the last CTA run the same straight-line code on a valid slot
-    double mx = 0.0;
-    const int N = V.N, dim = V.dim;
-    const double h = V.h, P0 = V.P0;
-    const double inv_h = 1.0 / h;
-    const double c12 = ssb_alpha(dim, h) * (-12.0) / (h * h);
-    const double eps_r = 0.001 * h, eps2 = 0.01 * h * h;
-    const double h2x = __dmul_rn(h, h);
-    const double ih7c = 25.066903536973515383e0 * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h * inv_h;
-    const double *ri = V.rec + (size_t) i * 16;
-    const ssb_d4 a0 = ssb_ld256(ri), a1 = ssb_ld256(ri + 4), a2 = ssb_ld256(ri + 8), a3 = ssb_ld256(ri + 12);
-    const double xi0 = a0.d, xi1 = a1.a, xi2 = a1.b;
-    const double vi0 = a1.c, vi1 = a1.d, vi2 = a2.a;
-    const double wi0 = a2.b - vi0, wi1 = a2.c - vi1, wi2 = a2.d - vi2;
-    const double rho_i = a3.a, m_i = a3.b, nu_i = a3.c;
-    // 1/rho, P/rho^2 and m/rho of both particles are recomputed from the record (two divisions per pair on an fp64 pipe that is
-    // ~30 % busy) rather than gathered from a second per-particle record: the sweep is bound by L1 tag lookups — each lane's
-    // gather touches its own 128-byte line — and a fifth sector per pair cost more (measured 0.77 -> 0.70 ms at 1 M particles).
-    const double rho0 = V.rho0, inv_rho0 = 1.0 / V.rho0;
-    const bool inv_exact = (__double_as_longlong(rho0) & 0x000fffffffffffffLL) == 0;    // power of two: rho * (1/rho0) == rho / rho0 bit for bit
-    const double inv_rho_i = 1.0 / rho_i;
-    const double aP_i = (P0 * (rho_i / rho0 - 1.0)) * inv_rho_i * inv_rho_i;
-    const double vol_i = m_i * inv_rho_i;
-    const double volsq_i = vol_i * vol_i, inv_m_i = 1.0 / m_i;
-    const double rv0 = rho_i * vi0, rv1 = rho_i * vi1, rv2 = rho_i * vi2;
-    const int type_i = (int) ((__double_as_longlong(a3.d) >> 32) & 0xffff);
-    double Ci[SSB_SC > 0 ? SSB_SC : 1], Qi[SSB_SC > 0 ? SSB_SC : 1], Dk[SSB_SC > 0 ? SSB_SC : 1], Dd[SSB_SD > 0 ? SSB_SD : 1];
-#pragma unroll
-    for (int s = 0; s < SSB_SC; s++) {
-        Ci[s] = V.C[(size_t) s * N + i];
-        Qi[s] = V.Q[(size_t) s * N + i];
-        int k = SSB_SC * (type_i - 1) + s;
-        Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
-    }
-#pragma unroll
-    for (int s = 0; s < SSB_SD; s++) Dd[s] = 0.0;
-    double F0 = V.F[0][i], F1 = V.F[1][i], F2 = V.F[2][i];
-    double B0 = V.Fbp[0][i], B1 = V.Fbp[1][i], B2 = V.Fbp[2][i];
-    double Frho = V.Frho[i];
-    const int cnt = (live && V.owned[i]) ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
-    // one accepted-or-rejected candidate j with its record in c0..c3 — verbatim pair body of k_force_mv
-    auto pair = [&](const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const int j) {
-        ssb_d4 e0;
-        e0.a = 1.0 / c3.a;
-        e0.b = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * e0.a * e0.a;
-        e0.c = c3.b * e0.a;
+    // one candidate j with its record in c0..c3 (rejected unless it is in ANN's exact set for THIS step's snapshot)
+    __device__ __forceinline__ void pair(const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const int j) {
+        const double inv_rho_j = 1.0 / c3.a;
+        const double aP_j = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * inv_rho_j * inv_rho_j;
+        const double vol_j = c3.b * inv_rho_j;
         const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
         const double r = sqrt(d2);
-        // candidate list -> ANN's exact set (the record loads above are issued before this test on purpose: a rejected
-        // candidate wastes 4 sectors, a dependent second round trip per accepted neighbour would cost far more)
-        if (V.filter && !((d2 <= h2x) && (d2 != 0.0) && !(r > h))) return;
+        // candidate list -> ANN's exact set (the record is fetched before this test on purpose: a rejected candidate wastes
+        // 4 sectors, a dependent second round trip per accepted neighbour would cost far more)
+        if (filter && !((d2 <= h2x) && (d2 != 0.0) && !(r > h))) return;
         double dx0 = xi0 - c0.d, dx1 = 0.0, dx2 = 0.0;
         if (dim > 1) dx1 = xi1 - c1.a;
         if (dim > 2) dx2 = xi2 - c1.b;
         const double vj0 = c1.c, vj1 = c1.d, vj2 = c2.a;
         const double wj0 = c2.b - vj0, wj1 = c2.c - vj1, wj2 = c2.d - vj2;
         const double rho_j = c3.a, m_j = c3.b, nu_j = c3.c;
-        const double inv_rho_j = e0.a, aP_j = e0.b, vol_j = e0.c;
         // one division for three reciprocals
         const double reg = r + eps_r, nusum = nu_i + nu_j, r2 = r * r;
         const double md = (m_i + m_j) * (r2 + eps2);
@@ -531,93 +361,20 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv_tile(SsbView V, unsig
             if (SSB_SC > 0) {
                 const double base = G * wr;
 #pragma unroll
-                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - V.C[(size_t) s * N + j]) * base;
+                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cg[(size_t) s * N + j]) * base;
             }
             if (SSB_SD > 0) {
                 const double hr = h - r;
                 const double Dij = G * (ih7c * hr * hr);                     // particle.cpp:182-187 (sign folded)
                 const int tj = (int) ((__double_as_longlong(c3.d) >> 32) & 0xffff) - 1;
 #pragma unroll
-                for (int s = 0; s < SSB_SD; s++) Dd[s] += V.dmat[s * V.num_types + tj] * Dij;
-            }
-        }
-    };
-    // ---- (1) which 64-slot blocks do this CTA's candidates fall into?  Lists are ascending (k_search walks the cell rows in
-    // storage order), so a thread's first / last entry bound its range.
-    if (threadIdx.x == 0) { s_min = 0x7fffffff; s_max = -1; s_nch = 0; s_fallback = 0; }
-    for (int w = threadIdx.x; w < SSB_TILE_WORDS; w += blockDim.x) s_bits[w] = 0u;
-    __syncthreads();
-    if (cnt > 0) {
-        atomicMin(&s_min, V.nbr[i]);
-        atomicMax(&s_max, V.nbr[(size_t) (cnt - 1) * N + i]);
-    }
-    __syncthreads();
-    const int base = (s_max >= 0) ? (s_min & ~(SSB_TILE_GRAN - 1)) : 0;
-    const int nblk = (s_max >= 0) ? (s_max - base) / SSB_TILE_GRAN + 1 : 0;
-    const bool too_wide = nblk > SSB_TILE_WORDS * 32;
-    if (!too_wide) {
-        for (int k = 0; k < cnt; k++) {
-            const int b = (V.nbr[(size_t) k * N + i] - base) / SSB_TILE_GRAN;
-            atomicOr(&s_bits[b >> 5], 1u << (b & 31));
-        }
-    }
-    __syncthreads();
-    // ---- (2) set blocks -> ascending chunks of at most SSB_TILE_REC consecutive records
-    if (threadIdx.x == 0) {
-        int n = 0, run_lo = -1, run_hi = -1, overflow = too_wide ? 1 : 0;
-        const int nwords = too_wide ? 0 : (nblk + 31) / 32;
-        for (int w = 0; w < nwords && !overflow; w++) {
-            unsigned bits = s_bits[w];
-            while (bits) {
-                const int b = w * 32 + __ffs((int) bits) - 1;
-                bits &= bits - 1u;
-                if (run_lo >= 0 && b == run_hi && (run_hi - run_lo) < SSB_TILE_REC / SSB_TILE_GRAN) { run_hi = b + 1; continue; }
-                if (run_lo >= 0) {
-                    if (n == SSB_TILE_MAXCH) { overflow = 1; break; }
-                    s_lo[n] = base + run_lo * SSB_TILE_GRAN; s_hi[n] = min(base + run_hi * SSB_TILE_GRAN, N); n++;
-                }
-                run_lo = b; run_hi = b + 1;
-            }
-        }
-        if (run_lo >= 0 && !overflow) {
-            if (n == SSB_TILE_MAXCH) overflow = 1;
-            else { s_lo[n] = base + run_lo * SSB_TILE_GRAN; s_hi[n] = min(base + run_hi * SSB_TILE_GRAN, N); n++; }
-        }
-        s_nch = overflow ? 0 : n;
-        s_fallback = overflow;
-    }
-    __syncthreads();
-    if (s_fallback) {
-        // candidates too scattered for the bitmap / chunk table: the gather loop of k_force_mv
-        for (int k = 0; k < cnt; k++) {
-            const int j = V.nbr[(size_t) k * N + i];
-            const double *rj = V.rec + (size_t) j * 16;
-            const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
-            pair(c0, c1, c2, c3, j);
-        }
-    } else {
-        // ---- (3) stage chunk by chunk; every thread consumes the candidates that fall into the staged chunk
-        const int nch = s_nch;
-        int k = 0;
-        int jn = (cnt > 0) ? V.nbr[i] : 0x7fffffff;                 // next candidate of this thread
-        double2 *s2 = reinterpret_cast<double2 *>(s_rec);
-        for (int c = 0; c < nch; c++) {
-            const int lo = s_lo[c], hi = s_hi[c];
-            if (c > 0) __syncthreads();                              // the previous chunk has been consumed by everybody
-            const double2 *g2 = reinterpret_cast<const double2 *>(V.rec + (size_t) lo * 16);
-            const int n2 = (hi - lo) * 8;                            // 16 doubles per record = 8 double2
-            for (int t = threadIdx.x; t < n2; t += blockDim.x) s2[t] = g2[t];
-            __syncthreads();
-            while (jn < hi) {                                        // jn >= lo: chunks and lists are both ascending
-                const double *rj = s_rec + (size_t) (jn - lo) * 16;
-                const ssb_d4 c0 = ssb_lds256(rj), c1 = ssb_lds256(rj + 4), c2 = ssb_lds256(rj + 8), c3 = ssb_lds256(rj + 12);
-                pair(c0, c1, c2, c3, jn);
-                k++;
-                jn = (k < cnt) ? V.nbr[(size_t) k * N + i] : 0x7fffffff;
+                for (int s = 0; s < SSB_SD; s++) Dd[s] += dmat[s * num_types + tj] * Dij;
             }
         }
     }
-    if (live) {
+
+    // results of particle i; returns max_s Ddiag_i[s] (window controller)
+    __device__ __forceinline__ double store(const SsbView &V, int i, unsigned step) {
         V.F[0][i] = F0; V.F[1][i] = F1; V.F[2][i] = F2;
         V.Fbp[0][i] = B0; V.Fbp[1][i] = B1; V.Fbp[2][i] = B2;
         V.Frho[i] = Frho;
@@ -644,8 +401,73 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv_tile(SsbView V, unsig
 #pragma unroll
             for (int s = 0; s < SSB_SC; s++) V.Q[(size_t) s * N + i] = Qi[s];
         }
+        double mx = 0.0;
 #pragma unroll
         for (int s = 0; s < SSB_SD; s++) { V.Ddiag[(size_t) s * N + i] = Dd[s]; mx = fmax(mx, Dd[s]); }
+        return mx;
+    }
+};
+
+// exchange one 32-byte sector with the quad partner `lane ^ xm`: lanes with keep_a == true keep `a` and trade `b`, the others
+// keep `b` and trade `a`
+__device__ __forceinline__ void quad_trade(ssb_d4 &a, ssb_d4 &b, bool keep_a, int xm, unsigned mask) {
+    ssb_d4 s = keep_a ? b : a;
+    s.a = __shfl_xor_sync(mask, s.a, xm); s.b = __shfl_xor_sync(mask, s.b, xm);
+    s.c = __shfl_xor_sync(mask, s.c, xm); s.d = __shfl_xor_sync(mask, s.d, xm);
+    if (keep_a) b = s; else a = s;
+}
+
+template <int COOP>
+__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
+    const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i_raw < V.N;
+    const int i = live ? i_raw : V.N - 1;          // idle lanes of the last CTA take part in the quad loads on a valid slot
+    double mx = 0.0;
+    if (COOP == 1) {
+        if (live) {
+            ForceSweep S;
+            S.init(V, i);
+            const int N = V.N;
+            const int cnt = V.owned[i] ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
+#pragma unroll 2
+            for (int k = 0; k < cnt; k++) {
+                const int j = V.nbr[(size_t) k * N + i];
+                const double *rj = V.rec + (size_t) j * 16;
+                const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
+                S.pair(c0, c1, c2, c3, j);
+            }
+            mx = S.store(V, i, step);
+        }
+    } else {
+        ForceSweep S;
+        S.init(V, i);
+        const int N = V.N;
+        const int cnt = (live && V.owned[i]) ? V.nbr_count[i] : 0;
+        const int lane = threadIdx.x & 31, sub = lane & 3, qbase = lane & ~3;
+        const unsigned qmask = 0xfu << qbase;
+        int kmax = cnt;                                           // the quad walks its four lists in lock step
+        kmax = max(kmax, __shfl_xor_sync(qmask, kmax, 1));
+        kmax = max(kmax, __shfl_xor_sync(qmask, kmax, 2));
+        const bool odd = (sub & 1) != 0, hi = (sub & 2) != 0;
+        for (int k = 0; k < kmax; k++) {
+            const bool have = k < cnt;
+            const int j = have ? V.nbr[(size_t) k * N + i] : i;  // (a lane whose list is exhausted offers its own record: a valid line)
+            // lane `sub` fetches sector `sub` of the four records of the quad: M[sub][q] = sector sub of record j_q
+            const int j0 = __shfl_sync(qmask, j, qbase), j1 = __shfl_sync(qmask, j, qbase + 1);
+            const int j2 = __shfl_sync(qmask, j, qbase + 2), j3 = __shfl_sync(qmask, j, qbase + 3);
+            ssb_d4 v0 = ssb_ld256(V.rec + (size_t) j0 * 16 + sub * 4);
+            ssb_d4 v1 = ssb_ld256(V.rec + (size_t) j1 * 16 + sub * 4);
+            ssb_d4 v2 = ssb_ld256(V.rec + (size_t) j2 * 16 + sub * 4);
+            ssb_d4 v3 = ssb_ld256(V.rec + (size_t) j3 * 16 + sub * 4);
+            // 4x4 transpose over the quad: after round 1 a lane holds two sectors of record (sub & 1) and of record (sub & 1) + 2,
+            // after round 2 the four sectors of its own record j_sub, in order
+            quad_trade(v0, v1, !odd, 1, qmask);
+            quad_trade(v2, v3, !odd, 1, qmask);
+            quad_trade(v0, v2, !hi, 2, qmask);
+            quad_trade(v1, v3, !hi, 2, qmask);
+            if (have) S.pair(v0, v1, v2, v3, j);
+        }
+        if (live) mx = S.store(V, i, step);
     }
     if (SSB_SD > 0) {
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1718,6 +1540,22 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window(SsbView V, double t_l
     flush_event_counters(V, n_rx, n_df);
 }
 
+// The step-end overshoot event of a SLAB-decomposed run (simulate_rdme.cpp:233-238; single-GPU twin: windows nwin+1 / nwin+2 of
+// k_rdme_windows_coop): the globally earliest pending clock t_min is a minimum over ranks that only exists in DEVICE memory (reduced
+// over peer-mapped boards, ssb_core.cu), so the window bounds are read from there — no host round trip.  deliver = 0: the event
+// window [t_end, t_min]; deliver = 1: the zero-length window (t_min, t_min) that delivers the molecule if it jumped.
+template <bool LEAP>
+__global__ void __launch_bounds__(SSB_BLOCK) k_rdme_window_dev(SsbView V, const unsigned long long *tmin_bits, double te, int deliver,
+                                                              double tau, uint64_t seed, uint64_t epoch, int buf) {
+    const double tmin = __longlong_as_double((long long) __ldcg(tmin_bits));
+    if (!(tmin < INFINITY) || !(tmin > te)) return;                  // nothing pending anywhere (uniform over the grid and over the ranks)
+    unsigned n_rx = 0, n_df = 0;
+    const double lo = deliver ? tmin : te;
+    if (LEAP) rdme_window_body_leap(V, lo, tmin, tau, seed, epoch, buf, n_rx, n_df);
+    else rdme_window_body(V, lo, tmin, tau, seed, epoch, buf, n_rx, n_df);
+    flush_event_counters(V, n_rx, n_df);
+}
+
 // All sSSA windows of one engine step in ONE cooperative launch: windows w = 0..nwin-1 of [t0, t0+dt], then the
 // zero-length closing window that delivers in-flight molecules; a grid-wide barrier separates consecutive windows
 // (a window's inbox writes must be complete before the next window reads them).  Removes the per-window launch
@@ -1786,8 +1624,7 @@ static int l_force(const SsbView *V, unsigned step, int full, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 static int l_force_mv(const SsbView *V, unsigned step, unsigned long long *max_bits, cudaStream_t st) {
-    if (V->flags & 256u) k_force_mv_tile<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);      // SSB_FLAG_TILE_SWEEP (opt-in)
-    else k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
+    k_force_mv<SSB_FORCE_COOP><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
     return (int) cudaGetLastError();
 }
 static int l_corrector(const SsbView *V, unsigned step, cudaStream_t st) {
@@ -1871,6 +1708,16 @@ static int l_rdme_window(const SsbView *V, double t_lo, double t_hi, double tau,
     return (int) cudaGetLastError();
 }
 
+static int l_rdme_window_dev(const SsbView *V, const unsigned long long *tmin_bits, double te, int deliver, double tau, uint64_t seed,
+                             uint64_t epoch, int buf, cudaStream_t st) {
+    const unsigned nchunks = grid_for(V->N);
+    unsigned grid = 148u * 8u;
+    if (grid > nchunks) grid = nchunks;
+    if (V->flags & 32u) k_rdme_window_dev<true><<<grid, SSB_BLOCK, 0, st>>>(*V, tmin_bits, te, deliver, tau, seed, epoch, buf);
+    else k_rdme_window_dev<false><<<grid, SSB_BLOCK, 0, st>>>(*V, tmin_bits, te, deliver, tau, seed, epoch, buf);
+    return (int) cudaGetLastError();
+}
+
 }  // namespace ssb_unit
 
 extern "C" const SsbModelUnit *ssbm_get_unit() {
@@ -1891,5 +1738,6 @@ extern "C" const SsbModelUnit *ssbm_get_unit() {
     u.block = SSB_BLOCK;
     u.rdme_window = ssb_unit::l_rdme_window;
     u.rdme_windows = ssb_unit::l_rdme_windows;
+    u.rdme_window_dev = ssb_unit::l_rdme_window_dev;
     return &u;
 }

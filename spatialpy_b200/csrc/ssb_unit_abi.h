@@ -8,7 +8,7 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 10
+#define SSB_UNIT_ABI 11
 
 struct SsbModelUnit {
     int abi;
@@ -27,6 +27,9 @@ struct SsbModelUnit {
     int (*rdme_window)(const SsbView *, double t_lo, double t_hi, double tau, uint64_t seed, uint64_t epoch, int buf, cudaStream_t);
     int (*rdme_windows)(const SsbView *, double t0, double dt, long long nwin, double tau, uint64_t seed, uint64_t epoch0, int buf0,
                         int *launches, cudaStream_t);
+    // slab runs: the step-end overshoot windows with the (global) earliest pending clock read from device memory
+    int (*rdme_window_dev)(const SsbView *, const unsigned long long *tmin_bits, double te, int deliver, double tau, uint64_t seed,
+                           uint64_t epoch, int buf, cudaStream_t);
 };
 
 extern "C" const SsbModelUnit *ssbm_get_unit();

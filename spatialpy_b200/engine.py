@@ -15,7 +15,7 @@ import numpy as np
 from . import codegen
 from .flatmodel import FlatModel
 
-SSB_ABI_VERSION = 3
+SSB_ABI_VERSION = 4
 FLAG_CORRECTED_NSM_SELECT = 1
 FLAG_CORRECTED_STOICH = 2
 FLAG_NO_VTK = 4
@@ -24,17 +24,17 @@ FLAG_LITERAL_KERNELS = 16
 FLAG_LEAP_DIFFUSION = 32
 FLAG_BINARY_STORE = 64
 FLAG_NO_STEP_OVERSHOOT = 128
-FLAG_TILE_SWEEP = 256        # opt-in shared-memory force sweep (moving domains); bit-identical to the default gather sweep
 
 ERR_NAMES = {1: "SSB_ERR_NAN", 2: "SSB_ERR_RDME", 3: "SSB_ERR_CUDA", 4: "SSB_ERR_ARG", 5: "SSB_ERR_IO",
-             6: "SSB_ERR_CANCELLED", 7: "SSB_ERR_MODEL_UNIT"}
+             6: "SSB_ERR_CANCELLED", 7: "SSB_ERR_MODEL_UNIT", 8: "SSB_ERR_HALO"}
 
 # every symbol include/ssb.h declares (tests check the library exports exactly these)
 EXPORTS = ["ssb_abi_version", "ssb_device_count", "ssb_create", "ssb_load_kernels", "ssb_destroy", "ssb_run",
            "ssb_reset", "ssb_step", "ssb_counters", "ssb_get_field", "ssb_get_neighbors", "ssb_cancel",
            "ssb_last_error", "ssb_launch_count", "ssb_step_timed", "ssb_profile", "ssb_profile_read", "ssb_io_bytes",
            "ssb_nbr_stats", "ssb_step_phase", "ssb_halo_pack", "ssb_halo_unpack", "ssb_halo_inbox_pack", "ssb_halo_inbox_add",
-           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats", "ssb_set_field", "ssb_get_step", "ssb_set_step", "ssb_write_snapshot"]
+           "ssb_halo_width", "ssb_mark", "ssb_mark_elapsed_ms", "ssb_skin_stats", "ssb_set_field", "ssb_get_step", "ssb_set_step", "ssb_write_snapshot",
+           "ssb_slab_setup", "ssb_slab_blob_bytes", "ssb_slab_export", "ssb_slab_connect", "ssb_slab_disconnect", "ssb_slab_step"]
 
 PH_PRE, PH_CORRECTOR, PH_FINISH, PH_RDME_PREP, PH_RDME_INIT, PH_RDME_WINDOW, PH_RDME_CLOSE, PH_END, PH_RDME_MIN, PH_RDME_EXTRA = range(10)
 
@@ -119,6 +119,12 @@ def load_library(path=None):
     lib.ssb_write_snapshot.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.ssb_slab_setup.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    lib.ssb_slab_blob_bytes.argtypes = []
+    lib.ssb_slab_export.argtypes = [H, C.c_void_p, C.c_int64]
+    lib.ssb_slab_connect.argtypes = [H, C.c_void_p, C.c_int64]
+    lib.ssb_slab_disconnect.argtypes = [H]
+    lib.ssb_slab_step.argtypes = [H, C.c_uint32, C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
     lib.ssb_mark.argtypes = [H, C.c_int]
     lib.ssb_mark_elapsed_ms.argtypes = [H, C.POINTER(C.c_double)]
     for name in EXPORTS:
@@ -304,6 +310,39 @@ class Engine:
 
     def inbox_add(self, ids_ptr, n, in_ptr):
         self._check(self.lib.ssb_halo_inbox_add(self._h, ids_ptr, int(n), in_ptr))
+
+    # -- native slab transport: windows in peer-mapped memory, stream-ordered exchanges (include/ssb.h ssb_slab_*) ----------
+    def slab_setup(self, rank, world, send_ids, recv_ids):
+        """send_ids / recv_ids: {neighbour rank: int32 local particle ids} as SlabPartition holds them."""
+        arrs = []
+        for nb in (rank - 1, rank + 1):
+            for d in (send_ids, recv_ids):
+                arrs.append(np.ascontiguousarray(d.get(nb, np.zeros(0, np.int32)), dtype=np.int32))
+        args = []
+        for a in arrs:
+            args += [a.ctypes.data_as(C.c_void_p), int(a.size)]
+        self._check(self.lib.ssb_slab_setup(self._h, int(rank), int(world), *args))
+
+    def slab_export(self):
+        n = self.lib.ssb_slab_blob_bytes()
+        buf = C.create_string_buffer(n)
+        self._check(self.lib.ssb_slab_export(self._h, buf, n))
+        return buf.raw
+
+    def slab_connect(self, blobs):
+        """blobs: the slab_export() of every rank, in rank order."""
+        raw = b"".join(blobs)
+        self._check(self.lib.ssb_slab_connect(self._h, raw, len(raw)))
+
+    def slab_disconnect(self):
+        if getattr(self, "_h", None):
+            self.lib.ssb_slab_disconnect(self._h)
+
+    def slab_step(self, n, travel_limit=0.0):
+        """n engine steps with device-side halo exchanges; returns (steps done, travel bound)."""
+        done, travel = C.c_uint32(0), C.c_double(0.0)
+        self._check(self.lib.ssb_slab_step(self._h, int(n), float(travel_limit), C.byref(done), C.byref(travel)))
+        return done.value, travel.value
 
     def skin_stats(self):
         a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)

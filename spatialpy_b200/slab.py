@@ -264,6 +264,15 @@ class DistComm:
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.MIN)
         return float(t.item())
 
+    def allgather_bytes(self, blob):
+        """Every rank's `blob` (bytes), in rank order — control plane of the native transport (IPC handles travel once per partition)."""
+        if self.world == 1:
+            return [blob]
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, blob)
+        return out
+
     def exchange_rows(self, send, width):
         """Variable-length exchange with the slab neighbours: {nb: float64 [n_nb, width]} -> {nb: float64 [m_nb, width]}
         (row counts first, then the rows)."""
@@ -323,15 +332,24 @@ class LoopbackComm:
         return self._round("s", {nb: np.array(a, dtype=np.float64, copy=True) for nb, a in send.items()},
                            lambda post: {nb: post(nb).reshape(-1, width) for nb in send})
 
+    def allgather_bytes(self, blob):
+        return self._round("g", {nb: blob for nb in range(self.world)}, lambda post: [post(nb) for nb in range(self.world)])
+
 
 class SlabEngine:
     """One rank of a slab-decomposed run: an Engine on the local model + the halo exchanges between the step phases."""
 
     def __init__(self, part, rank, world, device=0, flags=FLAG_SKIP_STATIC_FORCES, rdme_epsilon=0.0, comm=None,
-                 auto_repartition=True, repartition_every=0, engine_factory=None, torch_device=None):
+                 auto_repartition=True, repartition_every=0, engine_factory=None, torch_device=None, transport=None):
         import torch
         self.torch = torch
         self.rank, self.world = rank, world
+        # transport "native" (default with the CUDA engine): halo messages are written by the engine's pack kernels straight into
+        # the neighbour's receive window over NVLink and ordered by the engine stream (ssb_slab_*, include/ssb.h); `comm` is only the
+        # control plane (IPC handles once per partition, re-partition rows).  transport "host": every exchange is orchestrated
+        # from here through `comm` (phase API) — the protocol the CPU tier pins with a stand-in engine, and the cross-check of
+        # the native path on the GPU.
+        self.transport = transport or ("host" if engine_factory is not None else "native")
         if part.local.static_domain:
             raise ValueError("slab decomposition is implemented for moving domains (static ensembles shard by trajectory)")
         self.device_index = device
@@ -360,6 +378,12 @@ class SlabEngine:
         self.eng = self.engine_factory(part.local, device=self.device_index, flags=self.flags, rdme_epsilon=self.rdme_epsilon,
                                        owned=part.owned, rng_id=part.gids.astype(np.int32))
         self.Sd = part.local.num_stoch_species
+        self.travel_bound = 0.0       # upper bound on how far any particle has moved since the partition was made
+        self.steps_since_partition = 0
+        if self.transport == "native":
+            self.eng.slab_setup(self.rank, self.world, part.send_ids, part.recv_ids)
+            self.eng.slab_connect(self.comm.allgather_bytes(self.eng.slab_export()))
+            return
         self.send_ids = {nb: torch.as_tensor(v, device=self.dev) for nb, v in part.send_ids.items()}
         self.recv_ids = {nb: torch.as_tensor(v, device=self.dev) for nb, v in part.recv_ids.items()}
         self.buf = {}
@@ -370,18 +394,29 @@ class SlabEngine:
         # inbox traffic flows the other way: from my ghosts (recv_ids) to their owners (the neighbour's send_ids)
         self.ibuf = ({nb: torch.empty((len(v), max(self.Sd, 1)), dtype=torch.int32, device=self.dev) for nb, v in self.recv_ids.items()},
                      {nb: torch.empty((len(v), max(self.Sd, 1)), dtype=torch.int32, device=self.dev) for nb, v in self.send_ids.items()})
-        self.travel_bound = 0.0       # upper bound on how far any particle has moved since the partition was made
-        self.steps_since_partition = 0
+
+    def _retire_engine(self):
+        """Collective: unmap the neighbours' windows, meet, then free (nobody may still be writing into a window that goes away)."""
+        if self.eng is None:
+            return
+        if self.transport == "native":
+            self.eng.slab_disconnect()
+            if self.world > 1:
+                try:
+                    self.comm.allreduce(0.0, "max")
+                except Exception:       # noqa: BLE001 - a rank that already failed broke the meeting point; freeing is all that is left
+                    pass
+        self.eng.close()
+        self.eng = None
 
     def close(self):
-        if self.eng is not None:
-            self.eng.close()
+        self._retire_engine()
 
     def reset(self, seed):
         self.seed = seed
         self._carry = {"reactions": 0, "diffusions": 0, "seconds": 0.0, "windows": 0}
         if self.part is not self.part0:        # a re-partition replaced the model by a mid-trajectory state
-            self.eng.close()
+            self._retire_engine()
             self._build(self.part0)
         self.travel_bound = 0.0
         self.steps_since_partition = 0
@@ -408,7 +443,31 @@ class SlabEngine:
         for nb, ids in self.send_ids.items():          # mail for my owned particles that are ghosts over there
             self.eng.inbox_add(ids.data_ptr(), ids.numel(), recv[nb].data_ptr())
 
+    def _step_native(self, n):
+        """n engine steps through ssb_slab_step; the engine stops early (on every rank after the same step) when the travel bound
+        is used up, and the re-partition runs here."""
+        limit = 0.5 * (self.part.halo - 1.1 * self.part.local.h)
+        stale_is_error = (not self.auto_repartition and self.repartition_every <= 0) or self.part.edges is None
+        left = int(n)
+        while left > 0:
+            chunk = left
+            if self.repartition_every > 0:
+                chunk = min(chunk, max(1, self.repartition_every - self.steps_since_partition))
+            done, self.travel_bound = self.eng.slab_step(chunk, limit if self.world > 1 else 0.0)
+            left -= done
+            self.steps_since_partition += done
+            if done < chunk:
+                if stale_is_error:
+                    raise RuntimeError(f"slab partition is stale: particles may have travelled {self.travel_bound:g} since the "
+                                       f"partition (halo {self.part.halo:g}, h {self.part.local.h:g}); re-partition needed "
+                                       "(SlabEngine(auto_repartition=True))")
+                self.repartition()
+            elif self.world > 1 and self.repartition_every > 0 and self.steps_since_partition >= self.repartition_every:
+                self.repartition()
+
     def step(self, n=1):
+        if self.transport == "native":
+            return self._step_native(n)
         for _ in range(n):
             e = self.eng
             e.phase(PH_PRE)
@@ -429,7 +488,7 @@ class SlabEngine:
                     tmin = self.comm.allreduce(e.phase(PH_RDME_MIN), "min")
                     e.phase(PH_RDME_EXTRA, tmin)
                     self._sync_inbox()
-                    e.phase(PH_RDME_CLOSE)
+                    e.phase(PH_RDME_CLOSE, -1.0)       # delivers under the epoch the overshoot reserved (same numbering as one GPU)
             e.phase(PH_END)
             self.steps_since_partition += 1
             # a pair within h*(1+skin) must have both members present on the owner's rank, so nobody may travel further than
@@ -471,7 +530,7 @@ class SlabEngine:
         c = e.counters()
         for k in self._carry:
             self._carry[k] += c[k]
-        e.close()
+        self._retire_engine()
         self._build(part)
         self.eng.reset(self.seed)
         for name, val in fields.items():

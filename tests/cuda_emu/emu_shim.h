@@ -1,6 +1,6 @@
 // emu_shim.h — TEST INFRASTRUCTURE: run a CUDA kernel's SOURCE on the host, one std::thread per CUDA thread of a block, blocks one
 // after the other.  Enough of the execution model for kernels that use threadIdx/blockIdx, __shared__ arrays, __syncthreads,
-// shared/global integer atomics, __ffs and full-warp __shfl_xor_sync: the logic of a kernel (indexing, barriers, cursors,
+// shared/global integer atomics, __ffs and warp / quad shuffles: the logic of a kernel (indexing, barriers, cursors,
 // fallbacks) can be exercised without a GPU and compared with another kernel run the same way.  It says nothing about
 // performance, memory-model subtleties or fused multiply-add placement.
 #pragma once
@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
 #include <algorithm>
 #include <thread>
 #include <vector>
@@ -25,7 +28,6 @@ struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
 static thread_local EmuIdx threadIdx, blockIdx;
 static EmuIdx blockDim, gridDim;
 static std::barrier<> *emu_barrier = nullptr;
-static double emu_xchg[1024];
 
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
 using std::max;
@@ -46,14 +48,29 @@ static inline double __longlong_as_double(long long v) { double r; std::memcpy(&
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
-// full-warp xor shuffle (every thread of the block calls it the same number of times)
-static inline double __shfl_xor_sync(unsigned, double v, int lane_mask) {
-    emu_xchg[threadIdx.x] = v;
-    __syncthreads();
-    const double r = emu_xchg[threadIdx.x ^ (unsigned) lane_mask];
-    __syncthreads();
+// warp shuffles: the participants are the lanes named by `mask` — the full warp (0xffffffff) or one aligned quad (0xf << 4q).  Each
+// group has its own reusable barrier, so groups may call a different number of shuffles (quads walk lists of different lengths).
+static std::barrier<> *emu_warp_bar[32], *emu_quad_bar[256];
+static double emu_slot[1024];
+template <typename T>
+static inline T emu_shfl(unsigned mask, T v, unsigned src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    std::barrier<> *bar;
+    if (mask == 0xffffffffu) bar = emu_warp_bar[tid >> 5];
+    else if (mask == (0xfu << (lane & ~3u))) bar = emu_quad_bar[tid >> 2];
+    else { std::fprintf(stderr, "emu_shfl: unsupported mask %08x on lane %u\n", mask, lane); std::abort(); }
+    std::memcpy(&emu_slot[tid], &v, sizeof(T));
+    bar->arrive_and_wait();
+    T r;
+    std::memcpy(&r, &emu_slot[(tid & ~31u) + (src_lane & 31u)], sizeof(T));
+    bar->arrive_and_wait();
     return r;
 }
+static inline double __shfl_xor_sync(unsigned m, double v, int x) { return emu_shfl(m, v, (threadIdx.x & 31u) ^ (unsigned) x); }
+static inline int __shfl_xor_sync(unsigned m, int v, int x) { return emu_shfl(m, v, (threadIdx.x & 31u) ^ (unsigned) x); }
+static inline double __shfl_sync(unsigned m, double v, int src) { return emu_shfl(m, v, (unsigned) src); }
+static inline int __shfl_sync(unsigned m, int v, int src) { return emu_shfl(m, v, (unsigned) src); }
 
 // launch: kernel(args...) for every thread of every block
 template <typename K, typename... A>
@@ -62,6 +79,9 @@ static void emu_launch(unsigned blocks, unsigned threads, K kernel, A... args) {
     for (unsigned b = 0; b < blocks; b++) {
         std::barrier<> bar((std::ptrdiff_t) threads);
         emu_barrier = &bar;
+        std::vector<std::unique_ptr<std::barrier<>>> groups;       // (blocks are multiples of 32 threads)
+        for (unsigned w = 0; w < threads / 32; w++) { groups.emplace_back(new std::barrier<>(32)); emu_warp_bar[w] = groups.back().get(); }
+        for (unsigned q = 0; q < threads / 4; q++) { groups.emplace_back(new std::barrier<>(4)); emu_quad_bar[q] = groups.back().get(); }
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < threads; t++)
             pool.emplace_back([=]() { threadIdx.x = t; blockIdx.x = b; kernel(args...); });

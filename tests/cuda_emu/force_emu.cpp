@@ -1,6 +1,7 @@
-// force_emu.cpp — TEST INFRASTRUCTURE: the SOURCE of k_force_mv and k_force_mv_tile (extracted verbatim from
+// force_emu.cpp — TEST INFRASTRUCTURE: the SOURCE of the moving-domain force sweep k_force_mv<COOP> (extracted verbatim from
 // spatialpy_b200/csrc/ssb_model_unit.cuh by tests/test_cpu_abi.py into EMU_KERNELS) run on the host through emu_shim.h, so that
-// the tile form's logic can be compared with the gather form bit for bit without a GPU.
+// the quad-gather form (COOP = 4: cooperative record fetch + 4x4 shuffle transpose) can be compared with the one-gather-per-lane
+// form (COOP = 1) bit for bit without a GPU.
 #include "emu_shim.h"
 
 #include SSB_MODEL_HEADER          // generated ssb_gen namespace + SSB_* sizes of the test model (same text nvcc compiles)
@@ -28,7 +29,7 @@ struct EmuArgs {
     unsigned long long *max_bits;
 };
 
-extern "C" int emu_force(const EmuArgs *a, int tile, unsigned step) {
+extern "C" int emu_force(const EmuArgs *a, int coop, unsigned step) {
     SsbView V;
     std::memset(&V, 0, sizeof(V));
     V.N = a->N; V.dim = a->dim; V.num_types = a->num_types; V.filter = a->filter; V.flags = a->flags;
@@ -38,7 +39,7 @@ extern "C" int emu_force(const EmuArgs *a, int tile, unsigned step) {
     for (int d = 0; d < 3; d++) { V.F[d] = a->F[d]; V.Fbp[d] = a->Fbp[d]; }
     V.Frho = a->Frho; V.C = a->C; V.Q = a->Q; V.Ddiag = a->Ddiag; V.data_fn = a->data_fn; V.dmat = a->dmat;
     const unsigned blocks = (unsigned) ((a->N + SSB_BLOCK - 1) / SSB_BLOCK);
-    if (tile) emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv_tile, V, step, a->max_bits);
-    else emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv, V, step, a->max_bits);
+    if (coop == 4) emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv<4>, V, step, a->max_bits);
+    else emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv<1>, V, step, a->max_bits);
     return 0;
 }

@@ -552,79 +552,6 @@ def test_converted_expressions_evaluate_like_python():
                 assert abs(out[k] - want) < 5e-4 * max(1.0, abs(want)) or round(out[k] - want, 3) == 0, (expr, vals, out[k], want)
 
 
-def _tile_chunks(lists, n_slots, gran=64, rec=256, words=512, maxch=96):
-    """Python restatement of steps (1)-(2) of k_force_mv_tile (ssb_model_unit.cuh) for one CTA: ascending candidate lists ->
-    ascending chunks [lo, hi) of at most `rec` consecutive slots, or None for the gather fallback."""
-    firsts = [l[0] for l in lists if len(l)]
-    if not firsts:
-        return []
-    smin, smax = min(firsts), max(l[-1] for l in lists if len(l))
-    base = smin & ~(gran - 1)
-    nblk = (smax - base) // gran + 1
-    if nblk > words * 32:
-        return None
-    bits = np.zeros(nblk, bool)
-    for l in lists:
-        bits[(np.asarray(l, dtype=np.int64) - base) // gran] = True
-    chunks, run_lo, run_hi = [], -1, -1
-    for b in np.nonzero(bits)[0]:
-        if run_lo >= 0 and b == run_hi and (run_hi - run_lo) < rec // gran:
-            run_hi = b + 1
-            continue
-        if run_lo >= 0:
-            if len(chunks) == maxch:
-                return None
-            chunks.append((base + run_lo * gran, min(base + run_hi * gran, n_slots)))
-        run_lo, run_hi = b, b + 1
-    if run_lo >= 0:
-        if len(chunks) == maxch:
-            return None
-        chunks.append((base + run_lo * gran, min(base + run_hi * gran, n_slots)))
-    return chunks
-
-
-def test_tile_sweep_chunking_consumes_every_candidate_once_in_order():
-    """The algorithm of the opt-in shared-memory force sweep (k_force_mv_tile): on cell-sorted candidate lists of a jittered
-    tank, every CTA's chunks are ascending, disjoint, at most 256 records long and inside the array, and the per-thread cursor
-    consumes each candidate exactly once, in list order, while its record is staged — which is why the tile form can be
-    bit-identical to the gather form.  Also the fallback conditions."""
-    from scipy.spatial import cKDTree
-    from spatialpy_b200 import configs
-    fm = configs.tank_sdpd(n=16, nt=10, output_every=10)
-    rng = np.random.default_rng(1)
-    x = fm.x + rng.uniform(-0.002, 0.002, fm.x.shape)
-    rad = fm.h * 1.1
-    cell = np.floor((x - x.min(axis=0)) / rad).astype(np.int64)
-    ncell = cell.max(axis=0) + 1
-    key = (cell[:, 2] * ncell[1] + cell[:, 1]) * ncell[0] + cell[:, 0]          # storage order of the engine's cell list
-    order = np.argsort(key, kind="stable")
-    xs = x[order]
-    n = len(xs)
-    lists = [sorted(l) for l in cKDTree(xs).query_ball_point(xs, rad)]           # self included, like the candidate lists
-    staged_total, pairs_total = 0, 0
-    for b0 in range(0, n, 128):
-        cta = lists[b0:b0 + 128]
-        chunks = _tile_chunks(cta, n)
-        assert chunks is not None and 0 < len(chunks) <= 96
-        assert all(lo < hi <= n and hi - lo <= 256 for lo, hi in chunks)
-        assert all(chunks[c][1] <= chunks[c + 1][0] for c in range(len(chunks) - 1))
-        staged_total += sum(hi - lo for lo, hi in chunks)
-        for l in cta:                                                          # the cursor of one thread
-            k, seen = 0, []
-            for lo, hi in chunks:
-                while k < len(l) and l[k] < hi:
-                    assert l[k] >= lo                                          # its record is in the staged chunk
-                    seen.append(l[k])
-                    k += 1
-            assert seen == l
-            pairs_total += len(l)
-    assert staged_total < 0.6 * pairs_total            # the point of staging: far fewer record fetches than pairs
-    # fallbacks: candidates spread over more slots than the bitmap covers, or over more chunks than the table holds
-    assert _tile_chunks([[0, 64 * 512 * 32 + 5]], 10 ** 8) is None
-    assert _tile_chunks([[k * 128 for k in range(200)]], 10 ** 6) is None
-    assert _tile_chunks([[], []], 100) == []
-
-
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line with the contract's keys, timed on the
     unmodified reference executable built from /root/reference (oracle/_ref); skipped where that binary does not exist."""
@@ -725,13 +652,13 @@ def test_engine_writers_large_snapshot_threads_and_python_twin_agree(tmp_path, m
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# the opt-in tile force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu), against the
-# default gather sweep's source executed the same way
+# the moving-domain force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu) — the quad-gather
+# form (COOP = 4: four lanes fetch their four records together, 4x4 shuffle transpose) against one gather per lane (COOP = 1)
 # ----------------------------------------------------------------------------------------------------------------------
 def _build_force_emulator(fm, tmp_path, defines=()):
     from spatialpy_b200 import codegen
     src = open(os.path.join(codegen.CSRC, "ssb_model_unit.cuh")).read()
-    a = src.index("__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V")
+    a = src.index("// per-particle state of the sweep + the pair body")
     b = src.index("// ---------------------------------------------------------------------------------------------\n// Static-domain fast path")
     kern = tmp_path / "kernels.inc"
     kern.write_text(src[a:b])
@@ -793,7 +720,7 @@ def _force_sweep_inputs(fm, seed=2):
     return st
 
 
-def _run_force_emulator(lib, fm, st, tile):
+def _run_force_emulator(lib, fm, st, coop):
     n = st["n"]
     out = {k: np.ascontiguousarray(st[k]).copy() for k in ("F", "Fbp", "Frho", "Q")}
     out["Ddiag"] = np.full((max(st["Sd"], 1), n), -1.0)
@@ -808,44 +735,35 @@ def _run_force_emulator(lib, fm, st, tile):
         a.Fbp[d] = out["Fbp"][d].ctypes.data
     a.Frho, a.C, a.Q, a.Ddiag = out["Frho"].ctypes.data, keep[4].ctypes.data, out["Q"].ctypes.data, out["Ddiag"].ctypes.data
     a.data_fn, a.dmat, a.max_bits = None, keep[5].ctypes.data, mb.ctypes.data
-    assert lib.emu_force(ctypes.byref(a), int(tile), 3) == 0
+    assert lib.emu_force(ctypes.byref(a), int(coop), 3) == 0
     out["max_bits"] = mb
     return out
 
 
-def test_tile_force_sweep_source_equals_the_gather_sweep_on_the_host(tmp_path):
-    """k_force_mv_tile vs k_force_mv, both as CUDA SOURCE run by the block emulator (one host thread per CUDA thread, real
-    barriers, shared arrays, atomics): every output of the sweep is bit-identical — with the tile path taken, and with the
-    tile constants shrunk so that the bitmap-too-small and too-many-chunks fallbacks are taken."""
+def test_quad_gather_force_sweep_source_equals_one_gather_per_lane_on_the_host(tmp_path):
+    """k_force_mv<4> vs k_force_mv<1>, both as CUDA SOURCE run by the block emulator (one host thread per CUDA thread, real
+    barriers, quad and warp shuffles): every output of the sweep is bit-identical — ragged lists inside a quad, ghosts, idle
+    lanes of the last CTA included."""
     from spatialpy_b200 import configs
-    fm = configs.tank_sdpd(n=14, nt=10, output_every=10)     # ~2 000 particles: 16 CTAs whose candidates sit in several separate runs
+    fm = configs.tank_sdpd(n=14, nt=10, output_every=10)     # ~2 000 particles, 16 CTAs, the last one partly idle
     st = _force_sweep_inputs(fm)
-    chunks = [_tile_chunks([sorted(st["nbr"][:st["cnt"][i], i].tolist()) for i in range(b0, min(b0 + 128, st["n"]))], st["n"])
-              for b0 in range(0, st["n"], 128)]
-    assert all(c is not None for c in chunks) and max(len(c) for c in chunks) >= 3          # the tile path, with gaps between chunks
+    assert st["n"] % 128 != 0 and len(set(st["cnt"][:4].tolist())) > 1
     lib = _build_force_emulator(fm, tmp_path)
-    ref = _run_force_emulator(lib, fm, st, tile=0)
+    ref = _run_force_emulator(lib, fm, st, coop=1)
     assert np.abs(ref["F"] - st["F"]).max() > 0 and (ref["Ddiag"][:, st["owned"] == 1] >= 0).all()   # the sweep did something
-    got = _run_force_emulator(lib, fm, st, tile=1)
+    got = _run_force_emulator(lib, fm, st, coop=4)
     for k in ref:
         assert np.array_equal(ref[k], got[k]), k
-    for defines in (("SSB_TILE_REC=16", "SSB_TILE_GRAN=4", "SSB_TILE_WORDS=1", "SSB_TILE_MAXCH=96"),        # span > bitmap
-                    ("SSB_TILE_REC=64", "SSB_TILE_GRAN=64", "SSB_TILE_WORDS=512", "SSB_TILE_MAXCH=2"),     # chunk table overflow
-                    ("SSB_TILE_REC=128", "SSB_TILE_GRAN=32", "SSB_TILE_WORDS=512", "SSB_TILE_MAXCH=96")):  # other geometry
-        lib2 = _build_force_emulator(fm, tmp_path, defines)
-        got2 = _run_force_emulator(lib2, fm, st, tile=1)
-        for k in ref:
-            assert np.array_equal(ref[k], got2[k]), (defines, k)
 
 
-def test_tile_force_sweep_source_on_a_2d_model(tmp_path):
+def test_quad_gather_force_sweep_source_on_a_2d_model(tmp_path):
     """Same comparison on a 2-D moving model (cavity2d_rdme fixture: other species / reaction counts => another instantiation
     of the generated code)."""
     fm = load_model("cavity2d_rdme")
     st = _force_sweep_inputs(fm, seed=7)
     lib = _build_force_emulator(fm, tmp_path)
-    ref = _run_force_emulator(lib, fm, st, tile=0)
-    got = _run_force_emulator(lib, fm, st, tile=1)
+    ref = _run_force_emulator(lib, fm, st, coop=1)
+    got = _run_force_emulator(lib, fm, st, coop=4)
     assert np.abs(ref["F"] - st["F"]).max() > 0
     for k in ref:
         assert np.array_equal(ref[k], got[k]), k

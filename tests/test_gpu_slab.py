@@ -1,4 +1,5 @@
-"""GPU tier, 2 GPUs (skipped on a 1-GPU box): a slab-decomposed run over NCCL reproduces the single-GPU engine."""
+"""GPU tier: a slab-decomposed run reproduces the single-GPU engine — ranks as processes on 2 GPUs (windows shared through CUDA
+IPC; skipped on a 1-GPU box) and ranks as threads on one GPU (windows shared by pointer)."""
 import os
 import socket
 
@@ -158,12 +159,14 @@ def test_trajectory_continues_in_a_fresh_handle():
     assert int(got["xx"].sum()) == int(fm.u0.sum())
 
 
-def _loopback_run(world, steps, every):
-    """`world` slab ranks as threads of this process on cuda:0 (LoopbackComm), re-partitioning every `every` steps."""
+def _loopback_run(world, steps, every, transport="native", reactive=False):
+    """`world` slab ranks as threads of this process on cuda:0 (LoopbackComm), re-partitioning every `every` steps.
+    transport "native": halo messages written by the pack kernels into the neighbour's receive window, ordered by the engine
+    streams (ssb_slab_*; same process => the windows are shared by pointer); "host": every exchange orchestrated from Python."""
     import threading
     import torch
     from spatialpy_b200.slab import LoopbackComm, LoopbackHub, SlabEngine, partition
-    fm = _model(False)
+    fm = _model(reactive)
     hub = LoopbackHub(world, timeout=300.0)
     outs, errs = {}, {}
     from spatialpy_b200 import codegen
@@ -175,7 +178,7 @@ def _loopback_run(world, steps, every):
             torch.cuda.set_device(0)
             part = partition(fm, rank, world)
             se = SlabEngine(part, rank, world, device=0, comm=LoopbackComm(hub, rank, torch.device("cuda", 0)),
-                            auto_repartition=True, repartition_every=every)
+                            auto_repartition=True, repartition_every=every, transport=transport)
             se.reset(11)
             se.step(steps)
             out = {"gid": se.part.gids[se.part.owned == 1], "repartitions": se.repartitions, "counters": se.counters()}
@@ -216,15 +219,33 @@ def _check_against_single(fm, outs, steps):
     assert sum(outs[r]["counters"]["diffusions"] for r in range(world)) > 0
 
 
+@pytest.mark.parametrize("transport", ["native", "host"])
 @pytest.mark.parametrize("world,every", [(2, 0), (3, 0), (2, 5), (3, 4)])
-def test_loopback_slabs_with_repartition_match_single_gpu(world, every):
-    """The whole slab code path on ONE GPU: `world` ranks as threads, exchanges as device copies.  every = 0 is the fixed
-    partition (same as the 2-GPU NCCL test); every > 0 hands the trajectory over to fresh handles several times."""
+def test_loopback_slabs_with_repartition_match_single_gpu(world, every, transport):
+    """The whole slab code path on ONE GPU: `world` ranks as threads.  every = 0 is the fixed partition (same as the 2-GPU
+    test); every > 0 hands the trajectory over to fresh handles several times."""
     steps = 22
-    fm, outs = _loopback_run(world, steps, every)
+    fm, outs = _loopback_run(world, steps, every, transport)
     _check_against_single(fm, outs, steps)
     want = 0 if every == 0 else (steps // every)
     assert all(outs[r]["repartitions"] == want for r in range(world))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_native_transport_equals_host_orchestrated_exchange_bit_for_bit(world):
+    """Same kernels, same messages, same Philox numbering — only who moves the bytes differs (pack kernels writing into
+    peer-mapped windows behind sequence flags vs. Python-orchestrated pack / copy / unpack): every field and every
+    population of a REACTIVE run (births, deaths, jumps across the faces, the step-end overshoot events) must be identical."""
+    steps = 22
+    _, a = _loopback_run(world, steps, 0, "native", reactive=True)
+    _, b = _loopback_run(world, steps, 0, "host", reactive=True)
+    for r in range(world):
+        np.testing.assert_array_equal(a[r]["gid"], b[r]["gid"])
+        for f in _FIELDS + ("xx",):
+            np.testing.assert_array_equal(a[r][f], b[r][f], err_msg=f"rank {r} {f}")
+        assert a[r]["counters"]["reactions"] == b[r]["counters"]["reactions"]
+        assert a[r]["counters"]["diffusions"] == b[r]["counters"]["diffusions"]
+    assert sum(a[r]["counters"]["reactions"] for r in range(world)) > 0
 
 
 def _worker_repart(rank, world, port, q, steps, every):
@@ -268,14 +289,6 @@ def test_two_gpu_slab_with_repartition_matches_single_gpu():
     assert all(outs[r]["repartitions"] == steps // every for r in range(2))
 
 
-# written after the round-1 GPU budget was spent: the driver logic is CPU-tested with fake rank engines (tests/test_cpu_slab.py)
-# and its building blocks (loopback ranks, SlabEngine, both host writers) are GPU- / byte-tested; the end-to-end call awaits
-# its first GPU run
-slab_solver = pytest.mark.skipif(os.environ.get("SSB_PENDING_GPU_TESTS") != "1",
-                                 reason="Solver.run(decomposition='slab') awaits its first GPU run (set SSB_PENDING_GPU_TESTS=1)")
-
-
-@slab_solver
 def test_solver_slab_decomposition_leaves_the_single_gpu_file_set():
     """Solver.run(decomposition="slab", devices=[0, 0]): two slabs (two engine handles on cuda:0) leave the same files as the
     single-handle run — same names, same file -> step map, every field within 1e-9, the molecule count conserved."""

@@ -137,7 +137,6 @@ def test_leap_form_diffusion_parity_and_conservation():
 
 # written after the round-1 GPU budget was spent; the construction is pinned on the CPU (tests/test_cpu_gloo.py: the copies of a
 # replicated model pass the same KS test through the serial NSM restatement); the GPU run of it is pending
-@pytest.mark.skipif(__import__("os").environ.get("SSB_PENDING_GPU_TESTS") != "1", reason="awaits its first GPU run (set SSB_PENDING_GPU_TESTS=1)")
 @pytest.mark.parametrize("name", ["birth_death", "cdc42"])
 def test_batched_ensemble_has_the_reference_law(name):
     """run_ensemble_batched: 256 trajectories per engine handle as disjoint copies of the model.  Totals of every species at
