@@ -1,20 +1,20 @@
 #!/usr/bin/env python
 """bench.py — the ssa_sdpd hot path on B200, measured as BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cylinder|tank|box]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload box|tank|cylinder|ens_*]
 
-Workload at N=1 (default): BASELINE configs[1] — the 3D_Cylinder_Demo static-domain RDME + PDE model refined to
-~1.0 M fixed particles (spatialpy_b200/configs.py:cylinder_rdme).  One bench "step" = SPS
-engine timesteps (each: predictor, chemistry-flux sweep over the neighbour lists, corrector, and the sSSA windows)
-of one trajectory.  `value` = particle-steps/s with the model resident in HBM, timed with CUDA events on the engine's
-stream; `e2e` = the same metric through the public call a user makes (ssb_run: upload of the initial state from host
-memory, stepping, output snapshots copied back to pinned host memory) timed on the host clock.
-N>1: trajectories are independent units (solver.py:547-605) — each rank runs its own trajectory of the same model,
-no data-path collective, `scaling: weak`.
-
-`--impl reference` times the UNMODIFIED reference engine (oracle/_ref/bench_*/fast/ssa_sdpd.exe, built from
-/root/reference by oracle/oracle_build.py) on the host cores, on a bounded instance of the same workload (the
-reference cannot be compiled at 1 M particles: one C++ source line per particle).
+Workload (default `box`): the unit the metric's target is quoted on — BASELINE configs[4], the synthetic 3-D SDPD + sSSA box, 200^3 =
+8 M moving particles per GPU (spatialpy_b200/configs.py:box_sdpd_rdme).  One bench "step" = SPS engine
+timesteps, each = cell list / predictor / neighbour search (when due) / pairwise force sweep / corrector / BVF sweep / sSSA windows.
+  N = 1   one 8 M box on one GPU.  `value` = particle-steps/s with the model resident in HBM, CUDA events on the engine's stream;
+          `e2e` = the same through the C-ABI call a user's Solver.run makes (ssb_run: upload of the initial state from host memory,
+          stepping, output snapshots copied back to pinned host memory), host clock.  The line also carries `same_n` (our engine on
+          the very instance the reference arm runs: the like-for-like ratio) and `sub_records` (cylinder = configs[1], tank = configs[2]).
+  N > 1   ONE box of N x 8 M particles split into N slabs along x (weak scaling), halo exchange through peer-mapped windows over
+          NVLink (ssb_slab_*, include/ssb.h): `value` = owned particles of all ranks x steps / max-over-ranks device time.
+`--impl reference` times the UNMODIFIED reference engine (oracle/_ref/bench_*/fast/ssa_sdpd.exe, built from /root/reference by
+oracle/oracle_build.py) on the host cores on a bounded instance of the same workload (24^3 = 13 824 particles: the reference
+cannot be compiled at 8 M, one C++ source line per particle), as BASELINE.md 3.2 says: wall of the run minus a zero-step run.
 """
 import argparse
 import json
@@ -108,38 +108,7 @@ def algorithmic_bytes(fm, moving):
 # ---------------------------------------------------------------------------------------------------------
 # reference arm
 # ---------------------------------------------------------------------------------------------------------
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    name = {"cylinder": "bench_cylinder", "tank": "bench_tank", "box": "bench_tank"}[args.workload]
-    base = os.path.join(ROOT, "oracle", "_ref", name)
-    exe = os.path.join(base, "fast", "ssa_sdpd.exe")
-    if not os.path.exists(exe):
-        print(json.dumps({"impl": "reference", "unavailable": f"{exe} not built (oracle/oracle_build.py needs /root/reference)"}))
-        return
-    meta = json.load(open(os.path.join(base, "meta.json")))
-    cores = os.cpu_count() or 1
-    threads = cores
-    times = []
-    for it in range(args.warmup + args.steps):
-        d = tempfile.mkdtemp(prefix="ssb_ref_")
-        t0 = time.perf_counter()
-        subprocess.run([exe, "-t", str(threads), "-s", str(1000 + it)], cwd=d, stdout=subprocess.DEVNULL, check=True)
-        dt = time.perf_counter() - t0
-        subprocess.run(["rm", "-rf", d])
-        if it >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    value = meta["N"] * meta["nt"] / (ms / 1e3)
-    sample = (f"unmodified reference engine (g++ -O3), {meta['builder']}{meta['kwargs']}: N={meta['N']} particles x {meta['nt']} steps per run, "
-              f"-t {threads}; wall clock of the whole executable (includes particle construction and VTK output)")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload} (bounded CPU instance of the GPU workload)", "particles": meta["N"], "engine_steps_per_step": meta["nt"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+REF_NAME = {"cylinder": "bench_cylinder", "tank": "bench_tank", "box": "bench_box"}
 
 
 def _time_reference(exe, threads, seed=1000):
@@ -151,116 +120,108 @@ def _time_reference(exe, threads, seed=1000):
     return dt
 
 
-def cpu_baseline_sample(workload):
-    """Bounded sample of the reference on the host cores (rank 0, N=1 only).  `value` is the strongest CPU arm (g++ -O3, all
-    cores); `variants` adds what SURVEY.md 8(d) asks to see beside it: one thread, the reference's own default thread cap
-    (min(8, cores), E/propensity_file_template.cpp:129-132) and the build the reference actually ships (no -O, E/build/SConstruct:23)."""
-    name = {"cylinder": "bench_cylinder", "tank": "bench_tank", "box": "bench_tank"}[workload]
-    base = os.path.join(ROOT, "oracle", "_ref", name)
+def _reference_instance(workload):
+    base = os.path.join(ROOT, "oracle", "_ref", REF_NAME[workload])
     exe = os.path.join(base, "fast", "ssa_sdpd.exe")
     if not os.path.exists(exe):
         return None
     meta = json.load(open(os.path.join(base, "meta.json")))
+    zero = os.path.join(ROOT, "oracle", "_ref", REF_NAME[workload] + "_zero", "fast", "ssa_sdpd.exe")
+    return base, exe, (zero if os.path.exists(zero) else None), meta
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation on the box's host cores (rank 0 only).  Stepping-loop time = wall of the run minus
+    the wall of a zero-step run of the same model, so that process start, particle construction and the first
+    output do not count against the reference."""
+    if rank != 0:
+        return
+    if args.workload not in REF_NAME:
+        print(json.dumps({"impl": "reference", "unavailable": f"no reference instance for workload {args.workload}"}))
+        return
+    inst = _reference_instance(args.workload)
+    if inst is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (oracle/oracle_build.py needs /root/reference)"}))
+        return
+    base, exe, zero, meta = inst
+    threads = os.cpu_count() or 1
+    t_zero = min(_time_reference(zero, threads, 900 + k) for k in range(2)) if zero else 0.0
+    times = []
+    for it in range(args.warmup + args.steps):
+        dt = _time_reference(exe, threads, 1000 + it)
+        if it >= args.warmup:
+            times.append(max(dt - t_zero, 1e-9))
+    ms = 1e3 * sum(times) / len(times)
+    value = meta["N"] * meta["nt"] / (ms / 1e3)
+    sample = (f"unmodified reference engine (g++ -O3), {meta['builder']}{meta['kwargs']}: N={meta['N']} particles x {meta['nt']} steps per run, "
+              f"-t {threads}; wall of the executable minus a zero-step run of the same model ({t_zero:.3f} s)" if zero else
+              f"unmodified reference engine (g++ -O3), {meta['builder']}{meta['kwargs']}: N={meta['N']} particles x {meta['nt']} steps per run, "
+              f"-t {threads}; wall clock of the whole executable (includes particle construction and VTK output)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} (bounded CPU instance of the GPU workload)", "particles": meta["N"], "engine_steps_per_step": meta["nt"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(workload):
+    """Bounded sample of the reference on the host cores (rank 0, N=1 only).  `value` is the strongest CPU arm (g++ -O3, all
+    cores, stepping loop = wall minus a zero-step run where that executable exists); `variants` adds what SURVEY.md 8(d) asks to see
+    beside it: one thread, the reference's own default thread cap (min(8, cores), E/propensity_file_template.cpp:129-132) and the
+    build the reference actually ships (no -O, E/build/SConstruct:23)."""
+    inst = _reference_instance(workload)
+    if inst is None:
+        return None
+    base, exe, zero, meta = inst
     cores = os.cpu_count() or 1
     work = meta["N"] * meta["nt"]
-    dt = _time_reference(exe, cores)
+    t_zero = _time_reference(zero, cores, 900) if zero else 0.0
+    dt = max(_time_reference(exe, cores) - t_zero, 1e-9)
     variants = {f"O3_t{cores}": work / dt}
     try:
         # the extra arms stay inside the bench's time budget: skipped on a host where the strongest arm already takes long
         if dt < 12.0:
-            t1 = _time_reference(exe, 1)
+            t1 = max(_time_reference(exe, 1) - t_zero, 1e-9)
             variants["O3_t1"] = work / t1
             if cores > 8:
-                variants["O3_t8"] = work / _time_reference(exe, 8)
+                variants["O3_t8"] = work / max(_time_reference(exe, 8) - t_zero, 1e-9)
             shipped = os.path.join(base, "shipped", "ssa_sdpd.exe")
-            if os.path.exists(shipped) and t1 < 90.0:
-                variants[f"shipped_noopt_t{cores}"] = work / _time_reference(shipped, cores)
+            if os.path.exists(shipped) and t1 < 60.0:
+                variants[f"shipped_noopt_t{cores}"] = work / max(_time_reference(shipped, cores) - t_zero, 1e-9)
     except Exception:   # noqa: BLE001 - the extra arms are informative only
         pass
     return {"value": work / dt, "unit": UNIT, "cores": cores, "kind": "reference",
-            "sample": f"unmodified reference engine (g++ -O3) on {meta['builder']}{meta['kwargs']}: N={meta['N']} x {meta['nt']} steps, -t {cores}, {dt:.2f} s wall",
+            "sample": f"unmodified reference engine (g++ -O3) on {meta['builder']}{meta['kwargs']}: N={meta['N']} x {meta['nt']} steps, -t {cores}, "
+                      f"{dt:.2f} s stepping loop (wall minus {t_zero:.2f} s zero-step run)",
             "variants": {k: round(v, 1) for k, v in variants.items()}}
 
 
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
-    import torch
-    from spatialpy_b200.engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
-    use_dist = world > 1
-    if use_dist:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    fm, desc = make_workload(args.workload, args.scale)
-    moving = not fm.static_domain
-    if args.sps is None:
-        args.sps = 50 if moving else 200
-    N, SPS = fm.num_particles, args.sps
-    eng = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK | args.extra_flags)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if use_dist:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def allmax(v):
-        if not use_dist:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(v):
-        if not use_dist:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---- device-resident run: every bench step is the first SPS engine steps of a fresh trajectory (the same segment the
-    # end-to-end arm runs); the state upload (ssb_reset) happens BEFORE the timed region of each step -------------------
-    for w in range(args.warmup):
-        eng.reset(1000 + rank + 31 * w)
-        eng.step_timed(SPS)
-    ev_total, win_total = 0, 0
-    launches0 = eng.launch_count()
-    launches = 0
-    eng.profile(True)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    barrier()
-    dev_ms = 0.0
-    for k in range(args.steps):
-        eng.reset(5000 + rank + 17 * k)            # untimed: inputs are resident in HBM when the timed region starts
-        l0 = eng.launch_count()
-        dev_ms += eng.step_timed(SPS)              # CUDA events on the engine stream, synchronised on both sides
-        c = eng.counters()
-        ev_total += c["reactions"] + c["diffusions"]
-        win_total += c["windows"]
-        launches += eng.launch_count() - l0
-    barrier()
-    clk = clocks.stop()
-    prof = eng.profile_read()
-    eng.profile(False)
-    dev_ms = allmax(dev_ms)
-    events = allsum(float(ev_total))
-    ms_per_step = dev_ms / args.steps
-    value = world * N * SPS * args.steps / (dev_ms / 1e3)
-    events_per_s = events / (dev_ms / 1e3)
-    cap, nnz = eng.nbr_stats()
-
-    # ---- roofline of the dominant kernel (live CUDA-event durations over the timed region) ----------------------
-    dom = max(prof, key=lambda k: prof[k]["ms"])
+def _peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per particle per launch of `kernel`, from this round's `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by profiles/extract_traffic.py from the committed raw-page CSVs); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(path))[workload][kernel]["bytes_per_particle"])
+    except (OSError, KeyError, ValueError, TypeError):
+        return None
+
+
+def kernel_bytes_table(fm, moving):
+    """Algorithmic bytes per particle per launch (DESIGN.md section 4 = SURVEY.md 8d per-phase figures)."""
     Sc, Sd, R = fm.num_chem_species, fm.num_stoch_species, fm.num_stoch_rxns
-    kernel_bytes = {   # algorithmic bytes per particle per launch (DESIGN.md §4)
+    return {
         "force": (104 + 8 * Sc + 56 + 8 * Sc) if moving else (48 + 16 * Sc),
         "rdme_window": 8 + 4 * Sd,
         "finish": (80 + 16 * Sc + 56 + 8 * Sc) if moving else (24 * Sc + 8),
@@ -268,112 +229,213 @@ def run_ours(args, rank, local_rank, world):
         "cells": 96, "search": 24 + 24 + 4, "corrector": 70 + 32, "diff_init": 68 + 12 * Sd, "rdme_init": 4 * Sd + 8 * R + 24,
         "output": 0,
     }
-    # DRAM traffic of the dominant kernel, bytes per particle per launch, from the committed `ncu --set full` captures
-    # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_prof_cyl_r1b_metrics.csv, profiles/r1_prof_tank_r1b_metrics.csv)
-    ncu_traffic = {("cylinder", "force"): 862.6e6 / 1001382, ("tank", "force"): 420.9e6 / 987228}
-    # bytes the kernel must stream given the stored index-only neighbour lists: 4 B index per pair
-    # (+ 8 B cached coefficient per pair on the static fast path) on top of the SURVEY figure
-    mean_nbr = nnz / N
-    stream_bytes = dict(kernel_bytes)
-    stream_bytes["force"] = kernel_bytes["force"] + (12.0 if not moving else 4.0) * mean_nbr
+
+
+def roofline_of(workload, fm, moving, prof, N, nnz, value_per_gpu):
+    """Roofline record of the dominant kernel from the live per-category CUDA-event timers (ssb_profile)."""
+    peak, peak_src = _peak()
+    kb = kernel_bytes_table(fm, moving)
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    mean_nbr = nnz / max(N, 1)
+    stream_bytes = dict(kb)
+    # bytes the kernel must stream given the stored index-only candidate lists: 4 B index per pair (+ 8 B cached coefficient
+    # per pair on the static fast path) on top of the SURVEY figure
+    stream_bytes["force"] = kb["force"] + (12.0 if not moving else 4.0) * mean_nbr
     dn = max(prof[dom]["launches"], 1)
     dom_ms = prof[dom]["ms"] / dn
-    achieved = kernel_bytes[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ncu_traffic.get((args.workload, dom)) * N if ncu_traffic.get((args.workload, dom)) else None),
-                "traffic_note": "bytes per launch of the dominant kernel, ncu --set full (profiles/), scaled to this N",
-                "stream_achieved": (stream_bytes[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0),
-                "stream_frac": (stream_bytes[dom] * N / (dom_ms / 1e3) / 1e9 / peak if dom_ms > 0 else 0.0),
-                "stream_note": "algorithmic bytes + the stored neighbour-list stream (4 B/pair index, +8 B/pair cached coefficient when static)",
-                "peak_source": peak_src, "avg_launch_ms": dom_ms, "launches": prof[dom]["launches"],
-                "share_of_step": prof[dom]["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-30),
-                "algorithmic_bytes_per_particle": kernel_bytes[dom],
-                "whole_step_frac": (algorithmic_bytes(fm, moving) * value / world) / (peak * 1e9),
-                "kernels_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}}
+    achieved = kb[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = _ncu_traffic(workload, dom)
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (traffic * N if traffic else None),
+            "traffic_note": "dram bytes per launch of the dominant kernel: profiles/ncu_traffic.json (this round's ncu --set full capture), scaled to this N",
+            "stream_achieved": (stream_bytes[dom] * N / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0),
+            "stream_frac": (stream_bytes[dom] * N / (dom_ms / 1e3) / 1e9 / peak if dom_ms > 0 else 0.0),
+            "stream_note": "algorithmic bytes + the stored neighbour-list stream (4 B/pair index, +8 B/pair cached coefficient when static)",
+            "peak_source": peak_src, "avg_launch_ms": dom_ms, "launches": prof[dom]["launches"],
+            "share_of_step": prof[dom]["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-30),
+            "algorithmic_bytes_per_particle": kb[dom],
+            "whole_step_frac": (algorithmic_bytes(fm, moving) * value_per_gpu) / (peak * 1e9),
+            "kernels_ms": {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]}}, mean_nbr, dom_ms
 
-    # ---- end to end: the public call, host buffers in, host buffers out ------------------------------------------
-    fm_e2e = fm
-    fm_e2e.nt = SPS
-    fm_e2e.output_steps = __import__("numpy").array([0, SPS], dtype="uint32")
+
+def measure_single(args, workload, fm, desc, rank, local_rank, world, steps, warmup, SPS, comm, with_fp64=False, with_cpu=False):
+    """One trajectory of `fm` per GPU: device-resident value, roofline of the dominant kernel, end-to-end through ssb_run."""
+    from spatialpy_b200.engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+    import numpy as np
+    moving = not fm.static_domain
+    N = fm.num_particles
+    eng = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK | args.extra_flags)
+    # ---- device-resident run: every bench step is the first SPS engine steps of a fresh trajectory (the same segment the
+    # end-to-end arm runs); the state upload (ssb_reset) happens BEFORE the timed region of each step -------------------
+    for w in range(warmup):
+        eng.reset(1000 + rank + 31 * w)
+        eng.step_timed(SPS)
+    ev_total, win_total, launches = 0, 0, 0
+    eng.profile(True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    comm.barrier()
+    dev_ms = 0.0
+    for k in range(steps):
+        eng.reset(5000 + rank + 17 * k)            # untimed: inputs are resident in HBM when the timed region starts
+        l0 = eng.launch_count()
+        dev_ms += eng.step_timed(SPS)              # CUDA events on the engine stream, synchronised on both sides
+        c = eng.counters()
+        ev_total += c["reactions"] + c["diffusions"]
+        win_total += c["windows"]
+        launches += eng.launch_count() - l0
+    comm.barrier()
+    clk = clocks.stop()
+    prof = eng.profile_read()
+    eng.profile(False)
+    skin = eng.skin_stats() if moving else None
+    dev_ms = comm.allmax(dev_ms)
+    events = comm.allsum(float(ev_total))
+    value = world * N * SPS * steps / (dev_ms / 1e3)
+    cap, nnz = eng.nbr_stats()
+    roofline, mean_nbr, dom_ms = roofline_of(workload, fm, moving, prof, N, nnz, value / world)
     eng.close()
+
+    # ---- end to end: the C-ABI call behind Solver.run, host buffers in, host buffers out -------------------------------
+    fm.nt = SPS
+    fm.output_steps = np.array([0, SPS], dtype="uint32")
     t_create0 = time.perf_counter()
-    eng2 = Engine(fm_e2e, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK | args.extra_flags)
+    eng2 = Engine(fm, device=local_rank, flags=FLAG_SKIP_STATIC_FORCES | FLAG_NO_VTK | args.extra_flags)
     create_s = time.perf_counter() - t_create0
     eng2.run_no_files(2000 + rank, 1)           # warm-up trajectory
-    barrier()
+    comm.barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        eng2.run_no_files(3000 + rank + 17 * k, 1)   # reset (H2D of the initial state) + SPS steps + 2 output snapshots (D2H)
-    barrier()
-    e2e_s = allmax(time.perf_counter() - t0)
+    for k in range(steps):
+        eng2.run_no_files(3000 + rank + 17 * k, 1)   # reset (H2D of the initial state) + SPS steps + output snapshots (D2H)
+    comm.barrier()
+    e2e_s = comm.allmax(time.perf_counter() - t0)
     h2d, d2h = eng2.io_bytes()
-    e2e_value = world * N * SPS * args.steps / e2e_s
+    e2e_value = world * N * SPS * steps / e2e_s
     eng2.close()
 
-    # fp64 companion of the HBM roofline: the moving-domain sweeps are gather / fp64-issue bound, so their flop
-    # rate is reported against the MEASURED fp64 FMA peak of this device (child process: it cannot take the line with it)
-    if rank == 0:
+    if with_fp64 and rank == 0:
+        # fp64 companion of the HBM roofline (SURVEY.md 8d): the moving-domain sweeps are fp64-issue / gather bound, so their flop
+        # rate is reported against the MEASURED fp64 FMA peak of this device (child process: it cannot take the line with it)
         pk = fp64_peak_sample(local_rank)
         roofline["fp64"] = pk
-        if "fp64_tflops" in pk and moving and dom_ms > 0:
-            sweep_ms = prof["force"]["ms"] / max(prof["force"]["launches"], 1)
+        if "fp64_tflops" in pk and moving and prof["force"]["launches"]:
+            sweep_ms = prof["force"]["ms"] / prof["force"]["launches"]
             if sweep_ms > 0:
                 tf = 230.0 * mean_nbr * N / (sweep_ms / 1e3) / 1e12
-                pk.update(force_sweep_tflops=tf, force_sweep_frac=tf / pk["fp64_tflops"],
-                          note="SURVEY 8(d) pair figure: 230 flop per stored neighbour-list entry of the force sweep")
-    cpu = cpu_baseline_sample(args.workload) if (rank == 0 and world == 1 and not args.no_cpu) else None
-    # the other sharding mode, measured in the same run: ONE 8 M-particle-per-GPU SDPD+sSSA box split into slabs with NCCL
-    # halo exchange (BASELINE configs[4]); reported beside the headline so per-N lines carry both scaling modes
-    slab = None
-    if not args.no_slab:
+                pk.update(force_sweep_tflops=tf, force_sweep_frac=tf / pk["fp64_tflops"], force_sweep_ms=sweep_ms,
+                          note="SURVEY 8(d) pair figure: 230 flop per stored candidate-list entry of the force sweep")
+    cpu = cpu_baseline_sample(workload) if (with_cpu and rank == 0 and world == 1 and not args.no_cpu) else None
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "particles_per_gpu": N, "engine_steps_per_step": SPS, "static_domain": not moving,
+                   "species": fm.num_species, "reactions": fm.num_reactions, "mean_neighbours": nnz / N,
+                   "sssa_windows_per_engine_step": win_total / max(SPS * steps, 1),
+                   "trajectory_segment": f"each bench step = engine steps 0..{SPS} of a fresh trajectory (incl. the step-0 list build on the first one)",
+                   "parallelism": f"one trajectory per GPU x {world}" + ("" if world == 1 else " (independent replicas, no collective)"),
+                   "verlet_skin": skin,
+                   "l2": "working set (candidate lists + gather records + state) exceeds the 126 MB L2; no explicit flush"},
+        "rdme_events_per_s": events / (dev_ms / 1e3),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "includes": "ssb_run (the C-ABI call Solver.run makes): H2D of the initial state from host memory, stepping, output snapshots D2H "
+                            "into pinned host memory; no VTK text", "engine_create_s": create_s},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+    }
+
+
+class Comm:
+    """barrier / max / sum over the ranks of the torchrun launch (NCCL), or no-ops at N = 1."""
+
+    def __init__(self, local_rank, world):
+        import torch
+        self.torch, self.world = torch, world
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def _red(self, v, op):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def allmax(self, v):
+        return self._red(v, self.dist.ReduceOp.MAX if self.world > 1 else None)
+
+    def allsum(self, v):
+        return self._red(v, self.dist.ReduceOp.SUM if self.world > 1 else None)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def same_n_record(args, workload, rank, local_rank, comm):
+    """Our engine on EXACTLY the instance the reference arm runs (oracle/_ref/<name>/meta.json): the like-for-like companion of
+    the headline ratio.  Small models are launch-latency bound on a B200 — this is the honest same-size number, not the headline."""
+    inst = _reference_instance(workload)
+    if inst is None or rank != 0:
+        return None
+    from spatialpy_b200 import configs
+    meta = inst[3]
+    fm = getattr(configs, meta["builder"])(**meta["kwargs"])
+    nt = int(meta["nt"])
+    line = measure_single(args, workload, fm, f"{meta['builder']}{meta['kwargs']}", rank, local_rank, 1, 5, 2, nt, comm)
+    return {"particles": fm.num_particles, "engine_steps_per_step": nt, "value": line["value"], "e2e": line["e2e"]["value"], "unit": UNIT,
+            "ms_per_step": line["ms_per_step"], "note": "same model, same size, same number of steps as `--impl reference` runs on the host cores"}
+
+
+def run_ours(args, rank, local_rank, world):
+    comm = Comm(local_rank, world)
+    fm, desc = make_workload(args.workload, args.scale)
+    moving = not fm.static_domain
+    SPS = args.sps if args.sps is not None else (50 if moving else 200)
+    line = measure_single(args, args.workload, fm, desc, rank, local_rank, world, args.steps, args.warmup, SPS, comm,
+                          with_fp64=True, with_cpu=True)
+    if world == 1 and not args.no_sub:
         try:
-            sl = slab_measure(args, rank, local_rank, world, 3, 2, 5)
-            slab = {k: sl[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "rdme_events_per_s")}
-            slab.update(workload=sl["config"]["workload"], particles_per_gpu=sl["config"]["particles_per_gpu"],
-                        ghosts_per_gpu=sl["config"]["ghosts_per_gpu"], parallelism=sl["config"]["parallelism"],
-                        engine_steps_per_step=sl["config"]["engine_steps_per_step"], scaling="weak")
-        except Exception as err:      # never lose the headline line to the secondary measurement
-            slab = {"error": f"{type(err).__name__}: {err}"}
+            line["same_n"] = same_n_record(args, args.workload, rank, local_rank, comm)
+        except Exception as err:      # noqa: BLE001 - never lose the headline line to a companion measurement
+            line["same_n"] = {"error": f"{type(err).__name__}: {err}"[:300]}
+        subs = {}
+        for wl in ("tank", "cylinder"):
+            if wl == args.workload:
+                continue
+            try:
+                f2, d2 = make_workload(wl, args.scale)
+                sps2 = 50 if not f2.static_domain else 200
+                sub = measure_single(args, wl, f2, d2, rank, local_rank, 1, 3, 3, sps2, comm)
+                subs[wl] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "rdme_events_per_s", "roofline", "e2e", "gpu_launches", "clocks")}
+            except Exception as err:  # noqa: BLE001
+                subs[wl] = {"error": f"{type(err).__name__}: {err}"[:300]}
+        line["sub_records"] = subs
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "particles_per_gpu": N, "engine_steps_per_step": SPS, "static_domain": not moving,
-                       "species": fm.num_species, "reactions": fm.num_reactions, "mean_neighbours": nnz / N,
-                       "sssa_windows_per_engine_step": win_total / max(SPS * args.steps, 1),
-                       "trajectory_segment": f"each bench step = engine steps 0..{SPS} of a fresh trajectory (incl. the step-0 list build on the first one)",
-                       "parallelism": f"ensemble: one trajectory per GPU x {world}",
-                       "l2": "working set (neighbour lists + cached D_ij + state) exceeds the 126 MB L2; no explicit flush"},
-            "rdme_events_per_s": events_per_s,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": "ssb_run: H2D of the initial state, stepping, output snapshots D2H into pinned memory (no VTK text)",
-                    "engine_create_s": create_s},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-            "spatial_slab": slab,
-        }
         print(json.dumps(line))
-    if use_dist:
-        dist.destroy_process_group()
+    comm.close()
 
 
 # ---------------------------------------------------------------------------------------------------------
 # slab-decomposed arm: ONE domain split over the ranks (BASELINE configs[4]: weak scaling, fixed particles per GPU)
 # ---------------------------------------------------------------------------------------------------------
 def run_slab(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    line = slab_measure(args, rank, local_rank, world, args.steps, args.warmup, args.sps or 10)
+    comm = Comm(local_rank, world)
+    line = slab_measure(args, rank, local_rank, world, args.steps, args.warmup, args.sps or 20, comm)
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    comm.close()
 
 
 def fp64_peak_sample(device):
@@ -392,74 +454,79 @@ def fp64_peak_sample(device):
         return {"error": f"{type(err).__name__}: {err}"[:200]}
 
 
-def slab_measure(args, rank, local_rank, world, steps, warmup, SPS):
-    """One box domain of 200^3 * scale particles per GPU, slab-decomposed over the ranks; returns the bench line (dict)."""
-    import torch
-    import torch.distributed as dist
+def slab_measure(args, rank, local_rank, world, steps, warmup, SPS, comm):
+    """ONE box of world x n^3 particles (n = 200 at scale 1: 8 M per GPU), slab-decomposed along x over the ranks; the bench line."""
+    import numpy as np
     from spatialpy_b200 import configs
     from spatialpy_b200.slab import SlabEngine
     n = max(16, int(round(200 * args.scale ** (1.0 / 3.0))))
     part = configs.box_slab(rank, world, nx_per_rank=n, ny=n, nz=n)
-    se = SlabEngine(part, rank, world, device=local_rank)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def allred(v, op):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=op)
-        return float(t.item())
-
+    se = SlabEngine(part, rank, world, device=local_rank, transport=args.transport)
+    fm = part.local
     se.reset(1000)
     for _ in range(warmup):
         se.step(SPS)
+    se.eng.profile(True)
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0, c0 = se.eng.launch_count(), se.eng.counters()
-    barrier()
+    comm.barrier()
     t0 = time.perf_counter()
     se.eng.mark(0)
     for _ in range(steps):
         se.step(SPS)
     se.eng.mark(1)
-    dev_ms = se.eng.mark_elapsed_ms()           # CUDA events on the engine stream (includes the waits for the halo exchanges)
-    barrier()
+    dev_ms = se.eng.mark_elapsed_ms()           # CUDA events on the engine stream (includes the waits for the halo messages)
+    comm.barrier()
     wall_s = time.perf_counter() - t0
     clk = clocks.stop()
+    prof = se.eng.profile_read()
+    se.eng.profile(False)
     c1 = se.eng.counters()
-    dev_ms = allred(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
-    wall_s = allred(wall_s, dist.ReduceOp.MAX if world > 1 else None)
-    owned_total = allred(float(part.n_owned), dist.ReduceOp.SUM if world > 1 else None)
-    events = allred(float(c1["reactions"] + c1["diffusions"] - c0["reactions"] - c0["diffusions"]), dist.ReduceOp.SUM if world > 1 else None)
+    launches = int(se.eng.launch_count() - l0)
+    dev_ms = comm.allmax(dev_ms)
+    wall_s = comm.allmax(wall_s)
+    owned_total = comm.allsum(float(part.n_owned))
+    events = comm.allsum(float(c1["reactions"] + c1["diffusions"] - c0["reactions"] - c0["diffusions"]))
     nsteps = SPS * steps
     value = owned_total * nsteps / (dev_ms / 1e3)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
-    fm = part.local
-    per_step_bytes = algorithmic_bytes(fm, True)
+    cap, nnz = se.eng.nbr_stats()
+    roofline, mean_nbr, dom_ms = roofline_of("box", fm, True, prof, part.n_owned, nnz, value / world)
     ghosts = fm.num_particles - part.n_owned
-    halo_bytes = sum(len(v) for v in part.send_ids.values()) * 8 * (7 + fm.num_chem_species + 1 + 4)
-    line = ({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[4]: synthetic 3-D SDPD+sSSA box, {n}^3 owned particles per GPU, slab-decomposed along x",
-                       "particles_per_gpu": part.n_owned, "ghosts_per_gpu": ghosts, "engine_steps_per_step": SPS,
-                       "parallelism": f"spatial slabs x {world}, NCCL send/recv halo exchange (3 field groups + sSSA inboxes per step)",
-                       "halo_bytes_sent_per_engine_step_per_rank": halo_bytes,
-                       "l2": "working set exceeds the 126 MB L2; no explicit flush"},
-            "rdme_events_per_s": events / (dev_ms / 1e3),
-            "roofline": {"bound": "hbm", "kernel": "whole step (SURVEY 8d byte model)", "achieved": per_step_bytes * value / world / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": per_step_bytes * value / world / 1e9 / peak, "traffic": None},
-            "cpu_baseline": None,
-            "e2e": {"value": owned_total * nsteps / wall_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "includes": "host wall clock of the same stepping loop incl. Python orchestration and NCCL halo exchanges (state resident)"},
-            "gpu_launches": int(se.eng.launch_count() - l0), "clocks": clk})
+    Sc = fm.num_chem_species
+    halo_bytes = sum(len(v) for v in part.send_ids.values()) * 8 * (7 + Sc + 1 + 4)
+    # ---- end to end: host buffers in (ssb_reset uploads the rank's initial state), the same steps, owned state read back to the host
+    comm.barrier()
+    t1 = time.perf_counter()
+    se.reset(2000)
+    se.step(SPS)
+    d2h = 0
+    for f in ("x", "v", "rho", "C", "xx"):
+        d2h += se.eng.get(f).nbytes
+    comm.barrier()
+    e2e_s = comm.allmax(time.perf_counter() - t1)
+    h2d = se.eng.io_bytes()[0]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: synthetic 3-D SDPD+sSSA box of {world} x {n}^3 particles, slab-decomposed along x",
+                   "particles_per_gpu": part.n_owned, "ghosts_per_gpu": ghosts, "engine_steps_per_step": SPS,
+                   "mean_neighbours": nnz / max(part.n_owned, 1),
+                   "parallelism": (f"spatial slabs x {world}; transport = {se.transport}: " +
+                                   ("pack kernels store into the neighbour's receive window over NVLink (CUDA IPC peer memory), sequence flags, "
+                                    "stream-ordered; 3 field groups + sSSA inbox entries + 3 scalar boards per step" if se.transport == "native"
+                                    else "host-orchestrated NCCL send/recv")),
+                   "halo_bytes_sent_per_engine_step_per_rank": halo_bytes, "repartitions": se.repartitions,
+                   "l2": "working set exceeds the 126 MB L2; no explicit flush"},
+        "rdme_events_per_s": events / (dev_ms / 1e3),
+        "roofline": roofline,
+        "cpu_baseline": None,
+        "e2e": {"value": owned_total * SPS / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "includes": "per rank: ssb_reset (H2D of the initial state from host memory) + the same engine steps with halo exchanges + "
+                            "owned x, v, rho, C, xx read back to host memory; host clock, max over ranks",
+                "stepping_loop_wall_value": owned_total * nsteps / wall_s},
+        "gpu_launches": launches, "clocks": clk}
     se.close()
     return line
 
@@ -536,17 +603,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "tank", "box", "ens_birth_death", "ens_cdc42", "ens_cdc42_full"])
+    ap.add_argument("--workload", default="box", choices=["box", "tank", "cylinder", "ens_birth_death", "ens_cdc42", "ens_cdc42_full"])
     ap.add_argument("--trajectories", type=int, default=128, help="ensemble workloads: trajectories per GPU")
     ap.add_argument("--lanes", type=int, default=0, help="ensemble workloads: concurrent engine handles per GPU (0 = auto)")
     ap.add_argument("--batch", type=int, default=0, help="ensemble workloads: trajectories per engine handle as disjoint copies of the model (0 = off)")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full particle count (1.0 = BASELINE size)")
-    ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving)")
+    ap.add_argument("--sps", type=int, default=None, help="engine timesteps per bench step (default: 200 static, 50 moving, 20 slab)")
     ap.add_argument("--extra-flags", type=int, default=0, help="extra SSB_FLAG_* bits for the engine (diagnostics)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
-    ap.add_argument("--no-slab", action="store_true", help="skip the secondary slab-decomposed measurement")
-    ap.add_argument("--decomp", default="ensemble", choices=["ensemble", "slab"],
-                    help="N>1: independent trajectories per GPU (default) or ONE box domain split into slabs (BASELINE configs[4])")
+    ap.add_argument("--no-sub", action="store_true", help="skip the same-N companion and the cylinder / tank sub-records")
+    ap.add_argument("--decomp", default="auto", choices=["auto", "ensemble", "slab"],
+                    help="N>1: ONE box domain split into slabs (auto: the box workload) or independent trajectories per GPU")
+    ap.add_argument("--transport", default=None, choices=["native", "host"], help="slab runs: halo transport (default native)")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.impl == "reference":
@@ -555,7 +623,7 @@ def main():
     if args.workload.startswith("ens_"):
         run_ensemble_bench(args, rank, local_rank, world)
         return
-    if args.decomp == "slab":
+    if args.decomp == "slab" or (args.decomp == "auto" and args.workload == "box" and world > 1):
         run_slab(args, rank, local_rank, world)
         return
     run_ours(args, rank, local_rank, world)

@@ -49,6 +49,30 @@ def add_reference_to_path():
             sys.path.insert(0, p)
 
 
+def stage_reference_python():
+    """Copy the reference's PYTHON front end (spatialpy/ without the C++ engine tree), its own test models and the no-op plotly
+    stub into the untracked oracle/_ref/py/ so that the GPU box — which has no /root/reference — can `import spatialpy` and run the
+    reference's front door (Model.run -> Solver -> Result) against the CUDA engine (tests/test_gpu_frontdoor.py).  Build output
+    only: oracle/_ref/ is git-ignored and never imported by the product path."""
+    import shutil
+    dst = os.path.join(OUT, "py")
+    if not reference_available():
+        return dst if os.path.isdir(os.path.join(dst, "spatialpy")) else None
+    shutil.rmtree(dst, ignore_errors=True)
+    os.makedirs(dst)
+    shutil.copytree(os.path.join(REF_ROOT, "spatialpy"), os.path.join(dst, "spatialpy"),
+                    ignore=shutil.ignore_patterns("c_base", "__pycache__", "*.pyc"))
+    shutil.copytree(os.path.join(HERE, "stubs", "plotly"), os.path.join(dst, "plotly"), ignore=shutil.ignore_patterns("__pycache__"))
+    shutil.copytree(os.path.join(REF_ROOT, "test", "models"), os.path.join(dst, "ref_test_models"), ignore=shutil.ignore_patterns("__pycache__"))
+    return dst
+
+
+def staged_python_path():
+    """sys.path entry under which `import spatialpy` finds the staged reference front end (None if it was never staged)."""
+    dst = os.path.join(OUT, "py")
+    return dst if os.path.isdir(os.path.join(dst, "spatialpy")) else None
+
+
 def _run(cmd, **kw):
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
     if res.returncode != 0:

@@ -23,7 +23,12 @@ import build_ref  # noqa: E402
 BENCH_REF = {
     "bench_cylinder": ("cylinder_rdme", dict(delta=0.125, nt=100, output_every=100, dt=1e-3)),
     "bench_tank": ("tank_sdpd", dict(n=26, nt=20, output_every=20, dt=1e-5)),
+    # the bench's default workload (BASELINE configs[4] per-GPU unit, SDPD + sSSA) at a size the reference compiles: 24^3 = 13 824
+    "bench_box": ("box_sdpd_rdme", dict(nx=24, ny=24, nz=24, nt=20, output_every=20, dt=1e-5)),
 }
+# the stepping loop = wall of the executable minus the wall of a ZERO-STEP run of the same model (process
+# start, particle construction, the step-0 output); built for the default workload only
+ZERO_STEP = ("bench_box",)
 
 
 def build_bench_refs(variants=("fast", "shipped")):
@@ -34,6 +39,10 @@ def build_bench_refs(variants=("fast", "shipped")):
         for variant in variants:
             exe = build_ref.build_flat(fm, name, variant=variant, dump=False, model_opt="-O1" if variant == "fast" else None)
             out[f"{name}/{variant}"] = exe
+        if name in ZERO_STEP:
+            kw0 = dict(kw, nt=0)
+            fm0 = getattr(configs, builder)(**kw0)
+            out[f"{name}/fast0"] = build_ref.build_flat(fm0, name + "_zero", variant="fast", dump=False, model_opt="-O1")
         meta = dict(N=fm.num_particles, nt=int(fm.nt), dt=float(fm.dt), builder=builder, kwargs=kw,
                     Sc=fm.num_chem_species, Sd=fm.num_stoch_species, R=fm.num_reactions)
         with open(os.path.join(build_ref.OUT, name, "meta.json"), "w") as f:
@@ -47,6 +56,7 @@ def build_all():
         return
     for k, v in build_bench_refs().items():
         print("built", k, v)
+    print("staged", build_ref.stage_reference_python())
 
 
 if __name__ == "__main__":

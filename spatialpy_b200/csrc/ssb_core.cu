@@ -31,6 +31,8 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges cost a no-op call unless a profiler is attached
+
 #include "../../include/ssb.h"
 #include "ssb_device.cuh"
 #include "ssb_unit_abi.h"
@@ -209,11 +211,11 @@ __global__ void k_permute_rows32(int N, const int *perm, const int *src, int *ds
 // is still queued, and decides whether the next step keeps its candidate lists — no blocking read-back after the predictor and no
 // "skin exceeded" failure mode: a step whose displacement would not fit simply rebuilds.
 __global__ void k_lookahead(SsbView V, unsigned long long *out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
     double a = 0.0, b = 0.0, c = 0.0;
-    if (i < V.N) {
+    const double dt = V.dt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < V.N; i += gridDim.x * blockDim.x) {     // persistent grid: 3 atomics per CTA
         const bool moves = V.solid[i] == 0;
-        const double dt = V.dt;
+        double pa = 0.0, pb = 0.0, pc = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             const double x = V.x[d][i], xr = V.xref[d][i];
@@ -223,18 +225,22 @@ __global__ void k_lookahead(SsbView V, unsigned long long *out) {
                 const double vt = v + 0.5 * dt * V.Fbp[d][i];
                 xn = x + dt * vt;
             }
-            a += (xn - xr) * (xn - xr); b += (xn - x) * (xn - x); c += (x - xr) * (x - xr);
+            pa += (xn - xr) * (xn - xr); pb += (xn - x) * (xn - x); pc += (x - xr) * (x - xr);
         }
+        a = fmax(a, pa); b = fmax(b, pb); c = fmax(c, pc);
     }
+    __shared__ double sh[3][CORE_BLOCK / 32];
     for (int o = 16; o > 0; o >>= 1) {
         a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
         b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
         c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (a > 0.0) atomicMax(&out[0], (unsigned long long) __double_as_longlong(a));
-        if (b > 0.0) atomicMax(&out[1], (unsigned long long) __double_as_longlong(b));
-        if (c > 0.0) atomicMax(&out[2], (unsigned long long) __double_as_longlong(c));
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; sh[2][threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double m = 0.0;
+        for (int w = 0; w < CORE_BLOCK / 32; w++) m = fmax(m, sh[threadIdx.x][w]);
+        if (m > 0.0) atomicMax(&out[threadIdx.x], (unsigned long long) __double_as_longlong(m));
     }
 }
 
@@ -427,7 +433,7 @@ __global__ void k_inbox_add(SsbView V, int buf, const int *ids, int n, const int
 #define HALO_NCH 4                   // channels 0..2 = field groups 0..2, 3 = sSSA inbox (compacted entries)
 #define HALO_CH_INBOX 3
 #define HALO_HDR_BYTES 1024          // window header: flag[ch] at 64*ch, inbox entry count of parity q at 512 + 64*q
-#define HALO_TIMEOUT_NS 20000000000ull
+#define HALO_TIMEOUT_NS 10000000000ull
 #define SSB_BOARD_NCH 3              // scalar all-reduce boards: 0 max Ddiag (max), 1 earliest pending event (min), 2 step displacement (max)
 #define SSB_BOARD_MAXW 16
 struct HaloPackSide { const int *ids; int n; char *peer_buf; unsigned long long *peer_flag; unsigned long long *peer_count; };
@@ -503,7 +509,7 @@ __global__ void k_halo_recv(SsbView V, int group, HaloUnpackArgs A, const int *s
 // one warp: lane s < 2 waits for the flag of side s.  A peer that never arrives raises SSB_ERR_HALO instead of hanging the GPU.
 __global__ void k_halo_wait(const unsigned long long *flag0, const unsigned long long *flag1, unsigned long long seq, int *err_flag) {
     const unsigned long long *f = threadIdx.x == 0 ? flag0 : (threadIdx.x == 1 ? flag1 : nullptr);
-    if (f) {
+    if (f && *(volatile int *) err_flag != 8) {          // (a run that already lost a message fails fast instead of timing out again and again)
         const unsigned long long t0 = ssb_globaltimer();
         while (ssb_ld_flag(f) < seq) {
             __nanosleep(100);
@@ -569,7 +575,7 @@ __global__ void k_board_reduce(const unsigned long long *board, int world, int c
     if (r < world) {
         const unsigned long long *slot = board + board_slot(ch, (int) (seq & 1ull), r);
         const unsigned long long t0 = ssb_globaltimer();
-        while (ssb_ld_flag(slot + 1) < seq) {
+        while (ssb_ld_flag(slot + 1) < seq && *(volatile int *) err_flag != 8) {
             __nanosleep(100);
             if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) { atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/); break; }
         }
@@ -746,7 +752,12 @@ static void prof_harvest(ssb_handle *h) {
     }
     h->ev_cat.clear();
 }
+// kernel categories as NVTX ranges (nsys / ncu --nvtx timelines; SURVEY.md section 5 "tracing") and, with ssb_profile(1), as CUDA-event
+// pairs on the engine stream
+static const char *const CAT_NAMES[SSB_NCAT] = {"ssb:cell_list", "ssb:predictor", "ssb:neighbour_search", "ssb:force_sweep", "ssb:corrector",
+                                                "ssb:finish_bvf", "ssb:diffusion_matrix", "ssb:rdme_init", "ssb:sssa_windows", "ssb:output_staging"};
 static int prof_begin(ssb_handle *h, int cat, int nlaunch) {
+    nvtxRangePushA(CAT_NAMES[cat]);
     if (!h->profile) return -1;
     if (h->ev_cat.size() >= 4096) prof_harvest(h);
     size_t k = h->ev_cat.size();
@@ -760,7 +771,7 @@ static int prof_begin(ssb_handle *h, int cat, int nlaunch) {
     cudaEventRecord(h->ev_a[k], h->stream);
     return (int) k;
 }
-static void prof_end(ssb_handle *h, int slot) { if (slot >= 0) cudaEventRecord(h->ev_b[slot], h->stream); }
+static void prof_end(ssb_handle *h, int slot) { if (slot >= 0) cudaEventRecord(h->ev_b[slot], h->stream); nvtxRangePop(); }
 
 // ----------------------------------------------------------------------------------------------------
 // VTK writer (host thread) — byte format of E/src/output.cpp:104-229
@@ -1246,6 +1257,10 @@ extern "C" int ssb_destroy(ssb_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) ssb_sync(h);
     slab_free(h);
+    if (h->V.nbr) cudaFreeAsync(h->V.nbr, h->stream);           // (grown with cudaMallocAsync, neighbour_search)
+    if (h->V.coef) cudaFreeAsync(h->V.coef, h->stream);
+    if (h->V.Dij) cudaFreeAsync(h->V.Dij, h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->allocs) cudaFree(p);
     for (int b = 0; b < 2; b++) {
         OutputJob &J = h->jobs[b];
@@ -1432,8 +1447,10 @@ static int choose_skin(ssb_handle *h) {
     if ((rc = count_candidates(h, &exact))) return rc;
     V.filter = 1;
     double pick = 0.0;
-    // (skins below 2 % of h are not worth their bookkeeping: such clouds rebuild exact lists every step)
-    for (double sk = skin_max; sk >= 0.02; sk *= 0.5) {
+    // (lattice-like clouds have a neighbour shell just outside h — sqrt(5) d for h = 2.2 d, sqrt(6) d for h = 2.42 d — so the skin that
+    // qualifies is small, ~0.6-1.2 % of h; it still saves 10-20 list builds per rebuild at SDPD time steps, and a step that would
+    // not fit simply rebuilds (look-ahead displacement), so a small skin has no failure mode)
+    for (double sk = skin_max; sk >= 0.004; sk *= 0.5) {
         V.search_h2 = (V.h * (1.0 + sk)) * (V.h * (1.0 + sk));
         double cand = 0.0;
         if ((rc = count_candidates(h, &cand))) return rc;
@@ -1462,25 +1479,26 @@ static int neighbour_search(ssb_handle *h) {
         CK(ssb_sync(h));
         if (mx <= V.nbr_cap) return SSB_OK;
         // grow (with head-room on moving domains) and search again
+        // stream-ordered allocation (cudaMallocAsync / cudaFreeAsync): cudaMalloc and cudaFree synchronise the whole DEVICE, and
+        // on a device shared by several slab ranks (ranks as threads, one GPU) another rank's stream may at that moment hold a kernel
+        // that waits for THIS rank's halo message — a deadlock until the device-side timeout.  Also keeps the step loop free of a
+        // device-wide stall on every capacity growth.
         int cap = V.static_domain ? mx : (mx + mx / 4 + 8);
         int *nb = nullptr;
-        CK(cudaMalloc((void **) &nb, sizeof(int) * (size_t) cap * N));
-        if (V.nbr) { cudaFree(V.nbr); for (auto &p : h->allocs) if (p == V.nbr) p = nullptr; }
-        h->allocs.push_back(nb);
+        CK(cudaMallocAsync((void **) &nb, sizeof(int) * (size_t) cap * N, st));
+        if (V.nbr) CK(cudaFreeAsync(V.nbr, st));
         V.nbr = nb;
         V.nbr_cap = cap;
         if (V.static_domain && V.Sc > 0) {
             double *cf = nullptr;
-            CK(cudaMalloc((void **) &cf, sizeof(double) * (size_t) cap * N));
-            if (V.coef) { cudaFree(V.coef); for (auto &p : h->allocs) if (p == V.coef) p = nullptr; }
-            h->allocs.push_back(cf);
+            CK(cudaMallocAsync((void **) &cf, sizeof(double) * (size_t) cap * N, st));
+            if (V.coef) CK(cudaFreeAsync(V.coef, st));
             V.coef = cf;
         }
         if (V.static_domain && V.Sd > 0) {
             double *dj = nullptr;
-            CK(cudaMalloc((void **) &dj, sizeof(double) * (size_t) cap * N));
-            if (V.Dij) { cudaFree(V.Dij); for (auto &p : h->allocs) if (p == V.Dij) p = nullptr; }
-            h->allocs.push_back(dj);
+            CK(cudaMallocAsync((void **) &dj, sizeof(double) * (size_t) cap * N, st));
+            if (V.Dij) CK(cudaFreeAsync(V.Dij, st));
             V.Dij = dj;
         }
     }
@@ -1731,7 +1749,7 @@ static int mv_lookahead(ssb_handle *h) {
     cudaStream_t st = h->stream;
     int ps = prof_begin(h, CAT_FINISH, 1);
     CK(cudaMemsetAsync(h->d_look, 0, sizeof(unsigned long long) * 3, st));
-    k_lookahead<<<gridN(V.N), CORE_BLOCK, 0, st>>>(V, h->d_look);
+    k_lookahead<<<std::min(gridN(V.N), 148u * 8u), CORE_BLOCK, 0, st>>>(V, h->d_look);
     CK(cudaMemcpyAsync(h->pin, h->d_look, sizeof(unsigned long long) * 3, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev_look, st));
     prof_end(h, ps);
@@ -2432,6 +2450,7 @@ extern "C" int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const 
     CK(cudaMalloc((void **) &c->board, board_bytes));
     h->allocs.push_back(c->board);
     CK(cudaMemsetAsync(c->board, 0, board_bytes, h->stream));
+    if (!h->d_slot_of_id) CK(dalloc(h, &h->d_slot_of_id, (size_t) h->N));      // (no cudaMalloc once ranks may be waiting for each other)
     CK(dalloc(h, &c->d_done, 4)); CK(dalloc(h, &c->d_icount, 4)); CK(dalloc(h, &c->d_red, SSB_BOARD_NCH + 1)); CK(dalloc(h, &c->d_inf, 1));
     CK(cudaMemsetAsync(c->d_done, 0, 16, h->stream)); CK(cudaMemsetAsync(c->d_icount, 0, 16, h->stream));
     const unsigned long long inf_bits = 0x7ff0000000000000ull;
@@ -2539,7 +2558,10 @@ static void slab_free(ssb_handle *h) {
 }
 
 // one field group to both neighbours and back: pack+send (peer writes, flags raised by the last CTA), wait, unpack
+struct NvtxScope { explicit NvtxScope(const char *n) { nvtxRangePushA(n); } ~NvtxScope() { nvtxRangePop(); } };
+
 static int slab_exchange(ssb_handle *h, int group) {
+    NvtxScope nv("ssb:halo_exchange");
     SlabComm *c = h->slab;
     cudaStream_t st = h->stream;
     int rc = ensure_slot_map(h);
@@ -2570,6 +2592,7 @@ static int slab_exchange(ssb_handle *h, int group) {
 }
 // mail of the sSSA window that just ran: my ghosts' inboxes -> their owners (the neighbour's inbox of the same buffer)
 static int slab_exchange_inbox(ssb_handle *h) {
+    NvtxScope nv("ssb:halo_inbox");
     SlabComm *c = h->slab;
     cudaStream_t st = h->stream;
     if (h->V.Sd == 0) return SSB_OK;
@@ -2604,6 +2627,7 @@ static int slab_exchange_inbox(ssb_handle *h) {
 // scalar all-reduce, device to device: post my value to every board (engine stream), reduce my own board on `on` (the engine
 // stream, or the side stream when the host wants the result without stalling the engine stream) -> c->d_red[ch]
 static int slab_allreduce(ssb_handle *h, int ch, const unsigned long long *src, bool take_min, cudaStream_t on) {
+    NvtxScope nv("ssb:board_allreduce");
     SlabComm *c = h->slab;
     cudaStream_t st = h->stream;
     const unsigned long long seq = ++c->bseq[ch];

@@ -34,7 +34,7 @@ def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out
                  unit_path=None, on_engine=None, rank=0, world_size=1):
     """Run trajectories k = rank, rank+world_size, ... (seed + k each) on `devices`, `lanes` engine handles per device, each
     driven by its own host thread (ctypes releases the GIL during ssb_run).  Returns {k: counters} for the local trajectories;
-    raises the first EngineError.  `out_dirs[k]` (optional) receives trajectory k's VTK files."""
+    raises the first failure of any lane.  `out_dirs[k]` (optional) receives trajectory k's VTK files."""
     import threading
     from .engine import Engine, EngineError, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
     lanes = lanes or default_lanes(fm.num_particles)
@@ -85,9 +85,13 @@ def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out
                     c = eng.counters()
                     with lock:
                         results[k] = c
-        except EngineError as err:
+        except BaseException as err:      # noqa: BLE001 - any failure of a lane is the ensemble's failure (re-raised by the caller)
             with lock:
                 errors.append(err)
+            # a lane that failed will never arrive at the meeting points: break them, or the healthy lanes wait for ever
+            # (threading.Barrier needs all parties) and Solver.run hangs in join()
+            for b in (created_barrier, ready_barrier, done_barrier):
+                b.abort()
         finally:
             try:
                 done_barrier.wait()
@@ -128,6 +132,11 @@ def replicate_model(fm, copies, gap=None):
     copies = int(copies)
     if copies < 1:
         raise ValueError("copies must be >= 1")
+    # reference boundary conditions are coordinate predicates (`me->x[0] >= xmin && ...`, spatialpy/core/boundarycondition.py:121-146):
+    # in a translated copy they would select the wrong region, or nothing at all — silently wrong C, v, nu in every copy but the first
+    if (fm.bc_source or "").strip() and "me->x" in fm.bc_source:
+        raise ValueError("batched ensembles translate the copies of the model, but its boundary conditions test particle "
+                         "coordinates (me->x[...]); run this model with lanes (batch=None)")
     gap = 2.0 * fm.h if gap is None else float(gap)
     if gap < 1.5 * fm.h:
         raise ValueError("gap must be at least 1.5 h so that no neighbour list crosses copies")

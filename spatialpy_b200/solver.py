@@ -240,6 +240,7 @@ class Solver:
         engines, lock = [], threading.Lock()
         start = time.monotonic()
         state = {"error": None, "done": False}
+        totals = {"reactions": 0, "diffusions": 0}          # ParticleSystem::total_reactions / total_diffusion over the ensemble
         out_dirs = [r.result_dir for r in results]
 
         def body_slab():
@@ -247,13 +248,15 @@ class Solver:
             from .slab import run_slab_trajectory
             try:
                 for k in range(number_of_trajectories):
-                    run_slab_trajectory(self.flat, devices, seed + k, out_dirs[k], flags=flags & ~(FLAG_BINARY_STORE | FLAG_NO_VTK),
-                                        rdme_epsilon=rdme_epsilon, vtk=vtk, binary_store=binary_store,
-                                        cancelled=lambda: state.get("cancel", False))
+                    c = run_slab_trajectory(self.flat, devices, seed + k, out_dirs[k], flags=flags & ~(FLAG_BINARY_STORE | FLAG_NO_VTK),
+                                            rdme_epsilon=rdme_epsilon, vtk=vtk, binary_store=binary_store,
+                                            cancelled=lambda: state.get("cancel", False))
                     results[k].success = True
+                    for key in totals:
+                        totals[key] += c[key]
             except InterruptedError:
                 pass
-            except (EngineError, ValueError) as err:
+            except Exception as err:      # noqa: BLE001 - stale partition (RuntimeError), snapshot I/O (OSError), broken barrier, torch: all fail the run
                 state["error"] = err
             state["done"] = True
 
@@ -278,7 +281,10 @@ class Solver:
                     for k in res:
                         if k != "counters":
                             results[k0 + k].success = True
-                except (EngineError, ValueError) as err:
+                    with lock:
+                        for key in totals:
+                            totals[key] += res["counters"][key]
+                except Exception as err:  # noqa: BLE001 - re-raised as SimulationError by the caller's thread
                     shard_errors.append(err)
 
             workers = [threading.Thread(target=shard, args=(d,)) for d in range(len(devices))]
@@ -297,7 +303,9 @@ class Solver:
                                     on_engine=lambda e: (lock.acquire(), engines.append(e), lock.release()))
                 for k in done:
                     results[k].success = True
-            except EngineError as err:
+                    for key in totals:
+                        totals[key] += done[k][key]
+            except Exception as err:      # noqa: BLE001
                 state["error"] = err
             state["done"] = True
 
@@ -314,7 +322,11 @@ class Solver:
                         e.cancel()
                 t.join(0.05)
         if self.debug_level >= 1:
+            # what the reference's debug build prints when the NSM is torn down (E/src/simulate_rdme.cpp:71-72, typo included)
+            print("NSM: total # reacton events {}".format(totals["reactions"]))
+            print("NSM: total # diffusion events {}".format(totals["diffusions"]))
             print("Elapsed seconds: {:.2f}".format(time.monotonic() - start))
+        self.total_reactions, self.total_diffusion = totals["reactions"], totals["diffusions"]
         if timed_out:
             for r in results:
                 if not r.success:
@@ -323,6 +335,10 @@ class Solver:
             err = state["error"]
             code = getattr(err, "code", 4)       # SSB_ERR_ARG for a model the chosen decomposition cannot run
             raise SimulationError(f"Solver execution failed, return code = {code}") from err   # solver.py:595-597
+        elif not all(r.success for r in results):
+            # the reference raises on any failed trajectory (solver.py:595-597); a worker that died without reporting must not
+            # surface as a Result with missing files
+            raise SimulationError("Solver execution failed, return code = 4")
         first = results[0]
         for r in results[1:]:
             first.append(r)

@@ -4,6 +4,7 @@ checkout is importable; the GPU box consumes the generated .npz fixtures, never 
 Every builder seeds numpy first so scatter initial conditions are reproducible.
 """
 import os
+import sys
 
 import numpy
 
@@ -308,6 +309,35 @@ def cdc42_full():
     return cdc42(DX=50, end_time=0.001, steps=2)
 
 
-BUILDERS = {"birth_death": birth_death, "diffusion3d": diffusion3d, "cavity2d": cavity2d, "tank3d": tank3d,
+def cavity2d_bc(steps=22):
+    """Every boundary-condition target the reference emits (spatialpy/core/boundarycondition.py:147-166) on one moving domain:
+    `v` on the lid (as cavity2d), `rho` on the bottom wall rows, `nu` on the left wall columns and a deterministic species
+    concentration `C[0]` on a band of the fluid — so me->rho / me->nu / me->C[k] assignments are pinned against the reference's
+    taps, through the predictor, the corrector (rho_new carries the BC) and the final BC of a step."""
+    import spatialpy
+    model = cavity2d(steps=steps, with_species=True)
+    model.name = "cavity2d_bc"
+    model.add_boundary_condition(spatialpy.BoundaryCondition(ymax=-1e-9, target='rho', value=1.02))
+    model.add_boundary_condition(spatialpy.BoundaryCondition(xmax=-1e-9, target='nu', value=0.02))
+    model.add_boundary_condition(spatialpy.BoundaryCondition(xmin=0.4, xmax=0.6, ymin=0.2, ymax=0.8, target='A', deterministic=True,
+                                                             value=25.0, model=model))
+    return model
+
+
+def mid_cylinder():
+    """MID-SIZE fixture (15 957 particles, 125 CTAs): the bounded cylinder instance of the bench's reference arm
+    (oracle/oracle_build.py BENCH_REF) — multi-CTA cell lists, crowded clamped boundary cells, lists of up to ~70 entries."""
+    from spatialpy_b200 import configs
+    return configs.cylinder_rdme(delta=0.125, nt=25, output_every=25, dt=1e-3)
+
+
+def mid_tank():
+    """MID-SIZE fixture (13 576 moving particles): the bounded SDPD tank of the bench's reference arm, 25 steps through the
+    Shepard filter at steps 0 and 20 and several candidate-list rebuilds."""
+    from spatialpy_b200 import configs
+    return configs.tank_sdpd(n=26, nt=25, output_every=1, dt=1e-5)
+
+
+BUILDERS = {"cavity2d_bc": cavity2d_bc, "mid_cylinder": mid_cylinder, "mid_tank": mid_tank, "birth_death": birth_death, "diffusion3d": diffusion3d, "cavity2d": cavity2d, "tank3d": tank3d,
             "cylinder": cylinder, "cdc42": cdc42, "cavity2d_rdme": cavity2d_rdme, "cdc42_full": cdc42_full, "line1d": line1d, "line1d_isolated": line1d_isolated,
             "letters": letters, "datafn": datafn}

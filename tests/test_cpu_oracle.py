@@ -23,7 +23,7 @@ def test_oracle_neighbours_match_reference(name):
     assert rel_err(gd, rd) <= RTOL_STEP and rel_err(gw, rw) <= RTOL_STEP and rel_err(gD, rD) <= RTOL_STEP
 
 
-@pytest.mark.parametrize("name", ["cavity2d", "tank3d", "diffusion3d", "cavity2d_rdme", "line1d"])
+@pytest.mark.parametrize("name", ["cavity2d", "tank3d", "diffusion3d", "cavity2d_rdme", "line1d", "cavity2d_bc"])
 def test_oracle_trajectory_matches_reference(name):
     fm, ref = load_model(name), load_ref(name)
     o = sdpd_oracle.SdpdOracle(fm)

@@ -96,7 +96,7 @@ def test_cylinder_ensemble_matches_reference():
 def test_cdc42_ensemble_matches_reference():
     """BASELINE config 4 (yeast polarisation, coarse lattice, short horizon): 9 type-restricted species, 13 reactions, a custom
     propensity reading a data function, voxel volumes that differ across the membrane/cytoplasm interface."""
-    check_against_reference("cdc42", 400)
+    check_against_reference("cdc42", 1000)         # >= 1000 trajectories on both sides (north_star), reference ensemble: 1000
 
 
 def test_moving_domain_rdme_matches_reference():
