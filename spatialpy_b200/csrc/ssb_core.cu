@@ -287,6 +287,55 @@ __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_
     if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicMax(max_count, cnt); atomicAdd(total_count, (unsigned long long) tot); }
 }
 
+// ---- work items of the shared-memory force sweep (k_force_mv_rows, ssb_model_unit.cuh): every (cy, cz) cell row — a contiguous slot
+// range, x is the fastest cell coordinate — is cut into segments of <= ROW_SEG consecutive particles; an item also carries the nine
+// slot ranges (rows (cy+dy, cz+dz), x-cells one beyond the segment's own on both sides) that hold its particles' candidates.
+#define ROW_SEG 128
+__device__ __forceinline__ int cs_at(const int *cell_start, int c, int ncells, int N) { return c < ncells ? cell_start[c] : N; }
+__global__ void k_row_count(CellGrid g, int N, const int *cell_start, int *nseg) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, nrows = g.n[1] * g.n[2];
+    if (r >= nrows) return;
+    const int b = cs_at(cell_start, r * g.n[0], g.ncells, N), e = cs_at(cell_start, (r + 1) * g.n[0], g.ncells, N);
+    nseg[r] = (e - b + ROW_SEG - 1) / ROW_SEG;
+}
+// x-cell of row `r` that holds storage slot `slot` (the last cell whose start is <= slot)
+__device__ __forceinline__ int cell_of_slot(const int *cell_start, int row0, int nx, int ncells, int N, int slot) {
+    int lo = 0, hi = nx - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cs_at(cell_start, row0 + mid, ncells, N) <= slot) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void k_row_fill(CellGrid g, int N, const int *cell_start, const int *row_off, int *slot0, int *cnt, int *rng) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, nrows = g.n[1] * g.n[2];
+    if (r >= nrows) return;
+    const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
+    const int b = cs_at(cell_start, r * nx, g.ncells, N), e = cs_at(cell_start, (r + 1) * nx, g.ncells, N);
+    const int cy = r % ny, cz = r / ny;
+    int item = row_off[r];
+    for (int s0 = b; s0 < e; s0 += ROW_SEG, item++) {
+        const int n = min(ROW_SEG, e - s0);
+        slot0[item] = s0;
+        cnt[item] = n;
+        const int cxa = cell_of_slot(cell_start, r * nx, nx, g.ncells, N, s0);
+        const int cxb = cell_of_slot(cell_start, r * nx, nx, g.ncells, N, s0 + n - 1);
+        const int xa = max(cxa - 1, 0), xb = min(cxb + 1, nx - 1);
+        int *o = rng + (size_t) item * 18;
+        for (int dz = -1; dz <= 1; dz++)
+            for (int dy = -1; dy <= 1; dy++) {
+                const int yy = cy + dy, zz = cz + dz;
+                int lo = 0, hi = 0;
+                if (yy >= 0 && yy < ny && zz >= 0 && zz < nz) {
+                    const int row0 = (zz * ny + yy) * nx;
+                    lo = cs_at(cell_start, row0 + xa, g.ncells, N);
+                    hi = cs_at(cell_start, row0 + xb + 1, g.ncells, N);
+                }
+                *o++ = lo; *o++ = hi;
+            }
+    }
+}
+
 __global__ void k_iota(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 __global__ void k_copy64(int n, const double *src, double *dst) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] = src[i]; }
 
@@ -340,8 +389,9 @@ __global__ void k_nbr_export(SsbView V, const long long *ptr, int *idx, double *
         idx[base + o] = V.id[j];
         dist[base + o] = r;
         dWdr[base + o] = ssb_dWdr(alpha, r, V.h);
-        Dij[base + o] = V.Dij ? V.Dij[(size_t) k * N + i]
-                              : ssb_Dij(d2, r, V.h, V.mass[i], V.mass[j], V.rho_search[i], V.rho_search[j]);
+        double rho_i, rho_j;
+        ssb_search_rho(V, i, j, rho_i, rho_j);
+        Dij[base + o] = V.Dij ? V.Dij[(size_t) k * N + i] : ssb_Dij(d2, r, V.h, V.mass[i], V.mass[j], rho_i, rho_j);
         o++;
     }
 }
@@ -641,6 +691,9 @@ struct ssb_handle {
     CellGrid grid;
     int *d_key = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr, *d_perm = nullptr;
     int *d_tile_sums = nullptr, *d_flags = nullptr;  // d_flags[0]=nonidentity [1]=max nbr count
+    int use_rows = 0;                                // moving domains: shared-memory force sweep over row-segment work items
+    int *d_row_nseg = nullptr, *d_row_off = nullptr, *d_item_total = nullptr;
+    int item_cap = 0;
     unsigned long long *d_maxbits = nullptr;
     double *d_stage = nullptr;   // device staging for output/taps (id order)
     size_t stage_bytes = 0;
@@ -648,6 +701,7 @@ struct ssb_handle {
     double *init_f64 = nullptr;   // pinned
     int *init_i32 = nullptr;      // pinned
     double *rho_buf[2] = {nullptr, nullptr};
+    double *d_rho_pre = nullptr;  // step-0 densities before the predictor / BCs (models whose BC assigns rho; SsbView::rho_pre)
     // model unit
     void *unit_dl = nullptr;
     const SsbModelUnit *unit = nullptr;
@@ -1182,6 +1236,19 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     CK(dalloc(h, &h->d_tile_sums, (size_t) (h->grid.ncells / SCAN_TILE + 2)));
     CK(dalloc(h, &h->d_flags, 8));
     CK(dalloc(h, &h->d_maxbits, 2));
+    if (!V.static_domain && !(m->flags & SSB_FLAG_LITERAL_KERNELS)) {
+        // the shared-memory force sweep pays where a cell row holds enough particles to fill CTAs (3-D clouds, long 2-D rows);
+        // short rows keep the gather sweep.  SSB_ROWS=0 / 1 forces the choice (tests: both sweeps must agree bit for bit).
+        const int nrows = h->grid.n[1] * h->grid.n[2];
+        const char *e = getenv("SSB_ROWS");
+        h->use_rows = e ? (atoi(e) != 0) : ((double) N / (double) nrows >= 48.0);
+        if (h->use_rows) {
+            h->item_cap = nrows + N / ROW_SEG + 8;
+            CK(dalloc(h, &h->d_row_nseg, (size_t) nrows + 1)); CK(dalloc(h, &h->d_row_off, (size_t) nrows + 1)); CK(dalloc(h, &h->d_item_total, 4));
+            CK(dalloc(h, &V.item_slot0, (size_t) h->item_cap)); CK(dalloc(h, &V.item_cnt, (size_t) h->item_cap));
+            CK(dalloc(h, &V.item_rng, (size_t) h->item_cap * 18));
+        }
+    }
     // staging: the largest of an output snapshot and any single tap
     size_t per = (size_t) 3 * 8 * 2 + 4 * 8 + 8 + (size_t) Sc * 8 + (size_t) Sd * 8 + (size_t) Rd * 8 + 64;
     h->stage_bytes = per * N + 4096;
@@ -1233,6 +1300,7 @@ extern "C" int ssb_load_kernels(ssb_handle *h, const char *path) {
     if (h->unit_dl) dlclose(h->unit_dl);
     h->unit_dl = dl;
     h->unit = u;
+    if (u->bc_touches_rho && !h->d_rho_pre) { CK(cudaSetDevice(h->device)); CK(dalloc(h, &h->d_rho_pre, (size_t) h->N)); }
     return SSB_OK;
 }
 
@@ -1468,6 +1536,17 @@ static int neighbour_search(ssb_handle *h) {
     const int N = h->N;
     cudaStream_t st = h->stream;
     if (V.filter && !h->skin_chosen) { int rcs = choose_skin(h); if (rcs) return rcs; }
+    if (h->use_rows) {       // work items of the shared-memory force sweep for this storage order (row counts -> scan -> fill)
+        const int nrows = h->grid.n[1] * h->grid.n[2];
+        const int ntiles = (nrows + SCAN_TILE - 1) / SCAN_TILE;
+        k_row_count<<<gridN(nrows), CORE_BLOCK, 0, st>>>(h->grid, N, h->d_cell_start, h->d_row_nseg);
+        k_scan_tiles<<<ntiles, 256, 0, st>>>(nrows, h->d_row_nseg, h->d_row_off, h->d_tile_sums);
+        k_scan_sums<<<1, 256, 0, st>>>(ntiles, h->d_tile_sums, h->d_item_total);
+        k_scan_add<<<gridN(nrows), CORE_BLOCK, 0, st>>>(nrows, h->d_row_off, h->d_tile_sums);
+        k_row_fill<<<gridN(nrows), CORE_BLOCK, 0, st>>>(h->grid, N, h->d_cell_start, h->d_row_off, V.item_slot0, V.item_cnt, V.item_rng);
+        CK(cudaMemcpyAsync(&h->pin[12], h->d_item_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        h->launches += 5;
+    }
     for (int attempt = 0; attempt < 8; attempt++) {
         // (first build: the capacity is 0, so this pass only counts; the rows are then sized from the maximum)
         CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), st));
@@ -1477,6 +1556,11 @@ static int neighbour_search(ssb_handle *h) {
         int mx = 0;
         CK(cudaMemcpyAsync(&mx, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(ssb_sync(h));
+        if (h->use_rows) {
+            const int n_items = (int) (h->pin[12] & 0xffffffffull);
+            if (n_items > h->item_cap) return fail(h, SSB_ERR_CUDA, "row work items (%d) exceed their table (%d)", n_items, h->item_cap);
+            V.n_items = n_items;
+        }
         if (mx <= V.nbr_cap) return SSB_OK;
         // grow (with head-room on moving domains) and search again
         // stream-ordered allocation (cudaMallocAsync / cudaFreeAsync): cudaMalloc and cudaFree synchronise the whole DEVICE, and
@@ -1690,6 +1774,11 @@ static int mv_pre(ssb_handle *h) {
         prof_end(h, ps);
         if (rc) return rc;
     }
+    V.rho_pre = nullptr;
+    if (step == 0 && h->d_rho_pre) {      // (see SsbView::rho_pre: the step-0 lists freeze densities from before the predictor / BCs)
+        CK(cudaMemcpyAsync(h->d_rho_pre, V.rho, sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
+        V.rho_pre = h->d_rho_pre;
+    }
     ps = prof_begin(h, CAT_PREDICTOR, 1);
     if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
     prof_end(h, ps);
@@ -1709,6 +1798,13 @@ static int mv_pre(ssb_handle *h) {
         if (u->force_mv(&V, step, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "force launch failed");
         prof_end(h, ps);
         h->launches++;
+        if (V.Sd > 0 && V.rho_pre) {
+            // step 0 with density-assigning BCs: the fused Ddiag used post-BC densities for both particles of a pair; redo it with
+            // the reference's step-0 rule (k_diff_init -> pair_Dij -> ssb_search_rho).  One extra sweep, once per trajectory.
+            CK(cudaMemsetAsync(h->d_maxbits, 0, sizeof(unsigned long long), st));
+            if (u->diff_init(&V, h->d_maxbits, st)) return fail(h, SSB_ERR_CUDA, "diff_init launch failed");
+            h->launches++;
+        }
         if (V.Sd > 0) {
             CK(cudaMemcpyAsync(&h->pin[3], h->d_maxbits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(h->ev_maxd, st));
@@ -1797,6 +1893,11 @@ static int engine_step(ssb_handle *h) {
         rc = build_cells(h);
         prof_end(h, ps);
         if (rc) return rc;
+    }
+    V.rho_pre = nullptr;
+    if (step == 0 && h->d_rho_pre) {      // static domains keep their step-0 lists (and the D_i_j frozen then) for the whole run
+        CK(cudaMemcpyAsync(h->d_rho_pre, V.rho, sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
+        V.rho_pre = h->d_rho_pre;
     }
     ps = prof_begin(h, CAT_PREDICTOR, 1);
     if (u->predictor(&V, step, st)) return fail(h, SSB_ERR_CUDA, "predictor launch failed");
@@ -2453,6 +2554,7 @@ extern "C" int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const 
     if (!h->d_slot_of_id) CK(dalloc(h, &h->d_slot_of_id, (size_t) h->N));      // (no cudaMalloc once ranks may be waiting for each other)
     CK(dalloc(h, &c->d_done, 4)); CK(dalloc(h, &c->d_icount, 4)); CK(dalloc(h, &c->d_red, SSB_BOARD_NCH + 1)); CK(dalloc(h, &c->d_inf, 1));
     CK(cudaMemsetAsync(c->d_done, 0, 16, h->stream)); CK(cudaMemsetAsync(c->d_icount, 0, 16, h->stream));
+    CK(cudaMemsetAsync(c->d_red, 0, sizeof(unsigned long long) * (SSB_BOARD_NCH + 1), h->stream));       // ([3] stays 0: the constant a rank without a value posts)
     const unsigned long long inf_bits = 0x7ff0000000000000ull;
     CK(cudaMemcpyAsync(c->d_inf, &inf_bits, sizeof(inf_bits), cudaMemcpyHostToDevice, h->stream));
     for (int k = 0; k < SSB_BOARD_NCH; k++) {
@@ -2684,18 +2786,21 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
         if ((rc = mv_finish(h))) return rc;
         if ((rc = slab_exchange(h, 2))) return rc;
         if ((rc = mv_lookahead(h))) return rc;
-        if (V.filter) {
-            if ((rc = slab_allreduce(h, 2, h->d_look + 1, false, aux))) return rc;
+        {
+            // (a COLLECTIVE: every rank takes part whatever its own Verlet skin is — the skin is chosen per rank from local candidate
+            // statistics, and a rank that rebuilds exact lists every step has no look-ahead: it contributes 0)
+            if ((rc = slab_allreduce(h, 2, V.filter ? h->d_look + 1 : c->d_red + 3, false, aux))) return rc;
             CK(cudaMemcpyAsync(&h->pin[8 + (c->steps & 1)], c->d_red + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, aux));
-            CK(cudaEventRecord(c->ev_disp[c->steps & 1], aux));
-        } else {
-            h->pin[8 + (c->steps & 1)] = 0;
             CK(cudaEventRecord(c->ev_disp[c->steps & 1], aux));
         }
         if (V.Sd > 0) {
             CK(wait_event(h->ev_maxd));                      // every rank's force sweep is done; corrector .. look-ahead are still queued
             double mx;
             memcpy(&mx, &h->pin[4], 8);
+            if (getenv("SSB_SLAB_DEBUG")) {
+                double loc; memcpy(&loc, &h->pin[3], 8);
+                fprintf(stderr, "[slab %d/%d] step %u local max Ddiag %.6g global %.6g filter %d skin %g items %d\n", c->rank, c->world, step, loc, mx, V.filter, h->skin, V.n_items);
+            }
             h->ddiag_fresh = 0;
             if ((rc = set_windows(h, mx))) return rc;        // GLOBAL max Ddiag: every rank uses the same windows
             if (u->rdme_init(&V, V.dt * step, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");

@@ -50,10 +50,19 @@ struct SsbView {
     unsigned long long *disp_bits;
     double *Dij;        // [cap*N] cached D_i_j (static domains) or nullptr
     double *rho_search; // density at neighbour-search time (frozen into D_i_j, particle.cpp:187)
+    // Step 0 only, models whose boundary conditions ASSIGN rho: the reference searches at the top of take_step1 (simulate.cpp:61-63),
+    // BEFORE the particle's own predictor / BC, and runs take_step1 particle by particle — so the D_i_j of the step-0 lists see the
+    // particle's own density as it was (rho_pre) and a neighbour's density after its BC only if the neighbour comes earlier in the
+    // particle vector.  nullptr whenever the lists were built after step 0 (all of take_step1 is complete then).
+    double *rho_pre;
     // moving-domain gather record (written by k_predictor, read by the neighbour sweeps): one 128-byte line per particle
     //   rec[16*j + 0..2] x0   3..5 x   6..8 v   9..11 vt   12 rho   13 mass   14 nu   15 bits(id:32 | type:16 | solid:16)
     double *rec;
     int *solid_nbr;     // [N] moving domains: 1 if any CANDIDATE neighbour is a solid particle (written by k_search, read by k_finish)
+    // row-segment work items of the shared-memory force sweep (k_force_mv_rows; built at every list build, ssb_core.cu row_items):
+    // item = <= 128 consecutive slots of one (cy, cz) cell row + the nine ascending slot ranges [lo, hi) its candidates fall into
+    int n_items;        // 0 = use the gather sweep
+    int *item_slot0, *item_cnt, *item_rng;      // [n_items], [n_items], [n_items * 18]
     // static-domain fast path: cached chemistry pair coefficient dQc_base (model.cpp:155) and the double-buffered
     // half-stepped concentrations the next sweep reads (see k_static_step)
     double *coef;       // [cap*N] or nullptr
@@ -171,6 +180,12 @@ __device__ __forceinline__ double ssb_W(double alpha, double r, double h) {
 }
 
 // D_i_j (particle.cpp:182-187); always the 3-D constant, whatever the dimension
+// the densities D_i_j freezes for the pair (i, j) (see SsbView::rho_pre)
+__device__ __forceinline__ void ssb_search_rho(const SsbView &V, int i, int j, double &rho_i, double &rho_j) {
+    rho_i = V.rho_search[i]; rho_j = V.rho_search[j];
+    if (V.rho_pre) { rho_i = V.rho_pre[i]; if (!(V.gid[j] < V.gid[i])) rho_j = V.rho_pre[j]; }
+}
+
 __device__ __forceinline__ double ssb_Dij(double r2, double r, double h, double mi, double mj, double rhoi, double rhoj) {
     double ih = 1.0 / h;
     double ihsq = ih * ih;

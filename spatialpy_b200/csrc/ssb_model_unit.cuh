@@ -245,18 +245,24 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
 //     (m, rho, r^2) factor with the chemistry flux.
 // Results differ from the literal evaluation order by a few ulp per pair (parity gate: 1e-12 of the field scale).
 //
-// COOP = 4 (default, "quad gather"): the sweep is bound by L1 tag lookups, not by bytes — with one record per lane every LDG.E.256
-// of a warp touches 32 distinct 128-byte lines (32 wavefronts for 32 sectors).  Here the four lanes of a quad fetch the records of
-// their four candidates TOGETHER: lane q of the quad loads sector q of each of the four records (one line per quad and instruction:
-// 8 wavefronts, each delivering a whole line), and a 4x4 transpose over two shuffle rounds hands every lane the full record of its
-// own candidate.  Same records, same pair arithmetic in the same order => bit-identical to COOP = 1 (one gather per lane), which
-// stays as the cross-check (`-DSSB_FORCE_COOP=1`).  The round-1 shared-memory tile form measured 2x SLOWER than the plain gather
-// (1.42 vs 0.70 ms at 1 M particles, profiles/r2a_bench_tank_tile.json: 128-byte record stride = 32-way bank conflicts, a serial
-// chunk table per CTA, two barriers per chunk) and was deleted.
+//
+// Two kernels feed the ONE pair body below (ForceSweep::pair), both walking the same ascending candidate lists, so their results
+// are bit-identical:
+//   k_force_mv       one 128-byte gather per candidate and lane.  ncu (profiles/r2c_force_coop1_metrics.csv, box at 1 M): the L1
+//                    data pipe is the busiest unit (74 %: ~190 wavefronts per warp and candidate — 4 x 32 for the record, 2 x 32 for
+//                    the C_j gathers), the dominant stall is the long scoreboard (9.5 of ~13 warp cycles per issued instruction),
+//                    fp64 pipe 32 %, 16 warps per SM at 128 registers: latency- and wavefront-bound, not fp64- or DRAM-bound.
+//   k_force_mv_rows  shared-memory staging per ROW SEGMENT (default where rows are long enough, ssb_core.cu row_items): a CTA owns
+//                    <= 128 consecutive particles of ONE (cy, cz) cell row; their candidates lie in nine contiguous slot ranges (the
+//                    rows (cy+dy, cz+dz), x-cells [cxa-1, cxb+1]), which are staged one after the other with coalesced 16-byte loads
+//                    into padded records (stride 144 B: conflict-free 16-byte reads), C_j beside them; every thread then consumes
+//                    the part of its list that falls into the staged range from shared memory (~36 wavefronts per warp and
+//                    candidate, ~30-cycle latency).  Each record crosses L1 once per CTA (~12 per particle) instead of once per pair (~70).
+// History: the round-1 tile form (bitmap of touched 64-slot blocks, serial chunk table, unpadded 128-byte records = 32-way bank
+// conflicts) measured 2x SLOWER than the gather (profiles/r2a_bench_tank_tile.json) and was deleted; a quad-cooperative gather
+// (4 lanes fetch 4 records together, 4x4 shuffle transpose) cut the L1 wavefronts from 74 % to 47 % but doubled the instruction
+// count and measured the same time (profiles/r2c_force_coop4_metrics.csv) and was deleted too.
 // ---------------------------------------------------------------------------------------------
-#ifndef SSB_FORCE_COOP
-#define SSB_FORCE_COOP 4
-#endif
 
 // per-particle state of the sweep + the pair body (ONE copy, whatever feeds it the records)
 struct ForceSweep {
@@ -310,7 +316,8 @@ struct ForceSweep {
     }
 
     // one candidate j with its record in c0..c3 (rejected unless it is in ANN's exact set for THIS step's snapshot)
-    __device__ __forceinline__ void pair(const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const int j) {
+    // cj / cj_stride: where the neighbour's concentrations are (global: V.C + j, stride N; staged: its shared-memory row, stride 1)
+    __device__ __forceinline__ void pair(const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const double *cj, const size_t cj_stride) {
         const double inv_rho_j = 1.0 / c3.a;
         const double aP_j = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * inv_rho_j * inv_rho_j;
         const double vol_j = c3.b * inv_rho_j;
@@ -361,7 +368,7 @@ struct ForceSweep {
             if (SSB_SC > 0) {
                 const double base = G * wr;
 #pragma unroll
-                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cg[(size_t) s * N + j]) * base;
+                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - cj[(size_t) s * cj_stride]) * base;
             }
             if (SSB_SD > 0) {
                 const double hr = h - r;
@@ -408,67 +415,95 @@ struct ForceSweep {
     }
 };
 
-// exchange one 32-byte sector with the quad partner `lane ^ xm`: lanes with keep_a == true keep `a` and trade `b`, the others
-// keep `b` and trade `a`
-__device__ __forceinline__ void quad_trade(ssb_d4 &a, ssb_d4 &b, bool keep_a, int xm, unsigned mask) {
-    ssb_d4 s = keep_a ? b : a;
-    s.a = __shfl_xor_sync(mask, s.a, xm); s.b = __shfl_xor_sync(mask, s.b, xm);
-    s.c = __shfl_xor_sync(mask, s.c, xm); s.d = __shfl_xor_sync(mask, s.d, xm);
-    if (keep_a) b = s; else a = s;
-}
-
-template <int COOP>
 __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
-    const int i_raw = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i_raw < V.N;
-    const int i = live ? i_raw : V.N - 1;          // idle lanes of the last CTA take part in the quad loads on a valid slot
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double mx = 0.0;
-    if (COOP == 1) {
-        if (live) {
-            ForceSweep S;
-            S.init(V, i);
-            const int N = V.N;
-            const int cnt = V.owned[i] ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
-#pragma unroll 2
-            for (int k = 0; k < cnt; k++) {
-                const int j = V.nbr[(size_t) k * N + i];
-                const double *rj = V.rec + (size_t) j * 16;
-                const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
-                S.pair(c0, c1, c2, c3, j);
-            }
-            mx = S.store(V, i, step);
-        }
-    } else {
+    if (i < V.N) {
         ForceSweep S;
         S.init(V, i);
         const int N = V.N;
-        const int cnt = (live && V.owned[i]) ? V.nbr_count[i] : 0;
-        const int lane = threadIdx.x & 31, sub = lane & 3, qbase = lane & ~3;
-        const unsigned qmask = 0xfu << qbase;
-        int kmax = cnt;                                           // the quad walks its four lists in lock step
-        kmax = max(kmax, __shfl_xor_sync(qmask, kmax, 1));
-        kmax = max(kmax, __shfl_xor_sync(qmask, kmax, 2));
-        const bool odd = (sub & 1) != 0, hi = (sub & 2) != 0;
-        for (int k = 0; k < kmax; k++) {
-            const bool have = k < cnt;
-            const int j = have ? V.nbr[(size_t) k * N + i] : i;  // (a lane whose list is exhausted offers its own record: a valid line)
-            // lane `sub` fetches sector `sub` of the four records of the quad: M[sub][q] = sector sub of record j_q
-            const int j0 = __shfl_sync(qmask, j, qbase), j1 = __shfl_sync(qmask, j, qbase + 1);
-            const int j2 = __shfl_sync(qmask, j, qbase + 2), j3 = __shfl_sync(qmask, j, qbase + 3);
-            ssb_d4 v0 = ssb_ld256(V.rec + (size_t) j0 * 16 + sub * 4);
-            ssb_d4 v1 = ssb_ld256(V.rec + (size_t) j1 * 16 + sub * 4);
-            ssb_d4 v2 = ssb_ld256(V.rec + (size_t) j2 * 16 + sub * 4);
-            ssb_d4 v3 = ssb_ld256(V.rec + (size_t) j3 * 16 + sub * 4);
-            // 4x4 transpose over the quad: after round 1 a lane holds two sectors of record (sub & 1) and of record (sub & 1) + 2,
-            // after round 2 the four sectors of its own record j_sub, in order
-            quad_trade(v0, v1, !odd, 1, qmask);
-            quad_trade(v2, v3, !odd, 1, qmask);
-            quad_trade(v0, v2, !hi, 2, qmask);
-            quad_trade(v1, v3, !hi, 2, qmask);
-            if (have) S.pair(v0, v1, v2, v3, j);
+        const int cnt = V.owned[i] ? V.nbr_count[i] : 0;     // ghost copies receive F, Fbp, Frho, Q from their owner (halo exchange)
+#pragma unroll 2
+        for (int k = 0; k < cnt; k++) {
+            const int j = V.nbr[(size_t) k * N + i];
+            const double *rj = V.rec + (size_t) j * 16;
+            const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
+            S.pair(c0, c1, c2, c3, S.Cg + j, (size_t) N);
         }
-        if (live) mx = S.store(V, i, step);
+        mx = S.store(V, i, step);
     }
+    if (SSB_SD > 0) {
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
+    }
+}
+
+#ifndef SSB_ROWS_TR
+#define SSB_ROWS_TR 224           // records per staged chunk: 224 x 144 B = 31.5 KB (+ C_j), 4 CTAs per SM stay resident
+#endif
+#define SSB_ROWS_STRIDE 18        // doubles per staged record: 16 + 2 of padding (144 B: 16-byte reads of 8 lanes hit 8 different bank groups)
+
+__device__ __forceinline__ ssb_d4 ssb_lds256(const double *p) {
+    const double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + 2);
+    ssb_d4 r;
+    r.a = lo.x; r.b = lo.y; r.c = hi.x; r.d = hi.y;
+    return r;
+}
+
+// one CTA per work item (V.item_*): <= SSB_BLOCK consecutive particles of one cell row and the nine slot ranges their candidates
+// fall into (ascending, like the lists).  A candidate outside every staged range (its owner crossed a cell face in the predictor
+// of the list-build step) is fetched with the gather of k_force_mv, in list order, so the accumulation order never changes.
+__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv_rows(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
+    __shared__ __align__(16) double s_rec[SSB_ROWS_TR * SSB_ROWS_STRIDE];
+    __shared__ __align__(16) double s_C[SSB_ROWS_TR * (SSB_SC > 0 ? SSB_SC : 1)];
+    const int item = blockIdx.x;
+    const int slot0 = V.item_slot0[item], icnt = V.item_cnt[item];
+    const bool live = (int) threadIdx.x < icnt;
+    const int i = slot0 + (live ? (int) threadIdx.x : 0);
+    const int N = V.N;
+    ForceSweep S;
+    S.init(V, i);
+    const int cnt = (live && V.owned[i]) ? V.nbr_count[i] : 0;
+    int k = 0;
+    int jn = (cnt > 0) ? V.nbr[i] : 0x7fffffff;                    // next candidate of this thread
+    auto from_global = [&](const int j) {
+        const double *rj = V.rec + (size_t) j * 16;
+        const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
+        S.pair(c0, c1, c2, c3, S.Cg + j, (size_t) N);
+    };
+    const int *rng = V.item_rng + (size_t) item * 18;
+    double2 *s2 = reinterpret_cast<double2 *>(s_rec);
+    for (int r = 0; r < 9; r++) {
+        const int lo = rng[2 * r], hi = rng[2 * r + 1];
+        for (int c0 = lo; c0 < hi; c0 += SSB_ROWS_TR) {
+            const int c1 = min(c0 + SSB_ROWS_TR, hi), n = c1 - c0;
+            __syncthreads();                                         // the previous chunk has been consumed by everybody
+            const double2 *g2 = reinterpret_cast<const double2 *>(V.rec + (size_t) c0 * 16);
+            for (int t = threadIdx.x; t < n * 8; t += SSB_BLOCK) s2[(t >> 3) * (SSB_ROWS_STRIDE / 2) + (t & 7)] = g2[t];
+#pragma unroll
+            for (int sp = 0; sp < SSB_SC; sp++)
+                for (int t = threadIdx.x; t < n; t += SSB_BLOCK) s_C[t * SSB_SC + sp] = V.C[(size_t) sp * N + c0 + t];
+            __syncthreads();
+            while (jn < c1) {
+                if (jn >= c0) {
+                    const double *rj = s_rec + (size_t) (jn - c0) * SSB_ROWS_STRIDE;
+                    const ssb_d4 a0 = ssb_lds256(rj), a1 = ssb_lds256(rj + 4), a2 = ssb_lds256(rj + 8), a3 = ssb_lds256(rj + 12);
+                    S.pair(a0, a1, a2, a3, s_C + (size_t) (jn - c0) * SSB_SC, (size_t) 1);
+                } else {
+                    from_global(jn);
+                }
+                k++;
+                jn = (k < cnt) ? V.nbr[(size_t) k * N + i] : 0x7fffffff;
+            }
+        }
+    }
+    while (k < cnt) {                                                // beyond the last range
+        from_global(jn);
+        k++;
+        jn = (k < cnt) ? V.nbr[(size_t) k * N + i] : 0x7fffffff;
+    }
+    double mx = 0.0;
+    if (live) mx = S.store(V, i, step);
     if (SSB_SD > 0) {
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
@@ -751,7 +786,9 @@ __device__ __forceinline__ double pair_Dij(const SsbView &V, int i, int j, doubl
                                            double m_i, double rho_i) {
     const double d2 = ssb_dist2(V.dim, xi0, xi1, xi2, V.x0[0][j], V.x0[1][j], V.x0[2][j]);
     const double r = sqrt(d2);
-    return ssb_Dij(d2, r, V.h, m_i, V.mass[j], rho_i, V.rho_search[j]);
+    double rho_j;
+    ssb_search_rho(V, i, j, rho_i, rho_j);
+    return ssb_Dij(d2, r, V.h, m_i, V.mass[j], rho_i, rho_j);
 }
 
 __global__ void __launch_bounds__(SSB_BLOCK) k_diff_init(SsbView V, unsigned long long *max_ddiag_bits) {
@@ -1624,7 +1661,8 @@ static int l_force(const SsbView *V, unsigned step, int full, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 static int l_force_mv(const SsbView *V, unsigned step, unsigned long long *max_bits, cudaStream_t st) {
-    k_force_mv<SSB_FORCE_COOP><<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
+    if (V->n_items > 0) k_force_mv_rows<<<(unsigned) V->n_items, SSB_BLOCK, 0, st>>>(*V, step, max_bits);     // row-segment work items (ssb_core.cu)
+    else k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
     return (int) cudaGetLastError();
 }
 static int l_corrector(const SsbView *V, unsigned step, cudaStream_t st) {

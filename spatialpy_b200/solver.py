@@ -134,6 +134,9 @@ def _property_series(result, property_name, steps):
 def _result_class():
     """The reference's Result with `read_step` served from the binary side-store when the run kept one (SURVEY.md §8f item 1);
     everything else — get_species, plotting, __eq__, pickling of the result directory — is inherited unchanged."""
+    global _B200_RESULT
+    if _B200_RESULT is not None:
+        return _B200_RESULT
     from spatialpy.core.result import Result
 
     class B200Result(Result):
@@ -168,7 +171,22 @@ def _result_class():
                 return super().get_property(property_name, timepoints=timepoints)
             return _property_series(self, property_name, pos)
 
+    # picklable like the reference's Result (test_solver.py:187-195 pickles it): pickle finds a class by module + qualified name, so
+    # the class is published as spatialpy_b200.solver.B200Result (and rebuilt on demand by the module's __getattr__ when a fresh
+    # process unpickles one before any Solver ran)
+    B200Result.__qualname__ = "B200Result"
+    B200Result.__module__ = __name__
+    _B200_RESULT = B200Result
     return B200Result
+
+
+_B200_RESULT = None
+
+
+def __getattr__(name):
+    if name == "B200Result":
+        return _result_class()
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 class Solver:

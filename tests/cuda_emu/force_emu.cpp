@@ -1,7 +1,7 @@
-// force_emu.cpp — TEST INFRASTRUCTURE: the SOURCE of the moving-domain force sweep k_force_mv<COOP> (extracted verbatim from
+// force_emu.cpp — TEST INFRASTRUCTURE: the SOURCE of the moving-domain force sweep k_force_mv / k_force_mv_rows (extracted verbatim from
 // spatialpy_b200/csrc/ssb_model_unit.cuh by tests/test_cpu_abi.py into EMU_KERNELS) run on the host through emu_shim.h, so that
-// the quad-gather form (COOP = 4: cooperative record fetch + 4x4 shuffle transpose) can be compared with the one-gather-per-lane
-// form (COOP = 1) bit for bit without a GPU.
+// the shared-memory form (k_force_mv_rows: row-segment work items, staged ranges, cursor over the ascending lists, gather fallback)
+// can be compared with the gather form (k_force_mv) bit for bit without a GPU.
 #include "emu_shim.h"
 
 #include SSB_MODEL_HEADER          // generated ssb_gen namespace + SSB_* sizes of the test model (same text nvcc compiles)
@@ -27,9 +27,10 @@ struct EmuArgs {
     double *F[3], *Fbp[3], *Frho, *C, *Q, *Ddiag, *data_fn;
     const double *dmat;
     unsigned long long *max_bits;
+    int n_items; int *item_slot0, *item_cnt, *item_rng;
 };
 
-extern "C" int emu_force(const EmuArgs *a, int coop, unsigned step) {
+extern "C" int emu_force(const EmuArgs *a, int rows, unsigned step) {
     SsbView V;
     std::memset(&V, 0, sizeof(V));
     V.N = a->N; V.dim = a->dim; V.num_types = a->num_types; V.filter = a->filter; V.flags = a->flags;
@@ -39,7 +40,8 @@ extern "C" int emu_force(const EmuArgs *a, int coop, unsigned step) {
     for (int d = 0; d < 3; d++) { V.F[d] = a->F[d]; V.Fbp[d] = a->Fbp[d]; }
     V.Frho = a->Frho; V.C = a->C; V.Q = a->Q; V.Ddiag = a->Ddiag; V.data_fn = a->data_fn; V.dmat = a->dmat;
     const unsigned blocks = (unsigned) ((a->N + SSB_BLOCK - 1) / SSB_BLOCK);
-    if (coop == 4) emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv<4>, V, step, a->max_bits);
-    else emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv<1>, V, step, a->max_bits);
+    V.n_items = a->n_items; V.item_slot0 = a->item_slot0; V.item_cnt = a->item_cnt; V.item_rng = a->item_rng;
+    if (rows) emu_launch((unsigned) a->n_items, SSB_BLOCK, ssb_unit::k_force_mv_rows, V, step, a->max_bits);
+    else emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv, V, step, a->max_bits);
     return 0;
 }

@@ -652,8 +652,9 @@ def test_engine_writers_large_snapshot_threads_and_python_twin_agree(tmp_path, m
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# the moving-domain force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu) — the quad-gather
-# form (COOP = 4: four lanes fetch their four records together, 4x4 shuffle transpose) against one gather per lane (COOP = 1)
+# the moving-domain force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu) — the shared-memory
+# form (k_force_mv_rows: row-segment work items, nine staged slot ranges, a cursor over the ascending candidate lists, gather
+# fallback for candidates outside every range) against one gather per candidate (k_force_mv)
 # ----------------------------------------------------------------------------------------------------------------------
 def _build_force_emulator(fm, tmp_path, defines=()):
     from spatialpy_b200 import codegen
@@ -680,7 +681,35 @@ class _EmuArgs(ctypes.Structure):
                 ("P0", ctypes.c_double), ("rec", ctypes.c_void_p), ("nbr", ctypes.c_void_p), ("nbr_count", ctypes.c_void_p),
                 ("nbr_cap", ctypes.c_int), ("owned", ctypes.c_void_p), ("F", ctypes.c_void_p * 3), ("Fbp", ctypes.c_void_p * 3),
                 ("Frho", ctypes.c_void_p), ("C", ctypes.c_void_p), ("Q", ctypes.c_void_p), ("Ddiag", ctypes.c_void_p),
-                ("data_fn", ctypes.c_void_p), ("dmat", ctypes.c_void_p), ("max_bits", ctypes.c_void_p)]
+                ("data_fn", ctypes.c_void_p), ("dmat", ctypes.c_void_p), ("max_bits", ctypes.c_void_p),
+                ("n_items", ctypes.c_int), ("item_slot0", ctypes.c_void_p), ("item_cnt", ctypes.c_void_p), ("item_rng", ctypes.c_void_p)]
+
+
+def _row_items(cell_start, nc, n, seg=128, pad=1):
+    """Python restatement of k_row_count / k_row_fill (ssb_core.cu): (slot0, cnt, 9 x [lo, hi)) per row segment.  pad = 0 drops the
+    one-cell margin of the ranges, so that candidates in the neighbouring x-cells take the kernel's gather fallback."""
+    nx, ny, nz = nc
+    slot0, cnt, rng = [], [], []
+    for r in range(ny * nz):
+        b, e = int(cell_start[r * nx]), int(cell_start[(r + 1) * nx])
+        cy, cz = r % ny, r // ny
+        for s0 in range(b, e, seg):
+            m = min(seg, e - s0)
+            row = cell_start[r * nx:(r + 1) * nx]
+            cxa = int(np.searchsorted(row, s0, side="right") - 1)
+            cxb = int(np.searchsorted(row, s0 + m - 1, side="right") - 1)
+            xa, xb = max(cxa - pad, 0), min(cxb + pad, nx - 1)
+            slot0.append(s0)
+            cnt.append(m)
+            for dz in (-1, 0, 1):
+                for dy in (-1, 0, 1):
+                    yy, zz = cy + dy, cz + dz
+                    if 0 <= yy < ny and 0 <= zz < nz:
+                        row0 = (zz * ny + yy) * nx
+                        rng += [int(cell_start[row0 + xa]), int(cell_start[row0 + xb + 1])]
+                    else:
+                        rng += [0, 0]
+    return np.array(slot0, np.int32), np.array(cnt, np.int32), np.array(rng, np.int32)
 
 
 def _force_sweep_inputs(fm, seed=2):
@@ -693,8 +722,10 @@ def _force_sweep_inputs(fm, seed=2):
     x0 = fm.x + rng.uniform(-0.004, 0.004, fm.x.shape)
     cell = np.floor((x0 - x0.min(axis=0)) / rad).astype(np.int64)
     nc = cell.max(axis=0) + 1
-    order = np.argsort((cell[:, 2] * nc[1] + cell[:, 1]) * nc[0] + cell[:, 0], kind="stable")
+    key = (cell[:, 2] * nc[1] + cell[:, 1]) * nc[0] + cell[:, 0]
+    order = np.argsort(key, kind="stable")
     x0 = x0[order]
+    cell_start = np.searchsorted(key[order], np.arange(int(nc.prod()) + 1)).astype(np.int64)      # [ncells + 1], last = n
     typ, solid, mass, nu = fm.type[order], fm.solid[order], fm.mass[order], fm.nu[order]
     xl = x0 + rng.uniform(-1e-4, 1e-4, x0.shape) * (solid == 0)[:, None]       # live positions after the predictor
     v = rng.normal(size=(n, 3)) * 0.1 * (solid == 0)[:, None]
@@ -714,13 +745,14 @@ def _force_sweep_inputs(fm, seed=2):
     owned = np.ones(n, np.int32)
     owned[rng.choice(n, 9, replace=False)] = 0
     Sc, Sd = fm.num_chem_species, fm.num_stoch_species
-    st = dict(rec=rec, nbr=nbr, cnt=cnt, cap=cap, owned=owned, F=rng.normal(size=(3, n)), Fbp=rng.normal(size=(3, n)),
+    items = _row_items(cell_start, [int(v) for v in nc], n)
+    st = dict(items=items, cell_start=cell_start, nc=[int(v) for v in nc], rec=rec, nbr=nbr, cnt=cnt, cap=cap, owned=owned, F=rng.normal(size=(3, n)), Fbp=rng.normal(size=(3, n)),
               Frho=rng.normal(size=n), C=rng.random((max(Sc, 1), n)), Q=rng.normal(size=(max(Sc, 1), n)),
               dmat=np.ascontiguousarray(fm.diffusion_matrix, dtype=np.float64), Sd=Sd, n=n)
     return st
 
 
-def _run_force_emulator(lib, fm, st, coop):
+def _run_force_emulator(lib, fm, st, rows, items=None):
     n = st["n"]
     out = {k: np.ascontiguousarray(st[k]).copy() for k in ("F", "Fbp", "Frho", "Q")}
     out["Ddiag"] = np.full((max(st["Sd"], 1), n), -1.0)
@@ -735,35 +767,54 @@ def _run_force_emulator(lib, fm, st, coop):
         a.Fbp[d] = out["Fbp"][d].ctypes.data
     a.Frho, a.C, a.Q, a.Ddiag = out["Frho"].ctypes.data, keep[4].ctypes.data, out["Q"].ctypes.data, out["Ddiag"].ctypes.data
     a.data_fn, a.dmat, a.max_bits = None, keep[5].ctypes.data, mb.ctypes.data
-    assert lib.emu_force(ctypes.byref(a), int(coop), 3) == 0
+    it = [np.ascontiguousarray(v) for v in (items if items is not None else st["items"])]
+    a.n_items, a.item_slot0, a.item_cnt, a.item_rng = len(it[0]), it[0].ctypes.data, it[1].ctypes.data, it[2].ctypes.data
+    assert lib.emu_force(ctypes.byref(a), int(rows), 3) == 0
     out["max_bits"] = mb
     return out
 
 
-def test_quad_gather_force_sweep_source_equals_one_gather_per_lane_on_the_host(tmp_path):
-    """k_force_mv<4> vs k_force_mv<1>, both as CUDA SOURCE run by the block emulator (one host thread per CUDA thread, real
-    barriers, quad and warp shuffles): every output of the sweep is bit-identical — ragged lists inside a quad, ghosts, idle
-    lanes of the last CTA included."""
+def test_row_segment_force_sweep_source_equals_the_gather_sweep_on_the_host(tmp_path):
+    """k_force_mv_rows vs k_force_mv, both as CUDA SOURCE run by the block emulator (one host thread per CUDA thread, real barriers,
+    shared arrays): every output of the sweep is bit-identical — with all candidates staged, with the ranges cut so that candidates
+    take the gather fallback in the middle of a list, and with tiny chunks so that every range is staged in several pieces."""
     from spatialpy_b200 import configs
-    fm = configs.tank_sdpd(n=14, nt=10, output_every=10)     # ~2 000 particles, 16 CTAs, the last one partly idle
+    fm = configs.tank_sdpd(n=14, nt=10, output_every=10)     # ~2 000 particles; rows of ~70 particles, partly filled CTAs
     st = _force_sweep_inputs(fm)
-    assert st["n"] % 128 != 0 and len(set(st["cnt"][:4].tolist())) > 1
+    slot0, cnt, rng = st["items"]
+    assert int(cnt.sum()) == st["n"] and cnt.max() <= 128 and len(cnt) > 8
+    # the restated work items cover every candidate of every particle (pad = 1) ...
+    for it in range(len(cnt)):
+        r = rng[18 * it:18 * it + 18].reshape(9, 2)
+        for i in range(slot0[it], slot0[it] + cnt[it]):
+            for j in st["nbr"][:st["cnt"][i], i]:
+                assert ((r[:, 0] <= j) & (j < r[:, 1])).any()
     lib = _build_force_emulator(fm, tmp_path)
-    ref = _run_force_emulator(lib, fm, st, coop=1)
+    ref = _run_force_emulator(lib, fm, st, rows=0)
     assert np.abs(ref["F"] - st["F"]).max() > 0 and (ref["Ddiag"][:, st["owned"] == 1] >= 0).all()   # the sweep did something
-    got = _run_force_emulator(lib, fm, st, coop=4)
+    got = _run_force_emulator(lib, fm, st, rows=1)
     for k in ref:
         assert np.array_equal(ref[k], got[k]), k
+    # ... and with the margin dropped many candidates are outside every range: the fallback must keep the list order
+    cut = _row_items(st["cell_start"], st["nc"], st["n"], pad=0)
+    got = _run_force_emulator(lib, fm, st, rows=1, items=cut)
+    for k in ref:
+        assert np.array_equal(ref[k], got[k]), ("fallback", k)
+    lib2 = _build_force_emulator(fm, tmp_path, ("SSB_ROWS_TR=16",))
+    for items in (None, cut):
+        got = _run_force_emulator(lib2, fm, st, rows=1, items=items)
+        for k in ref:
+            assert np.array_equal(ref[k], got[k]), ("chunks", k)
 
 
-def test_quad_gather_force_sweep_source_on_a_2d_model(tmp_path):
+def test_row_segment_force_sweep_source_on_a_2d_model(tmp_path):
     """Same comparison on a 2-D moving model (cavity2d_rdme fixture: other species / reaction counts => another instantiation
-    of the generated code)."""
+    of the generated code; nz = 1 => only three of the nine ranges exist)."""
     fm = load_model("cavity2d_rdme")
     st = _force_sweep_inputs(fm, seed=7)
     lib = _build_force_emulator(fm, tmp_path)
-    ref = _run_force_emulator(lib, fm, st, coop=1)
-    got = _run_force_emulator(lib, fm, st, coop=4)
+    ref = _run_force_emulator(lib, fm, st, rows=0)
+    got = _run_force_emulator(lib, fm, st, rows=1)
     assert np.abs(ref["F"] - st["F"]).max() > 0
     for k in ref:
         assert np.array_equal(ref[k], got[k]), k
