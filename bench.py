@@ -583,6 +583,28 @@ def run_ensemble_bench(args, rank, local_rank, world):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dt, ev = float(tm[0].item()), float(t[1].item())
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        # reference arm of an ensemble: trajectories are independent processes (solver.py:547-605), so the host
+        # runs one per core side by side; trajectories/s = processes / wall
+        exe = os.path.join(ROOT, "oracle", "_ref", f"bench_{name}", "fast", "ssa_sdpd.exe")
+        if os.path.exists(exe):
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            procs, dirs = [], []
+            for k in range(cores):
+                d = tempfile.mkdtemp(prefix="ssb_ref_ens_")
+                dirs.append(d)
+                procs.append(subprocess.Popen([exe, "-t", "1", "-s", str(1000 + k)], cwd=d, stdout=subprocess.DEVNULL))
+            for p in procs:
+                p.wait()
+            wall = time.perf_counter() - t0
+            for d in dirs:
+                subprocess.run(["rm", "-rf", d])
+            cpu = {"value": fm.num_particles * fm.nt * cores / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "trajectories_per_s": cores / wall,
+                   "sample": f"unmodified reference engine (g++ -O3), {cores} trajectories of the same model as {cores} concurrent processes "
+                             f"(-t 1 each), {wall:.2f} s wall incl. process start and VTK output"}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": fm.num_particles * fm.nt * total / dt, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
@@ -590,7 +612,7 @@ def run_ensemble_bench(args, rank, local_rank, world):
             "config": {"workload": f"ensemble of {total} trajectories of the {name} fixture model ({fm.num_particles} particles, {fm.nt} steps, "
                                    f"{fm.num_species} species, {fm.num_reactions} reactions)", "trajectories_per_gpu": per_gpu,
                        "concurrent_engine_handles_per_gpu": lanes, "parallelism": f"ensemble: trajectory k -> GPU k mod {world}"},
-            "trajectories_per_s": total / dt, "rdme_events_per_s": ev / dt,
+            "trajectories_per_s": total / dt, "rdme_events_per_s": ev / dt, "cpu_baseline": cpu,
             "e2e": {"value": fm.num_particles * fm.nt * total / dt, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "includes": "host wall clock of ssb_run per trajectory incl. state upload and output staging (no VTK text)"}}))
     if use_dist:

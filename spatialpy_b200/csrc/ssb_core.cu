@@ -287,55 +287,6 @@ __global__ void k_search(SsbView V, CellGrid g, const int *cell_start, int *max_
     if ((threadIdx.x & 31) == 0 && cnt > 0) { atomicMax(max_count, cnt); atomicAdd(total_count, (unsigned long long) tot); }
 }
 
-// ---- work items of the shared-memory force sweep (k_force_mv_rows, ssb_model_unit.cuh): every (cy, cz) cell row — a contiguous slot
-// range, x is the fastest cell coordinate — is cut into segments of <= ROW_SEG consecutive particles; an item also carries the nine
-// slot ranges (rows (cy+dy, cz+dz), x-cells one beyond the segment's own on both sides) that hold its particles' candidates.
-#define ROW_SEG 128
-__device__ __forceinline__ int cs_at(const int *cell_start, int c, int ncells, int N) { return c < ncells ? cell_start[c] : N; }
-__global__ void k_row_count(CellGrid g, int N, const int *cell_start, int *nseg) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x, nrows = g.n[1] * g.n[2];
-    if (r >= nrows) return;
-    const int b = cs_at(cell_start, r * g.n[0], g.ncells, N), e = cs_at(cell_start, (r + 1) * g.n[0], g.ncells, N);
-    nseg[r] = (e - b + ROW_SEG - 1) / ROW_SEG;
-}
-// x-cell of row `r` that holds storage slot `slot` (the last cell whose start is <= slot)
-__device__ __forceinline__ int cell_of_slot(const int *cell_start, int row0, int nx, int ncells, int N, int slot) {
-    int lo = 0, hi = nx - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (cs_at(cell_start, row0 + mid, ncells, N) <= slot) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-__global__ void k_row_fill(CellGrid g, int N, const int *cell_start, const int *row_off, int *slot0, int *cnt, int *rng) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x, nrows = g.n[1] * g.n[2];
-    if (r >= nrows) return;
-    const int nx = g.n[0], ny = g.n[1], nz = g.n[2];
-    const int b = cs_at(cell_start, r * nx, g.ncells, N), e = cs_at(cell_start, (r + 1) * nx, g.ncells, N);
-    const int cy = r % ny, cz = r / ny;
-    int item = row_off[r];
-    for (int s0 = b; s0 < e; s0 += ROW_SEG, item++) {
-        const int n = min(ROW_SEG, e - s0);
-        slot0[item] = s0;
-        cnt[item] = n;
-        const int cxa = cell_of_slot(cell_start, r * nx, nx, g.ncells, N, s0);
-        const int cxb = cell_of_slot(cell_start, r * nx, nx, g.ncells, N, s0 + n - 1);
-        const int xa = max(cxa - 1, 0), xb = min(cxb + 1, nx - 1);
-        int *o = rng + (size_t) item * 18;
-        for (int dz = -1; dz <= 1; dz++)
-            for (int dy = -1; dy <= 1; dy++) {
-                const int yy = cy + dy, zz = cz + dz;
-                int lo = 0, hi = 0;
-                if (yy >= 0 && yy < ny && zz >= 0 && zz < nz) {
-                    const int row0 = (zz * ny + yy) * nx;
-                    lo = cs_at(cell_start, row0 + xa, g.ncells, N);
-                    hi = cs_at(cell_start, row0 + xb + 1, g.ncells, N);
-                }
-                *o++ = lo; *o++ = hi;
-            }
-    }
-}
-
 __global__ void k_iota(int n, int *a) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = i; }
 __global__ void k_copy64(int n, const double *src, double *dst) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] = src[i]; }
 
@@ -691,9 +642,6 @@ struct ssb_handle {
     CellGrid grid;
     int *d_key = nullptr, *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cursor = nullptr, *d_perm = nullptr;
     int *d_tile_sums = nullptr, *d_flags = nullptr;  // d_flags[0]=nonidentity [1]=max nbr count
-    int use_rows = 0;                                // moving domains: shared-memory force sweep over row-segment work items
-    int *d_row_nseg = nullptr, *d_row_off = nullptr, *d_item_total = nullptr;
-    int item_cap = 0;
     unsigned long long *d_maxbits = nullptr;
     double *d_stage = nullptr;   // device staging for output/taps (id order)
     size_t stage_bytes = 0;
@@ -1193,7 +1141,10 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     if (V.static_domain) { for (int d = 0; d < 3; d++) V.x0[d] = nullptr; }   // aliased to x after allocation (below)
     else { for (int d = 0; d < 3; d++) CK(dalloc(h, &V.x0[d], (size_t) N)); }
     CK(dalloc(h, &V.rho_new, (size_t) N));
-    if (!V.static_domain) { CK(dalloc(h, &V.rec, (size_t) 16 * N)); CK(dalloc(h, &V.solid_nbr, (size_t) N)); }
+    if (!V.static_domain) {
+        CK(dalloc(h, &V.rec, (size_t) 16 * N)); CK(dalloc(h, &V.solid_nbr, (size_t) N));
+        if (Sc <= 2) CK(dalloc(h, &V.rec2, (size_t) 4 * N));
+    }
     if (V.static_domain && Sc > 0) { CK(dalloc(h, &V.Cpre[0], (size_t) Sc * N)); CK(dalloc(h, &V.Cpre[1], (size_t) Sc * N)); }
     CK(dalloc(h, &V.nbr_count, (size_t) N));
     CK(cudaMemsetAsync(V.nbr_count, 0, sizeof(int) * N, h->stream));
@@ -1236,19 +1187,6 @@ extern "C" int ssb_create(const ssb_model *m, ssb_handle **out) {
     CK(dalloc(h, &h->d_tile_sums, (size_t) (h->grid.ncells / SCAN_TILE + 2)));
     CK(dalloc(h, &h->d_flags, 8));
     CK(dalloc(h, &h->d_maxbits, 2));
-    if (!V.static_domain && !(m->flags & SSB_FLAG_LITERAL_KERNELS)) {
-        // the shared-memory force sweep pays where a cell row holds enough particles to fill CTAs (3-D clouds, long 2-D rows);
-        // short rows keep the gather sweep.  SSB_ROWS=0 / 1 forces the choice (tests: both sweeps must agree bit for bit).
-        const int nrows = h->grid.n[1] * h->grid.n[2];
-        const char *e = getenv("SSB_ROWS");
-        h->use_rows = e ? (atoi(e) != 0) : ((double) N / (double) nrows >= 48.0);
-        if (h->use_rows) {
-            h->item_cap = nrows + N / ROW_SEG + 8;
-            CK(dalloc(h, &h->d_row_nseg, (size_t) nrows + 1)); CK(dalloc(h, &h->d_row_off, (size_t) nrows + 1)); CK(dalloc(h, &h->d_item_total, 4));
-            CK(dalloc(h, &V.item_slot0, (size_t) h->item_cap)); CK(dalloc(h, &V.item_cnt, (size_t) h->item_cap));
-            CK(dalloc(h, &V.item_rng, (size_t) h->item_cap * 18));
-        }
-    }
     // staging: the largest of an output snapshot and any single tap
     size_t per = (size_t) 3 * 8 * 2 + 4 * 8 + 8 + (size_t) Sc * 8 + (size_t) Sd * 8 + (size_t) Rd * 8 + 64;
     h->stage_bytes = per * N + 4096;
@@ -1536,17 +1474,6 @@ static int neighbour_search(ssb_handle *h) {
     const int N = h->N;
     cudaStream_t st = h->stream;
     if (V.filter && !h->skin_chosen) { int rcs = choose_skin(h); if (rcs) return rcs; }
-    if (h->use_rows) {       // work items of the shared-memory force sweep for this storage order (row counts -> scan -> fill)
-        const int nrows = h->grid.n[1] * h->grid.n[2];
-        const int ntiles = (nrows + SCAN_TILE - 1) / SCAN_TILE;
-        k_row_count<<<gridN(nrows), CORE_BLOCK, 0, st>>>(h->grid, N, h->d_cell_start, h->d_row_nseg);
-        k_scan_tiles<<<ntiles, 256, 0, st>>>(nrows, h->d_row_nseg, h->d_row_off, h->d_tile_sums);
-        k_scan_sums<<<1, 256, 0, st>>>(ntiles, h->d_tile_sums, h->d_item_total);
-        k_scan_add<<<gridN(nrows), CORE_BLOCK, 0, st>>>(nrows, h->d_row_off, h->d_tile_sums);
-        k_row_fill<<<gridN(nrows), CORE_BLOCK, 0, st>>>(h->grid, N, h->d_cell_start, h->d_row_off, V.item_slot0, V.item_cnt, V.item_rng);
-        CK(cudaMemcpyAsync(&h->pin[12], h->d_item_total, sizeof(int), cudaMemcpyDeviceToHost, st));
-        h->launches += 5;
-    }
     for (int attempt = 0; attempt < 8; attempt++) {
         // (first build: the capacity is 0, so this pass only counts; the rows are then sized from the maximum)
         CK(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(int), st));
@@ -1556,11 +1483,6 @@ static int neighbour_search(ssb_handle *h) {
         int mx = 0;
         CK(cudaMemcpyAsync(&mx, h->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(ssb_sync(h));
-        if (h->use_rows) {
-            const int n_items = (int) (h->pin[12] & 0xffffffffull);
-            if (n_items > h->item_cap) return fail(h, SSB_ERR_CUDA, "row work items (%d) exceed their table (%d)", n_items, h->item_cap);
-            V.n_items = n_items;
-        }
         if (mx <= V.nbr_cap) return SSB_OK;
         // grow (with head-room on moving domains) and search again
         // stream-ordered allocation (cudaMallocAsync / cudaFreeAsync): cudaMalloc and cudaFree synchronise the whole DEVICE, and
@@ -2660,6 +2582,23 @@ static void slab_free(ssb_handle *h) {
 }
 
 // one field group to both neighbours and back: pack+send (peer writes, flags raised by the last CTA), wait, unpack
+// SSB_SLAB_DEBUG: how many particles carry a non-positive / non-finite value in a field (owned, ghost) — blocking, diagnostics only
+__global__ void k_debug_count_bad(int N, const double *f, const int *owned, int *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double v = f[i];
+    if (!(v > 0.0) || !(v < 1e300)) atomicAdd(&out[owned[i] ? 0 : 1], 1);
+}
+static void slab_debug(ssb_handle *h, const char *tag, const double *field) {
+    if (!getenv("SSB_SLAB_DEBUG")) return;
+    int *d = h->d_flags + 4, bad[2] = {0, 0};
+    cudaMemsetAsync(d, 0, 8, h->stream);
+    k_debug_count_bad<<<gridN(h->N), CORE_BLOCK, 0, h->stream>>>(h->N, field, h->V.owned, d);
+    cudaMemcpyAsync(bad, d, 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    fprintf(stderr, "[slab %d/%d] step %u %-22s bad owned %d ghost %d\n", h->slab->rank, h->slab->world, h->current_step, tag, bad[0], bad[1]);
+}
+
 struct NvtxScope { explicit NvtxScope(const char *n) { nvtxRangePushA(n); } ~NvtxScope() { nvtxRangePop(); } };
 
 static int slab_exchange(ssb_handle *h, int group) {
@@ -2780,9 +2719,12 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
             CK(cudaMemcpyAsync(&h->pin[4], c->d_red + 0, sizeof(unsigned long long), cudaMemcpyDeviceToHost, aux));
             CK(cudaEventRecord(h->ev_maxd, aux));
         }
+        slab_debug(h, "rho after force", V.rho);
         if ((rc = slab_exchange(h, 0))) return rc;
         if ((rc = mv_corrector(h))) return rc;
+        slab_debug(h, "rho_new after corrector", V.rho_new);
         if ((rc = slab_exchange(h, 1))) return rc;
+        slab_debug(h, "rho_new after exchange", V.rho_new);
         if ((rc = mv_finish(h))) return rc;
         if ((rc = slab_exchange(h, 2))) return rc;
         if ((rc = mv_lookahead(h))) return rc;
@@ -2799,7 +2741,7 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
             memcpy(&mx, &h->pin[4], 8);
             if (getenv("SSB_SLAB_DEBUG")) {
                 double loc; memcpy(&loc, &h->pin[3], 8);
-                fprintf(stderr, "[slab %d/%d] step %u local max Ddiag %.6g global %.6g filter %d skin %g items %d\n", c->rank, c->world, step, loc, mx, V.filter, h->skin, V.n_items);
+                fprintf(stderr, "[slab %d/%d] step %u local max Ddiag %.6g global %.6g filter %d skin %g\n", c->rank, c->world, step, loc, mx, V.filter, h->skin);
             }
             h->ddiag_fresh = 0;
             if ((rc = set_windows(h, mx))) return rc;        // GLOBAL max Ddiag: every rank uses the same windows

@@ -59,10 +59,7 @@ struct SsbView {
     //   rec[16*j + 0..2] x0   3..5 x   6..8 v   9..11 vt   12 rho   13 mass   14 nu   15 bits(id:32 | type:16 | solid:16)
     double *rec;
     int *solid_nbr;     // [N] moving domains: 1 if any CANDIDATE neighbour is a solid particle (written by k_search, read by k_finish)
-    // row-segment work items of the shared-memory force sweep (k_force_mv_rows; built at every list build, ssb_core.cu row_items):
-    // item = <= 128 consecutive slots of one (cy, cz) cell row + the nine ascending slot ranges [lo, hi) its candidates fall into
-    int n_items;        // 0 = use the gather sweep
-    int *item_slot0, *item_cnt, *item_rng;      // [n_items], [n_items], [n_items * 18]
+    double *rec2;       // [4*N] moving domains, S_c <= 2: {1/rho, P/rho^2, C[0], C[1]} per particle (predictor -> force sweep), else nullptr
     // static-domain fast path: cached chemistry pair coefficient dQc_base (model.cpp:155) and the double-buffered
     // half-stepped concentrations the next sweep reads (see k_static_step)
     double *coef;       // [cap*N] or nullptr

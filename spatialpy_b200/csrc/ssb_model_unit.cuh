@@ -18,6 +18,11 @@
 #ifndef SSB_BLOCK
 #define SSB_BLOCK 128
 #endif
+// moving domains: a second, 32-byte gather record per particle — {1/rho, P/rho^2, C[0], C[1]} — written by the predictor, so that
+// the force sweep fetches the neighbour's concentrations and pressure term with ONE load instead of two gathers and a division
+#ifndef SSB_REC2
+#define SSB_REC2 (SSB_SC <= 2)
+#endif
 
 namespace ssb_unit {
 
@@ -100,6 +105,14 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_predictor(SsbView V, unsigned ste
         r2[5] = make_double2(V.vt[1][i], V.vt[2][i]);
         r2[6] = make_double2(p.rho, p.mass);
         r2[7] = make_double2(p.nu, __longlong_as_double(bits));
+#if SSB_REC2
+        if (V.rec2) {
+            const double inv_rho = 1.0 / p.rho;
+            double2 *e2 = reinterpret_cast<double2 *>(V.rec2 + (size_t) i * 4);
+            e2[0] = make_double2(inv_rho, (V.P0 * (p.rho / V.rho0 - 1.0)) * inv_rho * inv_rho);
+            e2[1] = make_double2(SSB_SC > 0 ? p.C[0] : 0.0, SSB_SC > 1 ? p.C[SSB_SC > 1 ? 1 : 0] : 0.0);
+        }
+#endif
     }
 #pragma unroll
     for (int s = 0; s < SSB_SC; s++) {
@@ -246,22 +259,17 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
 // Results differ from the literal evaluation order by a few ulp per pair (parity gate: 1e-12 of the field scale).
 //
 //
-// Two kernels feed the ONE pair body below (ForceSweep::pair), both walking the same ascending candidate lists, so their results
-// are bit-identical:
-//   k_force_mv       one 128-byte gather per candidate and lane.  ncu (profiles/r2c_force_coop1_metrics.csv, box at 1 M): the L1
-//                    data pipe is the busiest unit (74 %: ~190 wavefronts per warp and candidate — 4 x 32 for the record, 2 x 32 for
-//                    the C_j gathers), the dominant stall is the long scoreboard (9.5 of ~13 warp cycles per issued instruction),
-//                    fp64 pipe 32 %, 16 warps per SM at 128 registers: latency- and wavefront-bound, not fp64- or DRAM-bound.
-//   k_force_mv_rows  shared-memory staging per ROW SEGMENT (default where rows are long enough, ssb_core.cu row_items): a CTA owns
-//                    <= 128 consecutive particles of ONE (cy, cz) cell row; their candidates lie in nine contiguous slot ranges (the
-//                    rows (cy+dy, cz+dz), x-cells [cxa-1, cxb+1]), which are staged one after the other with coalesced 16-byte loads
-//                    into padded records (stride 144 B: conflict-free 16-byte reads), C_j beside them; every thread then consumes
-//                    the part of its list that falls into the staged range from shared memory (~36 wavefronts per warp and
-//                    candidate, ~30-cycle latency).  Each record crosses L1 once per CTA (~12 per particle) instead of once per pair (~70).
-// History: the round-1 tile form (bitmap of touched 64-slot blocks, serial chunk table, unpadded 128-byte records = 32-way bank
-// conflicts) measured 2x SLOWER than the gather (profiles/r2a_bench_tank_tile.json) and was deleted; a quad-cooperative gather
-// (4 lanes fetch 4 records together, 4x4 shuffle transpose) cut the L1 wavefronts from 74 % to 47 % but doubled the instruction
-// count and measured the same time (profiles/r2c_force_coop4_metrics.csv) and was deleted too.
+// What bounds it (ncu, box at 1 M particles, profiles/r2c_force_coop1_metrics.csv): the L1 data pipe — 74 % busy with ~190
+// wavefronts per warp and candidate (every lane's record is its own 128-byte line: an LDG.E.256 of a warp replays 32 times, and the
+// two C_j gathers another 2 x 32) — and, behind it, the long scoreboard (9.5 of 13 warp cycles per issued instruction); fp64 pipe
+// 32 %, DRAM 4 %, 16 warps per SM at 128 registers.  Measured alternatives, both deleted (one pair body stays):
+//   * quad-cooperative gather (4 lanes fetch 4 records together, 4x4 shuffle transpose): L1 wavefronts 74 % -> 47 %, but twice the
+//     instructions (issue 28 % -> 52 %) and the C_j gathers untouched: same time (1.79 vs 1.84 ms, profiles/r2c_force_coop4_metrics.csv);
+//   * shared-memory staging per row segment (<= 128 particles of one cell row, nine staged slot ranges, cursor over the lists):
+//     L1 34 %, long scoreboard 2.8 — but the nine phases leave 14 of 32 lanes active on average and double the instruction
+//     count: 2.66 ms (profiles/r2e_force_rows_metrics.csv); the round-1 bitmap tile form was 2x slower still.
+// What helped: the neighbour's concentrations and its 1/rho, P/rho^2 now come from ONE extra 32-byte sector (rec2, written by the
+// predictor) instead of two 8-byte gathers + a division per pair: 5 replayed loads per candidate instead of 6.
 // ---------------------------------------------------------------------------------------------
 
 // per-particle state of the sweep + the pair body (ONE copy, whatever feeds it the records)
@@ -316,10 +324,15 @@ struct ForceSweep {
     }
 
     // one candidate j with its record in c0..c3 (rejected unless it is in ANN's exact set for THIS step's snapshot)
-    // cj / cj_stride: where the neighbour's concentrations are (global: V.C + j, stride N; staged: its shared-memory row, stride 1)
-    __device__ __forceinline__ void pair(const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const double *cj, const size_t cj_stride) {
+    // c0..c3 = the neighbour's gather record; e = its derived sector rec2 = {1/rho, P/rho^2, C[0], C[1]} when SSB_REC2, else unused
+    // (1/rho and P/rho^2 are then recomputed here and the concentrations gathered from V.C)
+    __device__ __forceinline__ void pair(const ssb_d4 &c0, const ssb_d4 &c1, const ssb_d4 &c2, const ssb_d4 &c3, const ssb_d4 &e, const int j) {
+#if SSB_REC2
+        const double inv_rho_j = e.a, aP_j = e.b;
+#else
         const double inv_rho_j = 1.0 / c3.a;
         const double aP_j = (P0 * ((inv_exact ? c3.a * inv_rho0 : c3.a / rho0) - 1.0)) * inv_rho_j * inv_rho_j;
+#endif
         const double vol_j = c3.b * inv_rho_j;
         const double d2 = ssb_dist2(dim, xi0, xi1, xi2, c0.a, c0.b, c0.c);      // live x_i vs snapshot x0_j (particle.cpp:160)
         const double r = sqrt(d2);
@@ -368,7 +381,13 @@ struct ForceSweep {
             if (SSB_SC > 0) {
                 const double base = G * wr;
 #pragma unroll
-                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - cj[(size_t) s * cj_stride]) * base;
+#if SSB_REC2
+                Qi[0] += Dk[0] * (Ci[0] - e.c) * base;
+                if (SSB_SC > 1) Qi[SSB_SC > 1 ? 1 : 0] += Dk[SSB_SC > 1 ? 1 : 0] * (Ci[SSB_SC > 1 ? 1 : 0] - e.d) * base;
+#else
+#pragma unroll
+                for (int s = 0; s < SSB_SC; s++) Qi[s] += Dk[s] * (Ci[s] - Cg[(size_t) s * N + j]) * base;
+#endif
             }
             if (SSB_SD > 0) {
                 const double hr = h - r;
@@ -428,82 +447,15 @@ __global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned s
             const int j = V.nbr[(size_t) k * N + i];
             const double *rj = V.rec + (size_t) j * 16;
             const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
-            S.pair(c0, c1, c2, c3, S.Cg + j, (size_t) N);
+#if SSB_REC2
+            const ssb_d4 e = ssb_ld256(V.rec2 + (size_t) j * 4);
+#else
+            const ssb_d4 e = c3;
+#endif
+            S.pair(c0, c1, c2, c3, e, j);
         }
         mx = S.store(V, i, step);
     }
-    if (SSB_SD > 0) {
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
-    }
-}
-
-#ifndef SSB_ROWS_TR
-#define SSB_ROWS_TR 224           // records per staged chunk: 224 x 144 B = 31.5 KB (+ C_j), 4 CTAs per SM stay resident
-#endif
-#define SSB_ROWS_STRIDE 18        // doubles per staged record: 16 + 2 of padding (144 B: 16-byte reads of 8 lanes hit 8 different bank groups)
-
-__device__ __forceinline__ ssb_d4 ssb_lds256(const double *p) {
-    const double2 lo = *reinterpret_cast<const double2 *>(p), hi = *reinterpret_cast<const double2 *>(p + 2);
-    ssb_d4 r;
-    r.a = lo.x; r.b = lo.y; r.c = hi.x; r.d = hi.y;
-    return r;
-}
-
-// one CTA per work item (V.item_*): <= SSB_BLOCK consecutive particles of one cell row and the nine slot ranges their candidates
-// fall into (ascending, like the lists).  A candidate outside every staged range (its owner crossed a cell face in the predictor
-// of the list-build step) is fetched with the gather of k_force_mv, in list order, so the accumulation order never changes.
-__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv_rows(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
-    __shared__ __align__(16) double s_rec[SSB_ROWS_TR * SSB_ROWS_STRIDE];
-    __shared__ __align__(16) double s_C[SSB_ROWS_TR * (SSB_SC > 0 ? SSB_SC : 1)];
-    const int item = blockIdx.x;
-    const int slot0 = V.item_slot0[item], icnt = V.item_cnt[item];
-    const bool live = (int) threadIdx.x < icnt;
-    const int i = slot0 + (live ? (int) threadIdx.x : 0);
-    const int N = V.N;
-    ForceSweep S;
-    S.init(V, i);
-    const int cnt = (live && V.owned[i]) ? V.nbr_count[i] : 0;
-    int k = 0;
-    int jn = (cnt > 0) ? V.nbr[i] : 0x7fffffff;                    // next candidate of this thread
-    auto from_global = [&](const int j) {
-        const double *rj = V.rec + (size_t) j * 16;
-        const ssb_d4 c0 = ssb_ld256(rj), c1 = ssb_ld256(rj + 4), c2 = ssb_ld256(rj + 8), c3 = ssb_ld256(rj + 12);
-        S.pair(c0, c1, c2, c3, S.Cg + j, (size_t) N);
-    };
-    const int *rng = V.item_rng + (size_t) item * 18;
-    double2 *s2 = reinterpret_cast<double2 *>(s_rec);
-    for (int r = 0; r < 9; r++) {
-        const int lo = rng[2 * r], hi = rng[2 * r + 1];
-        for (int c0 = lo; c0 < hi; c0 += SSB_ROWS_TR) {
-            const int c1 = min(c0 + SSB_ROWS_TR, hi), n = c1 - c0;
-            __syncthreads();                                         // the previous chunk has been consumed by everybody
-            const double2 *g2 = reinterpret_cast<const double2 *>(V.rec + (size_t) c0 * 16);
-            for (int t = threadIdx.x; t < n * 8; t += SSB_BLOCK) s2[(t >> 3) * (SSB_ROWS_STRIDE / 2) + (t & 7)] = g2[t];
-#pragma unroll
-            for (int sp = 0; sp < SSB_SC; sp++)
-                for (int t = threadIdx.x; t < n; t += SSB_BLOCK) s_C[t * SSB_SC + sp] = V.C[(size_t) sp * N + c0 + t];
-            __syncthreads();
-            while (jn < c1) {
-                if (jn >= c0) {
-                    const double *rj = s_rec + (size_t) (jn - c0) * SSB_ROWS_STRIDE;
-                    const ssb_d4 a0 = ssb_lds256(rj), a1 = ssb_lds256(rj + 4), a2 = ssb_lds256(rj + 8), a3 = ssb_lds256(rj + 12);
-                    S.pair(a0, a1, a2, a3, s_C + (size_t) (jn - c0) * SSB_SC, (size_t) 1);
-                } else {
-                    from_global(jn);
-                }
-                k++;
-                jn = (k < cnt) ? V.nbr[(size_t) k * N + i] : 0x7fffffff;
-            }
-        }
-    }
-    while (k < cnt) {                                                // beyond the last range
-        from_global(jn);
-        k++;
-        jn = (k < cnt) ? V.nbr[(size_t) k * N + i] : 0x7fffffff;
-    }
-    double mx = 0.0;
-    if (live) mx = S.store(V, i, step);
     if (SSB_SD > 0) {
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(max_ddiag_bits, (unsigned long long) __double_as_longlong(mx));
@@ -1661,8 +1613,7 @@ static int l_force(const SsbView *V, unsigned step, int full, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 static int l_force_mv(const SsbView *V, unsigned step, unsigned long long *max_bits, cudaStream_t st) {
-    if (V->n_items > 0) k_force_mv_rows<<<(unsigned) V->n_items, SSB_BLOCK, 0, st>>>(*V, step, max_bits);     // row-segment work items (ssb_core.cu)
-    else k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
+    k_force_mv<<<grid_for(V->N), SSB_BLOCK, 0, st>>>(*V, step, max_bits);
     return (int) cudaGetLastError();
 }
 static int l_corrector(const SsbView *V, unsigned step, cudaStream_t st) {

@@ -1,7 +1,7 @@
-// force_emu.cpp — TEST INFRASTRUCTURE: the SOURCE of the moving-domain force sweep k_force_mv / k_force_mv_rows (extracted verbatim from
+// force_emu.cpp — TEST INFRASTRUCTURE: the SOURCE of the moving-domain force sweep k_force_mv (extracted verbatim from
 // spatialpy_b200/csrc/ssb_model_unit.cuh by tests/test_cpu_abi.py into EMU_KERNELS) run on the host through emu_shim.h, so that
-// the shared-memory form (k_force_mv_rows: row-segment work items, staged ranges, cursor over the ascending lists, gather fallback)
-// can be compared with the gather form (k_force_mv) bit for bit without a GPU.
+// its two record layouts (SSB_REC2: the neighbour's 1/rho, P/rho^2 and concentrations from one derived 32-byte sector, or
+// recomputed / gathered per pair) can be compared without a GPU.
 #include "emu_shim.h"
 
 #include SSB_MODEL_HEADER          // generated ssb_gen namespace + SSB_* sizes of the test model (same text nvcc compiles)
@@ -27,10 +27,10 @@ struct EmuArgs {
     double *F[3], *Fbp[3], *Frho, *C, *Q, *Ddiag, *data_fn;
     const double *dmat;
     unsigned long long *max_bits;
-    int n_items; int *item_slot0, *item_cnt, *item_rng;
+    double *rec2;
 };
 
-extern "C" int emu_force(const EmuArgs *a, int rows, unsigned step) {
+extern "C" int emu_force(const EmuArgs *a, unsigned step) {
     SsbView V;
     std::memset(&V, 0, sizeof(V));
     V.N = a->N; V.dim = a->dim; V.num_types = a->num_types; V.filter = a->filter; V.flags = a->flags;
@@ -40,8 +40,7 @@ extern "C" int emu_force(const EmuArgs *a, int rows, unsigned step) {
     for (int d = 0; d < 3; d++) { V.F[d] = a->F[d]; V.Fbp[d] = a->Fbp[d]; }
     V.Frho = a->Frho; V.C = a->C; V.Q = a->Q; V.Ddiag = a->Ddiag; V.data_fn = a->data_fn; V.dmat = a->dmat;
     const unsigned blocks = (unsigned) ((a->N + SSB_BLOCK - 1) / SSB_BLOCK);
-    V.n_items = a->n_items; V.item_slot0 = a->item_slot0; V.item_cnt = a->item_cnt; V.item_rng = a->item_rng;
-    if (rows) emu_launch((unsigned) a->n_items, SSB_BLOCK, ssb_unit::k_force_mv_rows, V, step, a->max_bits);
-    else emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv, V, step, a->max_bits);
+    V.rec2 = a->rec2;
+    emu_launch(blocks, SSB_BLOCK, ssb_unit::k_force_mv, V, step, a->max_bits);
     return 0;
 }

@@ -652,9 +652,9 @@ def test_engine_writers_large_snapshot_threads_and_python_twin_agree(tmp_path, m
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# the moving-domain force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu) — the shared-memory
-# form (k_force_mv_rows: row-segment work items, nine staged slot ranges, a cursor over the ascending candidate lists, gather
-# fallback for candidates outside every range) against one gather per candidate (k_force_mv)
+# the moving-domain force sweep run ON THE HOST: its CUDA source executed by a block emulator (tests/cuda_emu) — the default record
+# layout (SSB_REC2: the neighbour's 1/rho, P/rho^2, C from one derived 32-byte sector written by the predictor) against the layout
+# that recomputes / gathers them per pair, and against a plain numpy evaluation of the reference's pair formulas
 # ----------------------------------------------------------------------------------------------------------------------
 def _build_force_emulator(fm, tmp_path, defines=()):
     from spatialpy_b200 import codegen
@@ -682,34 +682,7 @@ class _EmuArgs(ctypes.Structure):
                 ("nbr_cap", ctypes.c_int), ("owned", ctypes.c_void_p), ("F", ctypes.c_void_p * 3), ("Fbp", ctypes.c_void_p * 3),
                 ("Frho", ctypes.c_void_p), ("C", ctypes.c_void_p), ("Q", ctypes.c_void_p), ("Ddiag", ctypes.c_void_p),
                 ("data_fn", ctypes.c_void_p), ("dmat", ctypes.c_void_p), ("max_bits", ctypes.c_void_p),
-                ("n_items", ctypes.c_int), ("item_slot0", ctypes.c_void_p), ("item_cnt", ctypes.c_void_p), ("item_rng", ctypes.c_void_p)]
-
-
-def _row_items(cell_start, nc, n, seg=128, pad=1):
-    """Python restatement of k_row_count / k_row_fill (ssb_core.cu): (slot0, cnt, 9 x [lo, hi)) per row segment.  pad = 0 drops the
-    one-cell margin of the ranges, so that candidates in the neighbouring x-cells take the kernel's gather fallback."""
-    nx, ny, nz = nc
-    slot0, cnt, rng = [], [], []
-    for r in range(ny * nz):
-        b, e = int(cell_start[r * nx]), int(cell_start[(r + 1) * nx])
-        cy, cz = r % ny, r // ny
-        for s0 in range(b, e, seg):
-            m = min(seg, e - s0)
-            row = cell_start[r * nx:(r + 1) * nx]
-            cxa = int(np.searchsorted(row, s0, side="right") - 1)
-            cxb = int(np.searchsorted(row, s0 + m - 1, side="right") - 1)
-            xa, xb = max(cxa - pad, 0), min(cxb + pad, nx - 1)
-            slot0.append(s0)
-            cnt.append(m)
-            for dz in (-1, 0, 1):
-                for dy in (-1, 0, 1):
-                    yy, zz = cy + dy, cz + dz
-                    if 0 <= yy < ny and 0 <= zz < nz:
-                        row0 = (zz * ny + yy) * nx
-                        rng += [int(cell_start[row0 + xa]), int(cell_start[row0 + xb + 1])]
-                    else:
-                        rng += [0, 0]
-    return np.array(slot0, np.int32), np.array(cnt, np.int32), np.array(rng, np.int32)
+                ("rec2", ctypes.c_void_p)]
 
 
 def _force_sweep_inputs(fm, seed=2):
@@ -745,14 +718,20 @@ def _force_sweep_inputs(fm, seed=2):
     owned = np.ones(n, np.int32)
     owned[rng.choice(n, 9, replace=False)] = 0
     Sc, Sd = fm.num_chem_species, fm.num_stoch_species
-    items = _row_items(cell_start, [int(v) for v in nc], n)
-    st = dict(items=items, cell_start=cell_start, nc=[int(v) for v in nc], rec=rec, nbr=nbr, cnt=cnt, cap=cap, owned=owned, F=rng.normal(size=(3, n)), Fbp=rng.normal(size=(3, n)),
-              Frho=rng.normal(size=n), C=rng.random((max(Sc, 1), n)), Q=rng.normal(size=(max(Sc, 1), n)),
+    Sc0 = fm.num_chem_species
+    Cfull = rng.random((max(Sc0, 1), n))
+    rec2 = np.zeros((n, 4))
+    rec2[:, 0] = 1.0 / rho
+    rec2[:, 1] = (fm.P0 * (rho / fm.rho0 - 1.0)) * rec2[:, 0] * rec2[:, 0]
+    for s_ in range(min(Sc0, 2)):
+        rec2[:, 2 + s_] = Cfull[s_]
+    st = dict(rec2=rec2, rec=rec, nbr=nbr, cnt=cnt, cap=cap, owned=owned, F=rng.normal(size=(3, n)), Fbp=rng.normal(size=(3, n)),
+              Frho=rng.normal(size=n), C=Cfull, Q=rng.normal(size=(max(Sc, 1), n)),
               dmat=np.ascontiguousarray(fm.diffusion_matrix, dtype=np.float64), Sd=Sd, n=n)
     return st
 
 
-def _run_force_emulator(lib, fm, st, rows, items=None):
+def _run_force_emulator(lib, fm, st):
     n = st["n"]
     out = {k: np.ascontiguousarray(st[k]).copy() for k in ("F", "Fbp", "Frho", "Q")}
     out["Ddiag"] = np.full((max(st["Sd"], 1), n), -1.0)
@@ -767,54 +746,25 @@ def _run_force_emulator(lib, fm, st, rows, items=None):
         a.Fbp[d] = out["Fbp"][d].ctypes.data
     a.Frho, a.C, a.Q, a.Ddiag = out["Frho"].ctypes.data, keep[4].ctypes.data, out["Q"].ctypes.data, out["Ddiag"].ctypes.data
     a.data_fn, a.dmat, a.max_bits = None, keep[5].ctypes.data, mb.ctypes.data
-    it = [np.ascontiguousarray(v) for v in (items if items is not None else st["items"])]
-    a.n_items, a.item_slot0, a.item_cnt, a.item_rng = len(it[0]), it[0].ctypes.data, it[1].ctypes.data, it[2].ctypes.data
-    assert lib.emu_force(ctypes.byref(a), int(rows), 3) == 0
+    r2 = np.ascontiguousarray(st["rec2"])
+    keep.append(r2)
+    a.rec2 = r2.ctypes.data
+    assert lib.emu_force(ctypes.byref(a), 3) == 0
     out["max_bits"] = mb
     return out
 
 
-def test_row_segment_force_sweep_source_equals_the_gather_sweep_on_the_host(tmp_path):
-    """k_force_mv_rows vs k_force_mv, both as CUDA SOURCE run by the block emulator (one host thread per CUDA thread, real barriers,
-    shared arrays): every output of the sweep is bit-identical — with all candidates staged, with the ranges cut so that candidates
-    take the gather fallback in the middle of a list, and with tiny chunks so that every range is staged in several pieces."""
+@pytest.mark.parametrize("which", ["tank", "cavity2d_rdme"])
+def test_force_sweep_source_record_layouts_agree_on_the_host(tmp_path, which):
+    """k_force_mv as CUDA SOURCE run by the block emulator, compiled with the derived sector (SSB_REC2 = 1, default for S_c <= 2)
+    and without it (SSB_REC2 = 0: 1/rho_j and P_j/rho_j^2 recomputed per pair, C_j gathered from V.C): same pair formulas, the
+    outputs agree to rounding (1e-13 of each field's scale) on a 3-D and on a 2-D moving model."""
     from spatialpy_b200 import configs
-    fm = configs.tank_sdpd(n=14, nt=10, output_every=10)     # ~2 000 particles; rows of ~70 particles, partly filled CTAs
-    st = _force_sweep_inputs(fm)
-    slot0, cnt, rng = st["items"]
-    assert int(cnt.sum()) == st["n"] and cnt.max() <= 128 and len(cnt) > 8
-    # the restated work items cover every candidate of every particle (pad = 1) ...
-    for it in range(len(cnt)):
-        r = rng[18 * it:18 * it + 18].reshape(9, 2)
-        for i in range(slot0[it], slot0[it] + cnt[it]):
-            for j in st["nbr"][:st["cnt"][i], i]:
-                assert ((r[:, 0] <= j) & (j < r[:, 1])).any()
-    lib = _build_force_emulator(fm, tmp_path)
-    ref = _run_force_emulator(lib, fm, st, rows=0)
-    assert np.abs(ref["F"] - st["F"]).max() > 0 and (ref["Ddiag"][:, st["owned"] == 1] >= 0).all()   # the sweep did something
-    got = _run_force_emulator(lib, fm, st, rows=1)
-    for k in ref:
-        assert np.array_equal(ref[k], got[k]), k
-    # ... and with the margin dropped many candidates are outside every range: the fallback must keep the list order
-    cut = _row_items(st["cell_start"], st["nc"], st["n"], pad=0)
-    got = _run_force_emulator(lib, fm, st, rows=1, items=cut)
-    for k in ref:
-        assert np.array_equal(ref[k], got[k]), ("fallback", k)
-    lib2 = _build_force_emulator(fm, tmp_path, ("SSB_ROWS_TR=16",))
-    for items in (None, cut):
-        got = _run_force_emulator(lib2, fm, st, rows=1, items=items)
-        for k in ref:
-            assert np.array_equal(ref[k], got[k]), ("chunks", k)
-
-
-def test_row_segment_force_sweep_source_on_a_2d_model(tmp_path):
-    """Same comparison on a 2-D moving model (cavity2d_rdme fixture: other species / reaction counts => another instantiation
-    of the generated code; nz = 1 => only three of the nine ranges exist)."""
-    fm = load_model("cavity2d_rdme")
-    st = _force_sweep_inputs(fm, seed=7)
-    lib = _build_force_emulator(fm, tmp_path)
-    ref = _run_force_emulator(lib, fm, st, rows=0)
-    got = _run_force_emulator(lib, fm, st, rows=1)
-    assert np.abs(ref["F"] - st["F"]).max() > 0
-    for k in ref:
-        assert np.array_equal(ref[k], got[k]), k
+    fm = configs.tank_sdpd(n=14, nt=10, output_every=10) if which == "tank" else load_model("cavity2d_rdme")
+    st = _force_sweep_inputs(fm, seed=2 if which == "tank" else 7)
+    a = _run_force_emulator(_build_force_emulator(fm, tmp_path), fm, st)
+    b = _run_force_emulator(_build_force_emulator(fm, tmp_path, ("SSB_REC2=0",)), fm, st)
+    assert np.abs(a["F"] - st["F"]).max() > 0 and (a["Ddiag"][:, st["owned"] == 1] >= 0).all()   # the sweep did something
+    for k in ("F", "Fbp", "Frho", "Q", "Ddiag"):
+        scale = max(float(np.abs(b[k]).max()), 1e-300)
+        assert float(np.abs(a[k] - b[k]).max()) / scale <= 1e-13, k
