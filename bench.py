@@ -432,7 +432,7 @@ def run_ours(args, rank, local_rank, world):
 # ---------------------------------------------------------------------------------------------------------
 def run_slab(args, rank, local_rank, world):
     comm = Comm(local_rank, world)
-    line = slab_measure(args, rank, local_rank, world, args.steps, args.warmup, args.sps or 20, comm)
+    line = slab_measure(args, rank, local_rank, world, args.steps, args.warmup, args.sps or 50, comm)
     if rank == 0:
         print(json.dumps(line))
     comm.close()
@@ -463,31 +463,37 @@ def slab_measure(args, rank, local_rank, world, steps, warmup, SPS, comm):
     part = configs.box_slab(rank, world, nx_per_rank=n, ny=n, nz=n)
     se = SlabEngine(part, rank, world, device=local_rank, transport=args.transport)
     fm = part.local
-    se.reset(1000)
-    for _ in range(warmup):
+    # the same protocol as the N = 1 line: every bench step is the first SPS engine steps of a fresh trajectory (state upload
+    # untimed, the step-0 list build and the initial A + B annihilation transient inside the timed region)
+    for w in range(warmup):
+        se.reset(1000 + 31 * w)
         se.step(SPS)
     se.eng.profile(True)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    l0, c0 = se.eng.launch_count(), se.eng.counters()
     comm.barrier()
-    t0 = time.perf_counter()
-    se.eng.mark(0)
-    for _ in range(steps):
+    dev_ms, wall_s, launches, ev = 0.0, 0.0, 0, 0
+    for k in range(steps):
+        se.reset(5000 + 17 * k)                 # untimed: the rank's initial state is resident in HBM when the timed region starts
+        comm.barrier()
+        l0 = se.eng.launch_count()
+        t0 = time.perf_counter()
+        se.eng.mark(0)
         se.step(SPS)
-    se.eng.mark(1)
-    dev_ms = se.eng.mark_elapsed_ms()           # CUDA events on the engine stream (includes the waits for the halo messages)
+        se.eng.mark(1)
+        dev_ms += se.eng.mark_elapsed_ms()      # CUDA events on the engine stream (includes the waits for the halo messages)
+        wall_s += time.perf_counter() - t0
+        c1 = se.eng.counters()
+        ev += c1["reactions"] + c1["diffusions"]
+        launches += int(se.eng.launch_count() - l0)
     comm.barrier()
-    wall_s = time.perf_counter() - t0
     clk = clocks.stop()
     prof = se.eng.profile_read()
     se.eng.profile(False)
-    c1 = se.eng.counters()
-    launches = int(se.eng.launch_count() - l0)
     dev_ms = comm.allmax(dev_ms)
     wall_s = comm.allmax(wall_s)
     owned_total = comm.allsum(float(part.n_owned))
-    events = comm.allsum(float(c1["reactions"] + c1["diffusions"] - c0["reactions"] - c0["diffusions"]))
+    events = comm.allsum(float(ev))
     nsteps = SPS * steps
     value = owned_total * nsteps / (dev_ms / 1e3)
     cap, nnz = se.eng.nbr_stats()
@@ -512,6 +518,7 @@ def slab_measure(args, rank, local_rank, world, steps, warmup, SPS, comm):
         "data": "synthetic",
         "config": {"workload": f"BASELINE configs[4]: synthetic 3-D SDPD+sSSA box of {world} x {n}^3 particles, slab-decomposed along x",
                    "particles_per_gpu": part.n_owned, "ghosts_per_gpu": ghosts, "engine_steps_per_step": SPS,
+                   "trajectory_segment": f"each bench step = engine steps 0..{SPS} of a fresh trajectory (incl. the step-0 list build), as at N = 1",
                    "mean_neighbours": nnz / max(part.n_owned, 1),
                    "parallelism": (f"spatial slabs x {world}; transport = {se.transport}: " +
                                    ("pack kernels store into the neighbour's receive window over NVLink (CUDA IPC peer memory), sequence flags, "

@@ -526,7 +526,10 @@ __global__ void k_halo_wait(const unsigned long long *flag0, const unsigned long
         const unsigned long long t0 = ssb_globaltimer();
         while (ssb_ld_flag(f) < seq) {
             __nanosleep(100);
-            if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) { atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/); break; }
+            if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) {
+                if (atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/) == 0) { err_flag[1] = 100 + (int) threadIdx.x; err_flag[2] = (int) seq; err_flag[3] = (int) ssb_ld_flag(f); }
+                break;
+            }
         }
     }
     __threadfence_system();
@@ -590,7 +593,10 @@ __global__ void k_board_reduce(const unsigned long long *board, int world, int c
         const unsigned long long t0 = ssb_globaltimer();
         while (ssb_ld_flag(slot + 1) < seq && *(volatile int *) err_flag != 8) {
             __nanosleep(100);
-            if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) { atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/); break; }
+            if (ssb_globaltimer() - t0 > HALO_TIMEOUT_NS) {
+                if (atomicCAS(err_flag, 0, 8 /*SSB_ERR_HALO*/) == 0) { err_flag[1] = 200 + 10 * ch + r; err_flag[2] = (int) seq; err_flag[3] = (int) ssb_ld_flag(slot + 1); }
+                break;
+            }
         }
         __threadfence_system();
         v = ssb_ld_flag(slot);
@@ -1527,12 +1533,17 @@ static int neighbour_search(ssb_handle *h) {
 // one engine step: simulate_threads.cpp:232-281 (three substeps, then the RDME)
 // ----------------------------------------------------------------------------------------------------
 static int check_device_error(ssb_handle *h) {
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, h->V.err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int flags[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(flags, h->V.err_flag, sizeof(flags), cudaMemcpyDeviceToHost, h->stream));
     CK(ssb_sync(h));
+    const int flag = flags[0];
     if (flag == SSB_ERR_NAN) return fail(h, SSB_ERR_NAN, "ERROR: nan/inf detected!!! (step %u)", h->current_step);
     if (flag == SSB_ERR_RDME) return fail(h, SSB_ERR_RDME, "RDME state error (negative population or propensity overflow) at step %u", h->current_step);
-    if (flag == SSB_ERR_HALO) return fail(h, SSB_ERR_HALO, "halo exchange timed out: a neighbouring slab rank did not deliver its message (step %u)", h->current_step);
+    if (flag == SSB_ERR_HALO && getenv("SSB_SLAB_DEBUG"))
+        fprintf(stderr, "[slab] HALO timeout at step %u: wait %d expected seq %d found %d\n", h->current_step, flags[1], flags[2], flags[3]);
+    if (flag == SSB_ERR_HALO)
+        return fail(h, SSB_ERR_HALO, "halo exchange timed out: a neighbouring slab rank did not deliver its message (step %u; wait %d: 10x = window flag "
+                    "of side x, 2cr = board channel c rank r; expected sequence %d, found %d)", h->current_step, flags[1], flags[2], flags[3]);
     return SSB_OK;
 }
 
@@ -2498,6 +2509,48 @@ extern "C" int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const 
         CK(cudaEventCreateWithFlags(&c->ev_red[k], cudaEventDisableTiming));
     }
     for (int k = 0; k < 2; k++) CK(cudaEventCreateWithFlags(&c->ev_disp[k], cudaEventDisableTiming));
+    // First launches behind us (see SsbModelUnit::warm): every kernel of a slab step once, on empty inputs.  Measured without this on
+    // a B200 with two ranks as threads of one process: whichever rank reached a not-yet-loaded kernel while its neighbour was already
+    // spinning on a flag waited for the neighbour's kernel to end — i.e. for the 10 s timeout of a message it had not sent yet.
+    {
+        cudaStream_t st = h->stream;
+        if (h->unit && h->unit->warm(&h->V, st)) return fail(h, SSB_ERR_CUDA, "kernel warm-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+        HaloPackArgs P; HaloUnpackArgs U; BoardPeers B;
+        memset(&P, 0, sizeof(P)); memset(&U, 0, sizeof(U)); memset(&B, 0, sizeof(B));
+        P.done = c->d_done; P.icount = c->d_icount;
+        k_slot_of_id<<<1, CORE_BLOCK, 0, st>>>(0, h->V.id, h->d_slot_of_id);
+        k_halo_send<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, P, h->d_slot_of_id);
+        k_inbox_send<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, P, h->d_slot_of_id);
+        k_halo_publish<<<1, 32, 0, st>>>(P, 0);
+        k_halo_wait<<<1, 32, 0, st>>>(nullptr, nullptr, 0ull, h->V.err_flag);
+        k_halo_recv<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, U, h->d_slot_of_id);
+        k_inbox_recv<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, U, h->d_slot_of_id, 128);
+        k_board_post<<<1, 32, 0, st>>>(B, 0, 0, 0, 0ull, c->d_red + 3);
+        k_board_reduce<<<1, 32, 0, st>>>((const unsigned long long *) c->board, 0, 0, 0ull, 0, c->d_red + 3, h->V.err_flag);
+        k_min_time<<<1, CORE_BLOCK, 0, st>>>(0, h->V.blk_tmin, c->d_red + 3);
+        SsbView V0 = h->V;
+        V0.N = 0;
+        k_lookahead<<<1, CORE_BLOCK, 0, st>>>(V0, h->d_look);
+        // ... and the list build (a rank may rebuild while its neighbour already waits for the step's first message)
+        PermTable T;
+        memset(&T, 0, sizeof(T));
+        k_cell_keys<<<1, CORE_BLOCK, 0, st>>>(0, h->grid, h->V.x[0], h->V.x[1], h->V.x[2], h->d_key, h->d_cell_count);
+        k_scan_tiles<<<1, 256, 0, st>>>(0, h->d_cell_count, h->d_cell_start, h->d_tile_sums);
+        k_scan_sums<<<1, 256, 0, st>>>(0, h->d_tile_sums, nullptr);
+        k_scan_add<<<1, CORE_BLOCK, 0, st>>>(0, h->d_cell_start, h->d_tile_sums);
+        k_scatter<<<1, CORE_BLOCK, 0, st>>>(0, h->d_key, h->d_cell_start, h->d_cursor, h->d_perm);
+        k_sort_cells<<<1, CORE_BLOCK, 0, st>>>(0, h->d_cell_start, 0, h->d_perm, h->d_flags);
+        k_permute<<<1, CORE_BLOCK, 0, st>>>(0, h->d_perm, T);
+        k_permute_rows64<<<1, CORE_BLOCK, 0, st>>>(0, h->d_perm, h->V.C, h->C_alt);
+        k_permute_rows32<<<1, CORE_BLOCK, 0, st>>>(0, h->d_perm, (const int *) h->V.xx, (int *) h->xx_alt);
+        k_search<<<1, CORE_BLOCK, 0, st>>>(V0, h->grid, h->d_cell_start, h->d_flags + 1, h->d_maxbits + 1);
+        k_iota<<<1, CORE_BLOCK, 0, st>>>(0, h->V.id);
+        k_unperm64<<<1, CORE_BLOCK, 0, st>>>(0, h->V.id, h->V.rho, h->d_stage, 1, 0);
+        k_unperm32<<<1, CORE_BLOCK, 0, st>>>(0, h->V.id, h->V.type, (int *) h->d_stage, 1, 0);
+        CK(cudaMemsetAsync(c->d_red, 0, sizeof(unsigned long long) * (SSB_BOARD_NCH + 1), st));
+        CK(cudaMemsetAsync(c->d_done, 0, 16, st));
+        CK(cudaGetLastError());
+    }
     CK(ssb_sync(h));
     return SSB_OK;
 }
@@ -2807,7 +2860,12 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
                 fprintf(stderr, "[slab %d/%d] step %u local max Ddiag %.6g global %.6g filter %d skin %g\n", c->rank, c->world, step, loc, mx, V.filter, h->skin);
             }
             h->ddiag_fresh = 0;
-            if ((rc = set_windows(h, mx))) { slab_probe_report(h); return rc; }        // GLOBAL max Ddiag: every rank uses the same windows
+            if ((rc = set_windows(h, mx))) {                  // GLOBAL max Ddiag: every rank uses the same windows
+                slab_probe_report(h);
+                if (getenv("SSB_SLAB_DEBUG")) fprintf(stderr, "[slab %d/%d] step %u: global max Ddiag %g is not usable\n", c->rank, c->world, step, mx);
+                const int rc2 = check_device_error(h);       // (a lost halo message upstream explains a garbage maximum: report that)
+                return rc2 ? rc2 : rc;
+            }
             if (u->rdme_init(&V, V.dt * step, 0.0, h->tau, h->seed, h->epoch++, st)) return fail(h, SSB_ERR_CUDA, "rdme_init launch failed");
             h->launches++;
             h->rdme_initialized = 1;
@@ -2840,15 +2898,6 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
         slab_sync_point(h, 3);
         slab_sync_point(h, 4);
         slab_sync_point(h, 5);
-        if (c->same_process_peers) {
-            // Ranks that are THREADS of one process share one CUDA context.  Measured on a B200 (2 ranks on one GPU): when the hosts
-            // run ahead of their devices, a rank's wait kernel regularly sits out its 10 s timeout although the neighbour's message
-            // is only a few launches away — the neighbour's launches do not reach the device while the waiting stream is backed up
-            // (the same runs pass with both streams drained once per step, and with one rank per process nothing is shared).
-            // So in-process ranks give up the run-ahead: one drain per step (~50 us of idle GPU per step).
-            CK(cudaStreamSynchronize(st));
-            CK(cudaStreamSynchronize(h->copy_stream));
-        }
         if ((c->steps & 15) == 0) { if ((rc = check_device_error(h))) return rc; }
         if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
     }

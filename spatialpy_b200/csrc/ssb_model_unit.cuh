@@ -1707,6 +1707,25 @@ static int l_rdme_window_dev(const SsbView *V, const unsigned long long *tmin_bi
     return (int) cudaGetLastError();
 }
 
+static int l_warm(const SsbView *V0, cudaStream_t st) {
+    SsbView V = *V0;
+    V.N = 0;                                         // every kernel below bounds its work by V.N (or by the chunk count derived from it)
+    k_predictor<<<1, SSB_BLOCK, 0, st>>>(V, 0u);
+    k_force<true><<<1, SSB_BLOCK, 0, st>>>(V, 0u);
+    k_force<false><<<1, SSB_BLOCK, 0, st>>>(V, 0u);
+    k_force_mv<<<1, SSB_BLOCK, 0, st>>>(V, 0u, nullptr);
+    k_corrector<<<1, SSB_BLOCK, 0, st>>>(V, 0u);
+    k_finish<true><<<1, SSB_BLOCK, 0, st>>>(V, 0u);
+    k_finish<false><<<1, SSB_BLOCK, 0, st>>>(V, 0u);
+    k_rdme_window<false><<<1, SSB_BLOCK, 0, st>>>(V, 0.0, 0.0, 1.0, 0ull, 0ull, 0);
+    k_rdme_window<true><<<1, SSB_BLOCK, 0, st>>>(V, 0.0, 0.0, 1.0, 0ull, 0ull, 0);
+    k_diff_init<<<1, SSB_BLOCK, 0, st>>>(V, nullptr);
+    // (the bounds word of the device-bounded windows: any readable word that is not a pending time — the event counter, >= 0 and "not > te")
+    k_rdme_window_dev<false><<<1, SSB_BLOCK, 0, st>>>(V, V.counters, 1e300, 0, 1.0, 0ull, 0ull, 0);
+    k_rdme_window_dev<true><<<1, SSB_BLOCK, 0, st>>>(V, V.counters, 1e300, 0, 1.0, 0ull, 0ull, 0);
+    return (int) cudaGetLastError();
+}
+
 }  // namespace ssb_unit
 
 extern "C" const SsbModelUnit *ssbm_get_unit() {
@@ -1728,5 +1747,6 @@ extern "C" const SsbModelUnit *ssbm_get_unit() {
     u.rdme_window = ssb_unit::l_rdme_window;
     u.rdme_windows = ssb_unit::l_rdme_windows;
     u.rdme_window_dev = ssb_unit::l_rdme_window_dev;
+    u.warm = ssb_unit::l_warm;
     return &u;
 }

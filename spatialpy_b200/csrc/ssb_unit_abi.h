@@ -8,7 +8,7 @@
 
 struct SsbView;
 
-#define SSB_UNIT_ABI 11
+#define SSB_UNIT_ABI 12
 
 struct SsbModelUnit {
     int abi;
@@ -30,6 +30,10 @@ struct SsbModelUnit {
     // slab runs: the step-end overshoot windows with the (global) earliest pending clock read from device memory
     int (*rdme_window_dev)(const SsbView *, const unsigned long long *tmin_bits, double te, int deliver, double tau, uint64_t seed,
                            uint64_t epoch, int buf, cudaStream_t);
+    // launch every kernel of the unit once on an EMPTY view (N = 0: all of them return at once).  Loading a kernel for the first
+    // time, or growing the device's local-memory pool for it, synchronises the whole CUDA context; slab ranks that share a context
+    // (ranks as threads) must have that behind them before one of them spins on a neighbour's message.
+    int (*warm)(const SsbView *, cudaStream_t);
 };
 
 extern "C" const SsbModelUnit *ssbm_get_unit();

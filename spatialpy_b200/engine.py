@@ -9,6 +9,10 @@ import os
 # streams alias onto the same queue and serialise behind each other's long sSSA kernels (measured: 16 lanes ran 4x slower per
 # trajectory); 32 queues restore full concurrency.  Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Slab ranks that run as THREADS of one process (Solver.run(decomposition="slab"), the 1-GPU tests) share one CUDA context, and a
+# kernel's first launch under lazy module loading synchronises that context: a rank reaching a not-yet-loaded kernel would wait for
+# its neighbour's spinning wait kernel, which waits for this rank's message.  Load every kernel when its module is loaded.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import numpy as np
 
