@@ -450,7 +450,6 @@ __device__ __forceinline__ unsigned long long ssb_ld_flag(const unsigned long lo
 }
 // last CTA of a pack kernel: everything every CTA wrote to the peer is fenced, raise the flags (and the inbox entry counts)
 __device__ __forceinline__ void halo_publish(const HaloPackArgs &A, bool with_counts) {
-    if (!A.done) return;                 // the flags are raised by a separate launch (k_halo_publish)
     __threadfence_system();
     __syncthreads();
     __shared__ int s_last;
@@ -464,17 +463,6 @@ __device__ __forceinline__ void halo_publish(const HaloPackArgs &A, bool with_co
             *(volatile unsigned long long *) S.peer_flag = A.seq;
         }
         if (threadIdx.x == 0) *A.done = 0u;
-    }
-}
-// publish as its own launch (SSB_SLAB_PUBLISH=kernel): the kernel boundary orders every store of the pack kernel before the flag
-__global__ void k_halo_publish(HaloPackArgs A, int with_counts) {
-    if (threadIdx.x < 2) {
-        const HaloPackSide &S = A.side[threadIdx.x];
-        if (S.peer_flag) {
-            if (with_counts) { *(volatile unsigned long long *) S.peer_count = (unsigned long long) atomicExch(&A.icount[threadIdx.x], 0u); }
-            __threadfence_system();
-            *(volatile unsigned long long *) S.peer_flag = A.seq;
-        }
     }
 }
 __global__ void k_halo_send(SsbView V, int group, HaloPackArgs A, const int *slot_of_id) {
@@ -2436,7 +2424,6 @@ struct HaloSide {
 };
 struct SlabComm {
     int rank = 0, world = 1, connected = 0;
-    int same_process_peers = 0;   // some rank lives in this process (ranks as threads): see the drain at the end of ssb_slab_step's loop
     HaloSide side[2];             // 0 = rank-1, 1 = rank+1
     unsigned long long seq[HALO_NCH] = {0, 0, 0, 0};
     char *board = nullptr;
@@ -2491,7 +2478,6 @@ extern "C" int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const 
         halo_layout(S.n_send, S.n_recv * std::max(h->V.Sd, 1), h->V.Sc, S.poff);
         CK(cudaMalloc((void **) &S.win, S.win_bytes));          // (own allocation: exported whole through CUDA IPC)
         h->allocs.push_back(S.win);
-        if (getenv("SSB_SLAB_PROBE")) CK(cudaMemsetAsync(S.win, 0xff, S.win_bytes, h->stream));     // (unwritten message rows read as NaN)
         CK(cudaMemsetAsync(S.win, 0, HALO_HDR_BYTES, h->stream));
     }
     const size_t board_bytes = sizeof(unsigned long long) * 2 * SSB_BOARD_NCH * 2 * SSB_BOARD_MAXW;
@@ -2521,7 +2507,6 @@ extern "C" int ssb_slab_setup(ssb_handle *h, int32_t rank, int32_t world, const 
         k_slot_of_id<<<1, CORE_BLOCK, 0, st>>>(0, h->V.id, h->d_slot_of_id);
         k_halo_send<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, P, h->d_slot_of_id);
         k_inbox_send<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, P, h->d_slot_of_id);
-        k_halo_publish<<<1, 32, 0, st>>>(P, 0);
         k_halo_wait<<<1, 32, 0, st>>>(nullptr, nullptr, 0ull, h->V.err_flag);
         k_halo_recv<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, U, h->d_slot_of_id);
         k_inbox_recv<<<1, CORE_BLOCK, 0, st>>>(h->V, 0, U, h->d_slot_of_id, 128);
@@ -2578,7 +2563,6 @@ static int slab_map(ssb_handle *h, const SlabBlob &B, int k, char **out, int *is
     *out = nullptr; *is_ipc = 0;
     if (!B.ptr[k]) return fail(h, SSB_ERR_ARG, "rank %d exported no window %d", B.rank, k);
     if (B.pid == (int64_t) getpid()) {                   // same process (ranks as threads): the pointer itself, peer access if another GPU
-        h->slab->same_process_peers = 1;
         if (B.device != h->device) {
             cudaError_t e = cudaDeviceEnablePeerAccess(B.device, 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, SSB_ERR_CUDA, "no peer access from GPU %d to GPU %d: %s", h->device, B.device, cudaGetErrorString(e));
@@ -2650,57 +2634,6 @@ static void slab_free(ssb_handle *h) {
 }
 
 // one field group to both neighbours and back: pack+send (peer writes, flags raised by the last CTA), wait, unpack
-// SSB_SLAB_DEBUG: how many particles carry a non-positive / non-finite value in a field (owned, ghost) — blocking, diagnostics only
-__global__ void k_debug_count_bad(int N, const double *f, const int *owned, int *out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const double v = f[i];
-    if (!(v > 0.0) || !(v < 1e300)) atomicAdd(&out[owned[i] ? 0 : 1], 1);
-}
-// SSB_SLAB_PROBE: asynchronous probes (no synchronisation, so the timing of the run is untouched): the FIRST particle whose value in
-// `field` (stride 1, or the rho slot of the gather record with stride 16) is not a positive finite number is recorded with a tag
-__global__ void k_probe(int N, const double *field, int stride, int offset, const int *owned, int tag, unsigned step, unsigned long long *out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const double v = field[(size_t) i * stride + offset];
-    if ((!(v > 0.0) || !(v < 1e300)) && atomicCAS(&out[0], 0ull, 1ull) == 0ull) {
-        out[1] = (unsigned long long) tag; out[2] = step; out[3] = (unsigned long long) i; out[4] = (unsigned long long) owned[i];
-        out[5] = (unsigned long long) __double_as_longlong(v);
-    }
-}
-static unsigned long long *g_probe_dev(ssb_handle *h) {
-    static thread_local unsigned long long *buf = nullptr;
-    static thread_local ssb_handle *owner = nullptr;
-    if (owner != h) { cudaMalloc((void **) &buf, 64); cudaMemset(buf, 0, 64); owner = h; }
-    return buf;
-}
-static void slab_probe(ssb_handle *h, int tag, const double *field, int stride, int offset) {
-    if (!getenv("SSB_SLAB_PROBE")) return;
-    k_probe<<<gridN(h->N), CORE_BLOCK, 0, h->stream>>>(h->N, field, stride, offset, h->V.owned, tag, h->current_step, g_probe_dev(h));
-}
-static void slab_probe_report(ssb_handle *h) {
-    if (!getenv("SSB_SLAB_PROBE")) return;
-    unsigned long long r[8] = {0};
-    cudaMemcpy(r, g_probe_dev(h), 64, cudaMemcpyDeviceToHost);
-    double v; memcpy(&v, &r[5], 8);
-    fprintf(stderr, "[slab %d/%d] probe: hit %llu tag %llu step %llu slot %llu owned %llu value %g\n", h->slab->rank, h->slab->world, r[0], r[1], r[2], r[3], r[4], v);
-}
-static void slab_sync_point(ssb_handle *h, int bit) {          // SSB_SLAB_SYNC=<mask>: bisecting aid (blocking synchronisation points)
-    static const int mask = getenv("SSB_SLAB_SYNC") ? atoi(getenv("SSB_SLAB_SYNC")) : 0;
-    if (!(mask & (1 << bit))) return;
-    if (bit != 5) cudaStreamSynchronize(h->stream);
-    if (bit == 3 || bit == 5) cudaStreamSynchronize(h->copy_stream);
-}
-static void slab_debug(ssb_handle *h, const char *tag, const double *field) {
-    if (!getenv("SSB_SLAB_DEBUG")) return;
-    int *d = h->d_flags + 4, bad[2] = {0, 0};
-    cudaMemsetAsync(d, 0, 8, h->stream);
-    k_debug_count_bad<<<gridN(h->N), CORE_BLOCK, 0, h->stream>>>(h->N, field, h->V.owned, d);
-    cudaMemcpyAsync(bad, d, 8, cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
-    fprintf(stderr, "[slab %d/%d] step %u %-22s bad owned %d ghost %d\n", h->slab->rank, h->slab->world, h->current_step, tag, bad[0], bad[1]);
-}
-
 struct NvtxScope { explicit NvtxScope(const char *n) { nvtxRangePushA(n); } ~NvtxScope() { nvtxRangePop(); } };
 
 static int slab_exchange(ssb_handle *h, int group) {
@@ -2726,10 +2659,7 @@ static int slab_exchange(ssb_handle *h, int group) {
         flag[sd] = (const unsigned long long *) (S.win + 64 * group);
     }
     const int ns = P.side[0].n + P.side[1].n, nr = U.side[0].n + U.side[1].n;
-    static const bool sep = getenv("SSB_SLAB_PUBLISH") && !strcmp(getenv("SSB_SLAB_PUBLISH"), "kernel");
-    if (sep) P.done = nullptr;
     k_halo_send<<<std::max(gridN(ns), 1u), CORE_BLOCK, 0, st>>>(h->V, group, P, h->d_slot_of_id);
-    if (sep) k_halo_publish<<<1, 32, 0, st>>>(P, 0);
     k_halo_wait<<<1, 32, 0, st>>>(flag[0], flag[1], seq, h->V.err_flag);
     if (nr > 0) k_halo_recv<<<gridN(nr), CORE_BLOCK, 0, st>>>(h->V, group, U, h->d_slot_of_id);
     CK(cudaGetLastError());
@@ -2763,10 +2693,7 @@ static int slab_exchange_inbox(ssb_handle *h) {
         flag[sd] = (const unsigned long long *) (S.win + 64 * HALO_CH_INBOX);
     }
     const int ns = P.side[0].n + P.side[1].n;
-    static const bool sep = getenv("SSB_SLAB_PUBLISH") && !strcmp(getenv("SSB_SLAB_PUBLISH"), "kernel");
-    if (sep) P.done = nullptr;
     k_inbox_send<<<std::max(gridN(ns), 1u), CORE_BLOCK, 0, st>>>(h->V, buf, P, h->d_slot_of_id);
-    if (sep) k_halo_publish<<<1, 32, 0, st>>>(P, 1);
     k_halo_wait<<<1, 32, 0, st>>>(flag[0], flag[1], seq, h->V.err_flag);
     k_inbox_recv<<<64, CORE_BLOCK, 0, st>>>(h->V, buf, U, h->d_slot_of_id, h->unit->block);
     CK(cudaGetLastError());
@@ -2804,8 +2731,7 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
     CK(cudaSetDevice(h->device));
     SsbView &V = h->V;
     const SsbModelUnit *u = h->unit;
-    static const bool noaux = getenv("SSB_SLAB_NOAUX") != nullptr;
-    cudaStream_t st = h->stream, aux = noaux ? h->stream : h->copy_stream;
+    cudaStream_t st = h->stream, aux = h->copy_stream;
     const bool overshoot = !(V.flags & (SSB_FLAG_CORRECTED_NSM_SELECT | SSB_FLAG_NO_STEP_OVERSHOOT));
     auto t0w = std::chrono::steady_clock::now();
     int rc;
@@ -2828,18 +2754,9 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
             CK(cudaMemcpyAsync(&h->pin[4], c->d_red + 0, sizeof(unsigned long long), cudaMemcpyDeviceToHost, aux));
             CK(cudaEventRecord(h->ev_maxd, aux));
         }
-        slab_debug(h, "rho after force", V.rho);
-        slab_probe(h, 1, V.rho, 1, 0);           // rho after predictor + force
-        slab_probe(h, 2, V.rec, 16, 12);         // the gather records' rho
-        slab_sync_point(h, 0);
         if ((rc = slab_exchange(h, 0))) return rc;
         if ((rc = mv_corrector(h))) return rc;
-        slab_debug(h, "rho_new after corrector", V.rho_new);
-        slab_sync_point(h, 1);
         if ((rc = slab_exchange(h, 1))) return rc;
-        slab_debug(h, "rho_new after exchange", V.rho_new);
-        slab_probe(h, 3, V.rho_new, 1, 0);       // rho_new after corrector + ghost refresh
-        slab_sync_point(h, 2);
         if ((rc = mv_finish(h))) return rc;
         if ((rc = slab_exchange(h, 2))) return rc;
         if ((rc = mv_lookahead(h))) return rc;
@@ -2850,7 +2767,6 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
             CK(cudaMemcpyAsync(&h->pin[8 + (c->steps & 1)], c->d_red + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, aux));
             CK(cudaEventRecord(c->ev_disp[c->steps & 1], aux));
         }
-        slab_sync_point(h, 6);
         if (V.Sd > 0) {
             CK(wait_event(h->ev_maxd));                      // every rank's force sweep is done; corrector .. look-ahead are still queued
             double mx;
@@ -2861,8 +2777,7 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
             }
             h->ddiag_fresh = 0;
             if ((rc = set_windows(h, mx))) {                  // GLOBAL max Ddiag: every rank uses the same windows
-                slab_probe_report(h);
-                if (getenv("SSB_SLAB_DEBUG")) fprintf(stderr, "[slab %d/%d] step %u: global max Ddiag %g is not usable\n", c->rank, c->world, step, mx);
+                            if (getenv("SSB_SLAB_DEBUG")) fprintf(stderr, "[slab %d/%d] step %u: global max Ddiag %g is not usable\n", c->rank, c->world, step, mx);
                 const int rc2 = check_device_error(h);       // (a lost halo message upstream explains a garbage maximum: report that)
                 return rc2 ? rc2 : rc;
             }
@@ -2875,7 +2790,6 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
                 if ((rc = slab_exchange_inbox(h))) return rc;
             }
             if ((rc = rdme_window_phase(h, true, 0))) return rc;
-            slab_sync_point(h, 7);
             if (overshoot) {
                 // the reference's one event past the end of the step (simulate_rdme.cpp:233-238): the globally earliest pending clock
                 // is reduced on the device and read by the two windows from device memory
@@ -2895,13 +2809,9 @@ extern "C" int ssb_slab_step(ssb_handle *h, uint32_t nsteps, double travel_limit
         }
         h->current_step++;
         c->steps++;
-        slab_sync_point(h, 3);
-        slab_sync_point(h, 4);
-        slab_sync_point(h, 5);
         if ((c->steps & 15) == 0) { if ((rc = check_device_error(h))) return rc; }
         if (h->cancel.load()) return fail(h, SSB_ERR_CANCELLED, "cancelled");
     }
-    slab_probe_report(h);
     if ((rc = check_device_error(h))) return rc;
     h->step_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0w).count();
     if (done) *done = s;

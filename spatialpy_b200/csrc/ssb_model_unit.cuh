@@ -434,7 +434,10 @@ struct ForceSweep {
     }
 };
 
-__global__ void __launch_bounds__(SSB_BLOCK, 4) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
+#ifndef SSB_FORCE_MINB
+#define SSB_FORCE_MINB 4          // resident CTAs per SM the register budget is held to (4 x 128 threads: 128 registers)
+#endif
+__global__ void __launch_bounds__(SSB_BLOCK, SSB_FORCE_MINB) k_force_mv(SsbView V, unsigned step, unsigned long long *max_ddiag_bits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double mx = 0.0;
     if (i < V.N) {

@@ -31,7 +31,7 @@ def default_lanes(num_particles):
 
 
 def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out_dirs=None, flags=None, rdme_epsilon=0.0,
-                 unit_path=None, on_engine=None, rank=0, world_size=1):
+                 unit_path=None, on_engine=None, rank=0, world_size=1, engine_factory=None):
     """Run trajectories k = rank, rank+world_size, ... (seed + k each) on `devices`, `lanes` engine handles per device, each
     driven by its own host thread (ctypes releases the GIL during ssb_run).  Returns {k: counters} for the local trajectories;
     raises the first failure of any lane.  `out_dirs[k]` (optional) receives trajectory k's VTK files."""
@@ -59,7 +59,7 @@ def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out
         try:
             try:
                 if ks:
-                    eng = Engine(fm, device=dev, flags=flags, rdme_epsilon=rdme_epsilon, unit_path=unit_path)
+                    eng = (engine_factory or Engine)(fm, device=dev, flags=flags, rdme_epsilon=rdme_epsilon, unit_path=unit_path)
                     if on_engine:
                         on_engine(eng)
                 try:
@@ -69,6 +69,12 @@ def run_ensemble(fm, number_of_trajectories, seed, devices=(0,), lanes=None, out
                 if eng is not None:
                     eng.reset(seed)          # one engine step sizes every lazily allocated buffer
                     eng.step(1)
+            except BaseException:
+                # this lane will never arrive at the meeting points: break them BEFORE waiting at one, or the healthy lanes wait
+                # for ever (threading.Barrier needs all parties) and Solver.run hangs in join()
+                for b in (created_barrier, ready_barrier, done_barrier):
+                    b.abort()
+                raise
             finally:
                 try:
                     ready_barrier.wait()

@@ -229,6 +229,19 @@ class Solver:
         self.prop_file_name = self.propfilename = self.unit_path[:-3] + ".cu"
         self.is_compiled = True
 
+    def _auto_batch(self, number_of_trajectories):
+        """Ensembles of SMALL STATIC models default to batched trajectories (disjoint copies of the model in one engine handle):
+        measured on 8 B200s, 1 024 Cdc42 trajectories of 2 500 voxels run at 199 trajectories/s batched vs 94 with 24 engine
+        handles per GPU (profiles/r2_ens_cdc42_full_n8_*.json).  Batching keeps the ensemble law, not the per-trajectory seed map
+        (batch b is seeded seed + first trajectory of b), so single runs and small ensembles stay on the lanes path, as do moving
+        domains and models whose boundary conditions test coordinates (ensemble.replicate_model refuses those)."""
+        fm = self.flat
+        if number_of_trajectories < 16 or not fm.static_domain or fm.num_particles > 20000 or fm.num_stoch_species == 0:
+            return None
+        if (fm.bc_source or "").strip() and "me->x" in fm.bc_source:
+            return None
+        return True
+
     def _new_result(self, outdir):
         if isinstance(self.model, FlatModel):
             return FlatResult(self.model, outdir)
@@ -246,6 +259,8 @@ class Solver:
         if decomposition not in (None, "ensemble", "slab"):
             raise SimulationError(f"unknown decomposition '{decomposition}' (None/'ensemble': trajectories over devices; 'slab': one domain over devices)")
         flags = FLAG_SKIP_STATIC_FORCES if flags is None else flags
+        if batch is None and decomposition != "slab":
+            batch = self._auto_batch(number_of_trajectories)
         if binary_store:                      # outputN.ssb next to outputN.vtk; vtk=False keeps only the binary files
             flags |= FLAG_BINARY_STORE | (0 if vtk else FLAG_NO_VTK)
         elif not vtk:
@@ -271,7 +286,7 @@ class Solver:
                                             cancelled=lambda: state.get("cancel", False))
                     results[k].success = True
                     for key in totals:
-                        totals[key] += c[key]
+                        totals[key] += (c or {}).get(key, 0)
             except InterruptedError:
                 pass
             except Exception as err:      # noqa: BLE001 - stale partition (RuntimeError), snapshot I/O (OSError), broken barrier, torch: all fail the run
@@ -301,7 +316,7 @@ class Solver:
                             results[k0 + k].success = True
                     with lock:
                         for key in totals:
-                            totals[key] += res["counters"][key]
+                            totals[key] += res.get("counters", {}).get(key, 0)
                 except Exception as err:  # noqa: BLE001 - re-raised as SimulationError by the caller's thread
                     shard_errors.append(err)
 
@@ -322,7 +337,7 @@ class Solver:
                 for k in done:
                     results[k].success = True
                     for key in totals:
-                        totals[key] += done[k][key]
+                        totals[key] += (done[k] or {}).get(key, 0)
             except Exception as err:      # noqa: BLE001
                 state["error"] = err
             state["done"] = True

@@ -211,3 +211,38 @@ def test_solver_batch_keyword_plumbing(monkeypatch):
     assert len(res) == 7 and all(r.success for r in res)
     with pytest.raises(SimulationError, match="return code = 4"):
         Solver(load_model("tank3d")).run(seed=1, batch=True)
+
+
+def test_ensemble_lane_that_fails_to_start_does_not_hang_the_others():
+    """A lane whose engine cannot be created (out of memory on one of 24 handles, a bad device ordinal) never arrives at the
+    lanes' meeting points; the healthy lanes must not wait for it for ever: run_ensemble raises the lane's error promptly."""
+    import threading
+    import time
+    from spatialpy_b200 import FlatModel
+    from spatialpy_b200.ensemble import run_ensemble
+    from conftest import GOLDEN
+    fm = FlatModel.load(os.path.join(GOLDEN, "birth_death.model.npz"))
+    made = []
+
+    class Stub:
+        def __init__(self, fm, device=0, **kw):
+            made.append(device)
+            if len(made) == 2:
+                raise MemoryError("lane 2 could not allocate")
+        def reset(self, seed): pass
+        def step(self, n): pass
+        def run_no_files(self, seed, n, first_traj=0): time.sleep(0.01)
+        def counters(self): return {"reactions": 0, "diffusions": 0, "seconds": 0.0, "windows": 0}
+        def close(self): pass
+
+    out = {}
+    def go():
+        try:
+            run_ensemble(fm, 8, 1, devices=[0], lanes=4, engine_factory=Stub)
+        except BaseException as err:  # noqa: BLE001
+            out["err"] = err
+    t = threading.Thread(target=go)
+    t.start()
+    t.join(20)
+    assert not t.is_alive(), "run_ensemble hangs when one lane fails to start"
+    assert isinstance(out.get("err"), MemoryError)
