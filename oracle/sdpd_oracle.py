@@ -207,7 +207,7 @@ class SdpdOracle:
                 k = self.Sc * (self.type[i] - 1) + s          # model.cpp:163 (transposed index, mirrored)
                 Dk = np.where(k < dm.size, dm[np.minimum(k, dm.size - 1)], 0.0)
                 np.add.at(self.Q[:, s], i, Dk * (self.C[i, s] - self.C[j, s]) * base)
-            self.det_reactions()
+            self.det_reactions(getattr(self, "corrected_stoich", False))
 
     def det_reactions(self, corrected=False):
         """model.cpp:181-189: Q[s] += stoichiometric_matrix[num_chem_rxns*rxn + s] * det_rxn(C, t, vol, data_fn, type).

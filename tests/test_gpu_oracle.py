@@ -158,3 +158,26 @@ def test_full_size_moving_tank_properties():
     assert a["stats"]["skin"] > 0 and b["stats"]["skin"] == 0 and a["stats"]["rebuilds"] == 1     # one list build served all 6 steps
     np.testing.assert_array_equal(a["nbr"], b["nbr"])                               # identical neighbour counts per particle
     assert rel_err(a["x"], b["x"]) <= RTOL_TRAJ and rel_err(a["rho"], b["rho"]) <= RTOL_TRAJ
+
+
+def test_corrected_stoichiometry_flag_matches_the_restatement_with_the_right_index():
+    """SSB_FLAG_CORRECTED_STOICH: the deterministic reaction term reads N[s][rxn] (species x reactions, row-major) instead of the
+    reference's transposed / out-of-bounds index (E/src/model.cpp:186-187).  On the Cdc42 model (9 species, 13 reactions: the
+    two indexings differ) the engine with the flag must follow the numpy restatement evaluated with the correct index — and
+    must differ from the parity mode, or the flag does nothing."""
+    import sdpd_oracle
+    from spatialpy_b200.engine import Engine, FLAG_CORRECTED_STOICH, FLAG_SKIP_STATIC_FORCES
+    from util import load_model, rel_err
+    fm = load_model("cdc42")
+    o = sdpd_oracle.SdpdOracle(fm)
+    o.corrected_stoich = True
+    out = {}
+    for name, flags in (("corrected", FLAG_SKIP_STATIC_FORCES | FLAG_CORRECTED_STOICH), ("parity", FLAG_SKIP_STATIC_FORCES)):
+        with Engine(fm, flags=flags) as eng:
+            eng.reset(1000)
+            eng.step(2)
+            out[name] = (eng.get("C"), eng.get("Q"))
+    for _ in range(2):
+        o.step()
+    assert rel_err(out["corrected"][1], o.Q) <= 1e-12 and rel_err(out["corrected"][0], o.C) <= 1e-12
+    assert rel_err(out["parity"][1], o.Q) > 1e-6
