@@ -84,7 +84,8 @@ typedef struct ssb_model {
     const int64_t *irG, *jcG;       /* dependency graph CSC, columns [species..., reactions...] (solver.py:256-257) */
     const double *diffusion_matrix; /* [S*num_types] input_subdomain_diffusion_matrix (solver.py:269-286) */
     const char *const *species_names; /* [S] input_species_names (solver.py:259-263) */
-    /* sSSA window controller: tau = rdme_epsilon / max_i max_s Ddiag_i[s]  (<=0 selects the default 0.05) */
+    /* sSSA window controller: tau = rdme_epsilon / max_i max_s Ddiag_i[s]  (<=0 selects the default 0.0125;
+     * the splitting error of the windowed scheme is first order in it while the spatial distribution relaxes) */
     double rdme_epsilon;
     int32_t device;                 /* CUDA device ordinal */
     int32_t reserved;
