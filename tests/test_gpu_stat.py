@@ -11,19 +11,31 @@ pytestmark = pytest.mark.gpu
 XBINS = 8
 
 
-def gpu_ensemble(name, ntraj, steps, seed0=50_000, **kw):
+def gpu_ensemble(name, ntraj, steps, seed0=50_000, workers=16, **kw):
+    """xx of `ntraj` trajectories (seed0 + k) at the requested steps.  Small models are launch-latency bound, so `workers` engine
+    handles run side by side on their own streams (ctypes releases the GIL during the engine calls); trajectory k's result does not
+    depend on which handle ran it (Philox is keyed by seed + particle id)."""
+    from concurrent.futures import ThreadPoolExecutor
     from spatialpy_b200.engine import Engine
+    from spatialpy_b200 import codegen
     fm = load_model(name)
-    out = {s: [] for s in steps}
-    with Engine(fm, **kw) as eng:
-        for k in range(ntraj):
-            eng.reset(seed0 + k)
-            done = 0
-            for s in steps:
-                eng.step(s - done)
-                done = s
-                out[s].append(eng.get("xx").astype(np.int64))
-    return {s: np.array(v) for s, v in out.items()}       # [ntraj, N, S]
+    codegen.build_model_unit(fm)                      # once, before the handles race for it
+    workers = max(1, min(workers, ntraj))
+    res = [None] * ntraj
+
+    def work(w):
+        with Engine(fm, **kw) as eng:
+            for k in range(w, ntraj, workers):
+                eng.reset(seed0 + k)
+                done, snaps = 0, {}
+                for s in steps:
+                    eng.step(s - done)
+                    done = s
+                    snaps[s] = eng.get("xx").astype(np.int64)
+                res[k] = snaps
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        list(ex.map(work, range(workers)))
+    return {s: np.array([r[s] for r in res]) for s in steps}       # [ntraj, N, S]
 
 
 def check_against_reference(name, ntraj, **kw):
