@@ -768,3 +768,40 @@ def test_force_sweep_source_record_layouts_agree_on_the_host(tmp_path, which):
     for k in ("F", "Fbp", "Frho", "Q", "Ddiag"):
         scale = max(float(np.abs(b[k]).max()), 1e-300)
         assert float(np.abs(a[k] - b[k]).max()) / scale <= 1e-13, k
+
+
+def test_codegen_guards_bc_density_assignment_and_reaction_count():
+    """(i) the static fast path is switched off by a boundary condition that ASSIGNS me->rho (boundarycondition.py:147-166, target
+    'rho') — not by any mention of the word; (ii) a model with more reactions than the 64-bit dependency masks hold is refused
+    at build time instead of silently never refreshing reactions 64 and above."""
+    import copy
+    from spatialpy_b200 import codegen
+    fm = load_model("cavity2d_bc")
+    assert "#define SSB_BC_TOUCHES_RHO 1" in codegen.generate_model_header(fm)
+    plain = load_model("cavity2d")
+    assert "#define SSB_BC_TOUCHES_RHO 0" in codegen.generate_model_header(plain)
+    mention = copy.copy(plain)
+    mention.bc_source = "if((me->x[0] >= system->rho0)){me->v[0]=0.0;}"          # reads a name containing "rho", assigns nothing to it
+    assert "#define SSB_BC_TOUCHES_RHO 0" in codegen.generate_model_header(mention)
+    big = copy.copy(load_model("birth_death"))
+    big.reactions = [big.reactions[k % 2] for k in range(65)]
+    with pytest.raises(codegen.BuildError):
+        codegen.generate_model_header(big)
+
+
+def test_batched_ensembles_refuse_models_whose_boundary_conditions_test_coordinates():
+    """replicate_model translates the copies of the model; a coordinate predicate (`me->x[0] >= xmin`, boundarycondition.py:129-140)
+    would select the wrong region in every copy but the first — refused, and Solver's automatic batching skips such models."""
+    import copy
+    from spatialpy_b200.ensemble import replicate_model
+    from spatialpy_b200.solver import Solver
+    fm = copy.copy(load_model("birth_death"))
+    assert replicate_model(fm, 3).num_particles == 3 * fm.num_particles
+    fm.bc_source = "if((me->x[0] >= 0.5)){me->nu=2.0;}"
+    with pytest.raises(ValueError):
+        replicate_model(fm, 3)
+    sol = Solver(fm)
+    sol.flat = fm.finalize()
+    assert sol._auto_batch(1024) is None
+    sol.flat = load_model("birth_death")
+    assert sol._auto_batch(1024) is True and sol._auto_batch(8) is None
