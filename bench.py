@@ -421,6 +421,11 @@ def run_ours(args, rank, local_rank, world):
                 subs[wl] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "rdme_events_per_s", "roofline", "e2e", "gpu_launches", "clocks")}
             except Exception as err:  # noqa: BLE001
                 subs[wl] = {"error": f"{type(err).__name__}: {err}"[:300]}
+        for key, name, ntraj in (("ens_birth_death", "birth_death", 256), ("ens_cdc42_full", "cdc42_full", 32)):
+            try:
+                subs[key] = ensemble_sub_record(name, ntraj, local_rank, not args.no_cpu) if rank == 0 else None
+            except Exception as err:  # noqa: BLE001
+                subs[key] = {"error": f"{type(err).__name__}: {err}"[:300]}
         line["sub_records"] = subs
     if rank == 0:
         print(json.dumps(line))
@@ -542,6 +547,52 @@ def slab_measure(args, rank, local_rank, world, steps, warmup, SPS, comm):
 # ensemble arm: many trajectories of a SMALL model (BASELINE configs[0] birth-death, configs[3] Cdc42), k mod G over the GPUs
 # and several concurrent engine handles per GPU
 # ---------------------------------------------------------------------------------------------------------
+def _ensemble_cpu_arm(name, fm):
+    """Reference arm of an ensemble: trajectories are independent processes (solver.py:547-605), so the host runs
+    one per core side by side; trajectories/s = processes / wall.  None when oracle/_ref/bench_<name>/ was not built."""
+    exe = os.path.join(ROOT, "oracle", "_ref", f"bench_{name}", "fast", "ssa_sdpd.exe")
+    if not os.path.exists(exe):
+        return None
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    procs, dirs = [], []
+    for k in range(cores):
+        d = tempfile.mkdtemp(prefix="ssb_ref_ens_")
+        dirs.append(d)
+        procs.append(subprocess.Popen([exe, "-t", "1", "-s", str(1000 + k)], cwd=d, stdout=subprocess.DEVNULL))
+    for p in procs:
+        p.wait()
+    wall = time.perf_counter() - t0
+    for d in dirs:
+        subprocess.run(["rm", "-rf", d])
+    return {"value": fm.num_particles * fm.nt * cores / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+            "trajectories_per_s": cores / wall,
+            "sample": f"unmodified reference engine (g++ -O3), {cores} trajectories of the same model as {cores} concurrent processes "
+                      f"(-t 1 each), {wall:.2f} s wall incl. process start and VTK output"}
+
+
+def ensemble_sub_record(name, ntraj, device, with_cpu):
+    """A bounded single-GPU sample of an ensemble config (BASELINE configs[0] birth-death, configs[3] Cdc42 at its named size) for the
+    default line's `sub_records`: `ntraj` trajectories as one batched engine handle (what `Solver.run` picks from 16 trajectories
+    on), host wall clock around the whole call (state upload, stepping, read-back of every trajectory's populations)."""
+    import torch
+    from spatialpy_b200 import FlatModel
+    from spatialpy_b200.ensemble import run_ensemble_batched
+    fm = FlatModel.load(os.path.join(ROOT, "tests", "golden", f"{name}.model.npz"))
+    run_ensemble_batched(fm, ntraj, 1, device=device, batch=ntraj)                      # warm-up: unit build, module load
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    res = run_ensemble_batched(fm, ntraj, 1000, device=device, batch=ntraj)
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    ev = float(res["counters"]["reactions"] + res["counters"]["diffusions"])
+    return {"value": fm.num_particles * fm.nt * ntraj / dt, "unit": UNIT, "trajectories": ntraj, "trajectories_per_s": ntraj / dt,
+            "rdme_events_per_s": ev / dt, "ms_per_step": dt * 1e3,
+            "config": {"workload": f"ensemble of {ntraj} trajectories of the {name} fixture model ({fm.num_particles} particles, {fm.nt} steps, "
+                                   f"{fm.num_species} species, {fm.num_reactions} reactions), one batched engine handle on one GPU"},
+            "cpu_baseline": _ensemble_cpu_arm(name, fm) if with_cpu else None}
+
+
 def run_ensemble_bench(args, rank, local_rank, world):
     import torch
     from spatialpy_b200 import FlatModel
@@ -590,28 +641,7 @@ def run_ensemble_bench(args, rank, local_rank, world):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         dt, ev = float(tm[0].item()), float(t[1].item())
-    cpu = None
-    if rank == 0 and not args.no_cpu:
-        # reference arm of an ensemble: trajectories are independent processes (solver.py:547-605), so the host
-        # runs one per core side by side; trajectories/s = processes / wall
-        exe = os.path.join(ROOT, "oracle", "_ref", f"bench_{name}", "fast", "ssa_sdpd.exe")
-        if os.path.exists(exe):
-            cores = os.cpu_count() or 1
-            t0 = time.perf_counter()
-            procs, dirs = [], []
-            for k in range(cores):
-                d = tempfile.mkdtemp(prefix="ssb_ref_ens_")
-                dirs.append(d)
-                procs.append(subprocess.Popen([exe, "-t", "1", "-s", str(1000 + k)], cwd=d, stdout=subprocess.DEVNULL))
-            for p in procs:
-                p.wait()
-            wall = time.perf_counter() - t0
-            for d in dirs:
-                subprocess.run(["rm", "-rf", d])
-            cpu = {"value": fm.num_particles * fm.nt * cores / wall, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "trajectories_per_s": cores / wall,
-                   "sample": f"unmodified reference engine (g++ -O3), {cores} trajectories of the same model as {cores} concurrent processes "
-                             f"(-t 1 each), {wall:.2f} s wall incl. process start and VTK output"}
+    cpu = _ensemble_cpu_arm(name, fm) if rank == 0 and not args.no_cpu else None
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": fm.num_particles * fm.nt * total / dt, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,

@@ -50,6 +50,12 @@ extern "C" {
 #define SSB_FLAG_BINARY_STORE 64u         /* also write outputN.ssb next to (or, with SSB_FLAG_NO_VTK, instead of) outputN.vtk: the same snapshot as raw
                                              little-endian arrays at full fp64 precision (layout in spatialpy_b200/vtk.py, read by Result.read_step;
                                              SURVEY.md 8f item 1 - the reference's pure-Python ASCII parser, vtkreader.py:29-56, bounds large N*T) */
+#define SSB_FLAG_CORRECTED_OUTPUT_STEPS 256u /* ssb_run: write file k at step output_steps[k] (one file per time point) instead of the reference's
+                                             gate (simulate_threads.cpp:231-247: files at steps 0, 1, f, 2f, ... plus the final state, i.e. one file
+                                             more than time points and file k >= 2 holding step (k-1)*f) */
+#define SSB_FLAG_CORRECTED_PDE_INDEX 512u  /* PDE flux: read the species-major diffusion table as [s*num_types + type-1] (the entry
+                                             simulate_rdme.cpp:146 uses) instead of the reference's [S_c*(type-1)+s] (model.cpp:163); identical when
+                                             the coefficients do not depend on the type */
 
 /* Flat model description.  Replaces the generated-literal inputs of solver.py:100-419. */
 typedef struct ssb_model {

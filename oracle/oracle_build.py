@@ -50,22 +50,24 @@ def build_bench_refs(variants=("fast", "shipped")):
     return out
 
 
-def build_ensemble_refs():
-    """BASELINE configs[3] (Cdc42 at its named size, the `ens_cdc42_full` bench workload) as a timing executable: the unmodified
-    reference through its own code generator (spatialpy front end), g++ -O3."""
+def build_ensemble_refs(names=("cdc42_full", "birth_death")):
+    """BASELINE configs[3] (Cdc42 at its named size, the `ens_cdc42_full` bench workload) and configs[0] (birth-death) as timing
+    executables: the unmodified reference through its own code generator (spatialpy front end), g++ -O3."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     build_ref.add_reference_to_path()
     import numpy as np
     import models
     from spatialpy_b200 import FlatModel
-    model = models.BUILDERS["cdc42_full"]()
-    np.random.seed(12345)
-    fm = FlatModel.from_spatialpy(model)
-    np.random.seed(12345)
-    exe = build_ref.build_model(model, "bench_cdc42_full", variant="fast", dump=False, h=fm.h)
-    with open(os.path.join(build_ref.OUT, "bench_cdc42_full", "meta.json"), "w") as f:
-        json.dump(dict(N=fm.num_particles, nt=int(fm.nt), dt=float(fm.dt), builder="tests/golden/models.py:cdc42_full", kwargs={}), f)
-    return exe
+    out = {}
+    for name in names:
+        model = models.BUILDERS[name]()
+        np.random.seed(12345)
+        fm = FlatModel.from_spatialpy(model)
+        np.random.seed(12345)
+        out[name] = build_ref.build_model(model, f"bench_{name}", variant="fast", dump=False, h=fm.h)
+        with open(os.path.join(build_ref.OUT, f"bench_{name}", "meta.json"), "w") as f:
+            json.dump(dict(N=fm.num_particles, nt=int(fm.nt), dt=float(fm.dt), builder=f"tests/golden/models.py:{name}", kwargs={}), f)
+    return out
 
 
 def build_all():
@@ -74,7 +76,8 @@ def build_all():
         return
     for k, v in build_bench_refs().items():
         print("built", k, v)
-    print("built bench_cdc42_full/fast", build_ensemble_refs())
+    for k, v in build_ensemble_refs().items():
+        print(f"built bench_{k}/fast", v)
     print("staged", build_ref.stage_reference_python())
 
 

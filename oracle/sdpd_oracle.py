@@ -205,6 +205,8 @@ class SdpdOracle:
             dm = self.fm.diffusion_matrix.reshape(-1)
             for s in range(self.Sc):
                 k = self.Sc * (self.type[i] - 1) + s          # model.cpp:163 (transposed index, mirrored)
+                if getattr(self, "corrected_pde_index", False):   # SSB_FLAG_CORRECTED_PDE_INDEX: the entry simulate_rdme.cpp:146 reads
+                    k = s * self.fm.num_types + (self.type[i] - 1)
                 Dk = np.where(k < dm.size, dm[np.minimum(k, dm.size - 1)], 0.0)
                 np.add.at(self.Q[:, s], i, Dk * (self.C[i, s] - self.C[j, s]) * base)
             self.det_reactions(getattr(self, "corrected_stoich", False))

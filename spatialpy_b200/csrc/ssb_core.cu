@@ -1966,8 +1966,18 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
         unsigned next_output_step = 0;
         size_t out_index = 0;
         unsigned file_index = 0;
+        // SSB_FLAG_CORRECTED_OUTPUT_STEPS: file k holds step output_steps[k], nothing else is written
+        const bool exact_steps = (h->m.flags & SSB_FLAG_CORRECTED_OUTPUT_STEPS) != 0;
         for (unsigned step = 0; step < nt; step++) {
-            if (step >= next_output_step) {
+            if (exact_steps) {
+                while (out_index < h->hout_steps.size() && h->hout_steps[out_index] <= step) {
+                    if (h->hout_steps[out_index] == step) {
+                        if ((rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;
+                        file_index++;
+                    }
+                    out_index++;
+                }
+            } else if (step >= next_output_step) {
                 if ((rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;
                 file_index++;
                 next_output_step = (out_index < h->hout_steps.size()) ? h->hout_steps[out_index] : 0xffffffffu;
@@ -1978,7 +1988,9 @@ extern "C" int ssb_run(ssb_handle *h, uint64_t seed, int32_t ntraj, int32_t firs
             if (h->cancel.load()) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled"); }
             if (cb && cb(cb_user, step + 1, nt)) { drain_writer(h); return fail(h, SSB_ERR_CANCELLED, "cancelled by callback"); }
         }
-        if ((rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;   // final timepoint (:283-285)
+        bool final_file = !exact_steps;                                                           // final timepoint (:283-285)
+        for (; exact_steps && out_index < h->hout_steps.size(); out_index++) final_file |= (h->hout_steps[out_index] == nt);
+        if (final_file && (rc = stage_output(h, write_files ? out_dirs[k] : nullptr, file_index))) return rc;
         CK(ssb_sync(h));
         h->step_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         unsigned long long cnt[2] = {0, 0};

@@ -176,6 +176,13 @@ __device__ __forceinline__ double ssb_W(double alpha, double r, double h) {
     return alpha * ((1 + 3 * R) * (q * q * q));
 }
 
+// index of (species s, type) in the species-major diffusion table for the PDE flux (model.cpp:163).  The reference reads
+// [S_c*(type-1)+s] — a type-major index into a species-major table (solver.py:269-286) — mirrored by default;
+// SSB_FLAG_CORRECTED_PDE_INDEX (512) reads [s*num_types + type-1], the entry simulate_rdme.cpp:146 uses for the same pair.
+__device__ __forceinline__ int ssb_pde_dindex(const SsbView &V, int sc, int type_i, int s) {
+    return (V.flags & 512u) ? s * V.num_types + (type_i - 1) : sc * (type_i - 1) + s;
+}
+
 // D_i_j (particle.cpp:182-187); always the 3-D constant, whatever the dimension
 // the densities D_i_j freezes for the pair (i, j) (see SsbView::rho_pre)
 __device__ __forceinline__ void ssb_search_rho(const SsbView &V, int i, int j, double &rho_i, double &rho_j) {

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_force(SsbView V, unsigned step) {
         Qi[s] = V.Q[(size_t) s * N + i];
         // NOTE the reference indexes the species-major table as [S_c*(type-1)+s] (model.cpp:163) — mirrored,
         // with a bounds guard (the read is in-bounds whenever S == num_types or D is type-independent).
-        int k = SSB_SC * (type_i - 1) + s;
+        int k = ssb_pde_dindex(V, SSB_SC, type_i, s);
         Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
     }
     double vi[3], vti[3], nu_i = 0, Pi = 0, Fa[3], Fb[3], Frho = 0;
@@ -313,7 +313,7 @@ struct ForceSweep {
         for (int s = 0; s < SSB_SC; s++) {
             Ci[s] = V.C[(size_t) s * N + i];
             Qi[s] = V.Q[(size_t) s * N + i];
-            int k = SSB_SC * (type_i - 1) + s;
+            int k = ssb_pde_dindex(V, SSB_SC, type_i, s);
             Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
         }
 #pragma unroll
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(SSB_BLOCK) k_static_step(SsbView V, unsigned s
 #pragma unroll
     for (int s = 0; s < SSB_SC; s++) {
         Qi[s] = 0.0;
-        int k = SSB_SC * (type_i - 1) + s;                                  // model.cpp:163 (mirrored index)
+        int k = ssb_pde_dindex(V, SSB_SC, type_i, s);                                  // model.cpp:163 (mirrored index)
         Dk[s] = (k >= 0 && k < SSB_S * V.num_types) ? V.dmat[k] : 0.0;
     }
     const int cnt = V.nbr_count[i];

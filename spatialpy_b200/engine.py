@@ -28,6 +28,8 @@ FLAG_LITERAL_KERNELS = 16
 FLAG_LEAP_DIFFUSION = 32
 FLAG_BINARY_STORE = 64
 FLAG_NO_STEP_OVERSHOOT = 128
+FLAG_CORRECTED_OUTPUT_STEPS = 256
+FLAG_CORRECTED_PDE_INDEX = 512
 
 ERR_NAMES = {1: "SSB_ERR_NAN", 2: "SSB_ERR_RDME", 3: "SSB_ERR_CUDA", 4: "SSB_ERR_ARG", 5: "SSB_ERR_IO",
              6: "SSB_ERR_CANCELLED", 7: "SSB_ERR_MODEL_UNIT", 8: "SSB_ERR_HALO"}

@@ -182,7 +182,7 @@ def run_ensemble_batched(fm, number_of_trajectories, seed, device=0, out_dirs=No
     file -> step map), written by the engine's own writers (`ssb_write_snapshot`) from the copies' slices of the state.
     Returns {k: {"xx_final": [N, S_d] populations}} plus the summed counters under key "counters"."""
     import numpy as np
-    from .engine import Engine, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
+    from .engine import Engine, FLAG_CORRECTED_OUTPUT_STEPS, FLAG_NO_VTK, FLAG_SKIP_STATIC_FORCES
     from .slab import output_schedule
     from .vtk import write_snapshot, write_snapshot_py
     if writer is None:      # the engine's C++ writers; the Python twins when a fake engine stands in (CPU tier)
@@ -193,7 +193,7 @@ def run_ensemble_batched(fm, number_of_trajectories, seed, device=0, out_dirs=No
     N, Sc, Sd = fm.num_particles, fm.num_chem_species, fm.num_stoch_species
     flags = (FLAG_SKIP_STATIC_FORCES if flags is None else flags) | FLAG_NO_VTK
     factory = engine_factory or Engine
-    schedule = output_schedule(fm.nt, fm.output_steps)
+    schedule = output_schedule(fm.nt, fm.output_steps, corrected=bool(flags & FLAG_CORRECTED_OUTPUT_STEPS))
     results, totals = {}, {"reactions": 0, "diffusions": 0, "seconds": 0.0, "windows": 0}
     eng, eng_copies = None, 0
     try:

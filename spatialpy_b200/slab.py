@@ -31,7 +31,7 @@ import threading
 
 import numpy as np
 
-from .engine import (Engine, FLAG_SKIP_STATIC_FORCES, PH_CORRECTOR, PH_END, PH_FINISH, PH_PRE, PH_RDME_CLOSE, PH_RDME_INIT,
+from .engine import (Engine, FLAG_CORRECTED_OUTPUT_STEPS, FLAG_SKIP_STATIC_FORCES, PH_CORRECTOR, PH_END, PH_FINISH, PH_PRE, PH_RDME_CLOSE, PH_RDME_INIT,
                      PH_RDME_PREP, PH_RDME_WINDOW, PH_RDME_MIN, PH_RDME_EXTRA)
 from .flatmodel import FlatModel
 
@@ -549,13 +549,24 @@ class SlabEngine:
 # ----------------------------------------------------------------------------------------------------------------------
 # a whole trajectory with output files, slab-decomposed over the GPUs of one process (what Solver.run(decomposition="slab") calls)
 # ----------------------------------------------------------------------------------------------------------------------
-def output_schedule(nt, output_steps):
+def output_schedule(nt, output_steps, corrected=False):
     """[(file index, engine step)] of one trajectory: the output gate of run_simulation (E/src/simulate_threads.cpp:231-247,
     283-288) exactly as ssb_run walks it — `next_output_step` starts at 0 and get_next_output() hands out the table from its
     first entry (so step 0 is written twice when the table starts with 0: the reference's file->step off-by-one), and the
-    final state is written once more after the last step."""
-    out, nxt, k, f = [], 0, 0, 0
+    final state is written once more after the last step.  `corrected` (SSB_FLAG_CORRECTED_OUTPUT_STEPS): file k holds step
+    output_steps[k] and nothing else is written."""
     steps = [int(v) for v in output_steps]
+    if corrected:
+        out, k = [], 0
+        for step in range(int(nt)):
+            while k < len(steps) and steps[k] <= step:
+                if steps[k] == step:
+                    out.append((len(out), step))
+                k += 1
+        if any(v == int(nt) for v in steps[k:]):
+            out.append((len(out), int(nt)))
+        return out
+    out, nxt, k, f = [], 0, 0, 0
     for step in range(int(nt)):
         if step >= nxt:
             out.append((f, step))
@@ -595,7 +606,7 @@ def run_slab_trajectory(fm, devices, seed, out_dir, flags=FLAG_SKIP_STATIC_FORCE
     hub = LoopbackHub(world, timeout=3600.0)
     snap = {"x": np.empty((N, 3)), "v": np.empty((N, 3)), "scal": np.empty((4, N)), "C": np.empty((Sc, N)),
             "type": np.empty(N, np.int32), "D": np.empty((Sd, N), np.uint32)}
-    schedule = output_schedule(fm.nt, fm.output_steps)
+    schedule = output_schedule(fm.nt, fm.output_steps, corrected=bool(flags & FLAG_CORRECTED_OUTPUT_STEPS))
     errs, counters = {}, {}
     if rank_engine is _default_rank_engine:
         from . import codegen

@@ -224,6 +224,10 @@ def test_slab_trajectory_driver_writes_the_reference_file_set(tmp_path):
     fm.nt, fm.output_steps = 12, np.array([0, 5, 10], dtype=np.uint32)
     _FakeRank._fm = fm
     assert output_schedule(12, [0, 5, 10]) == [(0, 0), (1, 1), (2, 5), (3, 10), (4, 12)]     # simulate_threads.cpp:231-247,283-288
+    # SSB_FLAG_CORRECTED_OUTPUT_STEPS: file k <-> step output_steps[k], no extra files (mirrors the branch in ssb_run)
+    assert output_schedule(12, [0, 5, 10], corrected=True) == [(0, 0), (1, 5), (2, 10)]
+    assert output_schedule(10, [0, 5, 10], corrected=True) == [(0, 0), (1, 5), (2, 10)]
+    assert output_schedule(10, [0, 5, 10, 20], corrected=True) == [(0, 0), (1, 5), (2, 10)]
     total = run_slab_trajectory(fm, [0, 0, 0], 3, str(tmp_path), vtk=True, binary_store=True, rank_engine=_FakeRank)
     assert total == {"reactions": 3, "diffusions": 9, "seconds": 1.0, "windows": 7}
     names = sorted(os.listdir(tmp_path))

@@ -181,3 +181,47 @@ def test_corrected_stoichiometry_flag_matches_the_restatement_with_the_right_ind
         o.step()
     assert rel_err(out["corrected"][1], o.Q) <= 1e-12 and rel_err(out["corrected"][0], o.C) <= 1e-12
     assert rel_err(out["parity"][1], o.Q) > 1e-6
+
+
+def test_corrected_pde_index_flag_reads_the_species_major_entry():
+    """SSB_FLAG_CORRECTED_PDE_INDEX: the PDE flux takes D[s, type] from the species-major table (the entry simulate_rdme.cpp:146
+    reads) instead of the reference's [S_c*(type-1)+s] (E/src/model.cpp:163).  Two species x two types with type-dependent
+    coefficients make the two indexings differ; all three sites are covered — the optimised force sweep, the literal sweep and
+    (on Cdc42, static) the streaming sweep — each against the numpy restatement evaluated with the same index."""
+    from spatialpy_b200 import configs
+    from spatialpy_b200.engine import (Engine, FLAG_CORRECTED_PDE_INDEX, FLAG_CORRECTED_STOICH, FLAG_LITERAL_KERNELS,
+                                       FLAG_SKIP_STATIC_FORCES)
+    from util import load_model
+    fm = _jitter(configs.box_sdpd_rdme(nx=7, ny=7, nz=7, nt=4, output_every=4, dt=1e-5), 5, 0.01)
+    fm.type = np.where(fm.x[:, 0] > np.median(fm.x[:, 0]), 2, 1).astype(fm.type.dtype)
+    fm.diffusion_matrix = np.array([[0.01, 0.03], [0.02, 0.005]])
+    fm.u0 = np.random.default_rng(6).integers(0, 40, size=fm.u0.shape).astype(fm.u0.dtype)     # concentration gradients
+    ref = {}
+    for corrected in (True, False):
+        o = sdpd_oracle.SdpdOracle(fm)
+        o.corrected_pde_index = corrected
+        o.step()
+        ref[corrected] = (o.Q.copy(), o.C.copy())
+    assert rel_err(ref[False][0], ref[True][0]) > 1e-3, "the fixture does not separate the two indexings"
+    for flags, want in ((FLAG_CORRECTED_PDE_INDEX, True), (FLAG_CORRECTED_PDE_INDEX | FLAG_LITERAL_KERNELS, True), (0, False)):
+        with Engine(fm, flags=flags) as eng:
+            eng.reset(1)
+            eng.step(1)
+            for f, a in (("Q", ref[want][0]), ("C", ref[want][1])):
+                err = rel_err(eng.get(f), a)
+                assert err <= RTOL_STEP, f"flags {flags} {f}: {err:.3e}"
+    # static streaming sweep (k_static_step): Cdc42, 9 species x 3 types
+    fm = load_model("cdc42")
+    o = sdpd_oracle.SdpdOracle(fm)
+    o.corrected_stoich = True
+    o.corrected_pde_index = True
+    for _ in range(2):
+        o.step()
+    out = {}
+    for name, extra in (("both", FLAG_CORRECTED_PDE_INDEX), ("stoich", 0)):
+        with Engine(fm, flags=FLAG_SKIP_STATIC_FORCES | FLAG_CORRECTED_STOICH | extra) as eng:
+            eng.reset(1000)
+            eng.step(2)
+            out[name] = (eng.get("C"), eng.get("Q"))
+    assert rel_err(out["both"][1], o.Q) <= 1e-12 and rel_err(out["both"][0], o.C) <= 1e-12
+    assert rel_err(out["stoich"][1], o.Q) > 1e-6

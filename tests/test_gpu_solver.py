@@ -175,3 +175,30 @@ def test_binary_only_run(tmp_path):
         assert r.get_species("A").shape[0] == 11
     with pytest.raises(SimulationError):
         sol.run(vtk=False)
+
+
+def test_corrected_output_steps_flag_writes_one_file_per_time_point(tmp_path):
+    """SSB_FLAG_CORRECTED_OUTPUT_STEPS: file k holds step output_steps[k].  The reference's gate (simulate_threads.cpp:231-247,
+    283-288) writes steps 0, 1, f, 2f, ... and the final state — one file more, and file k >= 2 holds step (k-1) f.  Same seed,
+    both gates: the corrected file k >= 1 must be byte-identical to the reference gate's file k+1, and file 0 to file 0."""
+    from spatialpy_b200.engine import Engine, FLAG_CORRECTED_OUTPUT_STEPS, FLAG_SKIP_STATIC_FORCES
+    from spatialpy_b200.slab import output_schedule
+    fm = load_model("diffusion3d")
+    fm.output_steps = np.array([0, 5, 10], dtype=fm.output_steps.dtype)      # nt = 10: reference gate -> steps 0, 1, 5, 10
+    assert [s for _, s in output_schedule(fm.nt, fm.output_steps)] == [0, 1, 5, 10]
+    dirs = {}
+    for name, extra in (("reference", 0), ("corrected", FLAG_CORRECTED_OUTPUT_STEPS)):
+        d = tmp_path / name
+        d.mkdir()
+        with Engine(fm, flags=FLAG_SKIP_STATIC_FORCES | extra) as eng:
+            eng.run(1000, [str(d)])
+        dirs[name] = d
+    vtk = lambda d: sorted((f for f in os.listdir(d) if f.startswith("output") and "bounding" not in f), key=lambda f: int(f[6:-4]))
+    ref_files, cor_files = vtk(dirs["reference"]), vtk(dirs["corrected"])
+    sched = output_schedule(fm.nt, fm.output_steps, corrected=True)
+    assert [s for _, s in sched] == [int(v) for v in fm.output_steps if v <= fm.nt]
+    assert len(cor_files) == len(sched) == len(ref_files) - 1
+    read = lambda d, f: open(os.path.join(d, f), "rb").read()
+    assert read(dirs["corrected"], cor_files[0]) == read(dirs["reference"], ref_files[0])
+    for k in range(1, len(cor_files)):
+        assert read(dirs["corrected"], cor_files[k]) == read(dirs["reference"], ref_files[k + 1]), k
