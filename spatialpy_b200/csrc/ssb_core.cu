@@ -672,6 +672,8 @@ struct ssb_handle {
     int lists_valid = 0;          // candidate lists + storage order from an earlier step are still usable
     double disp_prev = 0.0;       // max displacement from xref after the previous step
     double step_disp_max = 0.0;   // largest single-step displacement seen in this trajectory
+    double disp_step_next = 0.0;  // single-step displacement of the step that is about to run (k_lookahead out[1])
+    double disp_build = 0.0;      // the same quantity at the step that built the current candidate lists
     int64_t rebuilds = 0;
     int skin_chosen = 0;
     // slab decomposition support
@@ -1674,21 +1676,29 @@ static int rdme_step(ssb_handle *h) {
 }
 
 // ---- the pieces of a MOVING-domain step (shared by engine_step, the phase API and the native slab step) -----------------------
-// Verlet skin: the candidate lists of radius h*(1+skin) and the storage order survive while no pair that is within h NOW can lie
-// outside the candidate radius at the positions the lists were built from: |xref_i - xref_j| <= h + D(x_i) + D(x0_j) with
-// D = displacement from xref, x0 = the previous step's x.  Both displacements of the step that is about to run are known in
-// advance (k_lookahead), so the decision is exact and taken before anything of the step is queued.
+// Verlet skin: the candidate lists hold every j with |q_i - xref_j| <= h*(1+skin), q_i = the predicted position of the step that
+// built them and xref = the positions at the start of that step (the snapshot the build step searched).  A pair that is within h
+// NOW, |x_i - x0_j| <= h with x0 = the previous step's x, is on the list when D(x_i) + D(x0_j) + |q_i - xref_i| <= skin*h, D =
+// displacement from xref.  All three terms are known before the step is queued: the first two from k_lookahead, the last one is
+// the single-step displacement of the build step (`disp_build`, the same kernel's second output at that step).
+static int mv_lookahead(ssb_handle *h);
 static int mv_decide_keep(ssb_handle *h, bool *keep) {
     SsbView &V = h->V;
     *keep = false;
-    if (!V.filter || !h->lists_valid || !h->look_valid) return SSB_OK;
+    if (!V.filter) return SSB_OK;
+    if (!h->look_valid) {                 // first step of a trajectory, or the state was set from outside: look ahead now
+        int rc = mv_lookahead(h);
+        if (rc) return rc;
+    }
     CK(wait_event(h->ev_look));
     double d2next, s2next, d2cur;
     memcpy(&d2next, &h->pin[0], 8); memcpy(&s2next, &h->pin[1], 8); memcpy(&d2cur, &h->pin[2], 8);
+    h->disp_step_next = sqrt(s2next);
+    if (h->disp_step_next > h->step_disp_max) h->step_disp_max = h->disp_step_next;
+    if (!h->lists_valid) return SSB_OK;   // (xref is not meaningful yet: d2next, d2cur are unused)
     const double Dnext = sqrt(d2next), Dcur = sqrt(d2cur), budget = h->skin * V.h * (1.0 - 1e-9);
-    if (sqrt(s2next) > h->step_disp_max) h->step_disp_max = sqrt(s2next);
     h->disp_prev = Dcur;
-    *keep = (Dnext + Dcur <= budget);
+    *keep = (Dnext + Dcur + h->disp_build <= budget);
     return SSB_OK;
 }
 
@@ -1707,6 +1717,7 @@ static int mv_pre(ssb_handle *h) {
         if (!rc && V.filter) {
             for (int d = 0; d < 3; d++) CK(cudaMemcpyAsync(V.xref[d], V.x[d], sizeof(double) * V.N, cudaMemcpyDeviceToDevice, st));
             h->disp_prev = 0.0;
+            h->disp_build = h->disp_step_next;      // |q_i - xref_i| of the lists this step builds (mv_decide_keep)
         }
         h->rebuilds++;
         prof_end(h, ps);
