@@ -731,14 +731,14 @@ def _force_sweep_inputs(fm, seed=2):
     return st
 
 
-def _run_force_emulator(lib, fm, st):
+def _run_force_emulator(lib, fm, st, flags=8):
     n = st["n"]
     out = {k: np.ascontiguousarray(st[k]).copy() for k in ("F", "Fbp", "Frho", "Q")}
     out["Ddiag"] = np.full((max(st["Sd"], 1), n), -1.0)
     mb = np.zeros(1, np.uint64)
     keep = [np.ascontiguousarray(st[k]) for k in ("rec", "nbr", "cnt", "owned", "C", "dmat")]
     a = _EmuArgs()
-    a.N, a.dim, a.num_types, a.filter, a.flags = n, fm.dimension, fm.num_types, 1, 8
+    a.N, a.dim, a.num_types, a.filter, a.flags = n, fm.dimension, fm.num_types, 1, flags
     a.dt, a.h, a.rho0, a.P0 = fm.dt, fm.h, fm.rho0, fm.P0
     a.rec, a.nbr, a.nbr_count, a.nbr_cap, a.owned = keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, st["cap"], keep[3].ctypes.data
     for d in range(3):
@@ -768,6 +768,27 @@ def test_force_sweep_source_record_layouts_agree_on_the_host(tmp_path, which):
     for k in ("F", "Fbp", "Frho", "Q", "Ddiag"):
         scale = max(float(np.abs(b[k]).max()), 1e-300)
         assert float(np.abs(a[k] - b[k]).max()) / scale <= 1e-13, k
+
+
+def test_force_sweep_source_honours_the_corrected_pde_index_flag(tmp_path):
+    """SSB_FLAG_CORRECTED_PDE_INDEX (512) in k_force_mv's SOURCE, on the host: with two species and two types the reference's index
+    [S_c*(type-1)+s] (E/src/model.cpp:163) reads entry [type-1][s] of the 2x2 table and the corrected index reads [s][type-1], so
+    the corrected sweep on a table M must equal the parity sweep on M transposed bit for bit — and differ from the parity sweep
+    on M itself."""
+    from spatialpy_b200 import configs
+    fm = configs.box_sdpd_rdme(nx=7, ny=7, nz=7, nt=4, output_every=4, dt=1e-5)
+    fm.type = np.where(fm.x[:, 0] > np.median(fm.x[:, 0]), 2, 1).astype(fm.type.dtype)
+    fm.diffusion_matrix = np.array([[0.01, 0.03], [0.02, 0.005]])
+    lib = _build_force_emulator(fm, tmp_path)
+    st = _force_sweep_inputs(fm, seed=4)
+    corrected = _run_force_emulator(lib, fm, st, flags=8 | 512)
+    parity = _run_force_emulator(lib, fm, st, flags=8)
+    st_t = dict(st, dmat=np.ascontiguousarray(fm.diffusion_matrix.T))
+    parity_t = _run_force_emulator(lib, fm, st_t, flags=8)
+    np.testing.assert_array_equal(corrected["Q"], parity_t["Q"])
+    assert np.abs(corrected["Q"] - parity["Q"]).max() > 1e-3 * np.abs(parity["Q"]).max()
+    for k in ("F", "Fbp", "Frho"):                      # the flag touches nothing but the chemistry flux
+        np.testing.assert_array_equal(corrected[k], parity[k])
 
 
 def test_codegen_guards_bc_density_assignment_and_reaction_count():
