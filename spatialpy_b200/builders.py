@@ -137,3 +137,152 @@ def read_xml_mesh(filename, subdomain_file=None, type_ids=None):
     with np.errstate(invalid="ignore", divide="ignore"):
         dom.rho = dom.mass / dom.vol
     return dom
+
+
+def _subdomain_types(subdomain_file, type_ids, n):
+    """Per-vertex type ids from a StochSS v1.x subdomain file (`index,type` lines) with the reference's sticky rule: a vertex
+    without an entry inherits the type of the last vertex that had one (lattice.py:644-645, 776-777)."""
+    from spatialpy.core.spatialpyerror import LatticeError
+    names = {}
+    with open(subdomain_file, "r", encoding="utf-8") as f:
+        for lnum, line in enumerate(f):
+            try:
+                ndx, t = line.rstrip().split(",")
+                names[int(ndx)] = type_ids[t] if type_ids is not None else t
+            except ValueError as err:
+                raise LatticeError(f"Could not read in subdomain file, error on line {lnum}: {line}") from err
+    type_id = np.empty(n, dtype=object)
+    last = "UnAssigned"
+    for i in range(n):
+        last = names.get(i, last)
+        type_id[i] = last
+    return type_id
+
+
+def parse_msh(filename):
+    """Minimal Gmsh ASCII reader (format 2.2 and 4.1) -> (points [N,3], [(cell type, connectivity)] in file order), cell types named
+    as meshio names them ("vertex", "line", "triangle", "tetra").  Blocks follow meshio's grouping — 2.2: maximal runs of
+    consecutive elements of one type; 4.1: one block per entity block — because `MeshIOLattice.apply` (lattice.py:783-803) keeps
+    only the FIRST triangle block and the FIRST tetra block.  Node tags are mapped to 0-based positions in file order."""
+    from spatialpy.core.spatialpyerror import LatticeError
+    names = {15: ("vertex", 1), 1: ("line", 2), 2: ("triangle", 3), 4: ("tetra", 4)}
+    with open(filename, "r", encoding="utf-8") as f:
+        lines = f.read().split("\n")
+    sections, k = {}, 0
+    while k < len(lines):
+        tag = lines[k].strip()
+        if tag.startswith("$") and not tag.startswith("$End"):
+            end = "$End" + tag[1:]
+            j = k + 1
+            while j < len(lines) and lines[j].strip() != end:
+                j += 1
+            sections[tag[1:]] = lines[k + 1:j]
+            k = j
+        k += 1
+    try:
+        version = float(sections["MeshFormat"][0].split()[0])
+        if int(sections["MeshFormat"][0].split()[1]) != 0:
+            raise LatticeError("binary .msh files are not supported; export the mesh as ASCII")
+        nodes, elems = sections["Nodes"], sections["Elements"]
+    except (KeyError, IndexError, ValueError) as err:
+        raise LatticeError(f"{filename} is not a Gmsh .msh file") from err
+    blocks = []
+    if version < 4:
+        n = int(nodes[0])
+        body = np.array([ln.split() for ln in nodes[1:1 + n]], dtype=float)
+        tags, pts = body[:, 0].astype(np.int64), np.ascontiguousarray(body[:, 1:4])
+        cur_type, cur = None, []
+        for ln in elems[1:1 + int(elems[0])]:
+            t = ln.split()
+            et, ntags = int(t[1]), int(t[2])
+            if et != cur_type:
+                if cur:
+                    blocks.append((cur_type, cur))
+                cur_type, cur = et, []
+            cur.append(t[3 + ntags:])
+        if cur:
+            blocks.append((cur_type, cur))
+    else:
+        nblocks, n = int(nodes[0].split()[0]), int(nodes[0].split()[1])
+        tags, pts, k = np.empty(n, np.int64), np.empty((n, 3)), 1
+        filled = 0
+        for _ in range(nblocks):
+            cnt = int(nodes[k].split()[3])
+            tags[filled:filled + cnt] = [int(v) for v in nodes[k + 1:k + 1 + cnt]]
+            pts[filled:filled + cnt] = [[float(v) for v in ln.split()[:3]] for ln in nodes[k + 1 + cnt:k + 1 + 2 * cnt]]
+            filled += cnt
+            k += 1 + 2 * cnt
+        k = 1
+        for _ in range(int(elems[0].split()[0])):
+            _, _, et, cnt = (int(v) for v in elems[k].split())
+            blocks.append((et, [ln.split()[1:] for ln in elems[k + 1:k + 1 + cnt]]))
+            k += 1 + cnt
+    lookup = np.full(int(tags.max()) + 1, -1, dtype=np.int64)
+    lookup[tags] = np.arange(len(tags))
+    cells = []
+    for et, rows in blocks:
+        if et in names:
+            cells.append((names[et][0], lookup[np.array(rows, dtype=np.int64)[:, :names[et][1]]]))
+    return pts, cells
+
+
+def read_msh_file(filename, subdomain_file=None, type_ids=None):
+    """Array-at-a-time `Domain.read_msh_file` (domain.py:1063-1096; `MeshIOLattice.apply`, lattice.py:732-806) for Gmsh ASCII
+    meshes, without the `meshio` package the reference needs for this entry point: one particle per node in file order,
+    `triangles` / `tetrahedrons` = the first block of each kind, per-vertex volume = a quarter of every adjacent tetrahedron
+    (`calculate_vol`, domain.py:439-458), mass = vol, rho = 1.  Linear in the mesh size; the reference adds the nodes one
+    `add_point` at a time (O(N²))."""
+    from spatialpy.core.spatialpyerror import DomainError
+    pts, cells = parse_msh(filename)
+    n = len(pts)
+    type_id = "UnAssigned" if subdomain_file is None else _subdomain_types(subdomain_file, type_ids, n)
+    lims = [(pts[:, k].min(), pts[:, k].max()) for k in range(3)]
+    dom = domain_from_arrays(pts, type_id=type_id, vol=1.0, mass=1.0, nu=0.0, fixed=False, c=10.0, xlim=lims[0], ylim=lims[1],
+                             zlim=lims[2])
+    tris = [c for name, c in cells if name == "triangle"]
+    tets = [c for name, c in cells if name == "tetra"]
+    if tris:
+        dom.triangles = tris[0]
+    vol = np.zeros(n)
+    if tets:
+        dom.tetrahedrons = tets[0]
+        dom.tetrahedron_vol = _tetrahedron_volumes(pts, tets[0])
+        np.add.at(vol, tets[0].reshape(-1), np.repeat(dom.tetrahedron_vol / 4, 4))
+    if not np.count_nonzero(vol):
+        raise DomainError("Paritcles cannot have 0 volume")
+    dom.vol = vol
+    dom.mass = dom.vol
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dom.rho = dom.mass / dom.vol
+    return dom
+
+
+def read_stochss_domain(filename):
+    """Array-at-a-time `Domain.read_stochss_domain` (domain.py:1098-1118; `StochSSLattice.apply`, lattice.py:845-903): a StochSS
+    Domain (.domn) file, or the `domain` member of a StochSS Spatial Model (.smdl) file -> Domain.  Per particle: `point`, `type`
+    (looked up in `types[].typeID -> name`, '-' removed), `volume`, `mass`, `nu`, `fixed`, optional `rho` (default mass/volume)
+    and `c` (default 0); domain-wide `rho_0`, `c_0`, `p_0`, `gravity`; limits = the bounding box of the particles."""
+    import json
+    from spatialpy.core.spatialpyerror import LatticeError
+    try:
+        with open(filename, "r", encoding="utf-8") as f:
+            s = json.load(f)
+        if "domain" in s:
+            s = s["domain"]
+        names = {t["typeID"]: t["name"].replace("-", "") for t in s["types"]}
+        parts = s["particles"]
+        n = len(parts)
+        pts = np.array([p["point"][:3] for p in parts], dtype=float).reshape(n, 3)
+        mass = np.array([p["mass"] for p in parts], dtype=float)
+        vol = np.array([p["volume"] for p in parts], dtype=float)
+        rho = np.array([mass[i] / vol[i] if p.get("rho") is None else p["rho"] for i, p in enumerate(parts)], dtype=float)
+        tid = np.empty(n, dtype=object)
+        tid[:] = [names[p["type"]] for p in parts]
+        lims = [(pts[:, k].min(), pts[:, k].max()) if n else (0.0, 0.0) for k in range(3)]
+        dom = domain_from_arrays(pts, type_id=tid if n else "UnAssigned", vol=vol, mass=mass, nu=np.array([p["nu"] for p in parts], dtype=float),
+                                 fixed=np.array([p["fixed"] for p in parts], dtype=bool), rho=rho,
+                                 c=np.array([p.get("c", 0) for p in parts], dtype=float), xlim=lims[0], ylim=lims[1], zlim=lims[2],
+                                 rho0=s["rho_0"], c0=s["c_0"], P0=s["p_0"], gravity=s["gravity"])
+    except KeyError as err:
+        raise LatticeError("The file is not a StochSS Domain (.domn) or a StochSS Spatial Model (.smdl).") from err
+    return dom

@@ -465,6 +465,76 @@ def test_fast_xml_mesh_reader_equals_the_reference_reader(mesh, sub):
     assert abs(fast.find_h() - ref.find_h()) == 0.0
 
 
+def _same_domain(fast, ref, ulp_keys=("vol", "mass", "tetrahedron_vol", "rho")):
+    for key, val in vars(ref).items():
+        got = getattr(fast, key)
+        if key in ulp_keys and val is not None:
+            np.testing.assert_allclose(got, val, rtol=4e-16 * 8, atol=0, err_msg=key)
+        elif isinstance(val, np.ndarray):
+            assert got.dtype == val.dtype and got.shape == val.shape and (got == val).all(), key
+        elif key != "actions":
+            assert got == val, key
+
+
+def test_fast_msh_reader_equals_the_reference_paths():
+    """builders.read_msh_file (Gmsh ASCII 2.2 / 4.1, no meshio needed) against the reference two ways: (i) the 2.2 mesh the
+    reference ships in both formats — coli.msh must give the Domain that the reference's OWN xml reader gives for its dolfin twin
+    (vertices, tetrahedra, volumes); (ii) the 4.1 cube and the 2.2 hes1 cell: the parsed points / cell blocks handed to the
+    reference's `Domain.import_meshio_object` (domain.py:865-898, `MeshIOLattice.apply` lattice.py:732-806: first triangle block,
+    first tetra block, one add_point per node) give the same Domain attribute for attribute."""
+    _need_spatialpy()
+    import types
+    import spatialpy
+    from spatialpy_b200.builders import parse_msh, read_msh_file
+    root = os.environ.get("SSB_REFERENCE_ROOT", "/root/reference")
+    base = os.path.join(root, "examples", "Under_Construction", "Domain_Files")
+    twin = spatialpy.Domain.read_xml_mesh(os.path.join(base, "mesh", "coli.xml"))
+    fast = read_msh_file(os.path.join(base, "coli.msh"))
+    assert (fast.vertices == twin.vertices).all() and (fast.tetrahedrons == twin.tetrahedrons).all()
+    np.testing.assert_allclose(fast.vol, twin.vol, rtol=4e-16 * 8, atol=0)
+    assert fast.triangles.shape == (1492, 3) and fast.triangles.max() < len(fast.vertices)
+    for path in (os.path.join(root, "examples", "Tests", "Mesh_Files", "cube.msh"),):
+        pts, cells = parse_msh(path)
+        mesh = types.SimpleNamespace(points=pts, cells=[types.SimpleNamespace(type=name, data=conn) for name, conn in cells])
+        ref = spatialpy.Domain.import_meshio_object(mesh)
+        _same_domain(read_msh_file(path), ref)
+        assert abs(ref.vol.sum() - 1.0) < 1e-12                  # the unit cube
+    with pytest.raises(spatialpy.core.spatialpyerror.LatticeError):
+        parse_msh(os.path.join(base, "mesh", "coli.xml"))
+
+
+def test_fast_stochss_domain_reader_equals_the_reference_reader(tmp_path):
+    """builders.read_stochss_domain == Domain.read_stochss_domain (domain.py:1098-1118, `StochSSLattice.apply` lattice.py:845-903)
+    on a .domn file and on the same domain wrapped in a .smdl model file: optional `rho` / `c`, '-' stripped from type names,
+    domain-wide constants, limits; a file without the expected keys raises the reference's LatticeError."""
+    _need_spatialpy()
+    import json
+    import spatialpy
+    from spatialpy_b200.builders import read_stochss_domain
+    rng = np.random.default_rng(8)
+    parts = []
+    for k in range(57):
+        p = {"point": rng.normal(size=3).tolist(), "type": int(k % 3), "volume": float(rng.uniform(0.5, 2)), "mass": float(rng.uniform(0.5, 2)),
+             "nu": float(rng.random()), "fixed": bool(k % 5 == 0)}
+        if k % 2:
+            p["rho"] = float(rng.uniform(0.9, 1.1))
+        if k % 4 == 0:
+            p["c"] = float(rng.uniform(5, 15))
+        if k % 7 == 0:
+            p["rho"] = None
+        parts.append(p)
+    dom = {"rho_0": 1.5, "c_0": 12.0, "p_0": 3.0, "gravity": [0, -9.8, 0], "particles": parts,
+           "types": [{"typeID": 0, "name": "Un-Assigned"}, {"typeID": 1, "name": "Cyto-plasm"}, {"typeID": 2, "name": "Membrane"}]}
+    for name, body in (("d.domn", dom), ("m.smdl", {"name": "model", "domain": dom})):
+        path = tmp_path / name
+        path.write_text(json.dumps(body))
+        _same_domain(read_stochss_domain(str(path)), spatialpy.Domain.read_stochss_domain(str(path)), ulp_keys=())
+    bad = tmp_path / "bad.domn"
+    bad.write_text(json.dumps({"particles": []}))
+    with pytest.raises(spatialpy.core.spatialpyerror.LatticeError):
+        read_stochss_domain(str(bad))
+
+
 def test_header_is_valid_c_and_matches_the_ctypes_binding(tmp_path):
     """include/ssb.h + include/ssb_peaks.h compile as pedantic C11 and link from a plain-C program (tests/c/abi_smoke.c); the C
     struct the header declares has the size of the ctypes mirror in spatialpy_b200/engine.py; argument errors are return codes."""
