@@ -3,4 +3,4 @@ from .flatmodel import FlatModel, ReactionSource  # noqa: F401
 
 __version__ = "0.1.0"
 from .solver import Solver, install, SimulationError  # noqa: E402,F401
-from .builders import domain_from_arrays, read_msh_file, read_stochss_domain, read_xml_mesh  # noqa: E402,F401
+from .builders import domain_from_arrays, import_meshio_object, read_msh_file, read_stochss_domain, read_xml_mesh  # noqa: E402,F401

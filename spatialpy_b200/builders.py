@@ -226,14 +226,9 @@ def parse_msh(filename):
     return pts, cells
 
 
-def read_msh_file(filename, subdomain_file=None, type_ids=None):
-    """Array-at-a-time `Domain.read_msh_file` (domain.py:1063-1096; `MeshIOLattice.apply`, lattice.py:732-806) for Gmsh ASCII
-    meshes, without the `meshio` package the reference needs for this entry point: one particle per node in file order,
-    `triangles` / `tetrahedrons` = the first block of each kind, per-vertex volume = a quarter of every adjacent tetrahedron
-    (`calculate_vol`, domain.py:439-458), mass = vol, rho = 1.  Linear in the mesh size; the reference adds the nodes one
-    `add_point` at a time (O(N²))."""
+def _domain_from_mesh(pts, cells, subdomain_file, type_ids):
     from spatialpy.core.spatialpyerror import DomainError
-    pts, cells = parse_msh(filename)
+    pts = np.ascontiguousarray(np.asarray(pts, dtype=float)[:, :3])
     n = len(pts)
     type_id = "UnAssigned" if subdomain_file is None else _subdomain_types(subdomain_file, type_ids, n)
     lims = [(pts[:, k].min(), pts[:, k].max()) for k in range(3)]
@@ -247,7 +242,7 @@ def read_msh_file(filename, subdomain_file=None, type_ids=None):
     if tets:
         dom.tetrahedrons = tets[0]
         dom.tetrahedron_vol = _tetrahedron_volumes(pts, tets[0])
-        np.add.at(vol, tets[0].reshape(-1), np.repeat(dom.tetrahedron_vol / 4, 4))
+        np.add.at(vol, np.asarray(tets[0]).reshape(-1), np.repeat(dom.tetrahedron_vol / 4, 4))
     if not np.count_nonzero(vol):
         raise DomainError("Paritcles cannot have 0 volume")
     dom.vol = vol
@@ -255,6 +250,22 @@ def read_msh_file(filename, subdomain_file=None, type_ids=None):
     with np.errstate(invalid="ignore", divide="ignore"):
         dom.rho = dom.mass / dom.vol
     return dom
+
+
+def read_msh_file(filename, subdomain_file=None, type_ids=None):
+    """Array-at-a-time `Domain.read_msh_file` (domain.py:1063-1096; `MeshIOLattice.apply`, lattice.py:732-806) for Gmsh ASCII
+    meshes, without the `meshio` package the reference needs for this entry point: one particle per node in file order,
+    `triangles` / `tetrahedrons` = the first block of each kind, per-vertex volume = a quarter of every adjacent tetrahedron
+    (`calculate_vol`, domain.py:439-458), mass = vol, rho = 1.  Linear in the mesh size; the reference adds the nodes one
+    `add_point` at a time (O(N²))."""
+    pts, cells = parse_msh(filename)
+    return _domain_from_mesh(pts, cells, subdomain_file, type_ids)
+
+
+def import_meshio_object(mesh_obj, subdomain_file=None, type_ids=None):
+    """Array-at-a-time `Domain.import_meshio_object` (domain.py:865-898): any object with meshio's `points` ([N,3]) and `cells`
+    (blocks with `.type` / `.data`) -> Domain, same rules as `read_msh_file`."""
+    return _domain_from_mesh(mesh_obj.points, [(c.type, np.asarray(c.data)) for c in mesh_obj.cells], subdomain_file, type_ids)
 
 
 def read_stochss_domain(filename):

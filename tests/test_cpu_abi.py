@@ -498,6 +498,9 @@ def test_fast_msh_reader_equals_the_reference_paths():
         mesh = types.SimpleNamespace(points=pts, cells=[types.SimpleNamespace(type=name, data=conn) for name, conn in cells])
         ref = spatialpy.Domain.import_meshio_object(mesh)
         _same_domain(read_msh_file(path), ref)
+        from spatialpy_b200.builders import import_meshio_object
+        sub = os.path.join(root, "examples", "Domain_Files", "GRN_Spatial.subdomains.txt")      # index,type lines; sticky types
+        _same_domain(import_meshio_object(mesh, subdomain_file=sub), spatialpy.Domain.import_meshio_object(mesh, subdomain_file=sub))
         assert abs(ref.vol.sum() - 1.0) < 1e-12                  # the unit cube
     with pytest.raises(spatialpy.core.spatialpyerror.LatticeError):
         parse_msh(os.path.join(base, "mesh", "coli.xml"))
