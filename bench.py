@@ -421,9 +421,9 @@ def run_ours(args, rank, local_rank, world):
                 subs[wl] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "rdme_events_per_s", "roofline", "e2e", "gpu_launches", "clocks")}
             except Exception as err:  # noqa: BLE001
                 subs[wl] = {"error": f"{type(err).__name__}: {err}"[:300]}
-        for key, name, ntraj in (("ens_birth_death", "birth_death", 256), ("ens_cdc42_full", "cdc42_full", 32)):
+        for key, name, ntraj, batch in (("ens_birth_death", "birth_death", 256, 256), ("ens_cdc42_full", "cdc42_full", 128, 64)):
             try:
-                subs[key] = ensemble_sub_record(name, ntraj, local_rank, not args.no_cpu) if rank == 0 else None
+                subs[key] = ensemble_sub_record(name, ntraj, batch, local_rank, not args.no_cpu) if rank == 0 else None
             except Exception as err:  # noqa: BLE001
                 subs[key] = {"error": f"{type(err).__name__}: {err}"[:300]}
         line["sub_records"] = subs
@@ -571,25 +571,25 @@ def _ensemble_cpu_arm(name, fm):
                       f"(-t 1 each), {wall:.2f} s wall incl. process start and VTK output"}
 
 
-def ensemble_sub_record(name, ntraj, device, with_cpu):
+def ensemble_sub_record(name, ntraj, batch, device, with_cpu):
     """A bounded single-GPU sample of an ensemble config (BASELINE configs[0] birth-death, configs[3] Cdc42 at its named size) for the
-    default line's `sub_records`: `ntraj` trajectories as one batched engine handle (what `Solver.run` picks from 16 trajectories
-    on), host wall clock around the whole call (state upload, stepping, read-back of every trajectory's populations)."""
+    default line's `sub_records`: `ntraj` trajectories, `batch` at a time as disjoint copies in one engine handle (what `Solver.run`
+    picks from 16 trajectories on), host wall clock around the whole call (state upload, stepping, read-back of every trajectory's populations)."""
     import torch
     from spatialpy_b200 import FlatModel
     from spatialpy_b200.ensemble import run_ensemble_batched
     fm = FlatModel.load(os.path.join(ROOT, "tests", "golden", f"{name}.model.npz"))
-    run_ensemble_batched(fm, ntraj, 1, device=device, batch=ntraj)                      # warm-up: unit build, module load
+    run_ensemble_batched(fm, min(batch, 8), 1, device=device, batch=min(batch, 8))      # warm-up: unit build, module load
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
-    res = run_ensemble_batched(fm, ntraj, 1000, device=device, batch=ntraj)
+    res = run_ensemble_batched(fm, ntraj, 1000, device=device, batch=batch)
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
     ev = float(res["counters"]["reactions"] + res["counters"]["diffusions"])
     return {"value": fm.num_particles * fm.nt * ntraj / dt, "unit": UNIT, "trajectories": ntraj, "trajectories_per_s": ntraj / dt,
             "rdme_events_per_s": ev / dt, "ms_per_step": dt * 1e3,
             "config": {"workload": f"ensemble of {ntraj} trajectories of the {name} fixture model ({fm.num_particles} particles, {fm.nt} steps, "
-                                   f"{fm.num_species} species, {fm.num_reactions} reactions), one batched engine handle on one GPU"},
+                                   f"{fm.num_species} species, {fm.num_reactions} reactions), one engine handle holding {batch} copies at a time, on one GPU"},
             "cpu_baseline": _ensemble_cpu_arm(name, fm) if with_cpu else None}
 
 
