@@ -1,0 +1,213 @@
+"""CPU tier: the native slab transport kernels (spatialpy_b200/csrc/ssb_core.cu: k_halo_send/_recv/_wait, k_inbox_send/_recv,
+k_board_post/_reduce) run as SOURCE on the host by the block emulator (tests/cuda_emu): message layout in the receive window,
+last-CTA publish of the sequence flags, compaction of the sSSA inbox, the scalar all-reduce boards.  The reference has no domain
+decomposition; what these kernels must preserve is that a ghost copy carries its owner's values after every
+exchange at the substep boundaries of E/src/simulate_threads.cpp:232-281 and that no molecule is lost or duplicated."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P64 = ctypes.POINTER(ctypes.c_double)
+
+
+class _Rank(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("Sc", ctypes.c_int), ("Sd", ctypes.c_int), ("F", ctypes.c_void_p * 3), ("Fbp", ctypes.c_void_p * 3),
+                ("Frho", ctypes.c_void_p), ("Q", ctypes.c_void_p), ("rho_new", ctypes.c_void_p), ("v", ctypes.c_void_p * 3),
+                ("bvf", ctypes.c_void_p), ("inbox", ctypes.c_void_p * 2), ("inbox_src", ctypes.c_void_p * 2),
+                ("blk_mail", ctypes.c_void_p * 2), ("slot_of_id", ctypes.c_void_p)]
+
+
+class _Side(ctypes.Structure):
+    _fields_ = [("ids", ctypes.c_void_p), ("n", ctypes.c_int), ("buf", ctypes.c_void_p), ("flag", ctypes.c_void_p), ("count", ctypes.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    from spatialpy_b200 import codegen
+    tmp = tmp_path_factory.mktemp("halo_emu")
+    src = open(os.path.join(codegen.CSRC, "ssb_core.cu")).read()
+    a = src.index("__device__ __forceinline__ int halo_width(")
+    b = src.index("// =====", src.index("__global__ void k_board_reduce"))
+    text = src[a:b]
+    # the two inline-PTX helpers have host versions in the harness; everything else is the shipped text
+    text, n1 = re.subn(r"__device__ __forceinline__ unsigned long long ssb_globaltimer\(\) \{.*?\n", "", text)
+    text, n2 = re.subn(r"__device__ __forceinline__ unsigned long long ssb_ld_flag\(const unsigned long long \*p\) \{.*?\n\}\n", "", text, flags=re.S)
+    assert n1 == 1 and n2 == 1
+    kern = tmp / "halo_kernels.inc"
+    kern.write_text(text)
+    so = tmp / "halo_emu.so"
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(codegen.nvcc_path())), "include")
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-pthread", "-shared", "-fPIC", "-I", cuda_inc, "-I", codegen.CSRC,
+           "-I", os.path.join(ROOT, "tests", "cuda_emu"), f"-DEMU_KERNELS=\"{kern}\"",
+           os.path.join(ROOT, "tests", "cuda_emu", "halo_emu.cpp"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return ctypes.CDLL(str(so))
+
+
+class Rank:
+    """One slab rank's state in host memory, in a scrambled storage order (slot_of_id)."""
+    def __init__(self, n, Sc, Sd, seed):
+        rng = np.random.default_rng(seed)
+        self.n, self.Sc, self.Sd = n, Sc, Sd
+        self.slot = rng.permutation(n).astype(np.int32)
+        self.f = {k: rng.normal(size=(3, n)) for k in ("F", "Fbp", "v")}
+        self.f.update({k: rng.normal(size=n) for k in ("Frho", "rho_new", "bvf")})
+        self.f["Q"] = rng.normal(size=(max(Sc, 1), n))
+        self.inbox = [np.zeros((max(Sd, 1), n), np.uint32) for _ in range(2)]
+        self.inbox_src = [np.zeros(n, np.uint64) for _ in range(2)]
+        self.blk_mail = [np.zeros((n + 127) // 128, np.int32) for _ in range(2)]
+        r = _Rank()
+        r.N, r.Sc, r.Sd = n, Sc, Sd
+        for d in range(3):
+            r.F[d], r.Fbp[d], r.v[d] = self.f["F"][d].ctypes.data, self.f["Fbp"][d].ctypes.data, self.f["v"][d].ctypes.data
+        r.Frho, r.Q, r.rho_new, r.bvf = (self.f[k].ctypes.data for k in ("Frho", "Q", "rho_new", "bvf"))
+        for b in range(2):
+            r.inbox[b], r.inbox_src[b], r.blk_mail[b] = self.inbox[b].ctypes.data, self.inbox_src[b].ctypes.data, self.blk_mail[b].ctypes.data
+        r.slot_of_id = self.slot.ctypes.data
+        self.c = r
+
+    def rows(self, group, ids):
+        """The [W, len(ids)] message the transport must carry for `group` (halo_width: 7 + Sc | 1 | 4)."""
+        p = self.slot[ids]
+        if group == 0:
+            return np.concatenate([self.f["F"][:, p], self.f["Fbp"][:, p], self.f["Frho"][None, p], self.f["Q"][:self.Sc, p]])
+        if group == 1:
+            return self.f["rho_new"][None, p]
+        return np.concatenate([self.f["v"][:, p], self.f["bvf"][None, p]])
+
+
+class Window:
+    def __init__(self, words):
+        self.buf = np.zeros(words, np.float64)
+        self.flag = np.zeros(1, np.uint64)
+        self.count = np.zeros(1, np.uint64)
+
+
+def _sides(specs):
+    arr = (_Side * 2)()
+    keep = []
+    for k, sp in enumerate(specs):
+        if sp is None:
+            arr[k].n = 0
+            continue
+        ids, win = sp
+        ids = np.ascontiguousarray(ids, np.int32)
+        keep.append(ids)
+        arr[k].ids, arr[k].n, arr[k].buf = ids.ctypes.data, len(ids), win.buf.ctypes.data
+        arr[k].flag, arr[k].count = win.flag.ctypes.data, win.count.ctypes.data
+    return arr, keep
+
+
+@pytest.mark.parametrize("group", [0, 1, 2])
+@pytest.mark.parametrize("two_sided", [True, False])
+def test_halo_messages_carry_the_owner_rows_into_the_ghost_copies(emu, group, two_sided):
+    """k_halo_send writes the column-major message [field][row] into the neighbour's window and its LAST CTA raises the sequence
+    flag of every connected side (and rewinds the CTA counter for the next message); k_halo_wait passes once the flag is there;
+    k_halo_recv moves the rows into the receiver's ghost slots and touches nothing else.  Two CTAs (220 rows) and the one-sided
+    end-of-chain case (side without a peer)."""
+    Sc = 2
+    A, B, Cc = Rank(700, Sc, 1, 1), Rank(500, Sc, 1, 2), Rank(400, Sc, 1, 3)
+    rng = np.random.default_rng(10 + group)
+    n0, n1 = 150, 70
+    W = emu.emu_halo_width(group, Sc)
+    assert W == {0: 7 + Sc, 1: 1, 2: 4}[group]
+    a_left, a_right = rng.choice(A.n, n0, replace=False), rng.choice(A.n, n1, replace=False)      # A's owned rows next to each face
+    b_ghost, c_ghost = rng.choice(B.n, n0, replace=False), rng.choice(Cc.n, n1, replace=False)    # the neighbours' copies, same order
+    wb, wc = Window(W * n0 + 8), Window(W * n1 + 8)
+    done = np.zeros(1, np.uint32)
+    send, keep = _sides([(a_left, wb), (a_right, wc) if two_sided else None])
+    seq = 5
+    assert emu.emu_halo_send(ctypes.byref(A.c), group, send, ctypes.c_ulonglong(seq), done.ctypes.data_as(ctypes.c_void_p)) == 0
+    np.testing.assert_array_equal(wb.buf[:W * n0].reshape(W, n0), A.rows(group, a_left))
+    assert wb.buf[W * n0:].sum() == 0 and int(wb.flag[0]) == seq and int(done[0]) == 0
+    if two_sided:
+        np.testing.assert_array_equal(wc.buf[:W * n1].reshape(W, n1), A.rows(group, a_right))
+        assert int(wc.flag[0]) == seq
+    else:
+        assert int(wc.flag[0]) == 0 and not wc.buf.any()
+    err = np.zeros(4, np.int32)
+    emu.emu_halo_wait(wb.flag.ctypes.data_as(ctypes.c_void_p), wb.flag.ctypes.data_as(ctypes.c_void_p), ctypes.c_ulonglong(seq),
+                      err.ctypes.data_as(ctypes.c_void_p))
+    assert err[0] == 0
+    before = {k: v.copy() for k, v in B.f.items()}
+    recv, keep2 = _sides([(b_ghost, wb), None])
+    assert emu.emu_halo_recv(ctypes.byref(B.c), group, recv) == 0
+    np.testing.assert_array_equal(B.rows(group, b_ghost), A.rows(group, a_left))
+    untouched = np.ones(B.n, bool)
+    untouched[B.slot[b_ghost]] = False
+    for k, v in B.f.items():
+        np.testing.assert_array_equal(v[..., untouched], before[k][..., untouched])
+    groups_fields = {0: ("F", "Fbp", "Frho", "Q"), 1: ("rho_new",), 2: ("v", "bvf")}[group]
+    for k, v in B.f.items():
+        if k not in groups_fields:
+            np.testing.assert_array_equal(v, before[k])
+
+
+def test_inbox_entries_are_compacted_and_no_molecule_is_lost(emu):
+    """k_inbox_send reads-and-clears the ghost voxels' arrivals and appends one (row, species, count) entry per non-zero pair to
+    the owner's window, publishes the entry count with the flag and rewinds its counters; k_inbox_recv adds the entries to the
+    owner's voxels and raises the chunk mail flags.  Molecules are conserved; nothing but the listed rows changes."""
+    Sd = 3
+    A, B = Rank(900, 1, Sd, 4), Rank(600, 1, Sd, 5)
+    rng = np.random.default_rng(21)
+    n = 260                                                   # three CTAs
+    a_ghost, b_owned = rng.choice(A.n, n, replace=False), rng.choice(B.n, n, replace=False)
+    buf = 1
+    arrivals = (rng.random((Sd, n)) < 0.07) * rng.integers(1, 5, size=(Sd, n))
+    A.inbox[buf][:, A.slot[a_ghost]] = arrivals
+    A.inbox_src[buf][A.slot[a_ghost]] = 77
+    elsewhere = rng.integers(0, 3, size=(Sd, A.n)).astype(np.uint32)      # mail for A's own voxels must stay
+    mask = np.ones(A.n, bool)
+    mask[A.slot[a_ghost]] = False
+    A.inbox[buf][:, mask] = elsewhere[:, mask]
+    B.inbox[buf][:] = rng.integers(0, 2, size=(Sd, B.n))
+    b_before = B.inbox[buf].copy()
+    win = Window(4 * n * Sd + 8)                             # uint4 entries = 2 doubles each
+    done, icount = np.zeros(1, np.uint32), np.zeros(2, np.uint32)
+    send, keep = _sides([(a_ghost, win), None])
+    seq = 9
+    emu.emu_inbox_send(ctypes.byref(A.c), buf, send, ctypes.c_ulonglong(seq), done.ctypes.data_as(ctypes.c_void_p),
+                       icount.ctypes.data_as(ctypes.c_void_p))
+    nent = int(np.count_nonzero(arrivals))
+    assert nent > 10 and int(win.count[0]) == nent and int(win.flag[0]) == seq and int(done[0]) == 0 and not icount.any()
+    assert not A.inbox[buf][:, A.slot[a_ghost]].any() and not A.inbox_src[buf][A.slot[a_ghost]].any()
+    np.testing.assert_array_equal(A.inbox[buf][:, mask], elsewhere[:, mask])
+    ent = win.buf.view(np.uint32)[:4 * nent].reshape(nent, 4)
+    got = np.zeros((Sd, n), np.int64)
+    np.add.at(got, (ent[:, 1], ent[:, 0]), ent[:, 2])
+    np.testing.assert_array_equal(got, arrivals)              # every non-zero pair exactly once, whatever the order
+    recv, keep2 = _sides([(b_owned, win), None])
+    emu.emu_inbox_recv(ctypes.byref(B.c), buf, recv, 128)
+    want = b_before.astype(np.int64)
+    want[:, B.slot[b_owned]] += arrivals
+    np.testing.assert_array_equal(B.inbox[buf], want)
+    mail = np.zeros_like(B.blk_mail[buf])
+    mail[np.unique(B.slot[b_owned][arrivals.any(axis=0)] // 128)] = 1
+    np.testing.assert_array_equal(B.blk_mail[buf], mail)
+    assert int(B.inbox[buf].sum()) == int(b_before.sum()) + int(arrivals.sum())
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_board_all_reduce_gives_every_rank_the_same_extreme(emu, world):
+    """k_board_post / k_board_reduce: every rank stores (value, sequence) into its slot of EVERY rank's board; each rank reduces
+    its own board.  Maximum (Ddiag, displacement) and minimum (earliest pending event) of bit patterns of non-negative doubles;
+    consecutive sequence numbers use the two parities of a channel and do not disturb each other."""
+    words = emu.emu_board_words()
+    boards = [np.zeros(words, np.uint64) for _ in range(world)]
+    ptrs = (ctypes.c_void_p * world)(*[b.ctypes.data for b in boards])
+    rng = np.random.default_rng(world)
+    err = np.zeros(4, np.int32)
+    for seq, ch, take_min in ((1, 0, 0), (2, 0, 0), (1, 1, 1), (1, 2, 0), (3, 0, 0)):
+        vals = np.abs(rng.normal(size=world)) * 10.0 ** rng.integers(-3, 4, size=world)
+        bits = vals.view(np.uint64).copy()
+        out = np.zeros(world, np.uint64)
+        emu.emu_board_allreduce(ptrs, world, ch, ctypes.c_ulonglong(seq), take_min, bits.ctypes.data_as(ctypes.c_void_p),
+                                out.ctypes.data_as(ctypes.c_void_p), err.ctypes.data_as(ctypes.c_void_p))
+        want = vals.min() if take_min else vals.max()
+        assert (out.view(np.float64) == want).all() and err[0] == 0, (seq, ch)
