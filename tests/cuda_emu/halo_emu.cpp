@@ -26,7 +26,12 @@ static inline unsigned long long __shfl_xor_sync(unsigned m, unsigned long long 
 #include "ssb_device.cuh"
 #undef ssb_ld256
 
+// own namespace: libssb_core.so exports nvcc's host stubs of the very same kernels under the same mangled names, and it may
+// already be loaded (RTLD_GLOBAL) in the test process — a plain call to k_halo_send would bind to the stub
+namespace halo_emu {
 #include EMU_KERNELS
+}
+using namespace halo_emu;
 
 struct HaloEmuRank {
     int N, Sc, Sd;

@@ -42,7 +42,7 @@ def emu(tmp_path_factory):
     kern.write_text(text)
     so = tmp / "halo_emu.so"
     cuda_inc = os.path.join(os.path.dirname(os.path.dirname(codegen.nvcc_path())), "include")
-    cmd = ["g++", "-std=c++20", "-O1", "-w", "-pthread", "-shared", "-fPIC", "-I", cuda_inc, "-I", codegen.CSRC,
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-pthread", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", cuda_inc, "-I", codegen.CSRC,
            "-I", os.path.join(ROOT, "tests", "cuda_emu"), f"-DEMU_KERNELS=\"{kern}\"",
            os.path.join(ROOT, "tests", "cuda_emu", "halo_emu.cpp"), "-o", str(so)]
     res = subprocess.run(cmd, capture_output=True, text=True)
