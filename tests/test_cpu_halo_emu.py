@@ -211,3 +211,71 @@ def test_board_all_reduce_gives_every_rank_the_same_extreme(emu, world):
                                 out.ctypes.data_as(ctypes.c_void_p), err.ctypes.data_as(ctypes.c_void_p))
         want = vals.min() if take_min else vals.max()
         assert (out.view(np.float64) == want).all() and err[0] == 0, (seq, ch)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# k_lookahead: the displacement bookkeeping that lets a moving step decide "keep the candidate lists or rebuild" without a
+# read-back after the predictor
+# ----------------------------------------------------------------------------------------------------------------------
+class _LookArgs(ctypes.Structure):
+    _fields_ = [("N", ctypes.c_int), ("dt", ctypes.c_double), ("x", ctypes.c_void_p * 3), ("xref", ctypes.c_void_p * 3),
+                ("v", ctypes.c_void_p * 3), ("F", ctypes.c_void_p * 3), ("Fbp", ctypes.c_void_p * 3), ("solid", ctypes.c_void_p),
+                ("out", ctypes.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def look_emu(tmp_path_factory):
+    from spatialpy_b200 import codegen
+    tmp = tmp_path_factory.mktemp("look_emu")
+    src = open(os.path.join(codegen.CSRC, "ssb_core.cu")).read()
+    a = src.index("__global__ void k_lookahead(")
+    b = src.index("// neighbour search: query = live x_i")
+    kern = tmp / "look_kernels.inc"
+    kern.write_text(src[a:b])
+    so = tmp / "lookahead_emu.so"
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(codegen.nvcc_path())), "include")
+    cmd = ["g++", "-std=c++20", "-O1", "-w", "-ffp-contract=off", "-pthread", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I", cuda_inc,
+           "-I", codegen.CSRC, "-I", os.path.join(ROOT, "tests", "cuda_emu"), f"-DEMU_KERNELS=\"{kern}\"",
+           os.path.join(ROOT, "tests", "cuda_emu", "lookahead_emu.cpp"), "-o", str(so)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    return ctypes.CDLL(str(so))
+
+
+@pytest.mark.parametrize("which", ["tank", "cavity2d"])
+def test_lookahead_predicts_what_the_next_predictor_does(look_emu, which):
+    """After a step is complete, k_lookahead's three maxima — |x' - xref|^2, |x' - x|^2, |x - xref|^2 with x' = the position the
+    NEXT predictor will produce — must be exactly what the oracle's take_step1 (E/src/simulate.cpp:68-79; the boundary conditions
+    reassign v only after the position update) then does, on a 3-D tank and on the lid-driven cavity whose BC overwrites v."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sdpd_oracle
+    from spatialpy_b200 import configs
+    from util import load_model
+    if which == "tank":
+        fm = configs.tank_sdpd(n=9, nt=10, output_every=10, dt=2e-5)
+        fm.x = fm.x + np.random.default_rng(3).uniform(-0.01, 0.01, fm.x.shape)
+    else:
+        fm = load_model("cavity2d")
+    o = sdpd_oracle.SdpdOracle(fm)
+    o.step()
+    xref = o.x.copy()                                        # "the lists were built here"
+    for _ in range(3):
+        o.step()
+    st = {k: np.ascontiguousarray(getattr(o, k).T.copy()) for k in ("x", "v", "F", "Fbp")}     # [3, N] component arrays
+    xr = np.ascontiguousarray(xref.T.copy())
+    solid = np.ascontiguousarray(o.solid.astype(np.int32))
+    out = np.zeros(3, np.uint64)
+    a = _LookArgs()
+    a.N, a.dt = o.N, o.dt
+    for d in range(3):
+        a.x[d], a.xref[d], a.v[d], a.F[d], a.Fbp[d] = (arr[d].ctypes.data for arr in (st["x"], xr, st["v"], st["F"], st["Fbp"]))
+    a.solid, a.out = solid.ctypes.data, out.ctypes.data
+    assert look_emu.emu_lookahead(ctypes.byref(a), 3) == 0   # 3 CTAs of 256 threads, grid-stride
+    x_now = o.x.copy()
+    o.take_step1()
+    want = [((o.x - xref) ** 2).sum(axis=1).max(), ((o.x - x_now) ** 2).sum(axis=1).max(), ((x_now - xref) ** 2).sum(axis=1).max()]
+    got = out.view(np.float64)
+    assert want[1] > 0 and want[0] > want[1]
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
