@@ -1,6 +1,7 @@
 """CPU tier: the native slab transport kernels (spatialpy_b200/csrc/ssb_core.cu: k_halo_send/_recv/_wait, k_inbox_send/_recv,
 k_board_post/_reduce) run as SOURCE on the host by the block emulator (tests/cuda_emu): message layout in the receive window,
-last-CTA publish of the sequence flags, compaction of the sSSA inbox, the scalar all-reduce boards.  The reference has no domain
+last-CTA publish of the sequence flags, compaction of the sSSA inbox, the scalar all-reduce boards; further down, k_lookahead
+against the oracle's next predictor and a property test of the Verlet keep rule it feeds.  The reference has no domain
 decomposition; what these kernels must preserve is that a ghost copy carries its owner's values after every
 exchange at the substep boundaries of E/src/simulate_threads.cpp:232-281 and that no molecule is lost or duplicated."""
 import ctypes
